@@ -1,0 +1,175 @@
+/*
+ * osz_b200.h -- C ABI of the B200-native openseize hot path.
+ *
+ * The reference (mscaudill/openseize, pure Python) has no native/FFI boundary
+ * of its own: its operators call numpy/scipy routines chunk by chunk from the
+ * generator functions of src/openseize/core/numerical.py.  This header is the
+ * boundary a maintainer would bind (ctypes) to replace those per-chunk calls;
+ * each entry point names the reference call site it replaces.  See
+ * INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns 0 (OSZ_OK) or a negative osz_status; the message
+ *     of the last failure on the calling thread is osz_last_error().
+ *   - data pointers named *_dev are DEVICE pointers, *_host are host pointers.
+ *   - signals are time-contiguous rows: sample t of row r is p[r*ld + t]
+ *     (ld in elements).  Other layouts are packed with osz_pack_rows_f64.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     All exec calls are asynchronous on that stream.
+ *   - plans are immutable after creation and may be shared between streams.
+ *   - there is no CPU path: every exec call launches sm_100a kernels and fails
+ *     with OSZ_ERR_CUDA when no device is present.
+ */
+#ifndef OSZ_B200_H
+#define OSZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum osz_status {
+    OSZ_OK = 0,
+    OSZ_ERR_ARG = -1,      /* invalid argument                              */
+    OSZ_ERR_CUDA = -2,     /* CUDA runtime / launch failure                 */
+    OSZ_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+    OSZ_ERR_ALLOC = -4
+} osz_status;
+
+/* ---- library ---------------------------------------------------------- */
+int osz_version(void);
+const char *osz_last_error(void);
+/* sm_count, compute capability and opt-in shared memory of device `dev`. */
+int osz_device_info(int dev, int *sm_count, int *cc_major, int *cc_minor,
+                    int64_t *smem_optin_bytes, int64_t *global_mem_bytes);
+/* number of kernels this library has launched in this process (all threads);
+ * bench.py reports the difference across its timed region as gpu_launches. */
+int64_t osz_launch_count(void);
+
+/* ---- runtime plumbing (for hosts that do not bring their own allocator;
+ *      replaces nothing in the reference -- it is the pinned-host streaming
+ *      substrate under core/producer.py's chunk iterator) ----------------- */
+int osz_dev_malloc(void **p_dev, size_t bytes);
+int osz_dev_free(void *p_dev);
+int osz_host_alloc(void **p_host, size_t bytes);          /* pinned */
+int osz_host_free(void *p_host);
+int osz_stream_create(void **stream);
+int osz_stream_destroy(void *stream);
+int osz_stream_sync(void *stream);
+int osz_memcpy_h2d_async(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int osz_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int osz_memcpy_d2d_async(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
+/* strided rows (ArrayProducer yields views: core/producer.py:289-295) */
+int osz_memcpy2d_h2d_async(void *dst_dev, size_t dst_pitch_bytes, const void *src_host,
+                           size_t src_pitch_bytes, size_t width_bytes, size_t height,
+                           void *stream);
+int osz_memcpy2d_d2h_async(void *dst_host, size_t dst_pitch_bytes, const void *src_dev,
+                           size_t src_pitch_bytes, size_t width_bytes, size_t height,
+                           void *stream);
+int osz_memset_async(void *dst_dev, int value, size_t bytes, void *stream);
+
+/* (outer, n, inner) <-> (outer*inner rows, n) time-contiguous.
+ * src element (o, t, i) is src[(o*n + t)*inner + i]; row = o*inner + i.
+ * Replaces the axis-generic slicing of core/arraytools.py:43-82 for data
+ * whose sample axis is not the last one. */
+int osz_pack_rows_f64(const double *src_dev, int64_t outer, int64_t n, int64_t inner,
+                      double *dst_dev, int64_t ld_dst, void *stream);
+int osz_unpack_rows_f64(const double *src_dev, int64_t ld_src, int64_t outer, int64_t n,
+                        int64_t inner, double *dst_dev, void *stream);
+/* complex128 variant (STFT output) */
+int osz_unpack_rows_c128(const double *src_dev, int64_t ld_src, int64_t outer, int64_t n,
+                         int64_t inner, double *dst_dev, void *stream);
+/* widen float32 / int16 chunks to float64 on the device (the reference
+ * returns float64 for every input dtype). */
+int osz_widen_f32_f64(const float *src_dev, double *dst_dev, int64_t count, void *stream);
+int osz_widen_i16_f64(const int16_t *src_dev, double *dst_dev, int64_t count, void *stream);
+
+/* ---- FIR: replaces _cconvolve + overlap-add of nm.oaconvolve
+ *      (core/numerical.py:229-269) --------------------------------------- */
+typedef struct osz_fir_plan osz_fir_plan;
+enum { OSZ_FIR_AUTO = 0, OSZ_FIR_DIRECT = 1, OSZ_FIR_FFT = 2 };
+/* taps: the window the reference passes to oaconvolve (numerical.py:158). */
+int osz_fir_plan_create(osz_fir_plan **plan, const double *taps_host, int ntaps, int algo);
+int osz_fir_plan_destroy(osz_fir_plan *plan);
+int osz_fir_plan_algo(const osz_fir_plan *plan);   /* resolved algorithm */
+/* Valid linear convolution of one halo'd span per row:
+ *   y[r][i] = sum_{k<ntaps} taps[k] * x[r][i + ntaps-1-k],  0 <= i < n_out
+ * x_dev points at the FIRST halo sample; each row holds n_out + ntaps-1
+ * readable samples.  The host keeps the ntaps-1 halo between chunks (the
+ * reference's `overlap` carry, numerical.py:220-226,268-269). */
+int osz_fir_exec_f64(const osz_fir_plan *plan, const double *x_dev, int64_t ldx,
+                     int64_t rows, int64_t n_out, double *y_dev, int64_t ldy, void *stream);
+
+/* ---- IIR biquad cascade: replaces scipy.signal.sosfilt as called by
+ *      nm.sosfilt / nm.sosfiltfilt (core/numerical.py:334,399,402,410) and
+ *      scipy.signal.lfilter for len(a)=len(b)=3 (:445,508,511,519) -------- */
+typedef struct osz_sos_plan osz_sos_plan;
+/* sos: (nsec, 6) rows [b0 b1 b2 a0 a1 a2], a0 normalised like scipy. */
+int osz_sos_plan_create(osz_sos_plan **plan, const double *sos_host, int nsec);
+int osz_sos_plan_destroy(osz_sos_plan *plan);
+/* Filter n samples per row through the cascade (DF2T), as a time-parallel
+ * scan.  state_dev is (rows, nsec, 2) delay registers, read as the initial
+ * condition and overwritten with the final one (the reference's `z`,
+ * numerical.py:329-335).  reverse != 0 runs from sample n-1 down to 0 and
+ * writes y in place of the same index (flip -> sosfilt -> flip,
+ * numerical.py:401-403).  y_dev may be NULL: only the final state is wanted
+ * (the look-ahead pass, numerical.py:397-399). */
+int osz_sos_exec_f64(const osz_sos_plan *plan, const double *x_dev, int64_t ldx,
+                     int64_t rows, int64_t n, int reverse, double *state_dev,
+                     double *y_dev, int64_t ldy, void *stream);
+/* state[r][s][j] = zi[s][j] * x[r][sample]  (numerical.py:385,399,410):
+ * zi_host is scipy.signal.sosfilt_zi(sos), shape (nsec, 2). */
+int osz_sos_state_from_sample_f64(const osz_sos_plan *plan, const double *zi_host,
+                                  const double *x_dev, int64_t ldx, int64_t rows,
+                                  int64_t sample, double *state_dev, void *stream);
+
+/* ---- polyphase resampling: replaces scipy.signal.resample_poly/upfirdn as
+ *      called by nm.polyphase_resample (core/numerical.py:610,631) -------- */
+typedef struct osz_upfirdn_plan osz_upfirdn_plan;
+/* h: anti-alias taps exactly as handed to resample_poly(window=h) (the plan
+ * applies scipy's h *= up).  up/down already reduced by their gcd. */
+int osz_upfirdn_plan_create(osz_upfirdn_plan **plan, const double *h_host, int ntaps,
+                            int up, int down);
+int osz_upfirdn_plan_destroy(osz_upfirdn_plan *plan);
+/* Global output sample j of the resampled recording is
+ *   y[j] = sum_k h'[j*down + half - k*up] * x[k],  half = (ntaps-1)/2
+ * (scipy's resample_poly after its pre-pad/pre-remove bookkeeping).  This call
+ * computes j in [out_first, out_first + n_out) for each row.  x_dev[r*ldx + m]
+ * holds global input sample (x_first + m); samples outside [x_first,
+ * x_first + x_len) that the sum touches are taken as zero (recording edges). */
+int osz_upfirdn_exec_f64(const osz_upfirdn_plan *plan, const double *x_dev, int64_t ldx,
+                         int64_t rows, int64_t x_first, int64_t x_len, int64_t out_first,
+                         int64_t n_out, double *y_dev, int64_t ldy, void *stream);
+
+/* ---- windowed DFT: replaces detrend + window + rfft + scale of
+ *      nm.modified_dft / nm.periodogram (core/numerical.py:691-716,781-794)
+ *      applied to the sliding windows of nm._spectra_estimatives (:817-849) */
+typedef struct osz_spec_plan osz_spec_plan;
+enum { OSZ_DETREND_NONE = 0, OSZ_DETREND_CONSTANT = 1, OSZ_DETREND_LINEAR = 2 };
+/* window_host: nfft window coefficients (scipy.signal.get_window, :694);
+ * norm: 1/(fs*sum(w^2)) or 1/sum(w)^2 (:703-708). */
+int osz_spec_plan_create(osz_spec_plan **plan, int nfft, int stride,
+                         const double *window_host, int detrend, double norm);
+int osz_spec_plan_destroy(osz_spec_plan *plan);
+int osz_spec_plan_path(const osz_spec_plan *plan); /* 1 = shared-memory pow2, 2 = generic */
+/* Fused Welch accumulate: for each row adds the one-sided periodograms of
+ * segments s = 0..nseg-1 (segment s = x[r][s*stride .. s*stride+nfft)) into
+ * psd_sum_dev[r*ldp + k], k <= nfft/2.  The caller divides by the segment
+ * count (the reference's running mean, spectra/estimators.py:150-152). */
+int osz_welch_accum_f64(const osz_spec_plan *plan, const double *x_dev, int64_t ldx,
+                        int64_t rows, int64_t nseg, double *psd_sum_dev, int64_t ldp,
+                        void *stream);
+/* Per-segment outputs.  out is [seg][row][nfft/2+1]; periodogram: float64,
+ * modified DFT (STFT): interleaved complex128. */
+int osz_periodogram_f64(const osz_spec_plan *plan, const double *x_dev, int64_t ldx,
+                        int64_t rows, int64_t nseg, double *out_dev, void *stream);
+int osz_stft_f64(const osz_spec_plan *plan, const double *x_dev, int64_t ldx,
+                 int64_t rows, int64_t nseg, double *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSZ_B200_H */

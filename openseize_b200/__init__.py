@@ -1,0 +1,18 @@
+"""openseize_b200: a B200-native (sm_100a CUDA) implementation of openseize's
+chunked filtering and spectral hot path behind the reference's producer /
+operator API.
+
+    from openseize_b200 import producer
+    from openseize_b200.filtering.fir import Kaiser
+    from openseize_b200.filtering.iir import Butter, Notch
+    from openseize_b200.resampling.resampling import downsample, resample
+    from openseize_b200.spectra.estimators import psd, stft
+
+Importing the package does not touch CUDA; the first iteration of a producer
+built by one of the operators does, and raises if no device or no built
+library is present (there is no CPU fallback).
+"""
+
+from openseize_b200.core.producer import producer  # noqa: F401
+
+__version__ = "0.1.0"

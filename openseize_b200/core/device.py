@@ -1,0 +1,423 @@
+"""Device plumbing for the hot path: plans, kernel launches, and the pinned
+host <-> device chunk streaming under the producer iterator.
+
+torch is used only for device memory, streams and events; every arithmetic
+kernel is one of ours, called through the C ABI (``openseize_b200._abi``).
+Signals live on the device as time-contiguous rows ``(rows, n)``: for a chunk
+of shape ``(..., n, ...)`` with the sample axis at ``axis``, ``rows =
+outer * inner`` and row ``o * inner + i`` holds ``chunk[o, :, i]``.
+"""
+
+import ctypes
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+from openseize_b200 import _abi
+
+_torch = None
+DEVICE = "cuda"
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    """The hot path has no CPU implementation: fail loudly without a GPU."""
+    t = torch()
+    if not t.cuda.is_available():
+        raise RuntimeError(
+            "openseize_b200 runs its DSP kernels on a CUDA device (sm_100a) and "
+            "none is visible; there is no CPU fallback.")
+    _abi.load()
+    return t
+
+
+def _vp(addr):
+    return ctypes.c_void_p(int(addr))
+
+
+def _cur_stream():
+    return _vp(torch().cuda.current_stream().cuda_stream)
+
+
+def _rows_ptr(t):
+    """(pointer, leading dimension) of a 2-D float64 device tensor whose rows
+    are time-contiguous."""
+    assert t.dim() == 2 and t.dtype == torch().float64 and t.is_cuda
+    if t.shape[1] > 1:
+        assert t.stride(1) == 1, "rows must be time-contiguous"
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    return _vp(t.data_ptr()), int(ld)
+
+
+# --------------------------------------------------------------------------
+# side streams
+# --------------------------------------------------------------------------
+class _Streams:
+    _by_device = {}
+
+    @classmethod
+    def get(cls):
+        t = torch()
+        dev = t.cuda.current_device()
+        if dev not in cls._by_device:
+            cls._by_device[dev] = (t.cuda.Stream(), t.cuda.Stream())
+        return cls._by_device[dev]
+
+
+# --------------------------------------------------------------------------
+# layout of a chunk
+# --------------------------------------------------------------------------
+class Layout:
+    """Where the sample axis sits in the reference-facing ndarray."""
+
+    def __init__(self, shape, axis):
+        shape = tuple(int(s) for s in shape)
+        axis = int(np.arange(len(shape))[axis])
+        self.axis = axis
+        self.lead = shape[:axis]
+        self.trail = shape[axis + 1:]
+        self.outer = int(np.prod(self.lead, dtype=np.int64)) if self.lead else 1
+        self.inner = int(np.prod(self.trail, dtype=np.int64)) if self.trail else 1
+        self.rows = self.outer * self.inner
+
+    def host_shape(self, n):
+        return self.lead + (int(n),) + self.trail
+
+
+def upload(arr, layout):
+    """Host chunk -> device rows ``(rows, n)`` float64 on the current stream.
+
+    The copy is issued on a side stream from pinned memory (the chunk itself
+    when it already is pinned, else a pinned staging block from torch's
+    caching host allocator) so it overlaps the kernels of the previous chunk.
+    """
+    t = require_cuda()
+    a = np.asarray(arr)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    n = a.shape[layout.axis]
+    h2d, _ = _Streams.get()
+    cur = t.cuda.current_stream()
+    if layout.inner == 1:
+        a2 = a.reshape(layout.outer, n)
+        dev = t.empty((layout.outer, n), dtype=t.float64, device="cuda")
+        h2d.wait_stream(cur)     # dev's block may have been freed on `cur`
+        with t.cuda.stream(h2d):
+            direct = False
+            if a2.strides[1] == 8 and a2.strides[0] >= n * 8 and a2.flags.writeable:
+                try:
+                    direct = t.from_numpy(a2).is_pinned()
+                except Exception:      # exotic strides torch refuses to wrap
+                    direct = False
+            if direct:
+                rc = _abi.load().osz_memcpy2d_h2d_async(
+                    _vp(dev.data_ptr()), n * 8, _vp(a2.ctypes.data), a2.strides[0], n * 8,
+                    layout.outer, _vp(h2d.cuda_stream))
+                _abi.check(rc, "upload")
+                dev._osz_keepalive = a2
+            else:
+                stage = t.empty((layout.outer, n), dtype=t.float64, pin_memory=True)
+                np.copyto(stage.numpy(), a2)
+                dev.copy_(stage, non_blocking=True)
+        cur.wait_stream(h2d)
+        dev.record_stream(cur)
+        return dev
+    # sample axis is not last: ship the chunk as it is, transpose on the device
+    flat = np.ascontiguousarray(a).reshape(layout.outer, n, layout.inner)
+    stage = t.empty(flat.shape, dtype=t.float64, pin_memory=True)
+    np.copyto(stage.numpy(), flat)
+    h2d.wait_stream(cur)
+    with t.cuda.stream(h2d):
+        raw = t.empty(flat.shape, dtype=t.float64, device="cuda")
+        raw.copy_(stage, non_blocking=True)
+    cur.wait_stream(h2d)
+    raw.record_stream(cur)
+    dev = t.empty((layout.rows, n), dtype=t.float64, device="cuda")
+    rc = _abi.load().osz_pack_rows_f64(_vp(raw.data_ptr()), layout.outer, n, layout.inner,
+                                       _vp(dev.data_ptr()), n, _cur_stream())
+    _abi.check(rc, "pack_rows")
+    return dev
+
+
+class Pending:
+    """A device -> pinned-host copy in flight; ``get()`` waits and returns the
+    ndarray in the reference's layout (backed by the pinned block)."""
+
+    def __init__(self, host, event, shape, complex_=False):
+        self._host, self._event, self._shape, self._complex = host, event, shape, complex_
+
+    def get(self):
+        self._event.synchronize()
+        out = self._host.numpy()
+        if self._complex:
+            out = out.view(np.complex128)
+        return out.reshape(self._shape)
+
+
+def download(dev, layout, complex_=False):
+    """Device rows ``(rows, n)`` (float64, or complex128 stored as (rows, n, 2))
+    -> :class:`Pending` host array of shape ``layout.host_shape(n)``."""
+    t = require_cuda()
+    n = dev.shape[1]
+    cur = t.cuda.current_stream()
+    _, d2h = _Streams.get()
+    if layout.inner > 1:
+        shape = (layout.outer, n, layout.inner) + ((2,) if complex_ else ())
+        tmp = t.empty(shape, dtype=t.float64, device="cuda")
+        src = dev.contiguous()
+        fn = _abi.load().osz_unpack_rows_c128 if complex_ else _abi.load().osz_unpack_rows_f64
+        rc = fn(_vp(src.data_ptr()), n, layout.outer, n, layout.inner, _vp(tmp.data_ptr()),
+                _cur_stream())
+        _abi.check(rc, "unpack_rows")
+        dev = tmp
+    host = t.empty(tuple(dev.shape), dtype=t.float64, pin_memory=True)
+    d2h.wait_stream(cur)
+    with t.cuda.stream(d2h):
+        host.copy_(dev, non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record(d2h)
+    dev.record_stream(d2h)
+    return Pending(host, ev, layout.host_shape(n), complex_)
+
+
+# --------------------------------------------------------------------------
+# plans (cached by their defining coefficients)
+# --------------------------------------------------------------------------
+class _Plan:
+    _destroy = None
+
+    def __init__(self):
+        self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.handle and self._destroy:
+                getattr(_abi.load(), self._destroy)(self.handle)
+        except Exception:
+            pass
+
+
+class _Cache:
+    def __init__(self, size=32):
+        self.size, self.items = size, OrderedDict()
+
+    def get(self, key, make):
+        dev = torch().cuda.current_device()
+        key = (dev,) + key
+        if key in self.items:
+            self.items.move_to_end(key)
+            return self.items[key]
+        val = make()
+        self.items[key] = val
+        if len(self.items) > self.size:
+            self.items.popitem(last=False)
+        return val
+
+
+_plans = _Cache()
+
+
+class FirPlan(_Plan):
+    _destroy = "osz_fir_plan_destroy"
+
+    def __init__(self, taps, algo=_abi.FIR_AUTO):
+        super().__init__()
+        require_cuda()
+        arr, ptr = _abi.as_double_array(taps)
+        self.ntaps = int(arr.size)
+        rc = _abi.load().osz_fir_plan_create(ctypes.byref(self.handle), ptr, self.ntaps, int(algo))
+        _abi.check(rc, "fir_plan_create")
+        self.algo = _abi.load().osz_fir_plan_algo(self.handle)
+
+    @staticmethod
+    def cached(taps, algo=_abi.FIR_AUTO):
+        arr = np.ascontiguousarray(taps, dtype=np.float64)
+        return _plans.get(("fir", arr.tobytes(), int(algo)), lambda: FirPlan(arr, algo))
+
+    def run(self, xbuf, n_out, out=None):
+        """xbuf: (rows, >= n_out + ntaps - 1) halo'd input.  Returns (rows, n_out)."""
+        t = torch()
+        rows = xbuf.shape[0]
+        assert xbuf.shape[1] >= n_out + self.ntaps - 1
+        if out is None:
+            out = empty((rows, n_out))
+        xp, ldx = _rows_ptr(xbuf)
+        yp, ldy = _rows_ptr(out)
+        rc = _abi.load().osz_fir_exec_f64(self.handle, xp, ldx, rows, n_out, yp, ldy,
+                                          _cur_stream())
+        _abi.check(rc, "fir_exec")
+        return out
+
+
+class SosPlan(_Plan):
+    _destroy = "osz_sos_plan_destroy"
+
+    def __init__(self, sos):
+        super().__init__()
+        require_cuda()
+        arr, ptr = _abi.as_double_array(sos)
+        assert arr.ndim == 2 and arr.shape[1] == 6
+        self.nsec = int(arr.shape[0])
+        rc = _abi.load().osz_sos_plan_create(ctypes.byref(self.handle), ptr, self.nsec)
+        _abi.check(rc, "sos_plan_create")
+
+    @staticmethod
+    def cached(sos):
+        arr = np.ascontiguousarray(sos, dtype=np.float64)
+        return _plans.get(("sos", arr.tobytes()), lambda: SosPlan(arr))
+
+    def run(self, x, state, reverse=False, want_output=True, out=None):
+        """Filter x (rows, n) through the cascade; ``state`` (rows, nsec, 2) is
+        updated in place.  Returns y, or None when only the state is wanted."""
+        t = torch()
+        rows, n = x.shape
+        assert state.shape == (rows, self.nsec, 2) and state.is_contiguous()
+        xp, ldx = _rows_ptr(x)
+        if want_output:
+            if out is None:
+                out = empty((rows, n))
+            yp, ldy = _rows_ptr(out)
+        else:
+            out, yp, ldy = None, _vp(0), 0
+        rc = _abi.load().osz_sos_exec_f64(self.handle, xp, ldx, rows, n, int(bool(reverse)),
+                                          _vp(state.data_ptr()), yp, ldy, _cur_stream())
+        _abi.check(rc, "sos_exec")
+        return out
+
+    def state_from_sample(self, zi, x, sample):
+        """state[r, s, :] = zi[s, :] * x[r, sample]."""
+        t = torch()
+        rows = x.shape[0]
+        zarr, zptr = _abi.as_double_array(zi)
+        assert zarr.shape == (self.nsec, 2)
+        state = empty((rows, self.nsec, 2))
+        xp, ldx = _rows_ptr(x)
+        rc = _abi.load().osz_sos_state_from_sample_f64(self.handle, zptr, xp, ldx, rows,
+                                                       int(sample), _vp(state.data_ptr()),
+                                                       _cur_stream())
+        _abi.check(rc, "sos_state_from_sample")
+        return state
+
+
+class UpfirdnPlan(_Plan):
+    _destroy = "osz_upfirdn_plan_destroy"
+
+    def __init__(self, h, up, down):
+        super().__init__()
+        require_cuda()
+        arr, ptr = _abi.as_double_array(h)
+        self.ntaps, self.up, self.down = int(arr.size), int(up), int(down)
+        rc = _abi.load().osz_upfirdn_plan_create(ctypes.byref(self.handle), ptr, self.ntaps,
+                                                 self.up, self.down)
+        _abi.check(rc, "upfirdn_plan_create")
+
+    @staticmethod
+    def cached(h, up, down):
+        arr = np.ascontiguousarray(h, dtype=np.float64)
+        return _plans.get(("ufd", arr.tobytes(), int(up), int(down)),
+                          lambda: UpfirdnPlan(arr, up, down))
+
+    def run(self, x, x_first, out_first, n_out):
+        """x: (rows, m) holding global input samples x_first .. x_first+m-1.
+        Returns global output samples out_first .. out_first+n_out-1."""
+        t = torch()
+        rows, m = x.shape
+        out = empty((rows, n_out))
+        xp, ldx = _rows_ptr(x)
+        yp, ldy = _rows_ptr(out)
+        rc = _abi.load().osz_upfirdn_exec_f64(self.handle, xp, ldx, rows, int(x_first), m,
+                                              int(out_first), int(n_out), yp, ldy, _cur_stream())
+        _abi.check(rc, "upfirdn_exec")
+        return out
+
+
+class SpecPlan(_Plan):
+    _destroy = "osz_spec_plan_destroy"
+
+    def __init__(self, nfft, stride, window, detrend, norm):
+        super().__init__()
+        require_cuda()
+        arr, ptr = _abi.as_double_array(window)
+        assert arr.size == nfft
+        self.nfft, self.stride, self.nfreq = int(nfft), int(stride), int(nfft) // 2 + 1
+        rc = _abi.load().osz_spec_plan_create(ctypes.byref(self.handle), self.nfft, self.stride,
+                                              ptr, _abi.DETREND[detrend], float(norm))
+        _abi.check(rc, "spec_plan_create")
+        self.path = _abi.load().osz_spec_plan_path(self.handle)
+
+    @staticmethod
+    def cached(nfft, stride, window, detrend, norm):
+        arr = np.ascontiguousarray(window, dtype=np.float64)
+        key = ("spec", int(nfft), int(stride), arr.tobytes(), str(detrend), float(norm))
+        return _plans.get(key, lambda: SpecPlan(nfft, stride, arr, detrend, norm))
+
+    def nseg_available(self, width):
+        return (width - self.nfft) // self.stride + 1 if width >= self.nfft else 0
+
+    def welch_accum(self, x, nseg, psd_sum):
+        rows = x.shape[0]
+        assert x.shape[1] >= (nseg - 1) * self.stride + self.nfft
+        assert psd_sum.shape == (rows, self.nfreq) and psd_sum.is_contiguous()
+        xp, ldx = _rows_ptr(x)
+        rc = _abi.load().osz_welch_accum_f64(self.handle, xp, ldx, rows, int(nseg),
+                                             _vp(psd_sum.data_ptr()), self.nfreq, _cur_stream())
+        _abi.check(rc, "welch_accum")
+
+    def segments(self, x, nseg, complex_):
+        """Per-segment modified DFT (complex_) or periodogram: (nseg, rows, nfreq[, 2])."""
+        t = torch()
+        rows = x.shape[0]
+        assert x.shape[1] >= (nseg - 1) * self.stride + self.nfft
+        shape = (nseg, rows, self.nfreq) + ((2,) if complex_ else ())
+        out = empty(shape)
+        xp, ldx = _rows_ptr(x)
+        fn = _abi.load().osz_stft_f64 if complex_ else _abi.load().osz_periodogram_f64
+        rc = fn(self.handle, xp, ldx, rows, int(nseg), _vp(out.data_ptr()), _cur_stream())
+        _abi.check(rc, "stft" if complex_ else "periodogram")
+        return out
+
+
+def ceil_div(a, b):
+    return -(-int(a) // int(b))
+
+
+def cat_time(parts):
+    """Concatenate device row blocks along time."""
+    parts = [p for p in parts if p is not None and p.shape[1] > 0]
+    if len(parts) == 1:
+        return parts[0]
+    return torch().cat(parts, dim=1)
+
+
+def zeros(shape):
+    """Zero-filled float64 device tensor."""
+    t = require_cuda()
+    return t.zeros(tuple(shape), dtype=t.float64, device=DEVICE)
+
+
+def empty(shape):
+    t = require_cuda()
+    return t.empty(tuple(shape), dtype=t.float64, device=DEVICE)
+
+
+def zeros_rows(rows, n):
+    return zeros((rows, n))
+
+
+def from_host(arr):
+    """Small host ndarray -> device tensor (synchronous; coefficients / states)."""
+    t = require_cuda()
+    return t.from_numpy(np.array(arr, dtype=np.float64, order="C", copy=True)).to(DEVICE)
+
+
+def isfinite_number(x):
+    return isinstance(x, (int, float)) and math.isfinite(x)

@@ -1,0 +1,622 @@
+"""GPU generating functions with the names, positional order and chunk
+semantics of the reference's ``openseize.core.numerical`` (the hot path,
+reference core/numerical.py:158-1087).  The L4 operators build
+``functools.partial(nm.<genfunc>, pro, ...)`` and wrap it in a producer exactly
+as the reference does; nothing touches the GPU until the producer is iterated.
+
+Every generating function ``f`` has a device twin ``f.device`` that yields
+device row blocks instead of host ndarrays.  When the input producer of a GPU
+operator is itself a producer over one of these functions, the chain is run on
+the device end to end (``device_chunks``): one pull of each upstream chunk, no
+host round trips between stages -- the reference re-executes upstream stages
+once per downstream iterator; results are identical.
+
+There is no CPU arithmetic in this module: without a CUDA device every
+generator raises on first iteration.
+"""
+
+import functools
+
+import numpy as np
+import scipy.signal as sps
+
+from openseize_b200.core import device as dv
+from openseize_b200.core.arraytools import normalize_axis
+from openseize_b200.core.producer import GenProducer, Producer, producer
+
+# ---------------------------------------------------------------------------
+# shape helpers (pure index arithmetic, reference core/numerical.py:19-155)
+# ---------------------------------------------------------------------------
+
+
+def optimal_nffts(arr):
+    """The reference's block-size heuristic (numerical.py:19-38).  Kept for
+    API parity; the GPU kernels pick their own block size (results do not
+    depend on it)."""
+    return int(8 * 2 ** np.ceil(np.log2(len(arr))))
+
+
+def convolved_shape(shape1, shape2, mode, axis):
+    """Shape of the convolution of two arrays along ``axis`` (numerical.py:41-73)."""
+    m, n = shape1[axis], shape2[axis if len(shape2) > 1 else 0]
+    p, q = max(m, n), min(m, n)
+    out = list(shape1 if len(shape1) >= len(shape2) else shape2)
+    out[axis] = {"full": m + n - 1, "same": p, "valid": m + n - 1 - 2 * (q - 1)}[mode]
+    return tuple(out)
+
+
+def _mode_cuts(ntaps, mode):
+    """Samples of the full convolution dropped on the left / right by the numpy
+    convolve modes (numerical.py:143-150)."""
+    if mode == "full":
+        return 0, 0
+    if mode == "same":
+        return (ntaps - 1) // 2, int(np.ceil((ntaps - 1) / 2))
+    if mode == "valid":
+        return ntaps - 1, ntaps - 1
+    raise ValueError("mode must be one of 'full', 'same', 'valid', got {!r}".format(mode))
+
+
+# ---------------------------------------------------------------------------
+# device chunk streams
+# ---------------------------------------------------------------------------
+class _DeviceFifo:
+    """Device twin of FIFOArray: collects row blocks, releases fixed-size ones."""
+
+    def __init__(self):
+        self.parts, self.size = [], 0
+
+    def put(self, block):
+        if block.shape[1]:
+            self.parts.append(block)
+            self.size += block.shape[1]
+
+    def get(self, n):
+        n = min(n, self.size)
+        if self.parts and self.parts[0].shape[1] == n:
+            self.size -= n
+            return self.parts.pop(0)
+        buf = dv.cat_time(self.parts)
+        out, rest = buf[:, :n], buf[:, n:]
+        self.parts = [rest] if rest.shape[1] else []
+        self.size -= n
+        return out
+
+
+def _device_twin(pro):
+    """(device generating function, args, kwargs) if ``pro`` is a producer over
+    one of this module's GPU generating functions, else None."""
+    if not isinstance(pro, GenProducer) or pro.kwargs:
+        return None
+    func, args, kwargs = pro.data, (), {}
+    if isinstance(func, functools.partial):
+        func, args, kwargs = func.func, func.args, func.keywords
+    twin = getattr(func, "device", None)
+    return (twin, args, kwargs) if twin is not None else None
+
+
+def device_chunks(pro, axis):
+    """Yield ``pro``'s chunks as device rows ``(rows, chunk)``, on the chunk
+    grid of ``pro.chunksize`` (the last one may be shorter).
+
+    Host producers are streamed through pinned memory with the copy of chunk
+    k+1 issued while chunk k's kernels run; producers over GPU generating
+    functions are consumed on the device.
+    """
+    dv.require_cuda()
+    layout = dv.Layout(pro.shape, axis)
+    twin = _device_twin(pro)
+    if twin is None:
+        for arr in pro:
+            yield dv.upload(arr, layout)
+        return
+    func, args, kwargs = twin
+    fifo, cs = _DeviceFifo(), int(pro.chunksize)
+    for block in func(*args, **kwargs):
+        fifo.put(block)
+        while fifo.size >= cs:
+            yield fifo.get(cs)
+    if fifo.size:
+        yield fifo.get(cs)
+
+
+def _to_host(device_gen, layout, complex_=False):
+    """Drain a device generator to host ndarrays, one chunk behind the kernels
+    so the D2H copy of chunk k overlaps the compute of chunk k+1."""
+    pending = None
+    for block in device_gen:
+        nxt = dv.download(block, layout, complex_)
+        if pending is not None:
+            yield pending.get()
+        pending = nxt
+    if pending is not None:
+        yield pending.get()
+
+
+def _gpu_genfunc(device_func, out_layout):
+    """Build the host generating function of a device generating function.
+    ``out_layout(*args, **kwargs)`` gives the Layout of the yielded arrays."""
+
+    def decorate(host_stub):
+        @functools.wraps(host_stub)
+        def genfunc(*args, **kwargs):
+            layout = out_layout(*args, **kwargs)
+            yield from _to_host(device_func(*args, **kwargs), layout)
+
+        genfunc.device = device_func
+        return genfunc
+
+    return decorate
+
+
+def _layout_of(pro, axis):
+    return dv.Layout(pro.shape, axis)
+
+
+# ---------------------------------------------------------------------------
+# FIR  (reference core/numerical.py:158-298)
+# ---------------------------------------------------------------------------
+def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32):
+    window = np.asarray(window, dtype=np.float64)
+    ntaps, nsamp = len(window), pro.shape[axis]
+    if nsamp < ntaps:
+        raise ValueError("oaconvolve: data length {} along axis is shorter than the {} taps"
+                         .format(nsamp, ntaps))
+    left, right = _mode_cuts(ntaps, mode)
+    last_kept = nsamp + ntaps - 1 - right          # exclusive, in full-convolution index
+    plan = dv.FirPlan.cached(window)
+    rows = _layout_of(pro, axis).rows
+    halo = dv.zeros_rows(rows, ntaps - 1)
+    pos = 0                                         # full-convolution index of the next output
+    for chunk in device_chunks(pro, axis):
+        n = chunk.shape[1]
+        final = pos + n >= nsamp
+        parts = [halo, chunk] + ([dv.zeros_rows(rows, ntaps - 1)] if final else [])
+        buf = dv.cat_time(parts)
+        n_out = n + (ntaps - 1 if final else 0)
+        y = plan.run(buf, n_out)
+        lo = max(left - pos, 0)
+        hi = min(pos + n_out, last_kept) - pos
+        halo = buf[:, n:n + ntaps - 1]
+        pos += n_out
+        if hi > lo:
+            yield y if (lo == 0 and hi == n_out) else y[:, lo:hi]
+
+
+def _oaconvolve_layout(pro, window, axis, mode, nfft_factor=32):
+    return _layout_of(pro, axis)
+
+
+@_gpu_genfunc(_oaconvolve_device, _oaconvolve_layout)
+def oaconvolve(pro, window, axis, mode, nfft_factor=32):
+    """Convolve every 1-D slice of a producer along ``axis`` with ``window``;
+    numpy convolve modes.  ``nfft_factor`` is accepted for signature parity and
+    ignored (the GPU block size does not change the result).
+
+    Yields one block per input chunk (the reference yields FFT-step sized
+    blocks; the concatenation is identical)."""
+
+
+# ---------------------------------------------------------------------------
+# IIR  (reference core/numerical.py:301-520)
+# ---------------------------------------------------------------------------
+_MAX_SEC = 16
+
+
+def _sos_groups(sos):
+    sos = np.atleast_2d(np.asarray(sos, dtype=np.float64))
+    return [dv.SosPlan.cached(sos[i:i + _MAX_SEC]) for i in range(0, sos.shape[0], _MAX_SEC)]
+
+
+class _Cascade:
+    """A biquad cascade of any length as groups of <= 16 sections."""
+
+    def __init__(self, sos):
+        self.sos = np.atleast_2d(np.asarray(sos, dtype=np.float64))
+        self.plans = _sos_groups(self.sos)
+        self.nsec = self.sos.shape[0]
+
+    def split_state(self, state):
+        """(rows, nsec, 2) -> contiguous per-group states."""
+        out, s = [], 0
+        for p in self.plans:
+            out.append(state[:, s:s + p.nsec, :].contiguous())
+            s += p.nsec
+        return out
+
+    def zero_state(self, rows):
+        return [dv.zeros((rows, p.nsec, 2)) for p in self.plans]
+
+    def state_from_sample(self, zi, x, sample):
+        """Reference: zi * x[..., sample] per section (numerical.py:385,399,410).
+        Section s+1 sees the steady-state OUTPUT of section s, which
+        scipy.signal.sosfilt_zi has already folded into zi."""
+        out, s = [], 0
+        for p in self.plans:
+            out.append(p.state_from_sample(zi[s:s + p.nsec], x, sample))
+            s += p.nsec
+        return out
+
+    def run(self, x, states, reverse=False, want_output=True):
+        y = x
+        for i, (p, st) in enumerate(zip(self.plans, states)):
+            need = want_output or i < len(self.plans) - 1
+            y = p.run(y, st, reverse=reverse, want_output=need)
+        return y if want_output else None
+
+
+def _zi_to_rows(zi, layout, nsec):
+    """Reference zi layout (nsec, ..., 2, ...) -> (rows, nsec, 2) device tensor."""
+    zi = np.asarray(zi, dtype=np.float64)
+    full = (nsec,) + layout.host_shape(2)
+    zi = np.broadcast_to(zi, full).reshape(nsec, layout.outer, 2, layout.inner)
+    rows = np.ascontiguousarray(np.transpose(zi, (1, 3, 0, 2))).reshape(layout.rows, nsec, 2)
+    return dv.from_host(rows)
+
+
+def _sosfilt_device(pro, sos, axis, zi=None):
+    layout = _layout_of(pro, axis)
+    cascade = _Cascade(sos)
+    if zi is None:
+        states = cascade.zero_state(layout.rows)
+    else:
+        states = cascade.split_state(_zi_to_rows(zi, layout, cascade.nsec))
+    for chunk in device_chunks(pro, axis):
+        yield cascade.run(chunk, states)
+
+
+def _same_layout(pro, *args, **kwargs):
+    axis = args[1] if len(args) > 1 else kwargs["axis"]
+    return _layout_of(pro, axis)
+
+
+@_gpu_genfunc(_sosfilt_device, _same_layout)
+def sosfilt(pro, sos, axis, zi=None):
+    """Forward second-order-section filter with the delay registers carried
+    from chunk to chunk (reference numerical.py:301-335)."""
+
+
+def _filtfilt_device(pro, cascade, zi, axis):
+    """Shared forward-backward driver (reference numerical.py:338-411,449-520):
+    one global forward pass; each chunk's backward pass starts from the state
+    left by filtering the NEXT forward chunk backwards from zi * its last
+    sample; the last chunk starts from zi * its own last sample."""
+    fwd_states, prev = None, None
+    for chunk in device_chunks(pro, axis):
+        if fwd_states is None:
+            fwd_states = cascade.state_from_sample(zi, chunk, 0)
+        fwd = cascade.run(chunk, fwd_states)
+        if prev is not None:
+            look = cascade.state_from_sample(zi, fwd, fwd.shape[1] - 1)
+            cascade.run(fwd, look, reverse=True, want_output=False)
+            yield cascade.run(prev, look, reverse=True)
+        prev = fwd
+    if prev is not None:
+        last = cascade.state_from_sample(zi, prev, prev.shape[1] - 1)
+        yield cascade.run(prev, last, reverse=True)
+
+
+def _sosfiltfilt_device(pro, sos, axis):
+    cascade = _Cascade(sos)
+    zi = sps.sosfilt_zi(cascade.sos)
+    yield from _filtfilt_device(pro, cascade, zi, axis)
+
+
+@_gpu_genfunc(_sosfiltfilt_device, _same_layout)
+def sosfiltfilt(pro, sos, axis):
+    """Forward-backward SOS filter with the reference's chunk-dependent
+    semantics (numerical.py:338-411): the output depends on ``pro.chunksize``
+    exactly as the reference's does."""
+
+
+def _ba_to_sos(coeffs):
+    """(b, a) of order <= 2 as one DF2T biquad -- scipy's lfilter recurrence for
+    order 2 is the sosfilt section recurrence."""
+    b, a = (np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in coeffs)
+    if max(len(b), len(a)) > 3:
+        raise NotImplementedError(
+            "transfer-function (b, a) filters above second order are not on the GPU path "
+            "yet; design the filter with fmt='sos'")
+    b = np.pad(b, (0, 3 - len(b)))
+    a = np.pad(a, (0, 3 - len(a)))
+    return np.concatenate([b, a])[None, :]
+
+
+def _lfilter_zi_rows(coeffs, zi, layout):
+    """Reference lfilter zi layout (..., K-1, ...) -> biquad state rows."""
+    b, a = coeffs
+    k = int(max(len(b), len(a)) - 1)
+    zi = np.asarray(zi, dtype=np.float64)
+    zi = np.broadcast_to(zi, layout.host_shape(k))
+    pad = [(0, 0)] * zi.ndim
+    pad[layout.axis] = (0, 2 - k)
+    zi = np.pad(zi, pad)
+    return _zi_to_rows(zi[None], layout, 1)
+
+
+def _lfilter_device(pro, coeffs, axis, zi=None):
+    layout = _layout_of(pro, axis)
+    cascade = _Cascade(_ba_to_sos(coeffs))
+    if zi is None:
+        states = cascade.zero_state(layout.rows)
+    else:
+        states = cascade.split_state(_lfilter_zi_rows(coeffs, zi, layout))
+    for chunk in device_chunks(pro, axis):
+        yield cascade.run(chunk, states)
+
+
+@_gpu_genfunc(_lfilter_device, _same_layout)
+def lfilter(pro, coeffs, axis, zi=None):
+    """Forward (b, a) filter with carried state (reference numerical.py:414-446);
+    second order and below (``Notch`` always is, filtering/iir.py:391)."""
+
+
+def _filtfilt_ba_device(pro, coeffs, axis):
+    cascade = _Cascade(_ba_to_sos(coeffs))
+    z = np.atleast_1d(sps.lfilter_zi(*coeffs))        # numerical.py:487
+    zi = np.zeros((1, 2))
+    zi[0, :len(z)] = z
+    yield from _filtfilt_device(pro, cascade, zi, axis)
+
+
+@_gpu_genfunc(_filtfilt_ba_device, _same_layout)
+def filtfilt(pro, coeffs, axis):
+    """Forward-backward (b, a) filter, chunk-dependent like the reference
+    (numerical.py:449-520)."""
+
+
+# ---------------------------------------------------------------------------
+# polyphase resampling  (reference core/numerical.py:523-632)
+# ---------------------------------------------------------------------------
+def _resample_geometry(pro, L, M, axis):
+    """Chunk size and yield boundaries of the reference (numerical.py:574-587,
+    :617-632): csize <= N//3, multiple of M; the last two chunks are merged."""
+    nsamp = pro.shape[axis]
+    csize = int(pro.chunksize)
+    if csize > nsamp // 3:
+        csize = nsamp // 3
+    if csize % M > 0:
+        csize = int(np.ceil(csize / M) * M)
+    nchunks = dv.ceil_div(nsamp, csize)
+    return nsamp, csize, nchunks
+
+
+def _resample_taps(L, M, fs, fir, kwargs):
+    kwargs = dict(kwargs)
+    cutoff = fs / (2 * max(L, M))
+    fstop = kwargs.pop("fstop", cutoff + cutoff / 10)
+    fpass = kwargs.pop("fpass", cutoff - cutoff / 10)
+    gpass, gstop = kwargs.pop("gpass", 0.1), kwargs.pop("gstop", 40)
+    return np.asarray(fir(fpass, fstop, fs, gpass, gstop).coeffs, dtype=np.float64)
+
+
+def _polyphase_device(pro, L, M, fs, fir, axis, **kwargs):
+    nsamp = pro.shape[axis]
+    if M >= nsamp:
+        raise ValueError("Decimation factor must M={} be < pro.shape[{}] = {}"
+                         .format(M, axis, nsamp))
+    nsamp, csize, nchunks = _resample_geometry(pro, L, M, axis)
+    h = _resample_taps(L, M, fs, fir, kwargs)
+    plan = dv.UpfirdnPlan.cached(h, L, M)
+    ntaps = len(h)
+    half = (ntaps - 1) // 2
+    # input reach of one output sample, in input samples
+    reach_l = 2                                    # slack kept left of the next yield's reach
+    total_out = dv.ceil_div(nsamp * L, M)
+    per_chunk = csize * L // M
+
+    src = producer(pro, csize, axis)               # same mutation as numerical.py:590
+    window, w_first = None, 0                      # device rows and their first global index
+    emitted = 0                                    # chunks of output already yielded
+    seen = 0                                       # input samples received
+    for chunk in device_chunks(src, axis):
+        window = chunk if window is None else dv.cat_time([window, chunk])
+        seen += chunk.shape[1]
+        # yield k is computable once its right reach is inside the window, or at the end
+        while emitted < nchunks - 1:
+            last_yield = emitted == nchunks - 2
+            o_lo = emitted * per_chunk
+            o_hi = total_out if last_yield else (emitted + 1) * per_chunk
+            need_hi = nsamp if last_yield else min(nsamp, ((o_hi - 1) * M + half) // L + 1)
+            if seen < need_hi:
+                break
+            yield plan.run(window, w_first, o_lo, o_hi - o_lo)
+            emitted += 1
+            # drop input no later output needs
+            keep_from = max(((o_hi * M + half - (ntaps - 1)) // L) - reach_l, w_first)
+            if keep_from > w_first:
+                window = window[:, keep_from - w_first:]
+                w_first = keep_from
+
+
+def _polyphase_layout(pro, L, M, fs, fir, axis, **kwargs):
+    return _layout_of(pro, axis)
+
+
+@_gpu_genfunc(_polyphase_device, _polyphase_layout)
+def polyphase_resample(pro, L, M, fs, fir, axis, **kwargs):
+    """Resample by L/M with a Kaiser anti-alias filter (reference
+    numerical.py:523-632).  Yields ``nchunks - 1`` arrays of ``csize*L/M``
+    samples (the last one takes the remainder), bit-identical in length and
+    index to the reference."""
+
+
+# ---------------------------------------------------------------------------
+# spectra  (reference core/numerical.py:635-1087)
+# ---------------------------------------------------------------------------
+def _spec_norm(window, fs, scaling):
+    if scaling == "spectrum":
+        return 1 / np.sum(window) ** 2
+    if scaling == "density":
+        return 1 / (fs * np.sum(window ** 2))
+    raise ValueError("Unknown scaling: {}".format(scaling))
+
+
+def _spec_plan(fs, nfft, window, overlap, detrend, scaling):
+    nfft = int(nfft)
+    stride = nfft - int(nfft * overlap)
+    coeffs = sps.get_window(window, nfft)
+    norm = _spec_norm(coeffs, fs, scaling)
+    return dv.SpecPlan.cached(nfft, stride, coeffs, detrend, norm)
+
+
+def _segment_batches(pro, axis, plan, pad_left=0, pad_right=0, batch_samples=1 << 24):
+    """Yield (device rows, nseg): contiguous spans holding ``nseg`` whole
+    windows starting at stride multiples -- the device twin of the FIFO walk
+    in _spectra_estimatives (reference numerical.py:817-849).  Small chunks are
+    batched so each launch carries enough windows to fill the GPU."""
+    rows = _layout_of(pro, axis).rows
+    carry = dv.zeros_rows(rows, pad_left) if pad_left else None
+    parts, width = ([carry], pad_left) if pad_left else ([], 0)
+
+    def flush(final):
+        nonlocal parts, width
+        buf = dv.cat_time(parts)
+        nseg = plan.nseg_available(width)
+        if nseg > 0:
+            used = nseg * plan.stride
+            out = (buf, nseg)
+            rest = buf[:, used:]
+            parts, width = ([rest], rest.shape[1]) if rest.shape[1] else ([], 0)
+            return out
+        parts = [buf] if width else []
+        return None
+
+    for chunk in device_chunks(pro, axis):
+        parts.append(chunk)
+        width += chunk.shape[1]
+        if width * rows >= batch_samples and width >= plan.nfft:
+            out = flush(False)
+            if out:
+                yield out
+    if pad_right:
+        parts.append(dv.zeros_rows(rows, pad_right))
+        width += pad_right
+    if width >= plan.nfft:
+        out = flush(True)
+        if out:
+            yield out
+
+
+def modified_dft(arr, fs, nfft, window, axis, detrend, scaling):
+    """Windowed DFT of one in-memory segment (reference numerical.py:635-718).
+    Returns (freqs, X) with X complex128 of length nfft//2+1 along ``axis``."""
+    arr = np.asarray(arr, dtype=np.float64)
+    axis = normalize_axis(axis, arr.ndim)
+    nfft = int(nfft)
+    nsamp = arr.shape[axis]
+    if nfft < nsamp:
+        arr = arr[..., :nfft] if axis == arr.ndim - 1 else np.take(arr, np.arange(nfft), axis)
+    return _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_=True)
+
+
+def periodogram(arr, fs, nfft=None, window="hann", axis=-1, detrend="constant",
+                scaling="density"):
+    """Power spectrum of one in-memory segment (reference numerical.py:721-796)."""
+    arr = np.asarray(arr, dtype=np.float64)
+    axis = normalize_axis(axis, arr.ndim)
+    nfft = arr.shape[axis] if not nfft else int(nfft)
+    if nfft < arr.shape[axis]:
+        arr = arr[..., :nfft] if axis == arr.ndim - 1 else np.take(arr, np.arange(nfft), axis)
+    return _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_=False)
+
+
+def _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_):
+    nsamp = arr.shape[axis]
+    if nsamp == 0:
+        raise ValueError("cannot estimate the spectrum of an empty array")
+    if nsamp != nfft:
+        raise NotImplementedError(
+            "zero-padded DFTs (nfft > samples) are not on the GPU path; openseize's "
+            "estimators always use nfft-long segments")
+    layout = dv.Layout(arr.shape, axis)
+    coeffs = sps.get_window(window, nsamp)
+    plan = dv.SpecPlan.cached(nfft, nfft, coeffs, detrend, _spec_norm(coeffs, fs, scaling))
+    rows = dv.upload(arr, layout)
+    out = plan.segments(rows, 1, complex_)[0]
+    res = dv.download(out, layout, complex_).get()
+    return np.fft.rfftfreq(nfft, d=1 / fs), np.array(res)
+
+
+def _estimatives_device(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
+                        pad_left=0, pad_right=0, **kwargs):
+    """Device rows (rows, nfreq[, 2]) per window, in order."""
+    complex_ = func is modified_dft
+    if func is not modified_dft and func is not periodogram:
+        raise TypeError("func must be numerical.periodogram or numerical.modified_dft")
+    plan = _spec_plan(fs, nfft, window, overlap, detrend, scaling)
+    for buf, nseg in _segment_batches(pro, axis, plan, pad_left, pad_right):
+        out = plan.segments(buf, nseg, complex_)
+        for k in range(nseg):
+            yield out[k]
+
+
+def _spectra_estimatives(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
+                         pad_left=0, pad_right=0, **kwargs):
+    """One estimate per nfft window, windows ``stride`` apart, trailing partial
+    window dropped (reference numerical.py:799-849).  ``pad_left`` /
+    ``pad_right`` are zeros put around the recording (STFT boundary/padded)."""
+    complex_ = func is modified_dft
+    layout = _layout_of(pro, axis)
+    gen = _estimatives_device(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
+                              pad_left, pad_right)
+    yield from _to_host(gen, layout, complex_)
+
+
+_spectra_estimatives.device = _estimatives_device
+
+
+def welch(pro, fs, nfft, window, overlap, axis, detrend, scaling):
+    """(freqs, producer of one periodogram per Welch segment) -- reference
+    numerical.py:852-947, including its quirk that the producer's shape carries
+    the number of segments along ``axis``."""
+    genfunc = functools.partial(_spectra_estimatives, pro, fs, nfft, window, overlap, axis,
+                                detrend, scaling, func=periodogram)
+    freqs = np.fft.rfftfreq(nfft, 1 / fs)
+    nsegs = int((pro.shape[axis] - nfft) // (nfft * (1 - overlap)) + 1)
+    shape = list(pro.shape)
+    shape[axis] = nsegs
+    return freqs, producer(genfunc, chunksize=len(freqs), axis=axis, shape=shape)
+
+
+def welch_mean(pro, fs, nfft, window, overlap, axis, detrend, scaling):
+    """Fused Welch estimate: (segment count, mean periodogram ndarray).  The
+    per-segment periodograms never leave the SM: |FFT|^2 is accumulated in
+    registers and only the (rows, nfft//2+1) sum is written.  Equals the
+    reference's running mean over ``welch``'s producer
+    (spectra/estimators.py:150-152) up to rounding."""
+    dv.require_cuda()
+    plan = _spec_plan(fs, nfft, window, overlap, detrend, scaling)
+    layout = _layout_of(pro, axis)
+    psd_sum = dv.zeros((layout.rows, plan.nfreq))
+    cnt = 0
+    for buf, nseg in _segment_batches(pro, axis, plan):
+        plan.welch_accum(buf, nseg, psd_sum)
+        cnt += nseg
+    if cnt == 0:
+        raise ValueError("psd: the data holds no complete nfft={} segment".format(nfft))
+    return cnt, np.array(dv.download(psd_sum, layout).get()) / cnt
+
+
+def stft(pro, fs, nfft, window, overlap, axis, detrend, scaling, boundary, padded):
+    """(freqs, time, producer of one modified DFT per segment) -- reference
+    numerical.py:950-1087.  Zero extension (``boundary``: nfft//2 both ends;
+    ``padded``: one stride at the end when N % stride) happens on the device."""
+    noverlap = int(nfft * overlap)
+    stride = nfft - noverlap
+    nsamp = pro.shape[axis]
+    pad_left = nfft // 2 if boundary else 0
+    pad_right = pad_left + ((stride if nsamp % stride else 0) if padded else 0)
+    total = nsamp + pad_left + pad_right
+    genfunc = functools.partial(_spectra_estimatives, pro, fs, nfft, window, overlap, axis,
+                                detrend, scaling, func=modified_dft, pad_left=pad_left,
+                                pad_right=pad_right)
+    freqs = np.fft.rfftfreq(nfft, 1 / fs)
+    nsegs = int((total - nfft) // (nfft * (1 - overlap)) + 1)
+    shape = list(pro.shape)
+    shape[axis] = nsegs
+    if boundary:
+        time = 1 / fs * np.arange(0, total - nfft + 1, nfft - noverlap)
+    else:
+        time = 1 / fs * np.arange(nfft // 2, total + 1 - nfft // 2, nfft - noverlap)
+    return freqs, time, producer(genfunc, chunksize=len(freqs), axis=axis, shape=shape)

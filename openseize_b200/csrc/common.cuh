@@ -1,0 +1,103 @@
+// Shared helpers for the osz_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/osz_b200.h"
+
+namespace osz {
+
+// ---- error plumbing ------------------------------------------------------
+void set_error(const std::string &msg);
+extern std::atomic<long long> g_launches;
+
+inline int fail(osz_status code, const std::string &msg) {
+    set_error(msg);
+    return (int)code;
+}
+
+#define OSZ_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t err__ = (call);                                             \
+        if (err__ != cudaSuccess) {                                             \
+            return ::osz::fail(OSZ_ERR_CUDA, std::string(#call) + ": " +        \
+                                                 cudaGetErrorString(err__));    \
+        }                                                                       \
+    } while (0)
+
+// Check the launch that was just issued and count it.
+#define OSZ_LAUNCHED(name)                                                      \
+    do {                                                                        \
+        cudaError_t err__ = cudaGetLastError();                                 \
+        if (err__ != cudaSuccess) {                                             \
+            return ::osz::fail(OSZ_ERR_CUDA, std::string(name) + " launch: " +  \
+                                                 cudaGetErrorString(err__));    \
+        }                                                                       \
+        ::osz::g_launches.fetch_add(1, std::memory_order_relaxed);              \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();   // SMs of the current device (cached)
+
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ double ldg(const double *p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldg(const double2 *p) { return __ldg(p); }
+
+// streaming (evict-first) loads / stores for data touched once
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double *p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v));
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared::cta) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace osz

@@ -1,0 +1,232 @@
+// Shared-memory radix-16 Stockham FFT, complex float64, N = 2^8 .. 2^13.
+//
+// One CTA of N/16 threads transforms one N-point complex sequence.  Each
+// thread enters with 16 values in REGISTERS, v[r] = x[tid + r*N/16], and
+// leaves with v[r] = X[tid + r*N/16] -- the same strided-natural layout, so a
+// forward transform, a pointwise multiply and an inverse transform chain
+// without touching memory in between, and global loads/stores on either side
+// are coalesced.  Passes are [16, mid..., 16] with mid in {-, 2, 4, 8, 16,
+// 16*2}; between passes data is exchanged through shared memory (AoS
+// double2, one pad element per 16 so that both the stride-1 and the stride-16
+// patterns are bank-conflict free).
+//
+// Twiddles come from per-pass tables laid out [r-1][k] so that a warp reads
+// consecutive k (built on the host by make_fft_twiddles()).
+#pragma once
+
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace osz {
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) {
+    return make_double2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ double2 csub(double2 a, double2 b) {
+    return make_double2(a.x - b.x, a.y - b.y);
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// a * (-i)
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }
+
+#define OSZ_SQRT1_2 0.70710678118654752440
+#define OSZ_COS_PI_8 0.92387953251128675613
+#define OSZ_SIN_PI_8 0.38268343236508977173
+
+// a * W8^1 = a * (1 - i)/sqrt2
+__device__ __forceinline__ double2 mul_w8_1(double2 a) {
+    return make_double2((a.x + a.y) * OSZ_SQRT1_2, (a.y - a.x) * OSZ_SQRT1_2);
+}
+// a * W8^3 = a * (-1 - i)/sqrt2
+__device__ __forceinline__ double2 mul_w8_3(double2 a) {
+    return make_double2((a.y - a.x) * OSZ_SQRT1_2, -(a.x + a.y) * OSZ_SQRT1_2);
+}
+
+__device__ __forceinline__ void bfly2(double2 &a0, double2 &a1) {
+    double2 t = a0;
+    a0 = cadd(t, a1);
+    a1 = csub(t, a1);
+}
+
+// forward 4-point DFT, natural order in and out
+__device__ __forceinline__ void bfly4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {
+    double2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    double2 t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+// Forward R-point DFT of v[0..R), natural order in and out.
+template <int R>
+__device__ __forceinline__ void bfly(double2 *v);
+
+template <>
+__device__ __forceinline__ void bfly<2>(double2 *v) {
+    bfly2(v[0], v[1]);
+}
+template <>
+__device__ __forceinline__ void bfly<4>(double2 *v) {
+    bfly4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void bfly<8>(double2 *v) {
+    // n = 4*n1 + n2, k = k1 + 2*k2
+    bfly2(v[0], v[4]);
+    bfly2(v[1], v[5]);
+    bfly2(v[2], v[6]);
+    bfly2(v[3], v[7]);
+    v[5] = mul_w8_1(v[5]);
+    v[6] = mul_mi(v[6]);
+    v[7] = mul_w8_3(v[7]);
+    bfly4(v[0], v[1], v[2], v[3]);  // k1 = 0 -> X[0], X[2], X[4], X[6]
+    bfly4(v[4], v[5], v[6], v[7]);  // k1 = 1 -> X[1], X[3], X[5], X[7]
+    double2 o1 = v[4], o2 = v[1], o3 = v[5], o4 = v[2], o5 = v[6], o6 = v[3];
+    v[1] = o1;
+    v[2] = o2;
+    v[3] = o3;
+    v[4] = o4;
+    v[5] = o5;
+    v[6] = o6;
+}
+template <>
+__device__ __forceinline__ void bfly<16>(double2 *v) {
+    // n = 4*n1 + n2, k = k1 + 4*k2.  Stage 1: DFT over n1 for each n2.
+    bfly4(v[0], v[4], v[8], v[12]);
+    bfly4(v[1], v[5], v[9], v[13]);
+    bfly4(v[2], v[6], v[10], v[14]);
+    bfly4(v[3], v[7], v[11], v[15]);
+    // now v[n2 + 4*k1] = A[n2][k1]; twiddle by W16^(n2*k1)
+    const double2 w1 = make_double2(OSZ_COS_PI_8, -OSZ_SIN_PI_8);
+    const double2 w3 = make_double2(OSZ_SIN_PI_8, -OSZ_COS_PI_8);
+    v[5] = cmul(v[5], w1);                                       // n2=1,k1=1 : W^1
+    v[6] = mul_w8_1(v[6]);                                       // n2=2,k1=1 : W^2
+    v[7] = cmul(v[7], w3);                                       // n2=3,k1=1 : W^3
+    v[9] = mul_w8_1(v[9]);                                       // n2=1,k1=2 : W^2
+    v[10] = mul_mi(v[10]);                                       // n2=2,k1=2 : W^4
+    v[11] = mul_w8_3(v[11]);                                     // n2=3,k1=2 : W^6
+    v[13] = cmul(v[13], w3);                                     // n2=1,k1=3 : W^3
+    v[14] = mul_w8_3(v[14]);                                     // n2=2,k1=3 : W^6
+    v[15] = cmul(v[15], make_double2(-OSZ_COS_PI_8, OSZ_SIN_PI_8));  // n2=3,k1=3 : W^9
+    // Stage 2: DFT over n2 for each k1 -> X[k1 + 4*k2] lands in v[k2 + 4*k1]
+    bfly4(v[0], v[1], v[2], v[3]);
+    bfly4(v[4], v[5], v[6], v[7]);
+    bfly4(v[8], v[9], v[10], v[11]);
+    bfly4(v[12], v[13], v[14], v[15]);
+    // 4x4 transpose of register names -> natural order
+    double2 t;
+#define OSZ_SWAP(a, b) \
+    t = v[a];          \
+    v[a] = v[b];       \
+    v[b] = t;
+    OSZ_SWAP(1, 4)
+    OSZ_SWAP(2, 8)
+    OSZ_SWAP(3, 12)
+    OSZ_SWAP(6, 9)
+    OSZ_SWAP(7, 13)
+    OSZ_SWAP(11, 14)
+#undef OSZ_SWAP
+}
+
+template <int LOG2N>
+struct FftCfg {
+    static_assert(LOG2N >= 8 && LOG2N <= 13, "shared-memory FFT supports N = 256 .. 8192");
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int NT = N / 16;                 // threads per CTA
+    static constexpr int MIDBITS = LOG2N - 8;
+    static constexpr int R1 = MIDBITS >= 4 ? 16 : (1 << MIDBITS);   // first middle radix (1: none)
+    static constexpr int R2 = MIDBITS > 4 ? (1 << (MIDBITS - 4)) : 1;  // second middle radix
+    // twiddle table offsets (double2 elements)
+    static constexpr int OFF_M1 = 0;
+    static constexpr int OFF_M2 = OFF_M1 + (R1 > 1 ? (R1 - 1) * 16 : 0);
+    static constexpr int OFF_L = OFF_M2 + (R2 > 1 ? (R2 - 1) * 16 * R1 : 0);
+    static constexpr int TW_TOTAL = OFF_L + 15 * (N / 16);
+    static constexpr int SMEM_ELEMS = N + N / 16;     // padded double2 elements
+    static constexpr int SMEM_BYTES = SMEM_ELEMS * 16;
+};
+
+__device__ __forceinline__ int fft_phys(int i) { return i + (i >> 4); }
+
+// One middle pass (radix R, sub-transform length Ns) over the CTA's N points,
+// in place in shared memory: every thread reads all its inputs, the CTA
+// synchronises, then butterflies are written to their Stockham positions.
+template <int N, int R, int NS>
+__device__ __forceinline__ void fft_mid_pass(double2 *sm, const double2 *__restrict__ tw, int tid) {
+    constexpr int NT = N / 16;
+    constexpr int PER = 16 / R;  // butterflies per thread
+    double2 v[16];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int b = tid + q * NT;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[q * R + r] = sm[fft_phys(b + r * (N / R))];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int b = tid + q * NT;
+        const int k = b & (NS - 1);
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[q * R + r] = cmul(v[q * R + r], ldg(tw + (r - 1) * NS + k));
+        bfly<R>(v + q * R);
+        const int j0 = (b - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm[fft_phys(j0 + r * NS)] = v[q * R + r];
+    }
+    __syncthreads();
+}
+
+// Forward FFT, registers to registers (see file header).  `sm` must hold
+// FftCfg<LOG2N>::SMEM_ELEMS double2.  Contains its own leading barrier, so it
+// can be called back to back.
+template <int LOG2N>
+__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm,
+                                        const double2 *__restrict__ tw, int tid) {
+    using C = FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+    // pass 1: radix 16, Ns = 1, no twiddles
+    bfly<16>(v);
+    __syncthreads();  // previous users of sm are done
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[fft_phys(16 * tid + r)] = v[r];
+    __syncthreads();
+    if constexpr (C::R1 > 1) fft_mid_pass<N, C::R1, 16>(sm, tw + C::OFF_M1, tid);
+    if constexpr (C::R2 > 1) fft_mid_pass<N, C::R2, 16 * C::R1>(sm, tw + C::OFF_M2, tid);
+    // last pass: radix 16, Ns = N/16, k = tid, output index tid + r*NT
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = sm[fft_phys(tid + r * NT)];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], ldg(tw + C::OFF_L + (r - 1) * NT + tid));
+    bfly<16>(v);
+}
+
+// Host: twiddle tables for FftCfg<log2n>, as (re, im) pairs.
+inline std::vector<double> make_fft_twiddles(int log2n) {
+    const int N = 1 << log2n;
+    const int mid = log2n - 8;
+    const int R1 = mid >= 4 ? 16 : (1 << mid);
+    const int R2 = mid > 4 ? (1 << (mid - 4)) : 1;
+    std::vector<double> t;
+    auto emit = [&](int R, int Ns) {
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                // exp(-2 pi i r k / (Ns R)); long double keeps the table correctly rounded
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)r *
+                                (long double)k / ((long double)Ns * (long double)R);
+                t.push_back((double)cosl(a));
+                t.push_back((double)sinl(a));
+            }
+    };
+    if (R1 > 1) emit(R1, 16);
+    if (R2 > 1) emit(R2, 16 * R1);
+    emit(16, N / 16);
+    return t;
+}
+
+}  // namespace osz

@@ -1,0 +1,272 @@
+// FIR filtering of halo'd chunks: the per-chunk arithmetic of nm.oaconvolve
+// (reference core/numerical.py:229-269) as two sm_100a kernels.
+//
+//   fir_direct_kernel   short filters: chunk-plus-halo tile staged into shared
+//                       memory by a 1-D TMA bulk copy, taps in shared memory,
+//                       15 outputs per thread on a register sliding window
+//                       (one LDS per 15 DFMA).
+//   fir_fft_kernel      long filters: overlap-save blocks of N = 4096 / 8192.
+//                       Two consecutive blocks of a row ride as the real and
+//                       imaginary part of ONE complex transform (real taps =>
+//                       the two convolutions never mix), forward FFT, multiply
+//                       by H, inverse FFT, all register-to-register through
+//                       the shared-memory FFT of fft_core.cuh.  Blocks are
+//                       independent CTAs -- the scatter-free dual of the
+//                       reference's overlap-add (same sums, no carried tail).
+//
+// Both compute  y[r][i] = sum_k taps[k] * x[r][i + K-1-k]  (header contract).
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace osz {
+
+// ------------------------------------------------------------------ direct
+constexpr int FIR_NT = 128;   // threads per CTA
+constexpr int FIR_R = 15;     // outputs per thread (odd: conflict-free LDS.64 at stride R)
+constexpr int FIR_TILE = FIR_NT * FIR_R;
+constexpr int FIR_DIRECT_MAX_TAPS = 1024;
+
+__global__ void __launch_bounds__(FIR_NT, 4)
+fir_direct_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps, int kpad,
+                  const double *__restrict__ taps_rev /* kpad, zero padded */, double *__restrict__ y,
+                  int64_t ldy) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *gs = reinterpret_cast<double *>(smem_raw + 16);          // kpad taps
+    const int xs_off = (16 + kpad * 8 + 127) & ~127;
+    double *xs = reinterpret_cast<double *>(smem_raw + xs_off);      // tile + halo
+    const int xs_len = FIR_TILE + kpad + FIR_R + 2;
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t tile0 = (int64_t)blockIdx.x * FIR_TILE;
+    const double *xr = x + row * ldx + tile0;
+    const int64_t span_left = n_out + ntaps - 1 - tile0;             // readable from xr
+    const int mis = (int)((reinterpret_cast<uintptr_t>(xr) >> 3) & 1);
+    int64_t need = FIR_TILE + ntaps - 1;
+    if (need > span_left) need = span_left;
+    const int cnt = (int)((need + mis + 1) & ~(int64_t)1);           // even element count
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)cnt * 8u);
+        tma_load_1d(xs, xr - mis, (uint32_t)cnt * 8u, bar);
+    }
+    // meanwhile: taps, and zeros behind the TMA region (padded taps multiply them)
+    for (int i = tid; i < kpad; i += FIR_NT) gs[i] = taps_rev[i];
+    for (int i = cnt + tid; i < xs_len; i += FIR_NT) xs[i] = 0.0;
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const double *xt = xs + tid * FIR_R + mis;
+    double acc[FIR_R], w[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+        acc[r] = 0.0;
+        w[r] = xt[r];
+    }
+    for (int j0 = 0; j0 < kpad; j0 += FIR_R) {
+#pragma unroll
+        for (int u = 0; u < FIR_R; ++u) {
+            const double g = gs[j0 + u];
+#pragma unroll
+            for (int r = 0; r < FIR_R; ++r) acc[r] = fma(g, w[(r + u) % FIR_R], acc[r]);
+            w[u] = xt[j0 + u + FIR_R];
+        }
+    }
+    double *yr = y + row * ldy + tile0 + tid * FIR_R;
+    const int64_t left = n_out - (tile0 + tid * FIR_R);
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r)
+        if (r < left) st_stream(yr + r, acc[r]);
+}
+
+// --------------------------------------------------------------------- FFT
+template <int LOG2N>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
+fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
+               const double2 *__restrict__ H /* N, scaled 1/N */, const double2 *__restrict__ tw,
+               double *__restrict__ y, int64_t ldy) {
+    using C = FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t step = N - ntaps + 1;
+    const int64_t span = n_out + ntaps - 1;
+    const int64_t base_a = (int64_t)blockIdx.x * 2 * step;
+    const int64_t base_b = base_a + step;
+    const double *xr = x + row * ldx;
+
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int64_t ia = base_a + tid + r * NT, ib = base_b + tid + r * NT;
+        v[r].x = ia < span ? ld_stream(xr + ia) : 0.0;
+        v[r].y = ib < span ? ldg(xr + ib) : 0.0;
+    }
+    fft_r2r<LOG2N>(v, sm, tw, tid);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const double2 p = cmul(v[r], ldg(H + tid + r * NT));
+        v[r] = make_double2(p.y, p.x);  // swap: inverse transform via the forward kernel
+    }
+    fft_r2r<LOG2N>(v, sm, tw, tid);
+    double *yr = y + row * ldy;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int i = tid + r * NT;
+        if (i >= ntaps - 1) {
+            const int64_t oa = base_a + i - (ntaps - 1), ob = base_b + i - (ntaps - 1);
+            // after the swap back: real part = v.y, imaginary part = v.x
+            if (oa < n_out) st_stream(yr + oa, v[r].y);
+            if (ob < n_out) st_stream(yr + ob, v[r].x);
+        }
+    }
+}
+
+}  // namespace osz
+
+using namespace osz;
+
+struct osz_fir_plan {
+    int ntaps = 0;
+    int algo = OSZ_FIR_DIRECT;
+    int kpad = 0;
+    int log2n = 0;
+    double *d_taps_rev = nullptr;   // direct
+    double2 *d_H = nullptr;         // fft
+    double2 *d_tw = nullptr;
+};
+
+template <int LOG2N>
+static int launch_fir_fft(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                          int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
+    using C = FftCfg<LOG2N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OSZ_CUDA(cudaFuncSetAttribute(fir_fft_kernel<LOG2N>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t step = C::N - p->ntaps + 1;
+    const int64_t nblocks = (n_out + step - 1) / step;
+    const int64_t npairs = (nblocks + 1) / 2;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "fir: more than 65535 rows per call");
+    dim3 grid((unsigned)npairs, (unsigned)rows);
+    fir_fft_kernel<LOG2N><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, ldx, n_out, p->ntaps, p->d_H,
+                                                             p->d_tw, y, ldy);
+    OSZ_LAUNCHED("fir_fft_kernel");
+    return OSZ_OK;
+}
+
+extern "C" {
+
+int osz_fir_plan_create(osz_fir_plan **out, const double *taps, int ntaps, int algo) {
+    if (!out || !taps || ntaps < 1) return fail(OSZ_ERR_ARG, "osz_fir_plan_create: bad arguments");
+    if (algo == OSZ_FIR_AUTO) algo = ntaps <= 24 ? OSZ_FIR_DIRECT : OSZ_FIR_FFT;
+    if (algo == OSZ_FIR_DIRECT && ntaps > FIR_DIRECT_MAX_TAPS) algo = OSZ_FIR_FFT;
+    osz_fir_plan *p = new osz_fir_plan();
+    p->ntaps = ntaps;
+    p->algo = algo;
+    if (algo == OSZ_FIR_DIRECT) {
+        p->kpad = ((ntaps + FIR_R - 1) / FIR_R) * FIR_R;
+        std::vector<double> rev(p->kpad, 0.0);
+        for (int j = 0; j < ntaps; ++j) rev[j] = taps[ntaps - 1 - j];
+        if (cudaMalloc(&p->d_taps_rev, rev.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p->d_taps_rev, rev.data(), rev.size() * 8, cudaMemcpyHostToDevice) !=
+                cudaSuccess) {
+            osz_fir_plan_destroy(p);
+            return fail(OSZ_ERR_CUDA, "osz_fir_plan_create: device upload failed");
+        }
+    } else if (algo == OSZ_FIR_FFT) {
+        // block size: keep the overlap-save efficiency (N-K+1)/N at or above 3/4
+        if (ntaps <= 1025)
+            p->log2n = 12;
+        else if (ntaps <= 2049)
+            p->log2n = 13;
+        else {
+            delete p;
+            return fail(OSZ_ERR_UNSUPPORTED,
+                        "osz_fir_plan_create: more than 2049 taps is not supported yet");
+        }
+        const int N = 1 << p->log2n;
+        // H[k] = (1/N) sum_j taps[j] exp(-2 pi i j k / N), long double accumulation
+        std::vector<long double> cs(N), sn(N);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int m = 0; m < N; ++m) {
+            cs[m] = cosl(two_pi * m / N);
+            sn[m] = sinl(two_pi * m / N);
+        }
+        std::vector<double> H(2 * (size_t)N);
+        for (int k = 0; k < N; ++k) {
+            long double re = 0, im = 0;
+            for (int j = 0; j < ntaps; ++j) {
+                const int m = (int)(((long long)j * k) & (N - 1));
+                re += taps[j] * cs[m];
+                im -= taps[j] * sn[m];
+            }
+            H[2 * k] = (double)(re / N);
+            H[2 * k + 1] = (double)(im / N);
+        }
+        std::vector<double> tw = make_fft_twiddles(p->log2n);
+        if (cudaMalloc(&p->d_H, H.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p->d_H, H.data(), H.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&p->d_tw, tw.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p->d_tw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+            osz_fir_plan_destroy(p);
+            return fail(OSZ_ERR_CUDA, "osz_fir_plan_create: device upload failed");
+        }
+    } else {
+        delete p;
+        return fail(OSZ_ERR_ARG, "osz_fir_plan_create: unknown algorithm");
+    }
+    *out = p;
+    return OSZ_OK;
+}
+
+int osz_fir_plan_destroy(osz_fir_plan *p) {
+    if (!p) return OSZ_OK;
+    cudaFree(p->d_taps_rev);
+    cudaFree(p->d_H);
+    cudaFree(p->d_tw);
+    delete p;
+    return OSZ_OK;
+}
+
+int osz_fir_plan_algo(const osz_fir_plan *p) { return p ? p->algo : 0; }
+
+int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                     int64_t n_out, double *y, int64_t ldy, void *stream) {
+    if (!p || !x || !y) return fail(OSZ_ERR_ARG, "osz_fir_exec_f64: null argument");
+    if (rows <= 0 || n_out <= 0) return OSZ_OK;
+    cudaStream_t st = as_stream(stream);
+    if (p->algo == OSZ_FIR_DIRECT) {
+        static bool attr_set = false;
+        const int xs_off = (16 + p->kpad * 8 + 127) & ~127;
+        const int smem = xs_off + (FIR_TILE + p->kpad + FIR_R + 2) * 8;
+        if (!attr_set) {
+            OSZ_CUDA(cudaFuncSetAttribute(fir_direct_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_set = true;
+        }
+        if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "fir: more than 65535 rows per call");
+        dim3 grid((unsigned)((n_out + FIR_TILE - 1) / FIR_TILE), (unsigned)rows);
+        fir_direct_kernel<<<grid, FIR_NT, smem, st>>>(x, ldx, n_out, p->ntaps, p->kpad,
+                                                     p->d_taps_rev, y, ldy);
+        OSZ_LAUNCHED("fir_direct_kernel");
+        return OSZ_OK;
+    }
+    if (p->log2n == 12) return launch_fir_fft<12>(p, x, ldx, rows, n_out, y, ldy, st);
+    return launch_fir_fft<13>(p, x, ldx, rows, n_out, y, ldy, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Library plumbing: error state, device info, memory / stream wrappers and the
+// layout kernels (pack / unpack / widen).  No DSP here.
+#include "common.cuh"
+
+namespace osz {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+
+int sm_count() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// (outer, n, inner) -> rows (outer*inner, n): tiled transpose through shared
+// memory so both sides are coalesced.
+template <typename T, bool PACK>
+__global__ void transpose_rows_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t outer,
+                                      int64_t n, int64_t inner, int64_t ld) {
+    __shared__ T tile[32][33];
+    const int64_t o = blockIdx.z;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int64_t i0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    if (PACK) {
+        // read (t, i) with i fastest; write row (o*inner+i), t fastest
+        for (int k = ty; k < 32; k += 8) {
+            int64_t t = t0 + k, i = i0 + tx;
+            if (t < n && i < inner) tile[k][tx] = src[(o * n + t) * inner + i];
+        }
+        __syncthreads();
+        for (int k = ty; k < 32; k += 8) {
+            int64_t i = i0 + k, t = t0 + tx;
+            if (t < n && i < inner) dst[(o * inner + i) * ld + t] = tile[tx][k];
+        }
+    } else {
+        for (int k = ty; k < 32; k += 8) {
+            int64_t i = i0 + k, t = t0 + tx;
+            if (t < n && i < inner) tile[k][tx] = src[(o * inner + i) * ld + t];
+        }
+        __syncthreads();
+        for (int k = ty; k < 32; k += 8) {
+            int64_t t = t0 + k, i = i0 + tx;
+            if (t < n && i < inner) dst[(o * n + t) * inner + i] = tile[tx][k];
+        }
+    }
+}
+
+template <typename S>
+__global__ void widen_kernel(const S *__restrict__ src, double *__restrict__ dst, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += step) dst[i] = (double)src[i];
+}
+
+template <typename T, bool PACK>
+static int launch_transpose(const T *src, T *dst, int64_t outer, int64_t n, int64_t inner,
+                            int64_t ld, void *stream) {
+    if (outer <= 0 || n <= 0 || inner <= 0) return OSZ_OK;
+    if (outer > 65535 || (inner + 31) / 32 > 65535)
+        return fail(OSZ_ERR_UNSUPPORTED, "pack/unpack: outer or inner extent too large");
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((inner + 31) / 32), (unsigned)outer);
+    transpose_rows_kernel<T, PACK><<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, outer, n,
+                                                                                 inner, ld);
+    OSZ_LAUNCHED("transpose_rows");
+    return OSZ_OK;
+}
+
+}  // namespace osz
+
+using namespace osz;
+
+extern "C" {
+
+int osz_version(void) { return 100; }
+
+const char *osz_last_error(void) { return t_error.c_str(); }
+
+int64_t osz_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int osz_device_info(int dev, int *sms, int *cc_major, int *cc_minor, int64_t *smem_optin,
+                    int64_t *global_mem) {
+    cudaDeviceProp p;
+    OSZ_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (smem_optin) *smem_optin = (int64_t)p.sharedMemPerBlockOptin;
+    if (global_mem) *global_mem = (int64_t)p.totalGlobalMem;
+    return OSZ_OK;
+}
+
+int osz_dev_malloc(void **p, size_t bytes) {
+    if (!p) return fail(OSZ_ERR_ARG, "osz_dev_malloc: null out pointer");
+    OSZ_CUDA(cudaMalloc(p, bytes));
+    return OSZ_OK;
+}
+int osz_dev_free(void *p) {
+    OSZ_CUDA(cudaFree(p));
+    return OSZ_OK;
+}
+int osz_host_alloc(void **p, size_t bytes) {
+    if (!p) return fail(OSZ_ERR_ARG, "osz_host_alloc: null out pointer");
+    OSZ_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return OSZ_OK;
+}
+int osz_host_free(void *p) {
+    OSZ_CUDA(cudaFreeHost(p));
+    return OSZ_OK;
+}
+int osz_stream_create(void **s) {
+    if (!s) return fail(OSZ_ERR_ARG, "osz_stream_create: null out pointer");
+    cudaStream_t st;
+    OSZ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *s = (void *)st;
+    return OSZ_OK;
+}
+int osz_stream_destroy(void *s) {
+    OSZ_CUDA(cudaStreamDestroy(as_stream(s)));
+    return OSZ_OK;
+}
+int osz_stream_sync(void *s) {
+    OSZ_CUDA(cudaStreamSynchronize(as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memcpy_h2d_async(void *dst, const void *src, size_t bytes, void *s) {
+    OSZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memcpy_d2h_async(void *dst, const void *src, size_t bytes, void *s) {
+    OSZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memcpy_d2d_async(void *dst, const void *src, size_t bytes, void *s) {
+    OSZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memcpy2d_h2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                           size_t height, void *s) {
+    OSZ_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice,
+                               as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memcpy2d_d2h_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                           size_t height, void *s) {
+    OSZ_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost,
+                               as_stream(s)));
+    return OSZ_OK;
+}
+int osz_memset_async(void *dst, int value, size_t bytes, void *s) {
+    OSZ_CUDA(cudaMemsetAsync(dst, value, bytes, as_stream(s)));
+    return OSZ_OK;
+}
+
+int osz_pack_rows_f64(const double *src, int64_t outer, int64_t n, int64_t inner, double *dst,
+                      int64_t ld, void *stream) {
+    return launch_transpose<double, true>(src, dst, outer, n, inner, ld, stream);
+}
+int osz_unpack_rows_f64(const double *src, int64_t ld, int64_t outer, int64_t n, int64_t inner,
+                        double *dst, void *stream) {
+    return launch_transpose<double, false>(src, dst, outer, n, inner, ld, stream);
+}
+int osz_unpack_rows_c128(const double *src, int64_t ld, int64_t outer, int64_t n, int64_t inner,
+                         double *dst, void *stream) {
+    return launch_transpose<double2, false>(reinterpret_cast<const double2 *>(src),
+                                            reinterpret_cast<double2 *>(dst), outer, n, inner, ld,
+                                            stream);
+}
+int osz_widen_f32_f64(const float *src, double *dst, int64_t count, void *stream) {
+    if (count <= 0) return OSZ_OK;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    widen_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(src, dst, count);
+    OSZ_LAUNCHED("widen_f32");
+    return OSZ_OK;
+}
+int osz_widen_i16_f64(const int16_t *src, double *dst, int64_t count, void *stream) {
+    if (count <= 0) return OSZ_OK;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    widen_kernel<int16_t><<<blocks, 256, 0, as_stream(stream)>>>(src, dst, count);
+    OSZ_LAUNCHED("widen_i16");
+    return OSZ_OK;
+}
+
+}  // extern "C"

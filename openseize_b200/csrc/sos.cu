@@ -1,0 +1,335 @@
+// Cascaded biquads (DF2T) as a time-parallel scan.  Replaces the per-chunk
+// scipy.signal.sosfilt calls of nm.sosfilt / nm.sosfiltfilt (reference
+// core/numerical.py:334,399,402,410) and scipy.signal.lfilter for second
+// order (b, a) (:445,508,511,519).
+//
+// One section in state-space form (derived from the DF2T recurrence
+//   y = b0 x + z0 ; z0' = b1 x - a1 y + z1 ; z1' = b2 x - a2 y ):
+//   s' = A s + B x,  y = b0 x + s[0],  A = [[-a1, 1], [-a2, 0]].
+//
+// One CTA owns one row and walks it in blocks of 8192 samples; the 256
+// threads each own 32 consecutive samples in registers.  Per section:
+//   1. every thread runs the recurrence over its 32 samples from a ZERO state
+//      (the thread that holds the first real sample starts from the carried
+//      state instead) -> local outputs + local final state f;
+//   2. the true state at every thread boundary is the scan of
+//      e_p = M e_{p-1} + f_p, M = A^32: Kogge-Stone over the warp with the
+//      precomputed powers M^(2^k), then a serial combine over the 8 warps;
+//   3. every thread adds the zero-input response of its entering state to its
+//      32 outputs: y_i += g0[i]*S0 + g1[i]*S1, (g0, g1)[i] = row 0 of A^i.
+// The corrected outputs are the next section's inputs.  The carried state
+// after the last sample is written back, exactly as the reference carries `z`
+// between chunks.  All per-filter tables ride in the kernel parameter block
+// (constant bank), so concurrent plans never share mutable device state.
+#include <vector>
+
+#include "common.cuh"
+
+namespace osz {
+
+constexpr int SOS_NT = 256;
+constexpr int SOS_T = 32;
+constexpr int SOS_BLK = SOS_NT * SOS_T;   // 8192
+constexpr int SOS_MAXSEC = 16;
+constexpr int SOS_LD = SOS_T + 1;         // padded smem row
+
+struct SosSec {
+    double b0, b1, b2, a1, a2;
+    double g0[SOS_T], g1[SOS_T];
+    double P[5][4];     // M^(2^k), row major
+    double Q[4];        // M^32 (one warp)
+};
+struct SosParams {
+    int nsec;
+    int pad_;
+    SosSec sec[SOS_MAXSEC];
+};
+struct SosZi {
+    double zi[SOS_MAXSEC][2];
+};
+
+__device__ __forceinline__ void mat_apply(const double (&m)[4], double a0, double a1, double &o0,
+                                          double &o1) {
+    o0 = fma(m[0], a0, m[1] * a1);
+    o1 = fma(m[2], a0, m[3] * a1);
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(SOS_NT, 2)
+sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
+                int64_t n, int reverse, double *__restrict__ state, double *__restrict__ y,
+                int64_t ldy, const double *__restrict__ lanepow /* [sec][32][4] */) {
+    extern __shared__ __align__(16) double buf[];   // SOS_NT * SOS_LD
+    __shared__ double wtot[SOS_NT / 32][2];
+    __shared__ double carry[SOS_MAXSEC][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row = blockIdx.x;
+    const int nsec = prm.nsec;
+    const double *xr = x + row * ldx;
+    double *yr = WRITE ? y + row * ldy : nullptr;
+    double *st = state + row * nsec * 2;
+
+    if (tid < nsec * 2) carry[tid >> 1][tid & 1] = st[tid];
+
+    const int64_t nblk = (n + SOS_BLK - 1) / SOS_BLK;
+    const int64_t first_len = n - (nblk - 1) * SOS_BLK;
+
+    for (int64_t blk = 0; blk < nblk; ++blk) {
+        // The first block is the short one and sits at the END of the 8192
+        // slots, behind `off` virtual zero samples that keep a zero state.
+        const int off = blk == 0 ? (int)(SOS_BLK - first_len) : 0;
+        const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * SOS_BLK;
+        __syncthreads();   // carry[] visible / buf free
+#pragma unroll 4
+        for (int e = tid; e < SOS_BLK; e += SOS_NT) {
+            double val = 0.0;
+            if (e >= off) {
+                const int64_t s = pos0 + (e - off);
+                val = ld_stream(xr + (reverse ? n - 1 - s : s));
+            }
+            buf[(e >> 5) * SOS_LD + (e & 31)] = val;
+        }
+        __syncthreads();
+        double v[SOS_T];
+#pragma unroll
+        for (int i = 0; i < SOS_T; ++i) v[i] = buf[tid * SOS_LD + i];
+
+        const int pstar = off >> 5, ioff = off & 31;
+        for (int s = 0; s < nsec; ++s) {
+            const SosSec &c = prm.sec[s];
+            const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
+            double z0 = 0.0, z1 = 0.0;
+            if (blk != 0) {
+                if (tid == 0) {
+                    z0 = carry[s][0];
+                    z1 = carry[s][1];
+                }
+#pragma unroll
+                for (int i = 0; i < SOS_T; ++i) {
+                    const double xi = v[i];
+                    const double yi = fma(b0, xi, z0);
+                    z0 = fma(na1, yi, fma(b1, xi, z1));
+                    z1 = fma(na2, yi, b2 * xi);
+                    v[i] = yi;
+                }
+            } else {
+                const bool inj = tid == pstar;
+                const double c0 = carry[s][0], c1 = carry[s][1];
+#pragma unroll
+                for (int i = 0; i < SOS_T; ++i) {
+                    if (inj && i == ioff) {
+                        z0 = c0;
+                        z1 = c1;
+                    }
+                    const double xi = v[i];
+                    const double yi = fma(b0, xi, z0);
+                    z0 = fma(na1, yi, fma(b1, xi, z1));
+                    z1 = fma(na2, yi, b2 * xi);
+                    v[i] = yi;
+                }
+            }
+            // ---- warp-inclusive scan of e_p = M e_{p-1} + f_p
+            double f0 = z0, f1 = z1;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double g0 = __shfl_up_sync(0xffffffffu, f0, 1 << k);
+                const double g1 = __shfl_up_sync(0xffffffffu, f1, 1 << k);
+                if (lane >= (1 << k)) {
+                    f0 += fma(c.P[k][0], g0, c.P[k][1] * g1);
+                    f1 += fma(c.P[k][2], g0, c.P[k][3] * g1);
+                }
+            }
+            if (lane == 31) {
+                wtot[warp][0] = f0;
+                wtot[warp][1] = f1;
+            }
+            __syncthreads();
+            // ---- state entering this warp
+            double cw0 = 0.0, cw1 = 0.0;
+            for (int u = 0; u < warp; ++u) {
+                const double t0 = fma(c.Q[0], cw0, c.Q[1] * cw1) + wtot[u][0];
+                const double t1 = fma(c.Q[2], cw0, c.Q[3] * cw1) + wtot[u][1];
+                cw0 = t0;
+                cw1 = t1;
+            }
+            // ---- true state at the end of this thread's piece
+            const double *lp = lanepow + ((size_t)s * 32 + lane) * 4;
+            const double e0 = f0 + fma(ldg(lp + 0), cw0, ldg(lp + 1) * cw1);
+            const double e1 = f1 + fma(ldg(lp + 2), cw0, ldg(lp + 3) * cw1);
+            // ---- state entering this thread's piece
+            double s0 = __shfl_up_sync(0xffffffffu, e0, 1);
+            double s1 = __shfl_up_sync(0xffffffffu, e1, 1);
+            if (lane == 0) {
+                s0 = cw0;
+                s1 = cw1;
+            }
+            // zero-input response of the entering state (it is exactly zero for
+            // every thread up to and including the one that injected the carry)
+#pragma unroll
+            for (int i = 0; i < SOS_T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
+            if (tid == SOS_NT - 1) {
+                carry[s][0] = e0;
+                carry[s][1] = e1;
+            }
+            __syncthreads();   // wtot reusable, carry[s] published
+        }
+        if (WRITE) {
+#pragma unroll
+            for (int i = 0; i < SOS_T; ++i) buf[tid * SOS_LD + i] = v[i];
+            __syncthreads();
+#pragma unroll 4
+            for (int e = tid; e < SOS_BLK; e += SOS_NT) {
+                if (e >= off) {
+                    const int64_t s = pos0 + (e - off);
+                    st_stream(yr + (reverse ? n - 1 - s : s), buf[(e >> 5) * SOS_LD + (e & 31)]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nsec * 2) st[tid] = carry[tid >> 1][tid & 1];
+}
+
+__global__ void sos_state_from_sample_kernel(SosZi zi, int nsec, const double *__restrict__ x,
+                                             int64_t ldx, int64_t rows, int64_t sample,
+                                             double *__restrict__ state) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nsec * 2) return;
+    const int64_t row = i / (nsec * 2);
+    const int sj = (int)(i % (nsec * 2));
+    state[i] = zi.zi[sj >> 1][sj & 1] * x[row * ldx + sample];
+}
+
+}  // namespace osz
+
+using namespace osz;
+
+struct osz_sos_plan {
+    SosParams prm;
+    double *d_lanepow = nullptr;
+};
+
+namespace {
+struct M2 {
+    long double a, b, c, d;
+};
+M2 mul(const M2 &x, const M2 &y) {
+    return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c,
+            x.c * y.b + x.d * y.d};
+}
+}  // namespace
+
+extern "C" {
+
+int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
+    if (!out || !sos || nsec < 1) return fail(OSZ_ERR_ARG, "osz_sos_plan_create: bad arguments");
+    if (nsec > SOS_MAXSEC)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_sos_plan_create: more than 16 sections per plan "
+                                         "(split the cascade into several plans)");
+    osz_sos_plan *p = new osz_sos_plan();
+    p->prm.nsec = nsec;
+    p->prm.pad_ = 0;
+    std::vector<double> lanepow((size_t)nsec * 32 * 4);
+    for (int s = 0; s < nsec; ++s) {
+        const double *r = sos + 6 * s;
+        const long double a0 = r[3];
+        if (a0 == 0.0L) {
+            delete p;
+            return fail(OSZ_ERR_ARG, "osz_sos_plan_create: a0 == 0");
+        }
+        SosSec &c = p->prm.sec[s];
+        c.b0 = (double)(r[0] / a0);
+        c.b1 = (double)(r[1] / a0);
+        c.b2 = (double)(r[2] / a0);
+        c.a1 = (double)(r[4] / a0);
+        c.a2 = (double)(r[5] / a0);
+        const M2 A = {-(long double)c.a1, 1.0L, -(long double)c.a2, 0.0L};
+        M2 pw = {1.0L, 0.0L, 0.0L, 1.0L};   // A^i
+        for (int i = 0; i < SOS_T; ++i) {
+            c.g0[i] = (double)pw.a;
+            c.g1[i] = (double)pw.b;
+            pw = mul(A, pw);
+        }
+        M2 M = pw;                           // A^32
+        M2 q = M;
+        for (int k = 0; k < 5; ++k) {        // M^(2^k)
+            c.P[k][0] = (double)q.a;
+            c.P[k][1] = (double)q.b;
+            c.P[k][2] = (double)q.c;
+            c.P[k][3] = (double)q.d;
+            q = mul(q, q);
+        }
+        c.Q[0] = (double)q.a;                // M^32
+        c.Q[1] = (double)q.b;
+        c.Q[2] = (double)q.c;
+        c.Q[3] = (double)q.d;
+        M2 lp = M;                           // M^(lane+1)
+        for (int l = 0; l < 32; ++l) {
+            double *d = &lanepow[((size_t)s * 32 + l) * 4];
+            d[0] = (double)lp.a;
+            d[1] = (double)lp.b;
+            d[2] = (double)lp.c;
+            d[3] = (double)lp.d;
+            lp = mul(M, lp);
+        }
+    }
+    for (int s = nsec; s < SOS_MAXSEC; ++s) p->prm.sec[s] = SosSec{};
+    if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
+        cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+        osz_sos_plan_destroy(p);
+        return fail(OSZ_ERR_CUDA, "osz_sos_plan_create: device upload failed");
+    }
+    *out = p;
+    return OSZ_OK;
+}
+
+int osz_sos_plan_destroy(osz_sos_plan *p) {
+    if (!p) return OSZ_OK;
+    cudaFree(p->d_lanepow);
+    delete p;
+    return OSZ_OK;
+}
+
+int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t n,
+                     int reverse, double *state, double *y, int64_t ldy, void *stream) {
+    if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_exec_f64: null argument");
+    if (rows <= 0 || n <= 0) return OSZ_OK;
+    cudaStream_t st = as_stream(stream);
+    const int smem = SOS_NT * SOS_LD * 8;
+    if (y) {
+        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        sos_scan_kernel<true><<<(unsigned)rows, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse,
+                                                                    state, y, ldy, p->d_lanepow);
+    } else {
+        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        sos_scan_kernel<false><<<(unsigned)rows, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse,
+                                                                     state, nullptr, 0,
+                                                                     p->d_lanepow);
+    }
+    OSZ_LAUNCHED("sos_scan_kernel");
+    return OSZ_OK;
+}
+
+int osz_sos_state_from_sample_f64(const osz_sos_plan *p, const double *zi, const double *x,
+                                  int64_t ldx, int64_t rows, int64_t sample, double *state,
+                                  void *stream) {
+    if (!p || !zi || !x || !state)
+        return fail(OSZ_ERR_ARG, "osz_sos_state_from_sample_f64: null argument");
+    if (rows <= 0) return OSZ_OK;
+    SosZi z{};
+    for (int s = 0; s < p->prm.nsec; ++s) {
+        z.zi[s][0] = zi[2 * s];
+        z.zi[s][1] = zi[2 * s + 1];
+    }
+    const int64_t total = rows * p->prm.nsec * 2;
+    sos_state_from_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        z, p->prm.nsec, x, ldx, rows, sample, state);
+    OSZ_LAUNCHED("sos_state_from_sample_kernel");
+    return OSZ_OK;
+}
+
+}  // extern "C"

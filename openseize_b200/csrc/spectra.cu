@@ -1,0 +1,369 @@
+// Windowed DFT of sliding segments: Welch accumulate, per-segment periodogram
+// and STFT.  Replaces, per segment, detrend -> window -> rfft -> scale
+// (reference core/numerical.py:691-716) and |X|^2 with one-sided doubling
+// (:781-794), over the windows of _spectra_estimatives (:817-849).
+//
+// Power-of-two path (256 <= nfft <= 8192): TWO consecutive segments of a row
+// are transformed as the real and imaginary part of one nfft-point complex FFT
+// held in registers + shared memory (fft_core.cuh).  For Welch the two
+// segments' periodograms are summed anyway, and
+//     |X_a[k]|^2 + |X_b[k]|^2 = (|Z[k]|^2 + |Z[N-k]|^2) / 2 ,
+// so the kernel only accumulates |Z|^2 per bin in registers over all of a
+// row's segment pairs and folds bins k and N-k when it adds the result into
+// psd_sum -- no untangling pass, no per-segment memory traffic.
+// The STFT / periodogram kernels untangle X_a, X_b through shared memory.
+//
+// Other nfft (not a power of two, or outside 256..8192) use the generic path
+// in spectra_generic.cu.
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace osz {
+
+enum { SPEC_ACCUM = 0, SPEC_PGRAM = 1, SPEC_STFT = 2 };
+
+// Sum of up to four doubles over the CTA (NT threads).  `red` is 4*32 doubles.
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum(double (&val)[NV], double *red, int tid) {
+    constexpr int NW = NT / 32;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val[i] += __shfl_xor_sync(0xffffffffu, val[i], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + (tid >> 5)] = val[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[i * 32 + w];   // same order in every thread
+        val[i] = s;
+    }
+    __syncthreads();
+}
+
+// Load segments a (-> .x) and b (-> .y), detrend and window them.
+template <int LOG2N, int DETREND>
+__device__ __forceinline__ void load_pair(double2 (&v)[16], const double *__restrict__ xa,
+                                          bool has_b, int64_t stride,
+                                          const double *__restrict__ win, double *red, int tid) {
+    using C = FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int i = tid + r * NT;
+        v[r].x = ldg(xa + i);
+        v[r].y = has_b ? ldg(xa + stride + i) : 0.0;
+    }
+    if (DETREND == OSZ_DETREND_CONSTANT) {
+        double s[2] = {0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            s[0] += v[r].x;
+            s[1] += v[r].y;
+        }
+        block_sum<2, NT>(s, red, tid);
+        const double ma = s[0] / N, mb = s[1] / N;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double w = ldg(win + tid + r * NT);
+            v[r].x = (v[r].x - ma) * w;
+            v[r].y = (v[r].y - mb) * w;
+        }
+    } else if (DETREND == OSZ_DETREND_LINEAR) {
+        // least-squares line over t = 0..N-1 (scipy.signal.detrend type='linear')
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        const double tbar = 0.5 * (N - 1);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double tc = (double)(tid + r * NT) - tbar;
+            s[0] += v[r].x;
+            s[1] += v[r].y;
+            s[2] = fma(tc, v[r].x, s[2]);
+            s[3] = fma(tc, v[r].y, s[3]);
+        }
+        block_sum<4, NT>(s, red, tid);
+        const double stt = (double)N * ((double)N * N - 1.0) / 12.0;   // sum (t - tbar)^2
+        const double ma = s[0] / N, mb = s[1] / N;
+        const double ka = s[2] / stt, kb = s[3] / stt;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double tc = (double)(tid + r * NT) - tbar;
+            const double w = ldg(win + tid + r * NT);
+            v[r].x = (v[r].x - fma(ka, tc, ma)) * w;
+            v[r].y = (v[r].y - fma(kb, tc, mb)) * w;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double w = ldg(win + tid + r * NT);
+            v[r].x *= w;
+            v[r].y *= w;
+        }
+    }
+}
+
+// Welch: one CTA walks `pairs_per_cta` consecutive segment pairs of one row.
+template <int LOG2N, int DETREND>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
+welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
+                   const double *__restrict__ win, const double2 *__restrict__ tw, double norm,
+                   double *__restrict__ psd_sum, int64_t ldp, int64_t pairs_per_cta) {
+    using C = FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ double red[4 * 32];
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t npairs = (nseg + 1) / 2;
+    const int64_t p0 = (int64_t)blockIdx.x * pairs_per_cta;
+    int64_t p1 = p0 + pairs_per_cta;
+    if (p1 > npairs) p1 = npairs;
+    const double *xr = x + row * ldx;
+
+    double acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+
+    for (int64_t p = p0; p < p1; ++p) {
+        double2 v[16];
+        load_pair<LOG2N, DETREND>(v, xr + 2 * p * stride, 2 * p + 1 < nseg, stride, win, red, tid);
+        fft_r2r<LOG2N>(v, sm, tw, tid);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = fma(v[r].x, v[r].x, fma(v[r].y, v[r].y, acc[r]));
+    }
+    if (p0 >= p1) return;
+    // fold k and N-k:  psd[k] += norm * (A[k] + A[N-k]) for 0<k<N/2 (this is the
+    // one-sided doubling), psd[0] += norm*A[0], psd[N/2] += norm*A[N/2].
+    double *out = psd_sum + row * ldp;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int idx = tid + r * NT;
+        const int bin = idx <= N / 2 ? idx : N - idx;
+        atomicAdd(out + bin, acc[r] * norm);
+    }
+}
+
+// Per-segment outputs: one CTA per (segment pair, row).
+template <int LOG2N, int DETREND, int MODE>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
+spec_segments_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, int64_t nseg,
+                     int64_t stride, const double *__restrict__ win,
+                     const double2 *__restrict__ tw, double norm, double *__restrict__ out) {
+    using C = FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT, NF = N / 2 + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ double red[4 * 32];
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t sa = (int64_t)blockIdx.x * 2;
+    const bool has_b = sa + 1 < nseg;
+
+    double2 v[16];
+    load_pair<LOG2N, DETREND>(v, x + row * ldx + sa * stride, has_b, stride, win, red, tid);
+    fft_r2r<LOG2N>(v, sm, tw, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[fft_phys(tid + r * NT)] = v[r];
+    __syncthreads();
+
+    const double amp = sqrt(norm);
+    // bins k = tid + m*NT, m = 0..7 (k < N/2), plus k = N/2 on thread 0
+#pragma unroll
+    for (int m = 0; m <= 8; ++m) {
+        if (m == 8 && tid != 0) break;
+        const int k = tid + m * NT;
+        const double2 zk = v[m];
+        const double2 zn = sm[fft_phys((N - k) & (N - 1))];
+        // X_a = (Z[k] + conj Z[N-k]) / 2 ; X_b = (Z[k] - conj Z[N-k]) / (2i)
+        const double2 xa = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+        const double2 xb = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+        if (MODE == SPEC_STFT) {
+            double2 *o = reinterpret_cast<double2 *>(out);
+            o[(sa * rows + row) * NF + k] = make_double2(xa.x * amp, xa.y * amp);
+            if (has_b) o[((sa + 1) * rows + row) * NF + k] = make_double2(xb.x * amp, xb.y * amp);
+        } else {
+            const double f = (k == 0 || k == N / 2) ? norm : 2.0 * norm;
+            out[(sa * rows + row) * NF + k] = f * (xa.x * xa.x + xa.y * xa.y);
+            if (has_b) out[((sa + 1) * rows + row) * NF + k] = f * (xb.x * xb.x + xb.y * xb.y);
+        }
+    }
+}
+
+}  // namespace osz
+
+using namespace osz;
+
+struct osz_spec_plan {
+    int nfft = 0, stride = 0, detrend = 0, path = 0, log2n = 0;
+    double norm = 0.0;
+    double *d_win = nullptr;
+    double2 *d_tw = nullptr;
+    void *generic = nullptr;    // spectra_generic.cu state
+};
+
+// generic path (spectra_generic.cu)
+int osz_generic_create(void **state, int nfft);
+void osz_generic_destroy(void *state);
+int osz_generic_exec(void *state, const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
+                     int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st);
+// accessors used by the generic path
+int osz_spec_plan_nfft(const osz_spec_plan *p) { return p->nfft; }
+int osz_spec_plan_stride(const osz_spec_plan *p) { return p->stride; }
+int osz_spec_plan_detrend(const osz_spec_plan *p) { return p->detrend; }
+double osz_spec_plan_norm(const osz_spec_plan *p) { return p->norm; }
+const double *osz_spec_plan_window(const osz_spec_plan *p) { return p->d_win; }
+
+template <int LOG2N, int DETREND>
+static int launch_welch(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                        int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
+    using C = FftCfg<LOG2N>;
+    OSZ_CUDA(cudaFuncSetAttribute(welch_accum_kernel<LOG2N, DETREND>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    const int64_t npairs = (nseg + 1) / 2;
+    // enough CTAs for ~4 waves of 2 CTAs/SM, but at least 4 pairs per CTA so the
+    // register accumulators amortise the atomics
+    const int64_t target = (int64_t)sm_count() * 8;
+    int64_t per_row = (target + rows - 1) / rows;
+    if (per_row < 1) per_row = 1;
+    int64_t ppc = (npairs + per_row - 1) / per_row;
+    if (ppc < 4) ppc = 4;
+    const int64_t gx = (npairs + ppc - 1) / ppc;
+    dim3 grid((unsigned)gx, (unsigned)rows);
+    welch_accum_kernel<LOG2N, DETREND><<<grid, C::NT, C::SMEM_BYTES, st>>>(
+        x, ldx, nseg, p->stride, p->d_win, p->d_tw, p->norm, psd, ldp, ppc);
+    OSZ_LAUNCHED("welch_accum_kernel");
+    return OSZ_OK;
+}
+
+template <int LOG2N, int DETREND, int MODE>
+static int launch_segments(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                           int64_t nseg, double *out, cudaStream_t st) {
+    using C = FftCfg<LOG2N>;
+    OSZ_CUDA(cudaFuncSetAttribute(spec_segments_kernel<LOG2N, DETREND, MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    dim3 grid((unsigned)((nseg + 1) / 2), (unsigned)rows);
+    spec_segments_kernel<LOG2N, DETREND, MODE><<<grid, C::NT, C::SMEM_BYTES, st>>>(
+        x, ldx, rows, nseg, p->stride, p->d_win, p->d_tw, p->norm, out);
+    OSZ_LAUNCHED("spec_segments_kernel");
+    return OSZ_OK;
+}
+
+template <int LOG2N, int DETREND>
+static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
+                         int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st) {
+    if (mode == SPEC_ACCUM) return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+    if (mode == SPEC_PGRAM)
+        return launch_segments<LOG2N, DETREND, SPEC_PGRAM>(p, x, ldx, rows, nseg, out, st);
+    return launch_segments<LOG2N, DETREND, SPEC_STFT>(p, x, ldx, rows, nseg, out, st);
+}
+
+template <int LOG2N>
+static int dispatch_detrend(const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
+                            int64_t rows, int64_t nseg, double *out, int64_t ldp,
+                            cudaStream_t st) {
+    switch (p->detrend) {
+        case OSZ_DETREND_NONE:
+            return dispatch_mode<LOG2N, OSZ_DETREND_NONE>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case OSZ_DETREND_CONSTANT:
+            return dispatch_mode<LOG2N, OSZ_DETREND_CONSTANT>(p, mode, x, ldx, rows, nseg, out, ldp,
+                                                              st);
+        default:
+            return dispatch_mode<LOG2N, OSZ_DETREND_LINEAR>(p, mode, x, ldx, rows, nseg, out, ldp,
+                                                            st);
+    }
+}
+
+static int spec_exec(const osz_spec_plan *p, int mode, const double *x, int64_t ldx, int64_t rows,
+                     int64_t nseg, double *out, int64_t ldp, void *stream) {
+    if (!p || !x || !out) return fail(OSZ_ERR_ARG, "spectra exec: null argument");
+    if (rows <= 0 || nseg <= 0) return OSZ_OK;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "spectra: more than 65535 rows per call");
+    cudaStream_t st = as_stream(stream);
+    if (p->path == 2) return osz_generic_exec(p->generic, p, mode, x, ldx, rows, nseg, out, ldp, st);
+    switch (p->log2n) {
+        case 8: return dispatch_detrend<8>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case 9: return dispatch_detrend<9>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case 10: return dispatch_detrend<10>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case 11: return dispatch_detrend<11>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case 12: return dispatch_detrend<12>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+        case 13: return dispatch_detrend<13>(p, mode, x, ldx, rows, nseg, out, ldp, st);
+    }
+    return fail(OSZ_ERR_UNSUPPORTED, "spectra: unsupported nfft");
+}
+
+extern "C" {
+
+int osz_spec_plan_create(osz_spec_plan **out, int nfft, int stride, const double *window,
+                         int detrend, double norm) {
+    if (!out || !window || nfft < 2 || stride < 1 || stride > nfft)
+        return fail(OSZ_ERR_ARG, "osz_spec_plan_create: bad arguments");
+    if (detrend < OSZ_DETREND_NONE || detrend > OSZ_DETREND_LINEAR)
+        return fail(OSZ_ERR_ARG, "osz_spec_plan_create: unknown detrend");
+    osz_spec_plan *p = new osz_spec_plan();
+    p->nfft = nfft;
+    p->stride = stride;
+    p->detrend = detrend;
+    p->norm = norm;
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    const bool pow2 = (1 << log2n) == nfft && log2n >= 8 && log2n <= 13;
+    bool ok = cudaMalloc(&p->d_win, (size_t)nfft * 8) == cudaSuccess &&
+              cudaMemcpy(p->d_win, window, (size_t)nfft * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && pow2) {
+        p->path = 1;
+        p->log2n = log2n;
+        std::vector<double> tw = make_fft_twiddles(log2n);
+        ok = cudaMalloc(&p->d_tw, tw.size() * 8) == cudaSuccess &&
+             cudaMemcpy(p->d_tw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    } else if (ok) {
+        p->path = 2;
+        int rc = osz_generic_create(&p->generic, nfft);
+        if (rc != OSZ_OK) {
+            osz_spec_plan_destroy(p);
+            return rc;
+        }
+    }
+    if (!ok) {
+        osz_spec_plan_destroy(p);
+        return fail(OSZ_ERR_CUDA, "osz_spec_plan_create: device upload failed");
+    }
+    *out = p;
+    return OSZ_OK;
+}
+
+int osz_spec_plan_destroy(osz_spec_plan *p) {
+    if (!p) return OSZ_OK;
+    cudaFree(p->d_win);
+    cudaFree(p->d_tw);
+    if (p->generic) osz_generic_destroy(p->generic);
+    delete p;
+    return OSZ_OK;
+}
+
+int osz_spec_plan_path(const osz_spec_plan *p) { return p ? p->path : 0; }
+
+int osz_welch_accum_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                        int64_t nseg, double *psd_sum, int64_t ldp, void *stream) {
+    return spec_exec(p, SPEC_ACCUM, x, ldx, rows, nseg, psd_sum, ldp, stream);
+}
+int osz_periodogram_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                        int64_t nseg, double *out, void *stream) {
+    return spec_exec(p, SPEC_PGRAM, x, ldx, rows, nseg, out, 0, stream);
+}
+int osz_stft_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t nseg,
+                 double *out, void *stream) {
+    return spec_exec(p, SPEC_STFT, x, ldx, rows, nseg, out, 0, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+"""numpy stand-ins for the kernel-level calls (TEST INFRASTRUCTURE ONLY).
+
+Each stand-in implements the contract written in include/osz_b200.h for the
+matching C-ABI entry point, on CPU torch tensors, so the Python host logic of
+openseize_b200 can be exercised by `pytest -m "not gpu"`.  Installed by the
+`fake_gpu` fixture through monkeypatch; nothing in the package imports this.
+"""
+
+import numpy as np
+import scipy.signal as sps
+import torch
+
+from openseize_b200.core import device as dv
+
+
+def _t(a):
+    return torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True))
+
+
+class FakeFir:
+    def __init__(self, taps, algo=0):
+        self.taps = np.asarray(taps, dtype=np.float64)
+        self.ntaps = len(self.taps)
+        self.algo = 0
+
+    def run(self, xbuf, n_out, out=None):
+        x = xbuf.numpy()
+        k = self.ntaps
+        y = np.stack([np.convolve(r[:n_out + k - 1], self.taps, "valid") for r in x])
+        return _t(y)
+
+
+class FakeSos:
+    def __init__(self, sos):
+        self.sos = np.atleast_2d(np.asarray(sos, dtype=np.float64))
+        self.nsec = self.sos.shape[0]
+
+    def run(self, x, state, reverse=False, want_output=True, out=None):
+        xn = x.numpy()
+        if reverse:
+            xn = xn[:, ::-1]
+        zi = np.transpose(state.numpy(), (1, 0, 2))
+        y, zf = sps.sosfilt(self.sos, xn, axis=-1, zi=zi)
+        state.copy_(_t(np.transpose(zf, (1, 0, 2))))
+        if not want_output:
+            return None
+        return _t(y[:, ::-1] if reverse else y)
+
+    def state_from_sample(self, zi, x, sample):
+        zi = np.asarray(zi, dtype=np.float64)
+        return _t(zi[None, :, :] * x.numpy()[:, sample][:, None, None])
+
+
+class FakeUpfirdn:
+    def __init__(self, h, up, down):
+        self.h = np.asarray(h, dtype=np.float64) * up
+        self.ntaps, self.up, self.down = len(self.h), int(up), int(down)
+
+    def run(self, x, x_first, out_first, n_out):
+        xn = x.numpy()
+        half = (self.ntaps - 1) // 2
+        # u[m] = sum_k h'[m - k*up] x[k], m relative to x_first*up
+        u = sps.upfirdn(self.h, xn, up=self.up, down=1, axis=-1)
+        j = np.arange(out_first, out_first + n_out)
+        m = j * self.down + half - x_first * self.up
+        ok = (m >= 0) & (m < u.shape[1])
+        y = np.zeros((xn.shape[0], n_out))
+        y[:, ok] = u[:, m[ok]]
+        return _t(y)
+
+
+class FakeSpec:
+    def __init__(self, nfft, stride, window, detrend, norm):
+        self.nfft, self.stride, self.nfreq = int(nfft), int(stride), int(nfft) // 2 + 1
+        self.window = np.asarray(window, dtype=np.float64)
+        self.detrend, self.norm, self.path = detrend, float(norm), 1
+
+    def nseg_available(self, width):
+        return (width - self.nfft) // self.stride + 1 if width >= self.nfft else 0
+
+    def _dft(self, x, s):
+        seg = x[:, s * self.stride:s * self.stride + self.nfft]
+        if self.detrend in ("constant", "linear"):
+            seg = sps.detrend(seg, axis=-1, type=self.detrend)
+        return np.fft.rfft(seg * self.window, axis=-1)
+
+    def _pgram(self, X):
+        p = (X.real ** 2 + X.imag ** 2) * self.norm
+        if self.nfft % 2:
+            p[:, 1:] *= 2
+        else:
+            p[:, 1:-1] *= 2
+        return p
+
+    def welch_accum(self, x, nseg, psd_sum):
+        xn = x.numpy()
+        acc = psd_sum.numpy()
+        for s in range(nseg):
+            acc += self._pgram(self._dft(xn, s))
+
+    def segments(self, x, nseg, complex_):
+        xn = x.numpy()
+        outs = []
+        for s in range(nseg):
+            X = self._dft(xn, s)
+            if complex_:
+                X = X * np.sqrt(self.norm)
+                outs.append(np.stack([X.real, X.imag], axis=-1))
+            else:
+                outs.append(self._pgram(X))
+        return _t(np.stack(outs))
+
+
+class _Now:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def get(self):
+        return self.arr
+
+
+def _upload(arr, layout):
+    a = np.asarray(arr, dtype=np.float64)
+    n = a.shape[layout.axis]
+    a = np.moveaxis(a.reshape(layout.outer, n, layout.inner), 1, 2)
+    return _t(a.reshape(layout.rows, n))
+
+
+def _download(dev, layout, complex_=False):
+    a = dev.numpy()
+    n = a.shape[1]
+    if complex_:
+        a = a[..., 0] + 1j * a[..., 1]
+    a = np.moveaxis(a.reshape(layout.outer, layout.inner, n), 2, 1)
+    return _Now(np.ascontiguousarray(a).reshape(layout.host_shape(n)))
+
+
+def install(mp):
+    mp.setattr(dv, "DEVICE", "cpu")
+    mp.setattr(dv, "require_cuda", lambda: torch)
+    mp.setattr(dv, "upload", _upload)
+    mp.setattr(dv, "download", _download)
+    mp.setattr(dv.FirPlan, "cached", staticmethod(lambda taps, algo=0: FakeFir(taps, algo)))
+    mp.setattr(dv.SosPlan, "cached", staticmethod(lambda sos: FakeSos(sos)))
+    mp.setattr(dv.UpfirdnPlan, "cached",
+               staticmethod(lambda h, up, down: FakeUpfirdn(h, up, down)))
+    mp.setattr(dv.SpecPlan, "cached",
+               staticmethod(lambda nfft, stride, window, detrend, norm:
+                            FakeSpec(nfft, stride, window, detrend, norm)))

@@ -1,0 +1,277 @@
+"""Parity cases shared by the CPU host-logic tests (numpy stand-in kernels,
+`fake_gpu` fixture) and the GPU tests (real sm_100a kernels).
+
+Each case drives the reference-facing operator API of openseize_b200 and
+compares with (a) the golden vectors produced by the real reference
+(tests/golden, made by oracle/make_golden.py) and (b) the oracle on fresh
+seeded inputs.  Tolerance (BASELINE.json north_star): float64 results within
+1e-9 of the output peak; lengths, counts, frequency and time vectors exact.
+"""
+
+import numpy as np
+
+import oracle
+from openseize_b200 import producer
+from openseize_b200.core import numerical as nm
+from openseize_b200.filtering.fir import Kaiser
+from openseize_b200.filtering.iir import Butter, Notch
+from openseize_b200.resampling.resampling import downsample, resample, upsample
+from openseize_b200.spectra.estimators import psd, stft
+from tests.conftest import golden, relerr, signal
+
+TOL = 1e-9
+
+
+def close(mine, ref, tol=TOL):
+    mine, ref = np.asarray(mine), np.asarray(ref)
+    assert mine.shape == ref.shape, (mine.shape, ref.shape)
+    assert mine.dtype == ref.dtype, (mine.dtype, ref.dtype)
+    err = relerr(mine, ref)
+    assert err <= tol, err
+    return err
+
+
+# ------------------------------------------------------------------ FIR ----
+def fir_golden():
+    g = golden("fir_kaiser113")
+    fs, cs = int(g["fs"]), int(g["chunksize"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    assert x.sum() == float(g["x_sum"])
+    filt = Kaiser(fpass=500, fstop=600, fs=fs)
+    assert np.array_equal(filt.coeffs, g["taps"])
+    for mode in ("same", "full", "valid"):
+        y = filt(producer(x, cs, -1), cs, axis=-1, mode=mode).to_array()
+        close(y, g["y_" + mode])
+    # ndarray in -> ndarray out
+    close(filt(x, cs, axis=-1, mode="same"), g["y_same"])
+    # sample axis first
+    xt = np.ascontiguousarray(x[:2].T)
+    close(filt(producer(xt, cs, 0), cs, axis=0, mode="same").to_array(), g["y_same_axis0"])
+
+
+def fir_long_golden():
+    g = golden("fir_kaiser671")
+    fs, cs = int(g["fs"]), int(g["chunksize"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    filt = Kaiser(fpass=500, fstop=600, fs=fs)
+    assert len(filt.coeffs) == 671 and np.array_equal(filt.coeffs, g["taps"])
+    close(filt(producer(x, cs, -1), cs, axis=-1, mode="same").to_array(), g["y_same"])
+
+
+def fir_oracle_sweep():
+    """Reference tests/test_oaconvolve.py:14-94: lengths, axes, windows, modes."""
+    import scipy.signal as sps
+
+    rng = np.random.default_rng(0)
+    for n in (10007, 33333):
+        x = rng.standard_normal((3, 4, n))
+        win = sps.get_window("hann", 203)
+        for mode in ("same", "full", "valid"):
+            got = np.concatenate(list(nm.oaconvolve(producer(x, 5000, -1), win, -1, mode)), -1)
+            ref = np.concatenate(oracle.oaconvolve(x, win, 5000, -1, mode), -1)
+            close(got, ref)
+    x = rng.standard_normal((4, 6453, 2, 3))
+    win = sps.get_window("blackman", 76)
+    got = np.concatenate(list(nm.oaconvolve(producer(x, 1000, 1), win, 1, "same")), 1)
+    close(got, np.concatenate(oracle.oaconvolve(x, win, 1000, 1, "same"), 1))
+    x = rng.standard_normal((10622, 3))
+    for k in (50, 77, 120):
+        win = sps.get_window("hamming", k)
+        got = np.concatenate(list(nm.oaconvolve(producer(x, 2048, 0), win, 0, "same")), 0)
+        close(got, np.concatenate(oracle.oaconvolve(x, win, 2048, 0, "same"), 0))
+    # short filters (direct-form kernel) and a chunk smaller than the filter
+    x = rng.standard_normal((5, 9000))
+    for k, cs in ((1, 1000), (2, 1000), (9, 333), (24, 4000), (25, 4000), (113, 100)):
+        win = rng.standard_normal(k)
+        for mode in ("same", "full", "valid"):
+            got = np.concatenate(list(nm.oaconvolve(producer(x, cs, -1), win, -1, mode)), -1)
+            ref = np.stack([np.convolve(r, win, mode) for r in x])
+            close(got, ref)
+
+
+# ------------------------------------------------------------------ IIR ----
+def iir_golden():
+    g = golden("iir_butter8")
+    fs = int(g["fs"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    filt = Butter(fpass=[1, 100], fstop=[0.5, 200], fs=fs, gpass=1, gstop=40)
+    assert np.array_equal(filt.coeffs, g["sos"])
+    for cs in (4000, 5000):
+        y = filt(producer(x, cs, -1), cs, axis=-1, dephase=True).to_array()
+        close(y, g["y_filtfilt_cs%d" % cs])
+    close(filt(producer(x, 4000, -1), 4000, axis=-1, dephase=False).to_array(), g["y_fwd_cs4000"])
+    g = golden("iir_notch60")
+    fs, cs = int(g["fs"]), int(g["chunksize"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    notch = Notch(fstop=60, width=6, fs=fs)
+    assert np.array_equal(notch.coeffs[0], g["b"]) and np.array_equal(notch.coeffs[1], g["a"])
+    close(notch(producer(x, cs, -1), cs, axis=-1, dephase=True).to_array(), g["y_filtfilt"])
+    close(notch(producer(x, cs, -1), cs, axis=-1, dephase=False).to_array(), g["y_fwd"])
+
+
+def iir_oracle_sweep():
+    """Reference tests/test_iir.py:77-158,216-326: axes, chunk sizes, zi."""
+    import scipy.signal as sps
+
+    rng = np.random.default_rng(9)
+    sos = sps.butter(4, [1, 100], btype="bandpass", fs=5000, output="sos")
+    # long chunks: several 8192-sample scan blocks per chunk, ragged tail
+    x = rng.standard_normal((3, 70001)) + 3.0
+    for cs in (70001, 30000, 8192, 8191, 1000):
+        got = np.concatenate(list(nm.sosfiltfilt(producer(x, cs, -1), sos, -1)), -1)
+        close(got, np.concatenate(oracle.sosfiltfilt(x, sos, cs, -1), -1))
+        got = np.concatenate(list(nm.sosfilt(producer(x, cs, -1), sos, -1)), -1)
+        close(got, np.concatenate(oracle.sosfilt(x, sos, cs, -1)[0], -1))
+    # sample axis in the middle, explicit zi
+    x = rng.standard_normal((2, 20011, 3))
+    zi = rng.standard_normal((sos.shape[0], 2, 2, 3))
+    got = np.concatenate(list(nm.sosfilt(producer(x, 7000, 1), sos, 1, zi)), 1)
+    close(got, np.concatenate(oracle.sosfilt(x, sos, 7000, 1, zi)[0], 1))
+    got = np.concatenate(list(nm.sosfiltfilt(producer(x, 7000, 1), sos, 1)), 1)
+    close(got, np.concatenate(oracle.sosfiltfilt(x, sos, 7000, 1), 1))
+    # transfer-function format (Notch path), forward with zi and forward-backward
+    b, a = sps.iirnotch(60, 10, fs=5000)
+    x = rng.standard_normal((4, 25000))
+    zi = rng.standard_normal((4, 2))
+    got = np.concatenate(list(nm.lfilter(producer(x, 6000, -1), (b, a), -1, zi)), -1)
+    close(got, np.concatenate(oracle.lfilter(x, (b, a), 6000, -1, zi)[0], -1))
+    got = np.concatenate(list(nm.filtfilt(producer(x, 6000, -1), (b, a), -1)), -1)
+    close(got, np.concatenate(oracle.filtfilt(x, (b, a), 6000, -1), -1))
+    # more than 16 sections: split cascade
+    sos = sps.butter(20, [5, 400], btype="bandpass", fs=5000, output="sos")
+    assert sos.shape[0] == 20
+    x = rng.standard_normal((2, 30000))
+    got = np.concatenate(list(nm.sosfilt(producer(x, 9000, -1), sos, -1)), -1)
+    close(got, np.concatenate(oracle.sosfilt(x, sos, 9000, -1)[0], -1))
+
+
+# ------------------------------------------------------------- resample ----
+def resample_golden():
+    g = golden("resample")
+    fs = int(g["fs"])
+    xfull = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    for name in ("down20", "up2", "rs3_7"):
+        L, M, cs, nuse = (int(v) for v in g["LMcsn_" + name])
+        x = xfull[:, :nuse]
+        pro = resample(producer(x, cs, -1), L, M, fs, cs, axis=-1)
+        assert pro.shape == g["y_" + name].shape
+        close(pro.to_array(), g["y_" + name])
+        # raw generator: bit-exact yield lengths (reference numerical.py:617-632)
+        raw = [a.shape[-1] for a in
+               nm.polyphase_resample(producer(x, cs, -1), L, M, fs, Kaiser, -1)]
+        assert raw == list(g["raw_" + name]), (raw, list(g["raw_" + name]))
+    x = xfull[:, :30000]
+    close(downsample(x, 20, fs, 7000, axis=-1), g["y_down20"])
+    close(upsample(xfull[:, :9000], 2, fs, 2500, axis=-1), g["y_up2"])
+
+
+def resample_oracle_sweep():
+    """Reference tests/test_resampling.py:39-139: all L != M in 1..5, chunk
+    sizes, sizes x channels; the oracle is one global resample_poly call."""
+    import scipy.signal as sps
+
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal((6, 39968))
+    fs = 500
+    for L in range(1, 6):
+        for M in range(1, 6):
+            if np.gcd(L, M) != 1 or L == M:
+                continue
+            got = resample(producer(x, 10000, -1), L, M, fs, 10000, axis=-1).to_array()
+            h = oracle.resample_filter(L, M, fs)
+            ref = sps.resample_poly(x, L, M, axis=-1, window=h)
+            close(got, ref)
+    for cs in (1000, 3333, 13000, 39968):
+        got = downsample(producer(x, cs, -1), 10, fs, cs, axis=-1).to_array()
+        ref = sps.resample_poly(x, 1, 10, axis=-1, window=oracle.resample_filter(1, 10, fs))
+        close(got, ref)
+    xt = np.ascontiguousarray(x[:3].T)
+    got = downsample(producer(xt, 9000, 0), 4, fs, 9000, axis=0).to_array()
+    ref = sps.resample_poly(xt, 1, 4, axis=0, window=oracle.resample_filter(1, 4, fs))
+    close(got, ref)
+    assert resample(x, 3, 3, fs, 1000) is x          # identity returns the input itself
+
+
+# -------------------------------------------------------------- spectra ----
+def spectra_golden(name="pow2"):
+    g = golden("spectra_" + name)
+    fs, res = int(g["fs"]), float(g["resolution"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    for det in ("constant", "linear"):
+        for scal in ("density", "spectrum"):
+            cnt, f, p = psd(producer(x, 5000, -1), fs, axis=-1, resolution=res, detrend=det,
+                            scaling=scal)
+            assert cnt == int(g["psd_cnt"]) and np.array_equal(f, g["freqs"])
+            close(p, g["psd_%s_%s" % (det, scal)])
+    for bnd in (True, False):
+        for pad in (True, False):
+            f, t, X = stft(producer(x, 5000, -1), fs, axis=-1, resolution=res, boundary=bnd,
+                           padded=pad)
+            key = "stft_b%d_p%d" % (bnd, pad)
+            assert np.array_equal(f, g["freqs"]) and np.array_equal(t, g[key + "_time"])
+            assert X.shape[-1] == int(g[key + "_nseg"]) and X.dtype == np.complex128
+            close(X[..., g[key + "_idx"]], g[key + "_X"])
+
+
+def spectra_oracle_sweep(fs=1024, resolutions=(1.0, 2.0, 4.0)):
+    """Reference tests/test_spectra.py:164-615: sizes, overlaps, windows,
+    scalings, axes; welch producer and stft producer paths."""
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal((3, 41017)) + 2.0
+    for res in resolutions:
+        for ov in (0.1, 0.5, 0.75):
+            for win in ("hann", "hamming"):
+                cnt, f, p = psd(producer(x, 7000, -1), fs, resolution=res, window=win, overlap=ov)
+                rc, rf, rp = oracle.welch_psd(x, fs, -1, res, window=win, overlap=ov)
+                assert cnt == rc and np.array_equal(f, rf)
+                close(p, rp)
+    # sample axis first; ndarray input
+    xt = np.ascontiguousarray(x[:2, :20000].T)
+    cnt, f, p = psd(xt, fs, axis=0, resolution=resolutions[0])
+    rc, rf, rp = oracle.welch_psd(xt, fs, 0, resolutions[0])
+    assert cnt == rc
+    close(p, rp)
+    # welch as a producer of per-segment periodograms
+    nfft = int(fs / resolutions[0])
+    f, wpro = nm.welch(producer(x, 6000, -1), fs, nfft, "hann", 0.5, -1, "constant", "density")
+    segs = oracle.segments(x, nfft, 0.5, 6000, -1)
+    got = list(wpro)
+    assert len(got) == len(segs) == wpro.shape[-1]
+    for k in (0, 1, len(segs) - 1):
+        close(got[k], oracle.periodogram(segs[k], fs, nfft)[1])
+    # stft, all boundary / padding combinations, producer output
+    for bnd in (True, False):
+        for pad in (True, False):
+            f, t, X = stft(producer(x, 9000, -1), fs, resolution=resolutions[0], boundary=bnd,
+                           padded=pad, overlap=0.5)
+            rf, rt, rX = oracle.stft(x, fs, -1, resolutions[0], boundary=bnd, padded=pad)
+            assert np.array_equal(t, rt)
+            close(X, rX)
+    f, t, Xp = stft(producer(x, 9000, -1), fs, resolution=resolutions[0], asarray=False)
+    assert not isinstance(Xp, np.ndarray)
+    close(np.stack(list(Xp), -1), oracle.stft(x, fs, -1, resolutions[0])[2])
+
+
+# ------------------------------------------------------------- pipeline ----
+def pipeline_chain():
+    """Notch -> Kaiser FIR -> downsample -> psd, composed through producers
+    (config 5 of BASELINE.json at toy size).  On this package the chain stays on
+    the device; the oracle composes the same stages on whole arrays with the
+    chunk sizes the reference would have used."""
+    fs, cs = 5000, 8000
+    x = signal(77, 3, 60000, fs)
+    notch = Notch(fstop=60, width=6, fs=fs)
+    kais = Kaiser(fpass=500, fstop=600, fs=fs)
+    p1 = notch(producer(x, cs, -1), cs, axis=-1, dephase=True)
+    p2 = kais(p1, cs, axis=-1, mode="same")
+    p3 = downsample(p2, 4, fs, cs, axis=-1)
+    cnt, f, p = psd(p3, fs // 4, axis=-1, resolution=fs / 4 / 256)
+
+    r1 = np.concatenate(oracle.filtfilt(x, notch.coeffs, cs, -1), -1)
+    r2 = np.concatenate(oracle.oaconvolve(r1, kais.coeffs, cs, -1, "same"), -1)
+    r3 = np.concatenate(oracle.polyphase_resample(r2, 1, 4, fs, cs, -1), -1)
+    rc, rf, rp = oracle.welch_psd(r3, fs // 4, -1, fs / 4 / 256)
+    assert cnt == rc and np.array_equal(f, rf)
+    close(p, rp)
+    # and the intermediate producer is still iterable on the host
+    close(kais(notch(producer(x, cs, -1), cs, axis=-1), cs, axis=-1).to_array(), r2)

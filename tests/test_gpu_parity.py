@@ -1,0 +1,205 @@
+"""Parity of the sm_100a kernels, through the reference-facing operator API and
+the C ABI, against the golden vectors of the real reference and the CPU oracle.
+Run on the B200 box: `pytest -m gpu`."""
+
+import numpy as np
+import pytest
+import scipy.signal as sps
+
+from tests import parity_cases as pc
+from tests.conftest import has_cuda, relerr
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+
+@pytest.fixture(scope="module")
+def dv():
+    from openseize_b200.core import device
+
+    device.require_cuda()
+    return device
+
+
+def _dev(dv, a):
+    return dv.from_host(np.asarray(a, dtype=np.float64))
+
+
+def test_native_library_is_what_runs(dv):
+    from openseize_b200 import _abi
+
+    before = _abi.launch_count()
+    pc.fir_golden()
+    assert _abi.launch_count() > before, "no kernel of libosz_b200.so was launched"
+
+
+def test_fir_golden():
+    pc.fir_golden()
+    pc.fir_long_golden()
+
+
+def test_fir_oracle_sweep():
+    pc.fir_oracle_sweep()
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("ntaps", [1, 2, 15, 16, 31, 113, 400, 671, 1025])
+def test_fir_kernels_vs_numpy(dv, algo, ntaps):
+    """Both FIR kernels on ragged sizes: y = valid convolution of the halo'd span."""
+    rng = np.random.default_rng(ntaps)
+    taps = rng.standard_normal(ntaps)
+    plan = dv.FirPlan(taps, algo)
+    for rows, n_out in ((1, 1), (3, 1919), (2, 1921), (5, 10000), (2, 40001)):
+        x = rng.standard_normal((rows, n_out + ntaps - 1))
+        # odd leading dimension and an offset view: unaligned rows
+        buf = dv.zeros((rows, x.shape[1] + 3))
+        buf[:, 1:1 + x.shape[1]] = _dev(dv, x)
+        y = plan.run(buf[:, 1:1 + x.shape[1]], n_out).cpu().numpy()
+        ref = np.stack([np.convolve(r, taps, "valid") for r in x])
+        assert relerr(y, ref) < 1e-12, (algo, ntaps, rows, n_out)
+
+
+def test_fir_long_taps_block8192(dv):
+    rng = np.random.default_rng(5)
+    taps = rng.standard_normal(1500)
+    plan = dv.FirPlan(taps, 2)
+    x = rng.standard_normal((2, 30000 + 1499))
+    y = plan.run(_dev(dv, x), 30000).cpu().numpy()
+    ref = np.stack([np.convolve(r, taps, "valid") for r in x])
+    assert relerr(y, ref) < 1e-12
+
+
+def test_iir_golden():
+    pc.iir_golden()
+
+
+def test_iir_oracle_sweep():
+    pc.iir_oracle_sweep()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 8191, 8192, 8193, 16384, 50001])
+def test_sos_kernel_vs_scipy(dv, n):
+    """Scan kernel vs the sequential DF2T recurrence: forward and reversed,
+    random initial state, output and final state; C2's 8-section band-pass whose
+    poles sit at radius 0.99978 (hard part 2)."""
+    rng = np.random.default_rng(n)
+    sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+    plan = dv.SosPlan(sos)
+    rows = 3
+    x = rng.standard_normal((rows, n)) + 1.0
+    zi = rng.standard_normal((rows, sos.shape[0], 2))
+    for reverse in (False, True):
+        state = _dev(dv, zi)
+        y = plan.run(_dev(dv, x), state, reverse=reverse).cpu().numpy()
+        xr = x[:, ::-1] if reverse else x
+        ry, rz = sps.sosfilt(sos, xr, axis=-1, zi=np.transpose(zi, (1, 0, 2)))
+        ry = ry[:, ::-1] if reverse else ry
+        assert relerr(y, ry) < 1e-10, (n, reverse)
+        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 1e-9
+        state2 = _dev(dv, zi)
+        assert plan.run(_dev(dv, x), state2, reverse=reverse, want_output=False) is None
+        assert relerr(state2.cpu().numpy(), state.cpu().numpy()) < 1e-13
+
+
+def test_resample_golden():
+    pc.resample_golden()
+
+
+def test_resample_oracle_sweep():
+    pc.resample_oracle_sweep()
+
+
+@pytest.mark.parametrize("up,down,ntaps", [(1, 2, 41), (1, 20, 449), (1, 25, 561), (1, 60, 1301),
+                                           (1, 300, 901), (3, 7, 155), (5, 1, 99), (2, 3, 64)])
+def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps):
+    """Decimating (R = 16 / 8 / 4 tiles) and general kernels against one global
+    resample_poly call, windows that start and end inside the recording."""
+    rng = np.random.default_rng(ntaps)
+    h = sps.firwin(ntaps, 1.0 / max(up, down))
+    x = rng.standard_normal((3, 40000))
+    ref = sps.resample_poly(x, up, down, axis=-1, window=h)
+    plan = dv.UpfirdnPlan(h, up, down)
+    n_total = ref.shape[-1]
+    y = plan.run(_dev(dv, x), 0, 0, n_total).cpu().numpy()
+    assert relerr(y, ref) < 1e-12
+    # a window of the recording: outputs whose support lies inside it
+    lo, hi = 9000, 31000
+    o_lo = ((lo + ntaps) * up) // down + 2
+    o_hi = ((hi - ntaps) * up) // down - 2
+    y = plan.run(_dev(dv, x[:, lo:hi]), lo, o_lo, o_hi - o_lo).cpu().numpy()
+    assert relerr(y, ref[:, o_lo:o_hi]) < 1e-12
+
+
+def test_spectra_golden():
+    pc.spectra_golden("pow2")
+
+
+def test_spectra_oracle_sweep():
+    pc.spectra_oracle_sweep()
+
+
+@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("detrend", ["constant", "linear", None])
+def test_fft_sizes_vs_numpy(dv, nfft, detrend):
+    """Every shared-memory FFT size through the STFT and Welch kernels."""
+    rng = np.random.default_rng(nfft)
+    rows, stride, nseg = 3, nfft // 2, 7
+    x = rng.standard_normal((rows, (nseg - 1) * stride + nfft)) + 0.5
+    w = sps.get_window("hann", nfft)
+    norm = 1.0 / (1000.0 * np.sum(w ** 2))
+    plan = dv.SpecPlan(nfft, stride, w, detrend, norm)
+    X = plan.segments(_dev(dv, x), nseg, True).cpu().numpy()
+    X = X[..., 0] + 1j * X[..., 1]
+    psd_sum = dv.zeros((rows, nfft // 2 + 1))
+    plan.welch_accum(_dev(dv, x), nseg, psd_sum)
+    P = plan.segments(_dev(dv, x), nseg, False).cpu().numpy()
+    ref_sum = 0
+    for s in range(nseg):
+        seg = x[:, s * stride:s * stride + nfft]
+        if detrend:
+            seg = sps.detrend(seg, axis=-1, type=detrend)
+        R = np.fft.rfft(seg * w, axis=-1) * np.sqrt(norm)
+        assert relerr(X[s], R) < 1e-12, (nfft, s)
+        p = np.abs(R) ** 2
+        p[:, 1:-1] *= 2
+        assert relerr(P[s], p) < 1e-12
+        ref_sum = ref_sum + p
+    assert relerr(psd_sum.cpu().numpy(), ref_sum) < 1e-12
+
+
+def test_pipeline_chain_on_device():
+    pc.pipeline_chain()
+
+
+def test_full_size_properties(dv):
+    """BASELINE-sized chunk (64 rows x 1e6): size-independent properties --
+    impulse response reproduces the taps, linearity, filter-then-PSD of a sine
+    peaks at the sine's bin, forward scan == two half-length scans."""
+    rng = np.random.default_rng(3)
+    rows, n = 64, 1_000_000
+    from openseize_b200.filtering.fir import Kaiser
+
+    taps = Kaiser(500, 600, 5000).coeffs
+    k = len(taps)
+    plan = dv.FirPlan(taps)
+    x = dv.zeros((rows, n + k - 1))
+    x[:, k - 1 + 1000] = 1.0
+    y = plan.run(x, n)
+    got = y[:, 1000:1000 + k].cpu().numpy()
+    assert relerr(got, np.broadcast_to(taps, got.shape)) < 1e-13
+    assert float(y[:, :1000].abs().max()) < 1e-15 and float(y[:, 1000 + k:].abs().max()) < 1e-15
+    a = _dev(dv, rng.standard_normal((rows, 200000 + k - 1)))
+    b = _dev(dv, rng.standard_normal((rows, 200000 + k - 1)))
+    lin = plan.run(2.0 * a - 3.0 * b, 200000) - (2.0 * plan.run(a, 200000) - 3.0 * plan.run(b, 200000))
+    assert float(lin.abs().max()) < 1e-12
+    sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+    sp = dv.SosPlan(sos)
+    xs = _dev(dv, rng.standard_normal((rows, n)))
+    st = dv.zeros((rows, 8, 2))
+    whole = sp.run(xs, st)
+    st2 = dv.zeros((rows, 8, 2))
+    h1 = sp.run(xs[:, :n // 2 + 7], st2)
+    h2 = sp.run(xs[:, n // 2 + 7:], st2)
+    two = dv.cat_time([h1, h2])
+    assert float((whole - two).abs().max()) / float(whole.abs().max()) < 1e-10
+    assert relerr(st2.cpu().numpy(), st.cpu().numpy()) < 1e-9

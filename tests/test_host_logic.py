@@ -1,0 +1,112 @@
+"""Host-side logic (producers, chunk bookkeeping, carries, device chaining,
+resampler lengths) against the golden vectors and the oracle, with the
+kernel-level calls replaced by numpy stand-ins (`fake_gpu`).  No GPU needed."""
+
+import pickle
+from functools import partial
+
+import numpy as np
+import pytest
+
+from openseize_b200 import producer
+from openseize_b200.core import numerical as nm
+from openseize_b200.filtering.fir import Kaiser
+from openseize_b200.filtering.iir import Butter, Notch
+from openseize_b200.resampling.resampling import downsample
+from openseize_b200.spectra.estimators import psd
+from tests import parity_cases as pc
+
+
+def test_fir(fake_gpu):
+    pc.fir_golden()
+    pc.fir_long_golden()
+    pc.fir_oracle_sweep()
+
+
+def test_iir(fake_gpu):
+    pc.iir_golden()
+    pc.iir_oracle_sweep()
+
+
+def test_resample(fake_gpu):
+    pc.resample_golden()
+    pc.resample_oracle_sweep()
+
+
+def test_spectra(fake_gpu):
+    pc.spectra_golden("pow2")
+    pc.spectra_golden("nonpow2")
+    pc.spectra_oracle_sweep()
+    pc.spectra_oracle_sweep(fs=1000, resolutions=(0.5,))
+
+
+def test_pipeline_chain(fake_gpu):
+    pc.pipeline_chain()
+
+
+def test_no_cpu_fallback():
+    """Without a GPU (and without the test stand-ins) the operators raise."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    x = np.zeros((2, 5000))
+    with pytest.raises(RuntimeError):
+        Kaiser(500, 600, 5000)(x, 1000)
+    with pytest.raises(RuntimeError):
+        psd(x, 1024, resolution=1.0)
+
+
+def test_laziness_and_errors(fake_gpu):
+    x = np.random.default_rng(0).standard_normal((2, 5000))
+    calls = []
+
+    def source():
+        calls.append(1)
+        yield from (x[:, i:i + 1000] for i in range(0, 5000, 1000))
+
+    pro = producer(source, 1000, -1, shape=x.shape)
+    out = Kaiser(500, 600, 5000)(pro, 1000)
+    assert not calls, "building an operator result must not pull data"
+    assert out.shape == x.shape
+    out.to_array()
+    assert calls
+    with pytest.raises(TypeError):
+        producer(3.0, 10, -1)
+    with pytest.raises(ValueError):
+        producer(source, 10, -1)                      # generating function needs a shape
+    with pytest.raises(ValueError):
+        list(nm.polyphase_resample(producer(x, 1000, -1), 1, 6000, 5000, Kaiser, -1))
+    with pytest.raises(ValueError):
+        psd(producer(x, 100, -1), 5000, scaling="nope", resolution=5000 / 1024)
+    with pytest.raises(ValueError):
+        Kaiser([1, 2], [3], 100)
+    with pytest.raises(NotImplementedError):
+        list(nm.lfilter(producer(x, 1000, -1), (np.ones(5), np.ones(5)), -1))
+
+
+def test_producer_mutation_contract(fake_gpu):
+    """producer(Producer, cs, axis) mutates and returns the same object
+    (reference core/producer.py:114-117); psd forces chunksize=int(fs)."""
+    x = np.zeros((2, 40000))
+    pro = producer(x, 1000, -1)
+    assert producer(pro, 300, -1) is pro and pro.chunksize == 300
+    psd(pro, 1024, resolution=1.0)
+    assert pro.chunksize == 1024
+
+
+def test_picklable_recipes():
+    """Producers over partials of every GPU generating function pickle
+    (reference tests/test_concurrency.py:85-149): no CUDA state is captured
+    before iteration."""
+    x = np.random.default_rng(0).standard_normal((2, 6000))
+    pro = producer(x, 1000, -1)
+    k, b, n = Kaiser(500, 600, 5000), Butter([1, 100], [0.5, 200], 5000), Notch(60, 6, 5000)
+    recipes = [k(pro, 1000), b(pro, 1000), b(pro, 1000, dephase=False), n(pro, 1000),
+               n(pro, 1000, dephase=False), downsample(pro, 4, 5000, 1000),
+               nm.welch(pro, 1000, 256, "hann", 0.5, -1, "constant", "density")[1],
+               nm.stft(pro, 1000, 256, "hann", 0.5, -1, "constant", "density", True, True)[2]]
+    for r in recipes:
+        clone = pickle.loads(pickle.dumps(r))
+        assert clone.shape == r.shape and clone.chunksize == r.chunksize
+    assert pickle.loads(pickle.dumps(partial(nm.oaconvolve, pro, k.coeffs, -1, "same")))

@@ -1,0 +1,111 @@
+"""Per-kernel device timings at the BASELINE config sizes (CUDA events, inputs
+larger than L2).  Scratch tool for tuning; the contract numbers come from
+bench.py.  Usage on the GPU box: python tools/kernel_bench.py [name ...]"""
+
+import json
+import os
+import sys
+
+import numpy as np
+import scipy.signal as sps
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openseize_b200.core import device as dv  # noqa: E402
+
+PEAK = 6534.1
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    return float(np.median(ts))
+
+
+def report(name, secs, ch_samples, bytes_per):
+    gbs = ch_samples * bytes_per / secs / 1e9
+    print("%-34s %8.3f ms  %8.2f Gsamp/s  %8.1f GB/s alg  %5.1f%% of %.0f" %
+          (name, secs * 1e3, ch_samples / secs / 1e9, gbs, 100 * gbs / PEAK, PEAK), flush=True)
+
+
+def main(which):
+    dv.require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    def rnd(rows, n):
+        return torch.randn((rows, n), dtype=torch.float64, device="cuda", generator=g)
+
+    rows, n = 256, 1_000_000
+    from openseize_b200.filtering.fir import Kaiser
+
+    if not which or "fir" in which:
+        for fs, label in ((5000, "113"), (30000, "671")):
+            taps = Kaiser(500, 600, fs).coeffs
+            x = rnd(rows, n + len(taps) - 1)
+            y = torch.empty((rows, n), dtype=torch.float64, device="cuda")
+            for algo, an in ((1, "direct"), (2, "fft")):
+                if algo == 1 and len(taps) > 200:
+                    continue
+                plan = dv.FirPlan(taps, algo)
+                t = timeit(lambda: plan.run(x, n, out=y))
+                report("fir %s taps %s" % (label, an), t, rows * n, 16)
+            del x, y
+    if not which or "sos" in which:
+        sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+        plan = dv.SosPlan(sos)
+        for r in (64, 256):
+            x = rnd(r, n)
+            y = torch.empty_like(x)
+            st = dv.zeros((r, 8, 2))
+            report("sos 8 sections fwd rows=%d" % r, timeit(lambda: plan.run(x, st, out=y)), r * n, 16)
+            report("sos 8 sections state-only rows=%d" % r,
+                   timeit(lambda: plan.run(x, st, want_output=False)), r * n, 8)
+        b, a = sps.iirnotch(60, 10, fs=30000)
+        plan = dv.SosPlan(np.concatenate([b, a])[None])
+        x = rnd(256, n)
+        y = torch.empty_like(x)
+        st = dv.zeros((256, 1, 2))
+        report("notch biquad fwd rows=256", timeit(lambda: plan.run(x, st, out=y)), 256 * n, 16)
+        del x, y
+    if not which or "upfirdn" in which:
+        for fs, M in ((5000, 20), (30000, 25)):
+            import oracle
+
+            h = oracle.resample_filter(1, M, fs)
+            plan = dv.UpfirdnPlan(h, 1, M)
+            x = rnd(rows, n)
+            nout = n // M - 64
+            report("downsample M=%d taps=%d" % (M, len(h)),
+                   timeit(lambda: plan.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
+            del x
+    if not which or "welch" in which:
+        for nfft in (1024, 4096, 8192):
+            w = sps.get_window("hann", nfft)
+            plan = dv.SpecPlan(nfft, nfft // 2, w, "constant", 1.0 / (30000 * np.sum(w ** 2)))
+            x = rnd(rows, n)
+            nseg = plan.nseg_available(n)
+            acc = dv.zeros((rows, nfft // 2 + 1))
+            report("welch nfft=%d" % nfft, timeit(lambda: plan.welch_accum(x, nseg, acc)),
+                   rows * nseg * plan.stride, 8)
+            if nfft == 4096:
+                xs = rnd(32, n)
+                ns = plan.nseg_available(n)
+                report("stft nfft=4096 rows=32", timeit(lambda: plan.segments(xs, ns, True)),
+                       32 * ns * plan.stride, 24)
+            del x
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
