@@ -190,6 +190,25 @@ def download(dev, layout, complex_=False):
 
 
 # --------------------------------------------------------------------------
+# optional per-kernel timing (bench.py): TIMERS[name] = [(start, end, bytes)]
+# with CUDA events recorded on the launching stream around each launch
+# --------------------------------------------------------------------------
+TIMERS = None
+
+
+def _launch(name, alg_bytes, fn, *args):
+    if TIMERS is None:
+        return fn(*args)
+    t = torch()
+    start, end = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    start.record()
+    rc = fn(*args)
+    end.record()
+    TIMERS.setdefault(name, []).append((start, end, alg_bytes))
+    return rc
+
+
+# --------------------------------------------------------------------------
 # plans (cached by their defining coefficients)
 # --------------------------------------------------------------------------
 class _Plan:
@@ -252,8 +271,8 @@ class FirPlan(_Plan):
             out = empty((rows, n_out))
         xp, ldx = _rows_ptr(xbuf)
         yp, ldy = _rows_ptr(out)
-        rc = _abi.load().osz_fir_exec_f64(self.handle, xp, ldx, rows, n_out, yp, ldy,
-                                          _cur_stream())
+        rc = _launch("fir", 16 * rows * n_out, _abi.load().osz_fir_exec_f64, self.handle, xp,
+                     ldx, rows, n_out, yp, ldy, _cur_stream())
         _abi.check(rc, "fir_exec")
         return out
 
@@ -288,8 +307,9 @@ class SosPlan(_Plan):
             yp, ldy = _rows_ptr(out)
         else:
             out, yp, ldy = None, _vp(0), 0
-        rc = _abi.load().osz_sos_exec_f64(self.handle, xp, ldx, rows, n, int(bool(reverse)),
-                                          _vp(state.data_ptr()), yp, ldy, _cur_stream())
+        rc = _launch("sos" if want_output else "sos_state", (16 if want_output else 8) * rows * n,
+                     _abi.load().osz_sos_exec_f64, self.handle, xp, ldx, rows, n,
+                     int(bool(reverse)), _vp(state.data_ptr()), yp, ldy, _cur_stream())
         _abi.check(rc, "sos_exec")
         return out
 
@@ -334,8 +354,9 @@ class UpfirdnPlan(_Plan):
         out = empty((rows, n_out))
         xp, ldx = _rows_ptr(x)
         yp, ldy = _rows_ptr(out)
-        rc = _abi.load().osz_upfirdn_exec_f64(self.handle, xp, ldx, rows, int(x_first), m,
-                                              int(out_first), int(n_out), yp, ldy, _cur_stream())
+        rc = _launch("upfirdn", 8 * rows * (n_out * self.down // self.up + n_out),
+                     _abi.load().osz_upfirdn_exec_f64, self.handle, xp, ldx, rows, int(x_first),
+                     m, int(out_first), int(n_out), yp, ldy, _cur_stream())
         _abi.check(rc, "upfirdn_exec")
         return out
 
@@ -368,8 +389,9 @@ class SpecPlan(_Plan):
         assert x.shape[1] >= (nseg - 1) * self.stride + self.nfft
         assert psd_sum.shape == (rows, self.nfreq) and psd_sum.is_contiguous()
         xp, ldx = _rows_ptr(x)
-        rc = _abi.load().osz_welch_accum_f64(self.handle, xp, ldx, rows, int(nseg),
-                                             _vp(psd_sum.data_ptr()), self.nfreq, _cur_stream())
+        rc = _launch("welch", 8 * rows * int(nseg) * self.stride,
+                     _abi.load().osz_welch_accum_f64, self.handle, xp, ldx, rows, int(nseg),
+                     _vp(psd_sum.data_ptr()), self.nfreq, _cur_stream())
         _abi.check(rc, "welch_accum")
 
     def segments(self, x, nseg, complex_):

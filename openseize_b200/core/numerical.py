@@ -22,7 +22,7 @@ import scipy.signal as sps
 
 from openseize_b200.core import device as dv
 from openseize_b200.core.arraytools import normalize_axis
-from openseize_b200.core.producer import GenProducer, Producer, producer
+from openseize_b200.core.producer import DeviceProducer, GenProducer, Producer, producer
 
 # ---------------------------------------------------------------------------
 # shape helpers (pure index arithmetic, reference core/numerical.py:19-155)
@@ -105,14 +105,18 @@ def device_chunks(pro, axis):
     """
     dv.require_cuda()
     layout = dv.Layout(pro.shape, axis)
-    twin = _device_twin(pro)
-    if twin is None:
-        for arr in pro:
-            yield dv.upload(arr, layout)
-        return
-    func, args, kwargs = twin
+    if isinstance(pro, DeviceProducer):
+        source = pro.device_iter()
+    else:
+        twin = _device_twin(pro)
+        if twin is None:
+            for arr in pro:
+                yield dv.upload(arr, layout)
+            return
+        func, args, kwargs = twin
+        source = func(*args, **kwargs)
     fifo, cs = _DeviceFifo(), int(pro.chunksize)
-    for block in func(*args, **kwargs):
+    for block in source:
         fifo.put(block)
         while fifo.size >= cs:
             yield fifo.get(cs)

@@ -187,3 +187,29 @@ class MaskedProducer(Producer):
                 yield fifo.get()
         if not fifo.empty():
             yield fifo.get()
+
+
+class DeviceProducer(Producer):
+    """Chunks that already live on the GPU (device-resident recordings, and
+    bench.py's HBM-resident timing mode).  ``data`` is a callable returning an
+    iterator of float64 CUDA tensors of shape (rows, n) -- time-contiguous
+    rows, the package's device layout; ``shape`` is the (rows, total) shape.
+    GPU operators consume it without any host traffic; iterating it on the
+    host downloads each chunk."""
+
+    def __init__(self, data, chunksize, shape, **kwargs):
+        super().__init__(data, chunksize, axis=len(shape) - 1, **kwargs)
+        self._shape = tuple(int(s) for s in shape)
+        if len(self._shape) != 2:
+            raise ValueError("DeviceProducer holds 2-D (rows, samples) data")
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def device_iter(self):
+        return iter(self.data(**self.kwargs))
+
+    def __iter__(self):
+        for block in self.device_iter():
+            yield block.cpu().numpy()

@@ -27,12 +27,15 @@ enum { SPEC_ACCUM = 0, SPEC_PGRAM = 1, SPEC_STFT = 2 };
 // Sum of up to four doubles over the CTA (NT threads).  `red` is 4*32 doubles.
 template <int NV, int NT>
 __device__ __forceinline__ void block_sum(double (&val)[NV], double *red, int tid) {
-    constexpr int NW = NT / 32;
+    constexpr int LANES = NT < 32 ? NT : 32;            // N = 256 runs 16 threads
+    constexpr unsigned MASK = NT < 32 ? ((1u << NT) - 1u) : 0xffffffffu;
+    constexpr int NW = NT < 32 ? 1 : NT / 32;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val[i] += __shfl_xor_sync(0xffffffffu, val[i], o);
+        for (int o = LANES / 2; o > 0; o >>= 1) val[i] += __shfl_xor_sync(MASK, val[i], o);
     }
+    if (NW == 1) return;                                 // every lane holds the sum
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) red[i * 32 + (tid >> 5)] = val[i];

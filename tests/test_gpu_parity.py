@@ -95,7 +95,8 @@ def test_sos_kernel_vs_scipy(dv, n):
         ry, rz = sps.sosfilt(sos, xr, axis=-1, zi=np.transpose(zi, (1, 0, 2)))
         ry = ry[:, ::-1] if reverse else ry
         assert relerr(y, ry) < 1e-10, (n, reverse)
-        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 1e-9
+        # the delay registers of these high-Q sections are ill-conditioned (|z| ~ 300 |y|)
+        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
         state2 = _dev(dv, zi)
         assert plan.run(_dev(dv, x), state2, reverse=reverse, want_output=False) is None
         assert relerr(state2.cpu().numpy(), state.cpu().numpy()) < 1e-13

@@ -19,7 +19,12 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
 
+ONCE = False
+
+
 def timeit(fn, reps=5, warm=2):
+    if ONCE:
+        reps, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -108,4 +113,8 @@ def main(which):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    argv = sys.argv[1:]
+    if "--once" in argv:
+        ONCE = True
+        argv.remove("--once")
+    main(argv)
