@@ -93,8 +93,9 @@ class Layout:
         return self.lead + (int(n),) + self.trail
 
 
-def upload(arr, layout):
+def upload(arr, layout, alloc=None):
     """Host chunk -> device rows ``(rows, n)`` float64 on the current stream.
+    ``alloc(rows, n)`` places the rows in the consumer's staging ring.
 
     The copy is issued on a side stream from pinned memory (the chunk itself
     when it already is pinned, else a pinned staging block from torch's
@@ -109,7 +110,11 @@ def upload(arr, layout):
     cur = t.cuda.current_stream()
     if layout.inner == 1:
         a2 = a.reshape(layout.outer, n)
-        dev = t.empty((layout.outer, n), dtype=t.float64, device="cuda")
+        if alloc is not None:
+            dev = alloc(layout.outer, n)
+        else:
+            dev = t.empty((layout.outer, n), dtype=t.float64, device="cuda")
+        ldd = dev.stride(0) if layout.outer > 1 else n
         h2d.wait_stream(cur)     # dev's block may have been freed on `cur`
         with t.cuda.stream(h2d):
             direct = False
@@ -120,7 +125,7 @@ def upload(arr, layout):
                     direct = False
             if direct:
                 rc = _abi.load().osz_memcpy2d_h2d_async(
-                    _vp(dev.data_ptr()), n * 8, _vp(a2.ctypes.data), a2.strides[0], n * 8,
+                    _vp(dev.data_ptr()), ldd * 8, _vp(a2.ctypes.data), a2.strides[0], n * 8,
                     layout.outer, _vp(h2d.cuda_stream))
                 _abi.check(rc, "upload")
                 dev._osz_keepalive = a2
@@ -141,9 +146,13 @@ def upload(arr, layout):
         raw.copy_(stage, non_blocking=True)
     cur.wait_stream(h2d)
     raw.record_stream(cur)
-    dev = t.empty((layout.rows, n), dtype=t.float64, device="cuda")
+    if alloc is not None:
+        dev = alloc(layout.rows, n)
+    else:
+        dev = t.empty((layout.rows, n), dtype=t.float64, device="cuda")
+    ldd = dev.stride(0) if layout.rows > 1 else n
     rc = _abi.load().osz_pack_rows_f64(_vp(raw.data_ptr()), layout.outer, n, layout.inner,
-                                       _vp(dev.data_ptr()), n, _cur_stream())
+                                       _vp(dev.data_ptr()), ldd, _cur_stream())
     _abi.check(rc, "pack_rows")
     return dev
 
@@ -346,12 +355,12 @@ class UpfirdnPlan(_Plan):
         return _plans.get(("ufd", arr.tobytes(), int(up), int(down)),
                           lambda: UpfirdnPlan(arr, up, down))
 
-    def run(self, x, x_first, out_first, n_out):
+    def run(self, x, x_first, out_first, n_out, out=None):
         """x: (rows, m) holding global input samples x_first .. x_first+m-1.
         Returns global output samples out_first .. out_first+n_out-1."""
-        t = torch()
         rows, m = x.shape
-        out = empty((rows, n_out))
+        if out is None:
+            out = empty((rows, n_out))
         xp, ldx = _rows_ptr(x)
         yp, ldy = _rows_ptr(out)
         rc = _launch("upfirdn", 8 * rows * (n_out * self.down // self.up + n_out),

@@ -95,13 +95,19 @@ def _device_twin(pro):
     return (twin, args, kwargs) if twin is not None else None
 
 
-def device_chunks(pro, axis):
-    """Yield ``pro``'s chunks as device rows ``(rows, chunk)``, on the chunk
-    grid of ``pro.chunksize`` (the last one may be shorter).
+def device_chunks(pro, axis, regrid=True, alloc=None):
+    """Yield ``pro``'s chunks as device rows ``(rows, chunk)``.
 
     Host producers are streamed through pinned memory with the copy of chunk
     k+1 issued while chunk k's kernels run; producers over GPU generating
     functions are consumed on the device.
+
+    regrid: re-block a device upstream to the chunk grid of ``pro.chunksize``
+        (needed by the chunk-dependent forward-backward filters); stages whose
+        result does not depend on the grid take the upstream blocks as they come.
+    alloc: ``alloc(rows, n) -> (rows, n) device view`` -- where the consumer
+        wants the next block written (its halo'd staging ring), so neither an
+        upload nor an upstream kernel needs a second copy.
     """
     dv.require_cuda()
     layout = dv.Layout(pro.shape, axis)
@@ -111,10 +117,13 @@ def device_chunks(pro, axis):
         twin = _device_twin(pro)
         if twin is None:
             for arr in pro:
-                yield dv.upload(arr, layout)
+                yield dv.upload(arr, layout, alloc)
             return
         func, args, kwargs = twin
-        source = func(*args, **kwargs)
+        source = func(*args, **dict(kwargs, _out=alloc if not regrid else None))
+    if not regrid:
+        yield from source
+        return
     fifo, cs = _DeviceFifo(), int(pro.chunksize)
     for block in source:
         fifo.put(block)
@@ -122,6 +131,72 @@ def device_chunks(pro, axis):
             yield fifo.get(cs)
     if fifo.size:
         yield fifo.get(cs)
+
+
+def _new_rows(out, rows, n):
+    """Output block of a stage: in the consumer's staging ring when it asked."""
+    return out(rows, n) if out is not None else dv.empty((rows, n))
+
+
+class _TimeRing:
+    """Device staging for stages that need bounded history along time (FIR
+    halo, resampler reach, Welch overlap): blocks are appended at the write
+    position -- ideally written there directly by the upstream kernel or the
+    H2D copy through ``alloc`` -- and the stage reads ``window()``, the live
+    span, as one contiguous halo'd view.  Replaces the concat-on-put /
+    split-on-get of the reference's FIFOArray (core/queues.py:46-70)."""
+
+    def __init__(self, rows):
+        self.rows, self.buf, self.start, self.pos, self._pending = rows, None, 0, 0, None
+
+    def _reserve(self, n):
+        live = self.pos - self.start
+        if self.buf is None or self.pos + n > self.buf.shape[1]:
+            new = dv.empty((self.rows, live + 2 * n + 64))
+            if live:
+                new[:, :live].copy_(self.buf[:, self.start:self.pos])
+            self.buf, self.start, self.pos = new, 0, live
+
+    def alloc(self, rows, n):
+        assert rows == self.rows
+        self._reserve(n)
+        self._pending = self.buf[:, self.pos:self.pos + n]
+        return self._pending
+
+    def _in_buffer(self, block):
+        if self.buf is None:
+            return False
+        lo = self.buf.data_ptr()
+        return lo <= block.data_ptr() < lo + self.buf.numel() * 8
+
+    def push(self, block):
+        n = block.shape[1]
+        pend, self._pending = self._pending, None
+        in_place = (pend is not None and block.data_ptr() == pend.data_ptr()
+                    and tuple(block.shape) == tuple(pend.shape)
+                    and block.stride() == pend.stride())
+        if not in_place:
+            if self._in_buffer(block):
+                block = block.clone()        # a cut of the pending region: copy would overlap
+            self._reserve(n)
+            self.buf[:, self.pos:self.pos + n].copy_(block)
+        self.pos += n
+
+    def push_zeros(self, n):
+        if n > 0:
+            self._reserve(n)
+            self.buf[:, self.pos:self.pos + n].zero_()
+            self.pos += n
+
+    @property
+    def size(self):
+        return self.pos - self.start
+
+    def window(self):
+        return self.buf[:, self.start:self.pos]
+
+    def drop(self, k):
+        self.start += int(k)
 
 
 def _to_host(device_gen, layout, complex_=False):
@@ -160,7 +235,8 @@ def _layout_of(pro, axis):
 # ---------------------------------------------------------------------------
 # FIR  (reference core/numerical.py:158-298)
 # ---------------------------------------------------------------------------
-def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32):
+def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None):
+    dv.require_cuda()
     window = np.asarray(window, dtype=np.float64)
     ntaps, nsamp = len(window), pro.shape[axis]
     if nsamp < ntaps:
@@ -170,18 +246,20 @@ def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32):
     last_kept = nsamp + ntaps - 1 - right          # exclusive, in full-convolution index
     plan = dv.FirPlan.cached(window)
     rows = _layout_of(pro, axis).rows
-    halo = dv.zeros_rows(rows, ntaps - 1)
+    ring = _TimeRing(rows)
+    ring.push_zeros(ntaps - 1)                      # the reference's zero overlap (:221-223)
     pos = 0                                         # full-convolution index of the next output
-    for chunk in device_chunks(pro, axis):
+    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring.alloc):
         n = chunk.shape[1]
+        ring.push(chunk)
         final = pos + n >= nsamp
-        parts = [halo, chunk] + ([dv.zeros_rows(rows, ntaps - 1)] if final else [])
-        buf = dv.cat_time(parts)
+        if final:
+            ring.push_zeros(ntaps - 1)              # flush the tail (:285-298)
         n_out = n + (ntaps - 1 if final else 0)
-        y = plan.run(buf, n_out)
+        y = plan.run(ring.window(), n_out, out=_new_rows(_out, rows, n_out))
+        ring.drop(n_out)                            # keep the last ntaps-1 samples as halo
         lo = max(left - pos, 0)
         hi = min(pos + n_out, last_kept) - pos
-        halo = buf[:, n:n + ntaps - 1]
         pos += n_out
         if hi > lo:
             yield y if (lo == 0 and hi == n_out) else y[:, lo:hi]
@@ -241,11 +319,12 @@ class _Cascade:
             s += p.nsec
         return out
 
-    def run(self, x, states, reverse=False, want_output=True):
-        y = x
+    def run(self, x, states, reverse=False, want_output=True, out=None):
+        y, last = x, len(self.plans) - 1
         for i, (p, st) in enumerate(zip(self.plans, states)):
-            need = want_output or i < len(self.plans) - 1
-            y = p.run(y, st, reverse=reverse, want_output=need)
+            need = want_output or i < last
+            dst = _new_rows(out, x.shape[0], x.shape[1]) if (need and i == last) else None
+            y = p.run(y, st, reverse=reverse, want_output=need, out=dst)
         return y if want_output else None
 
 
@@ -258,15 +337,16 @@ def _zi_to_rows(zi, layout, nsec):
     return dv.from_host(rows)
 
 
-def _sosfilt_device(pro, sos, axis, zi=None):
+def _sosfilt_device(pro, sos, axis, zi=None, _out=None):
+    dv.require_cuda()
     layout = _layout_of(pro, axis)
     cascade = _Cascade(sos)
     if zi is None:
         states = cascade.zero_state(layout.rows)
     else:
         states = cascade.split_state(_zi_to_rows(zi, layout, cascade.nsec))
-    for chunk in device_chunks(pro, axis):
-        yield cascade.run(chunk, states)
+    for chunk in device_chunks(pro, axis, regrid=False):
+        yield cascade.run(chunk, states, out=_out)
 
 
 def _same_layout(pro, *args, **kwargs):
@@ -280,7 +360,7 @@ def sosfilt(pro, sos, axis, zi=None):
     from chunk to chunk (reference numerical.py:301-335)."""
 
 
-def _filtfilt_device(pro, cascade, zi, axis):
+def _filtfilt_device(pro, cascade, zi, axis, _out=None):
     """Shared forward-backward driver (reference numerical.py:338-411,449-520):
     one global forward pass; each chunk's backward pass starts from the state
     left by filtering the NEXT forward chunk backwards from zi * its last
@@ -293,17 +373,18 @@ def _filtfilt_device(pro, cascade, zi, axis):
         if prev is not None:
             look = cascade.state_from_sample(zi, fwd, fwd.shape[1] - 1)
             cascade.run(fwd, look, reverse=True, want_output=False)
-            yield cascade.run(prev, look, reverse=True)
+            yield cascade.run(prev, look, reverse=True, out=_out)
         prev = fwd
     if prev is not None:
         last = cascade.state_from_sample(zi, prev, prev.shape[1] - 1)
-        yield cascade.run(prev, last, reverse=True)
+        yield cascade.run(prev, last, reverse=True, out=_out)
 
 
-def _sosfiltfilt_device(pro, sos, axis):
+def _sosfiltfilt_device(pro, sos, axis, _out=None):
+    dv.require_cuda()
     cascade = _Cascade(sos)
     zi = sps.sosfilt_zi(cascade.sos)
-    yield from _filtfilt_device(pro, cascade, zi, axis)
+    yield from _filtfilt_device(pro, cascade, zi, axis, _out)
 
 
 @_gpu_genfunc(_sosfiltfilt_device, _same_layout)
@@ -338,15 +419,16 @@ def _lfilter_zi_rows(coeffs, zi, layout):
     return _zi_to_rows(zi[None], layout, 1)
 
 
-def _lfilter_device(pro, coeffs, axis, zi=None):
+def _lfilter_device(pro, coeffs, axis, zi=None, _out=None):
+    dv.require_cuda()
     layout = _layout_of(pro, axis)
     cascade = _Cascade(_ba_to_sos(coeffs))
     if zi is None:
         states = cascade.zero_state(layout.rows)
     else:
         states = cascade.split_state(_lfilter_zi_rows(coeffs, zi, layout))
-    for chunk in device_chunks(pro, axis):
-        yield cascade.run(chunk, states)
+    for chunk in device_chunks(pro, axis, regrid=False):
+        yield cascade.run(chunk, states, out=_out)
 
 
 @_gpu_genfunc(_lfilter_device, _same_layout)
@@ -355,12 +437,13 @@ def lfilter(pro, coeffs, axis, zi=None):
     second order and below (``Notch`` always is, filtering/iir.py:391)."""
 
 
-def _filtfilt_ba_device(pro, coeffs, axis):
+def _filtfilt_ba_device(pro, coeffs, axis, _out=None):
+    dv.require_cuda()
     cascade = _Cascade(_ba_to_sos(coeffs))
     z = np.atleast_1d(sps.lfilter_zi(*coeffs))        # numerical.py:487
     zi = np.zeros((1, 2))
     zi[0, :len(z)] = z
-    yield from _filtfilt_device(pro, cascade, zi, axis)
+    yield from _filtfilt_device(pro, cascade, zi, axis, _out)
 
 
 @_gpu_genfunc(_filtfilt_ba_device, _same_layout)
@@ -394,7 +477,8 @@ def _resample_taps(L, M, fs, fir, kwargs):
     return np.asarray(fir(fpass, fstop, fs, gpass, gstop).coeffs, dtype=np.float64)
 
 
-def _polyphase_device(pro, L, M, fs, fir, axis, **kwargs):
+def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, **kwargs):
+    dv.require_cuda()
     nsamp = pro.shape[axis]
     if M >= nsamp:
         raise ValueError("Decimation factor must M={} be < pro.shape[{}] = {}"
@@ -404,33 +488,35 @@ def _polyphase_device(pro, L, M, fs, fir, axis, **kwargs):
     plan = dv.UpfirdnPlan.cached(h, L, M)
     ntaps = len(h)
     half = (ntaps - 1) // 2
-    # input reach of one output sample, in input samples
-    reach_l = 2                                    # slack kept left of the next yield's reach
     total_out = dv.ceil_div(nsamp * L, M)
     per_chunk = csize * L // M
+    rows = _layout_of(pro, axis).rows
 
     src = producer(pro, csize, axis)               # same mutation as numerical.py:590
-    window, w_first = None, 0                      # device rows and their first global index
-    emitted = 0                                    # chunks of output already yielded
+    ring = _TimeRing(rows)                         # input window and its first global index
+    w_first = 0
+    emitted = 0                                    # yields done (the reference makes nchunks-1)
     seen = 0                                       # input samples received
-    for chunk in device_chunks(src, axis):
-        window = chunk if window is None else dv.cat_time([window, chunk])
+    # The values do not depend on the input blocking (one global resample_poly,
+    # SURVEY 8a5), only the yield boundaries do: take upstream blocks as they come.
+    for chunk in device_chunks(src, axis, regrid=False, alloc=ring.alloc):
+        ring.push(chunk)
         seen += chunk.shape[1]
-        # yield k is computable once its right reach is inside the window, or at the end
         while emitted < nchunks - 1:
             last_yield = emitted == nchunks - 2
             o_lo = emitted * per_chunk
             o_hi = total_out if last_yield else (emitted + 1) * per_chunk
+            # newest input sample output o_hi-1 touches
             need_hi = nsamp if last_yield else min(nsamp, ((o_hi - 1) * M + half) // L + 1)
             if seen < need_hi:
                 break
-            yield plan.run(window, w_first, o_lo, o_hi - o_lo)
+            out = _new_rows(_out, rows, o_hi - o_lo)
+            yield plan.run(ring.window(), w_first, o_lo, o_hi - o_lo, out=out)
             emitted += 1
-            # drop input no later output needs
-            keep_from = max(((o_hi * M + half - (ntaps - 1)) // L) - reach_l, w_first)
-            if keep_from > w_first:
-                window = window[:, keep_from - w_first:]
-                w_first = keep_from
+            # oldest input sample the next yield touches (2 samples of slack)
+            keep_from = max((o_hi * M + half - (ntaps - 1)) // L - 2, w_first)
+            ring.drop(keep_from - w_first)
+            w_first = keep_from
 
 
 def _polyphase_layout(pro, L, M, fs, fir, axis, **kwargs):
@@ -470,36 +556,21 @@ def _segment_batches(pro, axis, plan, pad_left=0, pad_right=0, batch_samples=1 <
     in _spectra_estimatives (reference numerical.py:817-849).  Small chunks are
     batched so each launch carries enough windows to fill the GPU."""
     rows = _layout_of(pro, axis).rows
-    carry = dv.zeros_rows(rows, pad_left) if pad_left else None
-    parts, width = ([carry], pad_left) if pad_left else ([], 0)
+    ring = _TimeRing(rows)
+    ring.push_zeros(pad_left)
 
-    def flush(final):
-        nonlocal parts, width
-        buf = dv.cat_time(parts)
-        nseg = plan.nseg_available(width)
+    def flush():
+        nseg = plan.nseg_available(ring.size)
         if nseg > 0:
-            used = nseg * plan.stride
-            out = (buf, nseg)
-            rest = buf[:, used:]
-            parts, width = ([rest], rest.shape[1]) if rest.shape[1] else ([], 0)
-            return out
-        parts = [buf] if width else []
-        return None
+            yield ring.window(), nseg
+            ring.drop(nseg * plan.stride)
 
-    for chunk in device_chunks(pro, axis):
-        parts.append(chunk)
-        width += chunk.shape[1]
-        if width * rows >= batch_samples and width >= plan.nfft:
-            out = flush(False)
-            if out:
-                yield out
-    if pad_right:
-        parts.append(dv.zeros_rows(rows, pad_right))
-        width += pad_right
-    if width >= plan.nfft:
-        out = flush(True)
-        if out:
-            yield out
+    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring.alloc):
+        ring.push(chunk)
+        if ring.size * rows >= batch_samples:
+            yield from flush()
+    ring.push_zeros(pad_right)
+    yield from flush()
 
 
 def modified_dft(arr, fs, nfft, window, axis, detrend, scaling):

@@ -10,8 +10,12 @@
 // double2, one pad element per 16 so that both the stride-1 and the stride-16
 // patterns are bank-conflict free).
 //
-// Twiddles come from per-pass tables laid out [r-1][k] so that a warp reads
-// consecutive k (built on the host by make_fft_twiddles()).
+// Twiddles: a thread's butterflies in a given pass always use the same base
+// twiddle w = exp(-2 pi i k / (Ns R)) (k depends only on the thread index), so
+// each thread loads its three base twiddles ONCE per kernel (FftTw) and forms
+// w^2 .. w^15 with a depth-4 product tree in registers -- no table traffic in
+// the transform loops (the first version read 30 twiddles per transform through
+// L1 and was LSU bound: profiles/r01_ncu_summary.md).
 #pragma once
 
 #include <math.h>
@@ -142,42 +146,96 @@ struct FftCfg {
     static constexpr int MIDBITS = LOG2N - 8;
     static constexpr int R1 = MIDBITS >= 4 ? 16 : (1 << MIDBITS);   // first middle radix (1: none)
     static constexpr int R2 = MIDBITS > 4 ? (1 << (MIDBITS - 4)) : 1;  // second middle radix
-    // twiddle table offsets (double2 elements)
+    // base-twiddle table offsets (double2 elements): [mid1: 16][mid2: 16*R1][last: N/16]
     static constexpr int OFF_M1 = 0;
-    static constexpr int OFF_M2 = OFF_M1 + (R1 > 1 ? (R1 - 1) * 16 : 0);
-    static constexpr int OFF_L = OFF_M2 + (R2 > 1 ? (R2 - 1) * 16 * R1 : 0);
-    static constexpr int TW_TOTAL = OFF_L + 15 * (N / 16);
+    static constexpr int OFF_M2 = 16;
+    static constexpr int OFF_L = 16 + 16 * R1;
+    static constexpr int TW_TOTAL = OFF_L + N / 16;
     static constexpr int SMEM_ELEMS = N + N / 16;     // padded double2 elements
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 16;
 };
 
 __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 4); }
+// padded offset of a multiple of 16: a compile-time constant, so every shared
+// memory access below is `one base register + immediate` (the first version
+// recomputed fft_phys() per element and the 48 addresses it kept live across
+// transforms spilled).
+__host__ __device__ constexpr int fft_pad16(int x) { return x + x / 16; }
+
+__device__ __forceinline__ double2 csqr(double2 a) {
+    return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y);
+}
+
+// v[r] *= w^r for r = 1 .. R-1, powers from a depth-4 product tree.
+template <int R>
+__device__ __forceinline__ void twiddle_pow(double2 *v, double2 w1) {
+    if constexpr (R >= 2) v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        const double2 w2 = csqr(w1), w3 = cmul(w2, w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            const double2 w4 = csqr(w2);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w1));
+            v[6] = cmul(v[6], cmul(w4, w2));
+            v[7] = cmul(v[7], cmul(w4, w3));
+            if constexpr (R >= 16) {
+                const double2 w8 = csqr(w4), w12 = cmul(w8, w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], w12);
+                v[13] = cmul(v[13], cmul(w12, w1));
+                v[14] = cmul(v[14], cmul(w12, w2));
+                v[15] = cmul(v[15], cmul(w12, w3));
+            }
+        }
+    }
+}
+
+// A thread's base twiddles for the middle passes and the last pass.
+struct FftTw {
+    double2 m1, m2, last;
+};
+
+template <int LOG2N>
+__device__ __forceinline__ FftTw fft_load_tw(const double2 *__restrict__ tw, int tid) {
+    using C = FftCfg<LOG2N>;
+    FftTw t;
+    t.m1 = ldg(tw + C::OFF_M1 + (tid & 15));
+    t.m2 = ldg(tw + C::OFF_M2 + (tid & (16 * C::R1 - 1)));
+    t.last = ldg(tw + C::OFF_L + tid);
+    return t;
+}
 
 // One middle pass (radix R, sub-transform length Ns) over the CTA's N points,
 // in place in shared memory: every thread reads all its inputs, the CTA
 // synchronises, then butterflies are written to their Stockham positions.
+// All of a thread's butterflies share k = tid mod Ns, hence one base twiddle.
 template <int N, int R, int NS>
-__device__ __forceinline__ void fft_mid_pass(double2 *sm, const double2 *__restrict__ tw, int tid) {
+__device__ __forceinline__ void fft_mid_pass(double2 *sm, double2 w1, int tid) {
     constexpr int NT = N / 16;
     constexpr int PER = 16 / R;  // butterflies per thread
+    static_assert(NT % NS == 0, "k must not depend on the butterfly index");
+    static_assert(NT % 16 == 0 && (N / R) % 16 == 0 && NS % 16 == 0, "padding arithmetic");
     double2 v[16];
+    const double2 *src = sm + fft_phys(tid);
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
-        const int b = tid + q * NT;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[q * R + r] = sm[fft_phys(b + r * (N / R))];
+        for (int r = 0; r < R; ++r) v[q * R + r] = src[fft_pad16(q * NT + r * (N / R))];
     }
     __syncthreads();
+    const int k = tid & (NS - 1);
+    double2 *dst = sm + fft_phys((tid - k) * R + k);
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
-        const int b = tid + q * NT;
-        const int k = b & (NS - 1);
-#pragma unroll
-        for (int r = 1; r < R; ++r) v[q * R + r] = cmul(v[q * R + r], ldg(tw + (r - 1) * NS + k));
+        twiddle_pow<R>(v + q * R, w1);
         bfly<R>(v + q * R);
-        const int j0 = (b - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) sm[fft_phys(j0 + r * NS)] = v[q * R + r];
+        for (int r = 0; r < R; ++r) dst[fft_pad16(q * NT * R + r * NS)] = v[q * R + r];
     }
     __syncthreads();
 }
@@ -186,46 +244,48 @@ __device__ __forceinline__ void fft_mid_pass(double2 *sm, const double2 *__restr
 // FftCfg<LOG2N>::SMEM_ELEMS double2.  Contains its own leading barrier, so it
 // can be called back to back.
 template <int LOG2N>
-__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm,
-                                        const double2 *__restrict__ tw, int tid) {
+__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm, const FftTw &tw, int tid) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT;
     // pass 1: radix 16, Ns = 1, no twiddles
     bfly<16>(v);
     __syncthreads();  // previous users of sm are done
+    {
+        double2 *dst = sm + 17 * tid;     // fft_phys(16 * tid + r) = 17 * tid + r
 #pragma unroll
-    for (int r = 0; r < 16; ++r) sm[fft_phys(16 * tid + r)] = v[r];
+        for (int r = 0; r < 16; ++r) dst[r] = v[r];
+    }
     __syncthreads();
-    if constexpr (C::R1 > 1) fft_mid_pass<N, C::R1, 16>(sm, tw + C::OFF_M1, tid);
-    if constexpr (C::R2 > 1) fft_mid_pass<N, C::R2, 16 * C::R1>(sm, tw + C::OFF_M2, tid);
+    if constexpr (C::R1 > 1) fft_mid_pass<N, C::R1, 16>(sm, tw.m1, tid);
+    if constexpr (C::R2 > 1) fft_mid_pass<N, C::R2, 16 * C::R1>(sm, tw.m2, tid);
     // last pass: radix 16, Ns = N/16, k = tid, output index tid + r*NT
+    {
+        const double2 *src = sm + fft_phys(tid);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = sm[fft_phys(tid + r * NT)];
-#pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], ldg(tw + C::OFF_L + (r - 1) * NT + tid));
+        for (int r = 0; r < 16; ++r) v[r] = src[fft_pad16(r * NT)];
+    }
+    twiddle_pow<16>(v, tw.last);
     bfly<16>(v);
 }
 
-// Host: twiddle tables for FftCfg<log2n>, as (re, im) pairs.
+// Host: base-twiddle tables for FftCfg<log2n>, as (re, im) pairs.
 inline std::vector<double> make_fft_twiddles(int log2n) {
     const int N = 1 << log2n;
     const int mid = log2n - 8;
     const int R1 = mid >= 4 ? 16 : (1 << mid);
     const int R2 = mid > 4 ? (1 << (mid - 4)) : 1;
     std::vector<double> t;
-    auto emit = [&](int R, int Ns) {
-        for (int r = 1; r < R; ++r)
-            for (int k = 0; k < Ns; ++k) {
-                // exp(-2 pi i r k / (Ns R)); long double keeps the table correctly rounded
-                long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)r *
-                                (long double)k / ((long double)Ns * (long double)R);
-                t.push_back((double)cosl(a));
-                t.push_back((double)sinl(a));
-            }
+    auto emit = [&](int count, long double period) {
+        for (int k = 0; k < count; ++k) {
+            // exp(-2 pi i k / period); long double keeps the table correctly rounded
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / period;
+            t.push_back((double)cosl(a));
+            t.push_back((double)sinl(a));
+        }
     };
-    if (R1 > 1) emit(R1, 16);
-    if (R2 > 1) emit(R2, 16 * R1);
-    emit(16, N / 16);
+    emit(16, 16.0L * R1);                 // mid pass 1: Ns = 16, radix R1
+    emit(16 * R1, 16.0L * R1 * R2);       // mid pass 2: Ns = 16 R1, radix R2
+    emit(N / 16, (long double)N);         // last pass: Ns = N/16, radix 16
     return t;
 }
 

@@ -15,6 +15,8 @@
 //                       reference's overlap-add (same sums, no carried tail).
 //
 // Both compute  y[r][i] = sum_k taps[k] * x[r][i + K-1-k]  (header contract).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -88,8 +90,9 @@ fir_direct_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int 
 }
 
 // --------------------------------------------------------------------- FFT
-template <int LOG2N>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
+// MINB = CTAs per SM the register budget is sized for (2: 128 regs, 3: 80 regs).
+template <int LOG2N, int MINB>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::NT, MINB)
 fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
                const double2 *__restrict__ H /* N, scaled 1/N */, const double2 *__restrict__ tw,
                double *__restrict__ y, int64_t ldy) {
@@ -102,33 +105,53 @@ fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int nta
     const int64_t row = blockIdx.y;
     const int64_t step = N - ntaps + 1;
     const int64_t span = n_out + ntaps - 1;
-    const int64_t base_a = (int64_t)blockIdx.x * 2 * step;
-    const int64_t base_b = base_a + step;
-    const double *xr = x + row * ldx;
+    const int64_t base_a = (int64_t)blockIdx.x * 2 * step;     // block b starts base_a + step
+    const double *pa = x + row * ldx + base_a + tid;
+    const double *pb = pa + step;
+    const int64_t la = span - base_a, lb = la - step;
+    const int lim_a = (int)(la > N ? N : la), lim_b = (int)(lb > N ? N : (lb < 0 ? 0 : lb));
+    const FftTw ftw = fft_load_tw<LOG2N>(tw, tid);
 
     double2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        const int64_t ia = base_a + tid + r * NT, ib = base_b + tid + r * NT;
-        v[r].x = ia < span ? ld_stream(xr + ia) : 0.0;
-        v[r].y = ib < span ? ldg(xr + ib) : 0.0;
+        const int i = tid + r * NT;
+        v[r].x = i < lim_a ? ld_stream(pa + r * NT) : 0.0;
+        v[r].y = i < lim_b ? ld_stream(pb + r * NT) : 0.0;
     }
-    fft_r2r<LOG2N>(v, sm, tw, tid);
+    fft_r2r<LOG2N>(v, sm, ftw, tid);
+    const double2 *hp = H + tid;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        const double2 p = cmul(v[r], ldg(H + tid + r * NT));
+        const double2 p = cmul(v[r], ldg(hp + r * NT));
         v[r] = make_double2(p.y, p.x);  // swap: inverse transform via the forward kernel
     }
-    fft_r2r<LOG2N>(v, sm, tw, tid);
-    double *yr = y + row * ldy;
+    // The inverse transform re-reads its base twiddles with volatile loads:
+    // otherwise ptxas keeps the 30 twiddle powers of the forward transform
+    // alive for reuse and spills ~300 B per thread (profiles/r01_ncu_summary.md).
+    FftTw ftw2;
+    {
+        const volatile double2 *vt = tw;
+        ftw2.m1.x = vt[C::OFF_M1 + (tid & 15)].x;
+        ftw2.m1.y = vt[C::OFF_M1 + (tid & 15)].y;
+        ftw2.m2.x = vt[C::OFF_M2 + (tid & (16 * C::R1 - 1))].x;
+        ftw2.m2.y = vt[C::OFF_M2 + (tid & (16 * C::R1 - 1))].y;
+        ftw2.last.x = vt[C::OFF_L + tid].x;
+        ftw2.last.y = vt[C::OFF_L + tid].y;
+    }
+    fft_r2r<LOG2N>(v, sm, ftw2, tid);
+    const int k1 = ntaps - 1;
+    double *ya = y + row * ldy + base_a + tid - k1;
+    double *yb = ya + step;
+    const int64_t oa = n_out - base_a + k1, ob = oa - step;
+    const int out_a = (int)(oa > N ? N : oa), out_b = (int)(ob > N ? N : (ob < 0 ? 0 : ob));
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int i = tid + r * NT;
-        if (i >= ntaps - 1) {
-            const int64_t oa = base_a + i - (ntaps - 1), ob = base_b + i - (ntaps - 1);
+        if (i >= k1) {
             // after the swap back: real part = v.y, imaginary part = v.x
-            if (oa < n_out) st_stream(yr + oa, v[r].y);
-            if (ob < n_out) st_stream(yr + ob, v[r].x);
+            if (i < out_a) st_stream(ya + r * NT, v[r].y);
+            if (i < out_b) st_stream(yb + r * NT, v[r].x);
         }
     }
 }
@@ -147,22 +170,18 @@ struct osz_fir_plan {
     double2 *d_tw = nullptr;
 };
 
-template <int LOG2N>
+template <int LOG2N, int MINB>
 static int launch_fir_fft(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
                           int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
     using C = FftCfg<LOG2N>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        OSZ_CUDA(cudaFuncSetAttribute(fir_fft_kernel<LOG2N>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    OSZ_CUDA(cudaFuncSetAttribute(fir_fft_kernel<LOG2N, MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const int64_t step = C::N - p->ntaps + 1;
     const int64_t nblocks = (n_out + step - 1) / step;
     const int64_t npairs = (nblocks + 1) / 2;
     if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "fir: more than 65535 rows per call");
     dim3 grid((unsigned)npairs, (unsigned)rows);
-    fir_fft_kernel<LOG2N><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, ldx, n_out, p->ntaps, p->d_H,
+    fir_fft_kernel<LOG2N, MINB><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, ldx, n_out, p->ntaps, p->d_H,
                                                              p->d_tw, y, ldy);
     OSZ_LAUNCHED("fir_fft_kernel");
     return OSZ_OK;
@@ -250,14 +269,10 @@ int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_
     if (rows <= 0 || n_out <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
     if (p->algo == OSZ_FIR_DIRECT) {
-        static bool attr_set = false;
         const int xs_off = (16 + p->kpad * 8 + 127) & ~127;
         const int smem = xs_off + (FIR_TILE + p->kpad + FIR_R + 2) * 8;
-        if (!attr_set) {
-            OSZ_CUDA(cudaFuncSetAttribute(fir_direct_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr_set = true;
-        }
+        OSZ_CUDA(cudaFuncSetAttribute(fir_direct_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "fir: more than 65535 rows per call");
         dim3 grid((unsigned)((n_out + FIR_TILE - 1) / FIR_TILE), (unsigned)rows);
         fir_direct_kernel<<<grid, FIR_NT, smem, st>>>(x, ldx, n_out, p->ntaps, p->kpad,
@@ -265,8 +280,16 @@ int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_
         OSZ_LAUNCHED("fir_direct_kernel");
         return OSZ_OK;
     }
-    if (p->log2n == 12) return launch_fir_fft<12>(p, x, ldx, rows, n_out, y, ldy, st);
-    return launch_fir_fft<13>(p, x, ldx, rows, n_out, y, ldy, st);
+    if (p->log2n == 12) {
+        // tuning knob: OSZ_FIR_MINB=2 sizes registers for two CTAs per SM
+        static const int minb = [] {
+            const char *e = getenv("OSZ_FIR_MINB");
+            return e ? atoi(e) : 3;
+        }();
+        if (minb == 2) return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st);
+        return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st);
+    }
+    return launch_fir_fft<13, 1>(p, x, ldx, rows, n_out, y, ldy, st);
 }
 
 }  // extern "C"

@@ -81,14 +81,28 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
         const int off = blk == 0 ? (int)(SOS_BLK - first_len) : 0;
         const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * SOS_BLK;
         __syncthreads();   // carry[] visible / buf free
-#pragma unroll 4
-        for (int e = tid; e < SOS_BLK; e += SOS_NT) {
-            double val = 0.0;
-            if (e >= off) {
-                const int64_t s = pos0 + (e - off);
-                val = ld_stream(xr + (reverse ? n - 1 - s : s));
+        if (blk != 0) {
+            // full block: 32 independent coalesced loads in flight per thread
+            const double *src = reverse ? xr + (n - 1 - pos0) - tid : xr + pos0 + tid;
+            double tmp[SOS_T];
+#pragma unroll
+            for (int it = 0; it < SOS_T; ++it)
+                tmp[it] = ld_stream(reverse ? src - it * SOS_NT : src + it * SOS_NT);
+#pragma unroll
+            for (int it = 0; it < SOS_T; ++it) {
+                const int e = tid + it * SOS_NT;
+                buf[(e >> 5) * SOS_LD + (e & 31)] = tmp[it];
             }
-            buf[(e >> 5) * SOS_LD + (e & 31)] = val;
+        } else {
+#pragma unroll 8
+            for (int e = tid; e < SOS_BLK; e += SOS_NT) {
+                double val = 0.0;
+                if (e >= off) {
+                    const int64_t s = pos0 + (e - off);
+                    val = ld_stream(xr + (reverse ? n - 1 - s : s));
+                }
+                buf[(e >> 5) * SOS_LD + (e & 31)] = val;
+            }
         }
         __syncthreads();
         double v[SOS_T];

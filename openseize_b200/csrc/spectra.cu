@@ -122,6 +122,10 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
     constexpr int N = C::N, NT = C::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+    // per-thread |Z|^2 accumulators live in shared memory ([r][tid], conflict
+    // free): in registers they pushed the FFT over the 128-register budget of
+    // two CTAs per SM and spilled (profiles/r01_ncu_summary.md)
+    double *accs = reinterpret_cast<double *>(smem_raw + C::SMEM_BYTES);
     __shared__ double red[4 * 32];
 
     const int tid = threadIdx.x;
@@ -131,17 +135,18 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
     int64_t p1 = p0 + pairs_per_cta;
     if (p1 > npairs) p1 = npairs;
     const double *xr = x + row * ldx;
+    const FftTw ftw = fft_load_tw<LOG2N>(tw, tid);
 
-    double acc[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+    for (int r = 0; r < 16; ++r) accs[r * NT + tid] = 0.0;
 
     for (int64_t p = p0; p < p1; ++p) {
         double2 v[16];
         load_pair<LOG2N, DETREND>(v, xr + 2 * p * stride, 2 * p + 1 < nseg, stride, win, red, tid);
-        fft_r2r<LOG2N>(v, sm, tw, tid);
+        fft_r2r<LOG2N>(v, sm, ftw, tid);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = fma(v[r].x, v[r].x, fma(v[r].y, v[r].y, acc[r]));
+        for (int r = 0; r < 16; ++r)
+            accs[r * NT + tid] = fma(v[r].x, v[r].x, fma(v[r].y, v[r].y, accs[r * NT + tid]));
     }
     if (p0 >= p1) return;
     // fold k and N-k:  psd[k] += norm * (A[k] + A[N-k]) for 0<k<N/2 (this is the
@@ -151,7 +156,7 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
     for (int r = 0; r < 16; ++r) {
         const int idx = tid + r * NT;
         const int bin = idx <= N / 2 ? idx : N - idx;
-        atomicAdd(out + bin, acc[r] * norm);
+        atomicAdd(out + bin, accs[r * NT + tid] * norm);
     }
 }
 
@@ -171,10 +176,11 @@ spec_segments_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, in
     const int64_t row = blockIdx.y;
     const int64_t sa = (int64_t)blockIdx.x * 2;
     const bool has_b = sa + 1 < nseg;
+    const FftTw ftw = fft_load_tw<LOG2N>(tw, tid);
 
     double2 v[16];
     load_pair<LOG2N, DETREND>(v, x + row * ldx + sa * stride, has_b, stride, win, red, tid);
-    fft_r2r<LOG2N>(v, sm, tw, tid);
+    fft_r2r<LOG2N>(v, sm, ftw, tid);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; ++r) sm[fft_phys(tid + r * NT)] = v[r];
@@ -231,8 +237,9 @@ template <int LOG2N, int DETREND>
 static int launch_welch(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                         int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
     using C = FftCfg<LOG2N>;
+    constexpr int SMEM = C::SMEM_BYTES + C::N * 8;   // FFT exchange + accumulators
     OSZ_CUDA(cudaFuncSetAttribute(welch_accum_kernel<LOG2N, DETREND>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int64_t npairs = (nseg + 1) / 2;
     // enough CTAs for ~4 waves of 2 CTAs/SM, but at least 4 pairs per CTA so the
     // register accumulators amortise the atomics
@@ -243,7 +250,7 @@ static int launch_welch(const osz_spec_plan *p, const double *x, int64_t ldx, in
     if (ppc < 4) ppc = 4;
     const int64_t gx = (npairs + ppc - 1) / ppc;
     dim3 grid((unsigned)gx, (unsigned)rows);
-    welch_accum_kernel<LOG2N, DETREND><<<grid, C::NT, C::SMEM_BYTES, st>>>(
+    welch_accum_kernel<LOG2N, DETREND><<<grid, C::NT, SMEM, st>>>(
         x, ldx, nseg, p->stride, p->d_win, p->d_tw, p->norm, psd, ldp, ppc);
     OSZ_LAUNCHED("welch_accum_kernel");
     return OSZ_OK;

@@ -48,20 +48,30 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
     const int64_t in0 = (out_first + o0) * M + half - (K - 1);
     const double *xr = x + row * ldx;
 
-    // stage [TO + Q] decimated samples of every phase, phase-major, skewed
+    // stage [TO + Q] decimated samples of every phase, phase-major, skewed;
+    // eight independent loads in flight per thread
     const int n_in = (TO + Q) * M;
     {
-        int p = tid % M, m = tid / M;
+        constexpr int U = 8;
         const int dp = UFD_NT % M, dm = UFD_NT / M;
-        for (int e = tid; e < n_in; e += UFD_NT) {
-            const int64_t g = in0 + e - x_first;
-            const double val = (g >= 0 && g < x_len) ? ld_stream(xr + g) : 0.0;
-            xs[p * ldm + ufd_phys<R>(m)] = val;
-            p += dp;
-            m += dm;
-            if (p >= M) {
-                p -= M;
-                m += 1;
+        int p = tid % M, m = tid / M;
+        for (int e0 = tid; e0 < n_in; e0 += U * UFD_NT) {
+            double val[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * UFD_NT;
+                const int64_t g = in0 + e - x_first;
+                val[u] = (e < n_in && g >= 0 && g < x_len) ? ld_stream(xr + g) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (e0 + u * UFD_NT < n_in) xs[p * ldm + ufd_phys<R>(m)] = val[u];
+                p += dp;
+                m += dm;
+                if (p >= M) {
+                    p -= M;
+                    m += 1;
+                }
             }
         }
     }
@@ -111,15 +121,16 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
         s = p * Q + q1;
     }
     __syncthreads();   // tile no longer needed: reuse it for the cross-warp sum
-    double *red = smem;   // [NW][TO + pad]
-    constexpr int LDR = TO + 1;
+    double *red = smem;   // [NW][32 lanes][R + 1]: the +1 keeps the stride-R stores conflict free
+    constexpr int LDR = 32 * (R + 1);
 #pragma unroll
-    for (int r = 0; r < R; ++r) red[warp * LDR + lane * R + r] = acc[r];
+    for (int r = 0; r < R; ++r) red[warp * LDR + lane * (R + 1) + r] = acc[r];
     __syncthreads();
     for (int o = tid; o < TO; o += UFD_NT) {
+        const int idx = (o / R) * (R + 1) + (o % R);
         double sum = 0.0;
 #pragma unroll
-        for (int w8 = 0; w8 < UFD_NW; ++w8) sum += red[w8 * LDR + o];
+        for (int w8 = 0; w8 < UFD_NW; ++w8) sum += red[w8 * LDR + idx];
         if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
     }
 }
@@ -180,7 +191,7 @@ static size_t dec_smem(int R, int M, int Q, int *ldm_out) {
     if ((ldm & 1) == 0) ++ldm;
     *ldm_out = ldm;
     size_t tile = ((size_t)M * ldm + (size_t)M * Q) * 8;
-    size_t red = (size_t)UFD_NW * (TO + 1) * 8;
+    size_t red = (size_t)UFD_NW * 32 * (R + 1) * 8;
     return tile > red ? tile : red;
 }
 

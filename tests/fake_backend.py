@@ -17,6 +17,14 @@ def _t(a):
     return torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True))
 
 
+def _ret(y, out):
+    """Write into the caller's buffer when one is given (the C ABI contract)."""
+    if out is None:
+        return _t(y)
+    out.copy_(_t(y))
+    return out
+
+
 class FakeFir:
     def __init__(self, taps, algo=0):
         self.taps = np.asarray(taps, dtype=np.float64)
@@ -27,7 +35,7 @@ class FakeFir:
         x = xbuf.numpy()
         k = self.ntaps
         y = np.stack([np.convolve(r[:n_out + k - 1], self.taps, "valid") for r in x])
-        return _t(y)
+        return _ret(y, out)
 
 
 class FakeSos:
@@ -44,7 +52,7 @@ class FakeSos:
         state.copy_(_t(np.transpose(zf, (1, 0, 2))))
         if not want_output:
             return None
-        return _t(y[:, ::-1] if reverse else y)
+        return _ret(y[:, ::-1] if reverse else y, out)
 
     def state_from_sample(self, zi, x, sample):
         zi = np.asarray(zi, dtype=np.float64)
@@ -56,7 +64,7 @@ class FakeUpfirdn:
         self.h = np.asarray(h, dtype=np.float64) * up
         self.ntaps, self.up, self.down = len(self.h), int(up), int(down)
 
-    def run(self, x, x_first, out_first, n_out):
+    def run(self, x, x_first, out_first, n_out, out=None):
         xn = x.numpy()
         half = (self.ntaps - 1) // 2
         # u[m] = sum_k h'[m - k*up] x[k], m relative to x_first*up
@@ -66,7 +74,7 @@ class FakeUpfirdn:
         ok = (m >= 0) & (m < u.shape[1])
         y = np.zeros((xn.shape[0], n_out))
         y[:, ok] = u[:, m[ok]]
-        return _t(y)
+        return _ret(y, out)
 
 
 class FakeSpec:
@@ -119,11 +127,11 @@ class _Now:
         return self.arr
 
 
-def _upload(arr, layout):
+def _upload(arr, layout, alloc=None):
     a = np.asarray(arr, dtype=np.float64)
     n = a.shape[layout.axis]
     a = np.moveaxis(a.reshape(layout.outer, n, layout.inner), 1, 2)
-    return _t(a.reshape(layout.rows, n))
+    return _ret(a.reshape(layout.rows, n), alloc(layout.rows, n) if alloc else None)
 
 
 def _download(dev, layout, complex_=False):
