@@ -108,14 +108,28 @@ def upload(arr, layout, alloc=None):
     n = a.shape[layout.axis]
     h2d, _ = _Streams.get()
     cur = t.cuda.current_stream()
+
+    def fence():
+        # The H2D copy runs on a side stream so it overlaps the kernels of the
+        # previous chunk.  It only has to wait for whoever used the destination
+        # memory before: nothing for blocks allocated on the copy stream itself
+        # (torch's allocator orders their reuse), the ring's allocation event for
+        # space inside a consumer's staging ring.
+        ev = getattr(alloc, "ready_event", None)
+        if ev is not None:
+            h2d.wait_event(ev)
+        elif alloc is not None:
+            h2d.wait_stream(cur)
+
+    def fresh(shape):
+        with t.cuda.stream(h2d):
+            return t.empty(shape, dtype=t.float64, device="cuda")
+
     if layout.inner == 1:
         a2 = a.reshape(layout.outer, n)
-        if alloc is not None:
-            dev = alloc(layout.outer, n)
-        else:
-            dev = t.empty((layout.outer, n), dtype=t.float64, device="cuda")
+        dev = alloc(layout.outer, n) if alloc is not None else fresh((layout.outer, n))
         ldd = dev.stride(0) if layout.outer > 1 else n
-        h2d.wait_stream(cur)     # dev's block may have been freed on `cur`
+        fence()
         with t.cuda.stream(h2d):
             direct = False
             if a2.strides[1] == 8 and a2.strides[0] >= n * 8 and a2.flags.writeable:
@@ -140,9 +154,8 @@ def upload(arr, layout, alloc=None):
     flat = np.ascontiguousarray(a).reshape(layout.outer, n, layout.inner)
     stage = t.empty(flat.shape, dtype=t.float64, pin_memory=True)
     np.copyto(stage.numpy(), flat)
-    h2d.wait_stream(cur)
+    raw = fresh(flat.shape)
     with t.cuda.stream(h2d):
-        raw = t.empty(flat.shape, dtype=t.float64, device="cuda")
         raw.copy_(stage, non_blocking=True)
     cur.wait_stream(h2d)
     raw.record_stream(cur)
@@ -442,6 +455,16 @@ def empty(shape):
 
 def zeros_rows(rows, n):
     return zeros((rows, n))
+
+
+def record_event():
+    """Event on the current (compute) stream, or None off-GPU (test stand-ins)."""
+    t = torch()
+    if DEVICE != "cuda":
+        return None
+    ev = t.cuda.Event()
+    ev.record()
+    return ev
 
 
 def from_host(arr):

@@ -148,6 +148,7 @@ class _TimeRing:
 
     def __init__(self, rows):
         self.rows, self.buf, self.start, self.pos, self._pending = rows, None, 0, 0, None
+        self.ready_event = None      # compute-stream point after which the buffer is ours
 
     def _reserve(self, n):
         live = self.pos - self.start
@@ -156,6 +157,10 @@ class _TimeRing:
             if live:
                 new[:, :live].copy_(self.buf[:, self.start:self.pos])
             self.buf, self.start, self.pos = new, 0, live
+            self.ready_event = dv.record_event()
+
+    def __call__(self, rows, n):
+        return self.alloc(rows, n)
 
     def alloc(self, rows, n):
         assert rows == self.rows
@@ -249,7 +254,7 @@ def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None):
     ring = _TimeRing(rows)
     ring.push_zeros(ntaps - 1)                      # the reference's zero overlap (:221-223)
     pos = 0                                         # full-convolution index of the next output
-    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring.alloc):
+    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring):
         n = chunk.shape[1]
         ring.push(chunk)
         final = pos + n >= nsamp
@@ -499,7 +504,7 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, **kwargs):
     seen = 0                                       # input samples received
     # The values do not depend on the input blocking (one global resample_poly,
     # SURVEY 8a5), only the yield boundaries do: take upstream blocks as they come.
-    for chunk in device_chunks(src, axis, regrid=False, alloc=ring.alloc):
+    for chunk in device_chunks(src, axis, regrid=False, alloc=ring):
         ring.push(chunk)
         seen += chunk.shape[1]
         while emitted < nchunks - 1:
@@ -565,7 +570,7 @@ def _segment_batches(pro, axis, plan, pad_left=0, pad_right=0, batch_samples=1 <
             yield ring.window(), nseg
             ring.drop(nseg * plan.stride)
 
-    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring.alloc):
+    for chunk in device_chunks(pro, axis, regrid=False, alloc=ring):
         ring.push(chunk)
         if ring.size * rows >= batch_samples:
             yield from flush()

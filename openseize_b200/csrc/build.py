@@ -20,7 +20,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "-diag-suppress", "20208",
 ]
 
 

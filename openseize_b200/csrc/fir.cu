@@ -281,13 +281,15 @@ int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_
         return OSZ_OK;
     }
     if (p->log2n == 12) {
-        // tuning knob: OSZ_FIR_MINB=2 sizes registers for two CTAs per SM
+        // Two CTAs per SM at 128 registers beat three at 80 (104 B of spills):
+        // 217 vs 184 G samples/s at 113 taps (profiles/r01_kernel_bench.md).
+        // OSZ_FIR_MINB=3 selects the other build for re-measurement.
         static const int minb = [] {
             const char *e = getenv("OSZ_FIR_MINB");
-            return e ? atoi(e) : 3;
+            return e ? atoi(e) : 2;
         }();
-        if (minb == 2) return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st);
-        return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st);
+        if (minb == 3) return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st);
+        return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st);
     }
     return launch_fir_fft<13, 1>(p, x, ldx, rows, n_out, y, ldy, st);
 }

@@ -133,6 +133,7 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps):
 
 def test_spectra_golden():
     pc.spectra_golden("pow2")
+    pc.spectra_golden("nonpow2")          # nfft = 2000: generic mixed-radix path
 
 
 def test_spectra_oracle_sweep():
@@ -166,6 +167,50 @@ def test_fft_sizes_vs_numpy(dv, nfft, detrend):
         assert relerr(P[s], p) < 1e-12
         ref_sum = ref_sum + p
     assert relerr(psd_sum.cpu().numpy(), ref_sum) < 1e-12
+
+
+@pytest.mark.parametrize("nfft", [2, 3, 60, 97, 250, 1001, 1009, 2000, 10000, 16384])
+def test_generic_nfft_vs_numpy(dv, nfft):
+    """Mixed-radix (2..16, 3, 5, 7, 11, 13) and Bluestein (97, 1009) lengths,
+    odd and even, through the periodogram / STFT / Welch entry points."""
+    rng = np.random.default_rng(nfft)
+    rows, nseg = 3, 5
+    stride = max(1, nfft // 2)
+    x = rng.standard_normal((rows, (nseg - 1) * stride + nfft)) + 0.5
+    w = sps.get_window("hann", nfft) if nfft > 3 else np.ones(nfft)
+    norm = 1.0 / (1000.0 * np.sum(w ** 2))
+    for detrend in ("constant", "linear", None):
+        if detrend == "linear" and nfft < 3:
+            continue
+        plan = dv.SpecPlan(nfft, stride, w, detrend, norm)
+        assert plan.path == 2
+        X = plan.segments(_dev(dv, x), nseg, True).cpu().numpy()
+        X = X[..., 0] + 1j * X[..., 1]
+        P = plan.segments(_dev(dv, x), nseg, False).cpu().numpy()
+        psd_sum = dv.zeros((rows, nfft // 2 + 1))
+        plan.welch_accum(_dev(dv, x), nseg, psd_sum)
+        ref_sum = 0
+        for s in range(nseg):
+            seg = x[:, s * stride:s * stride + nfft]
+            if detrend:
+                seg = sps.detrend(seg, axis=-1, type=detrend)
+            R = np.fft.rfft(seg * w, axis=-1) * np.sqrt(norm)
+            scale = max(np.max(np.abs(R)), 1e-300)
+            assert np.max(np.abs(X[s] - R)) / scale < 1e-11, (nfft, detrend, s)
+            p = np.abs(R) ** 2
+            if nfft % 2:
+                p[:, 1:] *= 2
+            else:
+                p[:, 1:-1] *= 2
+            assert np.max(np.abs(P[s] - p)) / max(np.max(p), 1e-300) < 1e-11
+            ref_sum = ref_sum + p
+        got = psd_sum.cpu().numpy()
+        assert np.max(np.abs(got - ref_sum)) / max(np.max(ref_sum), 1e-300) < 1e-11
+
+
+def test_default_resolution_psd():
+    """psd() with the reference's default resolution (0.5 Hz -> nfft = 2 fs)."""
+    pc.spectra_oracle_sweep(fs=1000, resolutions=(0.5,))
 
 
 def test_pipeline_chain_on_device():
