@@ -659,12 +659,11 @@ def welch(pro, fs, nfft, window, overlap, axis, detrend, scaling):
     return freqs, producer(genfunc, chunksize=len(freqs), axis=axis, shape=shape)
 
 
-def welch_mean(pro, fs, nfft, window, overlap, axis, detrend, scaling):
-    """Fused Welch estimate: (segment count, mean periodogram ndarray).  The
-    per-segment periodograms never leave the SM: |FFT|^2 is accumulated in
-    registers and only the (rows, nfft//2+1) sum is written.  Equals the
-    reference's running mean over ``welch``'s producer
-    (spectra/estimators.py:150-152) up to rounding."""
+def welch_sum(pro, fs, nfft, window, overlap, axis, detrend, scaling):
+    """(segment count, DEVICE (rows, nfft//2+1) SUM of the segment
+    periodograms).  The per-segment periodograms never leave the SM: |FFT|^2
+    is accumulated on chip and only the sum is written.  This is the quantity
+    time-sharded ranks all-reduce (openseize_b200.sharding)."""
     dv.require_cuda()
     plan = _spec_plan(fs, nfft, window, overlap, detrend, scaling)
     layout = _layout_of(pro, axis)
@@ -673,8 +672,17 @@ def welch_mean(pro, fs, nfft, window, overlap, axis, detrend, scaling):
     for buf, nseg in _segment_batches(pro, axis, plan):
         plan.welch_accum(buf, nseg, psd_sum)
         cnt += nseg
+    return cnt, psd_sum
+
+
+def welch_mean(pro, fs, nfft, window, overlap, axis, detrend, scaling):
+    """Fused Welch estimate: (segment count, mean periodogram ndarray).  Equals
+    the reference's running mean over ``welch``'s producer
+    (spectra/estimators.py:150-152) up to rounding."""
+    cnt, psd_sum = welch_sum(pro, fs, nfft, window, overlap, axis, detrend, scaling)
     if cnt == 0:
         raise ValueError("psd: the data holds no complete nfft={} segment".format(nfft))
+    layout = _layout_of(pro, axis)
     return cnt, np.array(dv.download(psd_sum, layout).get()) / cnt
 
 

@@ -38,6 +38,7 @@ struct SosSec {
     double g0[SOS_T], g1[SOS_T];
     double P[5][4];     // M^(2^k), row major
     double Q[4];        // M^32 (one warp)
+    double A8[4];       // A^8: state transition over one 8-sample sub-piece
 };
 struct SosParams {
     int nsec;
@@ -115,18 +116,40 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
             double z0 = 0.0, z1 = 0.0;
             if (blk != 0) {
+                // Four independent 8-sample chains per thread (the single
+                // 32-sample chain left the FP64 pipe 2/3 idle waiting on its own
+                // results): sub-piece 0 starts from the thread's entering state
+                // (the carry for thread 0, else zero), sub-pieces 1..3 from zero
+                // and are fixed up in-thread with the same zero-input tables.
+                double za0[4] = {0.0, 0.0, 0.0, 0.0}, za1[4] = {0.0, 0.0, 0.0, 0.0};
                 if (tid == 0) {
-                    z0 = carry[s][0];
-                    z1 = carry[s][1];
+                    za0[0] = carry[s][0];
+                    za1[0] = carry[s][1];
                 }
 #pragma unroll
-                for (int i = 0; i < SOS_T; ++i) {
-                    const double xi = v[i];
-                    const double yi = fma(b0, xi, z0);
-                    z0 = fma(na1, yi, fma(b1, xi, z1));
-                    z1 = fma(na2, yi, b2 * xi);
-                    v[i] = yi;
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double xi = v[8 * j + i];
+                        const double yi = fma(b0, xi, za0[j]);
+                        za0[j] = fma(na1, yi, fma(b1, xi, za1[j]));
+                        za1[j] = fma(na2, yi, b2 * xi);
+                        v[8 * j + i] = yi;
+                    }
                 }
+                double e0 = za0[0], e1 = za1[0];           // state at the end of sub-piece 0
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[8 * j + i] = fma(c.g0[i], e0, fma(c.g1[i], e1, v[8 * j + i]));
+                    const double t0 = fma(c.A8[0], e0, c.A8[1] * e1) + za0[j];
+                    const double t1 = fma(c.A8[2], e0, c.A8[3] * e1) + za1[j];
+                    e0 = t0;
+                    e1 = t1;
+                }
+                z0 = e0;
+                z1 = e1;
             } else {
                 const bool inj = tid == pstar;
                 const double c0 = carry[s][0], c1 = carry[s][1];
@@ -261,6 +284,12 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         const M2 A = {-(long double)c.a1, 1.0L, -(long double)c.a2, 0.0L};
         M2 pw = {1.0L, 0.0L, 0.0L, 1.0L};   // A^i
         for (int i = 0; i < SOS_T; ++i) {
+            if (i == 8) {
+                c.A8[0] = (double)pw.a;
+                c.A8[1] = (double)pw.b;
+                c.A8[2] = (double)pw.c;
+                c.A8[3] = (double)pw.d;
+            }
             c.g0[i] = (double)pw.a;
             c.g1[i] = (double)pw.b;
             pw = mul(A, pw);

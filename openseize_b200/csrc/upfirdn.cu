@@ -49,28 +49,48 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
     const double *xr = x + row * ldx;
 
     // stage [TO + Q] decimated samples of every phase, phase-major, skewed;
-    // eight independent loads in flight per thread
+    // eight independent loads in flight per thread.  Tiles that lie wholly
+    // inside the supplied window (all but the recording's edges) skip the
+    // per-element bounds arithmetic.
     const int n_in = (TO + Q) * M;
     {
         constexpr int U = 8;
         const int dp = UFD_NT % M, dm = UFD_NT / M;
         int p = tid % M, m = tid / M;
-        for (int e0 = tid; e0 < n_in; e0 += U * UFD_NT) {
+        const int64_t rel0 = in0 - x_first;
+        const bool interior = rel0 >= 0 && rel0 + n_in <= x_len;
+        const double *src = xr + rel0 + tid;
+        for (int e0 = tid; e0 < n_in; e0 += U * UFD_NT, src += U * UFD_NT) {
             double val[U];
+            if (interior && e0 + (U - 1) * UFD_NT < n_in) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * UFD_NT;
-                const int64_t g = in0 + e - x_first;
-                val[u] = (e < n_in && g >= 0 && g < x_len) ? ld_stream(xr + g) : 0.0;
-            }
+                for (int u = 0; u < U; ++u) val[u] = ld_stream(src + u * UFD_NT);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (e0 + u * UFD_NT < n_in) xs[p * ldm + ufd_phys<R>(m)] = val[u];
-                p += dp;
-                m += dm;
-                if (p >= M) {
-                    p -= M;
-                    m += 1;
+                for (int u = 0; u < U; ++u) {
+                    xs[p * ldm + ufd_phys<R>(m)] = val[u];
+                    p += dp;
+                    m += dm;
+                    if (p >= M) {
+                        p -= M;
+                        m += 1;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * UFD_NT;
+                    const int64_t g = rel0 + e;
+                    val[u] = (e < n_in && g >= 0 && g < x_len) ? ld_stream(xr + g) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u * UFD_NT < n_in) xs[p * ldm + ufd_phys<R>(m)] = val[u];
+                    p += dp;
+                    m += dm;
+                    if (p >= M) {
+                        p -= M;
+                        m += 1;
+                    }
                 }
             }
         }

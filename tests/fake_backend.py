@@ -155,3 +155,13 @@ def install(mp):
     mp.setattr(dv.SpecPlan, "cached",
                staticmethod(lambda nfft, stride, window, detrend, norm:
                             FakeSpec(nfft, stride, window, detrend, norm)))
+
+
+def install_raw():
+    """Same as install() without pytest's monkeypatch (spawned gloo workers)."""
+    class _Set:
+        @staticmethod
+        def setattr(obj, name, value):
+            setattr(obj, name, value)
+
+    install(_Set)
