@@ -51,8 +51,8 @@ WORKLOAD = ("C5 pipeline: Notch(60,w6) filtfilt -> Kaiser(500,600) 671-tap FIR '
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--chunk", type=int, default=CHUNK)
@@ -156,7 +156,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -361,9 +361,16 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     if dom:
+        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full
+        # capture of this kernel at this shape (profiles/r01_ncu_summary.md)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and rows == ROWS and chunk == CHUNK:
+            traffic = json.load(open(tpath)).get(dom, {}).get("bytes_per_launch")
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["alg_GBps"],
                     "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kernels[dom]["alg_GBps"] / hbm_peak, "traffic": None,
+                    "frac": kernels[dom]["alg_GBps"] / hbm_peak, "traffic": traffic,
+                    "alg_bytes_per_launch": 16 * rows * chunk if dom in ("sos", "fir") else None,
                     "peak_source": peak_src,
                     "share_of_step": kernels[dom]["ms_total"] / (secs * 1e3)}
     del pool, src

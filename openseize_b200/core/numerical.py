@@ -302,6 +302,20 @@ class _Cascade:
         self.sos = np.atleast_2d(np.asarray(sos, dtype=np.float64))
         self.plans = _sos_groups(self.sos)
         self.nsec = self.sos.shape[0]
+        self.settle = self._settle_samples()
+
+    def _settle_samples(self, tol=1e-24):
+        """Samples after which the cascade has forgotten its initial state to
+        within ``tol`` (relative): every state transient decays like
+        ``rmax**n`` (times a polynomial in n for repeated poles, covered by the
+        squared tolerance).  None if a pole sits on or outside the unit circle."""
+        a = self.sos[:, 3:] / self.sos[:, 3:4]
+        rmax = max(float(np.max(np.abs(np.roots(sec)))) if np.any(sec[1:]) else 0.0 for sec in a)
+        if rmax >= 1.0:
+            return None
+        if rmax == 0.0:
+            return 2 * self.nsec
+        return int(np.ceil(np.log(tol) / np.log(rmax))) + 64 * self.nsec
 
     def split_state(self, state):
         """(rows, nsec, 2) -> contiguous per-group states."""
@@ -376,8 +390,16 @@ def _filtfilt_device(pro, cascade, zi, axis, _out=None):
             fwd_states = cascade.state_from_sample(zi, chunk, 0)
         fwd = cascade.run(chunk, fwd_states)
         if prev is not None:
-            look = cascade.state_from_sample(zi, fwd, fwd.shape[1] - 1)
-            cascade.run(fwd, look, reverse=True, want_output=False)
+            # Look-ahead pass (numerical.py:397-399): only its final state is
+            # used.  A stable cascade forgets where it started after `settle`
+            # samples, so filtering the first `settle` samples of the next chunk
+            # backwards from zi * (that sample) leaves the same state as the
+            # reference's run from the chunk's far end, to ~1e-24 relative.
+            m = fwd.shape[1]
+            if cascade.settle is not None and cascade.settle < m:
+                m = cascade.settle
+            look = cascade.state_from_sample(zi, fwd, m - 1)
+            cascade.run(fwd[:, :m], look, reverse=True, want_output=False)
             yield cascade.run(prev, look, reverse=True, out=_out)
         prev = fwd
     if prev is not None:

@@ -137,6 +137,19 @@ def iir_oracle_sweep():
     close(got, np.concatenate(oracle.lfilter(x, (b, a), 6000, -1, zi)[0], -1))
     got = np.concatenate(list(nm.filtfilt(producer(x, 6000, -1), (b, a), -1)), -1)
     close(got, np.concatenate(oracle.filtfilt(x, (b, a), 6000, -1), -1))
+    # chunks longer than the cascade's settle length: the look-ahead pass of the
+    # forward-backward filters is cut to the samples that still matter
+    x = rng.standard_normal((2, 130001)) + 5.0
+    from openseize_b200.core.numerical import _ba_to_sos
+
+    settle = nm._Cascade(_ba_to_sos((b, a))).settle
+    assert settle < 40000
+    got = np.concatenate(list(nm.filtfilt(producer(x, 40000, -1), (b, a), -1)), -1)
+    close(got, np.concatenate(oracle.filtfilt(x, (b, a), 40000, -1), -1), tol=1e-12)
+    lp = sps.butter(4, 300, fs=5000, output="sos")
+    assert nm._Cascade(lp).settle < 40000
+    got = np.concatenate(list(nm.sosfiltfilt(producer(x, 40000, -1), lp, -1)), -1)
+    close(got, np.concatenate(oracle.sosfiltfilt(x, lp, 40000, -1), -1), tol=1e-12)
     # more than 16 sections: split cascade
     sos = sps.butter(20, [5, 400], btype="bandpass", fs=5000, output="sos")
     assert sos.shape[0] == 20
