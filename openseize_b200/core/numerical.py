@@ -120,7 +120,9 @@ def device_chunks(pro, axis, regrid=True, alloc=None):
                 yield dv.upload(arr, layout, alloc)
             return
         func, args, kwargs = twin
-        source = func(*args, **dict(kwargs, _out=alloc if not regrid else None))
+        # _free: the consumer does not care where the upstream cuts its blocks
+        source = func(*args, **dict(kwargs, _out=alloc if not regrid else None,
+                                    _free=not regrid))
     if not regrid:
         yield from source
         return
@@ -240,7 +242,7 @@ def _layout_of(pro, axis):
 # ---------------------------------------------------------------------------
 # FIR  (reference core/numerical.py:158-298)
 # ---------------------------------------------------------------------------
-def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None):
+def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None, _free=False):
     dv.require_cuda()
     window = np.asarray(window, dtype=np.float64)
     ntaps, nsamp = len(window), pro.shape[axis]
@@ -356,7 +358,7 @@ def _zi_to_rows(zi, layout, nsec):
     return dv.from_host(rows)
 
 
-def _sosfilt_device(pro, sos, axis, zi=None, _out=None):
+def _sosfilt_device(pro, sos, axis, zi=None, _out=None, _free=False):
     dv.require_cuda()
     layout = _layout_of(pro, axis)
     cascade = _Cascade(sos)
@@ -407,7 +409,7 @@ def _filtfilt_device(pro, cascade, zi, axis, _out=None):
         yield cascade.run(prev, last, reverse=True, out=_out)
 
 
-def _sosfiltfilt_device(pro, sos, axis, _out=None):
+def _sosfiltfilt_device(pro, sos, axis, _out=None, _free=False):
     dv.require_cuda()
     cascade = _Cascade(sos)
     zi = sps.sosfilt_zi(cascade.sos)
@@ -446,7 +448,7 @@ def _lfilter_zi_rows(coeffs, zi, layout):
     return _zi_to_rows(zi[None], layout, 1)
 
 
-def _lfilter_device(pro, coeffs, axis, zi=None, _out=None):
+def _lfilter_device(pro, coeffs, axis, zi=None, _out=None, _free=False):
     dv.require_cuda()
     layout = _layout_of(pro, axis)
     cascade = _Cascade(_ba_to_sos(coeffs))
@@ -464,7 +466,7 @@ def lfilter(pro, coeffs, axis, zi=None):
     second order and below (``Notch`` always is, filtering/iir.py:391)."""
 
 
-def _filtfilt_ba_device(pro, coeffs, axis, _out=None):
+def _filtfilt_ba_device(pro, coeffs, axis, _out=None, _free=False):
     dv.require_cuda()
     cascade = _Cascade(_ba_to_sos(coeffs))
     z = np.atleast_1d(sps.lfilter_zi(*coeffs))        # numerical.py:487
@@ -504,7 +506,7 @@ def _resample_taps(L, M, fs, fir, kwargs):
     return np.asarray(fir(fpass, fstop, fs, gpass, gstop).coeffs, dtype=np.float64)
 
 
-def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, **kwargs):
+def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs):
     dv.require_cuda()
     nsamp = pro.shape[axis]
     if M >= nsamp:
@@ -526,9 +528,24 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, **kwargs):
     seen = 0                                       # input samples received
     # The values do not depend on the input blocking (one global resample_poly,
     # SURVEY 8a5), only the yield boundaries do: take upstream blocks as they come.
+    done = 0                                       # outputs already yielded (free mode)
     for chunk in device_chunks(src, axis, regrid=False, alloc=ring):
         ring.push(chunk)
         seen += chunk.shape[1]
+        if _free:
+            # A device consumer takes blocks of any size: emit every output whose
+            # input support has arrived, so the ring only ever holds the filter's
+            # reach instead of waiting for the reference's chunk boundary.
+            o_hi = total_out if seen >= nsamp else min(total_out, max(
+                done, ((seen - 1) * L - half) // M + 1))
+            if o_hi > done:
+                out = _new_rows(_out, rows, o_hi - done)
+                yield plan.run(ring.window(), w_first, done, o_hi - done, out=out)
+                done = o_hi
+                keep_from = max((o_hi * M + half - (ntaps - 1)) // L - 2, w_first)
+                ring.drop(keep_from - w_first)
+                w_first = keep_from
+            continue
         while emitted < nchunks - 1:
             last_yield = emitted == nchunks - 2
             o_lo = emitted * per_chunk
@@ -641,7 +658,7 @@ def _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_):
 
 
 def _estimatives_device(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
-                        pad_left=0, pad_right=0, **kwargs):
+                        pad_left=0, pad_right=0, _out=None, _free=False, **kwargs):
     """Device rows (rows, nfreq[, 2]) per window, in order."""
     complex_ = func is modified_dft
     if func is not modified_dft and func is not periodogram:
