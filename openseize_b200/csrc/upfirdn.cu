@@ -107,17 +107,27 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
 
+    // Shared-memory position of window element i of lane l is
+    //   l*(R+1) + T(i),  T(i) = i + i/R   (ufd_phys of l*R + i, R a power of two).
+    // Along a run of taps the index advances by one per step, so with
+    // rem = (first index) % R fixed for the run, T(j+d) - T(j) = d + [rem + d >= R]
+    // (+1 more for d >= R): every load is `one of two base pointers + immediate`.
     int s = s_lo;
     while (s < s_hi) {
         const int p = s / Q, q0 = s - p * Q;
         int q1 = Q;
         if (p * Q + q1 > s_hi) q1 = s_hi - p * Q;
-        // window over X_p[lane*R + r + q], q = q0 .. q1-1
-        const double *xp = xs + p * ldm;
         const double *gp = gs + p * Q;
+        const unsigned uq = (unsigned)q0;
+        const unsigned rem = uq % R;
+        const double *pa = xs + p * ldm + lane * (R + 1) + (uq + uq / R);   // T(q0), crossing not passed
+        const double *pb = pa + 1;                                          // crossing passed
+        bool c[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) c[u] = rem + u >= R;
         double w[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) w[r] = xp[ufd_phys<R>(lane * R + r + q0)];
+        for (int r = 0; r < R; ++r) w[r] = (c[r] ? pb : pa)[r];
         int q = q0;
         for (; q + R <= q1; q += R) {
 #pragma unroll
@@ -125,8 +135,10 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
                 const double g = gp[q + u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(g, w[(r + u) % R], acc[r]);
-                w[u] = xp[ufd_phys<R>(lane * R + q + u + R)];
+                w[u] = (c[u] ? pb : pa)[u + R + 1];
             }
+            pa += R + 1;
+            pb += R + 1;
         }
         // remainder (< R taps): same rotation, guarded
 #pragma unroll
@@ -135,7 +147,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
                 const double g = gp[q + u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(g, w[(r + u) % R], acc[r]);
-                w[u] = xp[ufd_phys<R>(lane * R + q + u + R)];
+                w[u] = (c[u] ? pb : pa)[u + R + 1];
             }
         }
         s = p * Q + q1;
