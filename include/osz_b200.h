@@ -86,6 +86,11 @@ int osz_unpack_rows_c128(const double *src_dev, int64_t ld_src, int64_t outer, i
  * returns float64 for every input dtype). */
 int osz_widen_f32_f64(const float *src_dev, double *dst_dev, int64_t count, void *stream);
 int osz_widen_i16_f64(const int16_t *src_dev, double *dst_dev, int64_t count, void *stream);
+/* row-strided variants: chunk rows land inside a consumer's halo'd buffer */
+int osz_widen_rows_f32_f64(const float *src_dev, int64_t ld_src, double *dst_dev, int64_t ld_dst,
+                           int64_t rows, int64_t n, void *stream);
+int osz_widen_rows_i16_f64(const int16_t *src_dev, int64_t ld_src, double *dst_dev,
+                           int64_t ld_dst, int64_t rows, int64_t n, void *stream);
 
 /* ---- FIR: replaces _cconvolve + overlap-add of nm.oaconvolve
  *      (core/numerical.py:229-269) --------------------------------------- */

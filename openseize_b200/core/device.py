@@ -103,11 +103,37 @@ def upload(arr, layout, alloc=None):
     """
     t = require_cuda()
     a = np.asarray(arr)
-    if a.dtype != np.float64:
+    narrow = a.dtype in (np.float32, np.int16) and layout.inner == 1
+    if a.dtype != np.float64 and not narrow:
         a = a.astype(np.float64)
     n = a.shape[layout.axis]
     h2d, _ = _Streams.get()
     cur = t.cuda.current_stream()
+    if narrow:
+        # float32 / int16 recordings (EDF samples are int16) cross PCIe in their
+        # own width and are widened to float64 on the device -- the reference
+        # returns float64 for every input dtype.
+        tdt = t.float32 if a.dtype == np.float32 else t.int16
+        a2 = np.ascontiguousarray(a.reshape(layout.outer, n))
+        with t.cuda.stream(h2d):
+            raw = t.empty((layout.outer, n), dtype=tdt, device="cuda")
+            src = t.from_numpy(a2) if a2.flags.writeable else t.from_numpy(a2.copy())
+            if not src.is_pinned():
+                stage = t.empty((layout.outer, n), dtype=tdt, pin_memory=True)
+                stage.copy_(src)
+                src = stage
+            raw.copy_(src, non_blocking=True)
+            raw._osz_keepalive = src
+        cur.wait_stream(h2d)
+        raw.record_stream(cur)
+        dev = alloc(layout.outer, n) if alloc is not None else t.empty(
+            (layout.outer, n), dtype=t.float64, device="cuda")
+        lib = _abi.load()
+        fn = lib.osz_widen_rows_f32_f64 if a.dtype == np.float32 else lib.osz_widen_rows_i16_f64
+        ldd = dev.stride(0) if layout.outer > 1 else n
+        _abi.check(fn(_vp(raw.data_ptr()), n, _vp(dev.data_ptr()), ldd, layout.outer, n,
+                      _cur_stream()), "widen")
+        return dev
 
     def fence():
         # The H2D copy runs on a side stream so it overlaps the kernels of the

@@ -29,6 +29,7 @@ constexpr int FIR_NT = 128;   // threads per CTA
 constexpr int FIR_R = 15;     // outputs per thread (odd: conflict-free LDS.64 at stride R)
 constexpr int FIR_TILE = FIR_NT * FIR_R;
 constexpr int FIR_DIRECT_MAX_TAPS = 1024;
+constexpr int FIR_FFT_MAX_TAPS = 2049;     // one N = 8192 block: (N-K+1)/N >= 3/4
 
 __global__ void __launch_bounds__(FIR_NT, 4)
 fir_direct_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps, int kpad,
@@ -95,7 +96,7 @@ template <int LOG2N, int MINB>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::NT, MINB)
 fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
                const double2 *__restrict__ H /* N, scaled 1/N */, const double2 *__restrict__ tw,
-               double *__restrict__ y, int64_t ldy) {
+               double *__restrict__ y, int64_t ldy, int accumulate) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,8 +151,13 @@ fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int nta
         const int i = tid + r * NT;
         if (i >= k1) {
             // after the swap back: real part = v.y, imaginary part = v.x
-            if (i < out_a) st_stream(ya + r * NT, v[r].y);
-            if (i < out_b) st_stream(yb + r * NT, v[r].x);
+            if (accumulate) {   // a later partition of a filter longer than one block allows
+                if (i < out_a) ya[r * NT] += v[r].y;
+                if (i < out_b) yb[r * NT] += v[r].x;
+            } else {
+                if (i < out_a) st_stream(ya + r * NT, v[r].y);
+                if (i < out_b) st_stream(yb + r * NT, v[r].x);
+            }
         }
     }
 }
@@ -165,6 +171,10 @@ struct osz_fir_plan {
     int algo = OSZ_FIR_DIRECT;
     int kpad = 0;
     int log2n = 0;
+    // filters longer than FIR_FFT_MAX_TAPS: partitions of the taps, each a plan of
+    // its own; exec adds their valid convolutions (y = sum_p h_p * x shifted)
+    std::vector<osz_fir_plan *> parts;
+    std::vector<int> part_end;      // exclusive end tap index of each partition
     double *d_taps_rev = nullptr;   // direct
     double2 *d_H = nullptr;         // fft
     double2 *d_tw = nullptr;
@@ -172,7 +182,7 @@ struct osz_fir_plan {
 
 template <int LOG2N, int MINB>
 static int launch_fir_fft(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
-                          int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
+                          int64_t n_out, double *y, int64_t ldy, cudaStream_t st, int accumulate) {
     using C = FftCfg<LOG2N>;
     OSZ_CUDA(cudaFuncSetAttribute(fir_fft_kernel<LOG2N, MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -181,8 +191,8 @@ static int launch_fir_fft(const osz_fir_plan *p, const double *x, int64_t ldx, i
     const int64_t npairs = (nblocks + 1) / 2;
     if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "fir: more than 65535 rows per call");
     dim3 grid((unsigned)npairs, (unsigned)rows);
-    fir_fft_kernel<LOG2N, MINB><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, ldx, n_out, p->ntaps, p->d_H,
-                                                             p->d_tw, y, ldy);
+    fir_fft_kernel<LOG2N, MINB><<<grid, C::NT, C::SMEM_BYTES, st>>>(
+        x, ldx, n_out, p->ntaps, p->d_H, p->d_tw, y, ldy, accumulate);
     OSZ_LAUNCHED("fir_fft_kernel");
     return OSZ_OK;
 }
@@ -213,9 +223,20 @@ int osz_fir_plan_create(osz_fir_plan **out, const double *taps, int ntaps, int a
         else if (ntaps <= 2049)
             p->log2n = 13;
         else {
-            delete p;
-            return fail(OSZ_ERR_UNSUPPORTED,
-                        "osz_fir_plan_create: more than 2049 taps is not supported yet");
+            // partition the taps; every part is an ordinary N = 8192 plan
+            for (int t0 = 0; t0 < ntaps; t0 += FIR_FFT_MAX_TAPS) {
+                const int t1 = t0 + FIR_FFT_MAX_TAPS < ntaps ? t0 + FIR_FFT_MAX_TAPS : ntaps;
+                osz_fir_plan *part = nullptr;
+                int rc = osz_fir_plan_create(&part, taps + t0, t1 - t0, OSZ_FIR_FFT);
+                if (rc != OSZ_OK) {
+                    osz_fir_plan_destroy(p);
+                    return rc;
+                }
+                p->parts.push_back(part);
+                p->part_end.push_back(t1);
+            }
+            *out = p;
+            return OSZ_OK;
         }
         const int N = 1 << p->log2n;
         // H[k] = (1/N) sum_j taps[j] exp(-2 pi i j k / N), long double accumulation
@@ -254,6 +275,7 @@ int osz_fir_plan_create(osz_fir_plan **out, const double *taps, int ntaps, int a
 
 int osz_fir_plan_destroy(osz_fir_plan *p) {
     if (!p) return OSZ_OK;
+    for (osz_fir_plan *part : p->parts) osz_fir_plan_destroy(part);
     cudaFree(p->d_taps_rev);
     cudaFree(p->d_H);
     cudaFree(p->d_tw);
@@ -263,11 +285,30 @@ int osz_fir_plan_destroy(osz_fir_plan *p) {
 
 int osz_fir_plan_algo(const osz_fir_plan *p) { return p ? p->algo : 0; }
 
+static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                    int64_t n_out, double *y, int64_t ldy, cudaStream_t st, int accumulate);
+
 int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
                      int64_t n_out, double *y, int64_t ldy, void *stream) {
     if (!p || !x || !y) return fail(OSZ_ERR_ARG, "osz_fir_exec_f64: null argument");
     if (rows <= 0 || n_out <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
+    if (!p->parts.empty()) {
+        // taps [t0, t1) of the filter see the span shifted by ntaps - t1
+        for (size_t i = 0; i < p->parts.size(); ++i) {
+            int rc = fir_exec(p->parts[i], x + (p->ntaps - p->part_end[i]), ldx, rows, n_out, y,
+                              ldy, st, i > 0);
+            if (rc != OSZ_OK) return rc;
+        }
+        return OSZ_OK;
+    }
+    return fir_exec(p, x, ldx, rows, n_out, y, ldy, st, 0);
+}
+
+}  // extern "C"
+
+static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                    int64_t n_out, double *y, int64_t ldy, cudaStream_t st, int accumulate) {
     if (p->algo == OSZ_FIR_DIRECT) {
         const int xs_off = (16 + p->kpad * 8 + 127) & ~127;
         const int smem = xs_off + (FIR_TILE + p->kpad + FIR_R + 2) * 8;
@@ -288,10 +329,8 @@ int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_
             const char *e = getenv("OSZ_FIR_MINB");
             return e ? atoi(e) : 2;
         }();
-        if (minb == 3) return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st);
-        return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st);
+        if (minb == 3) return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st, accumulate);
+        return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st, accumulate);
     }
-    return launch_fir_fft<13, 1>(p, x, ldx, rows, n_out, y, ldy, st);
+    return launch_fir_fft<13, 1>(p, x, ldx, rows, n_out, y, ldy, st, accumulate);
 }
-
-}  // extern "C"

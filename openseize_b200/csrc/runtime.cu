@@ -65,6 +65,31 @@ __global__ void widen_kernel(const S *__restrict__ src, double *__restrict__ dst
     for (; i < count; i += step) dst[i] = (double)src[i];
 }
 
+template <typename S>
+__global__ void widen_rows_kernel(const S *__restrict__ src, int64_t ld_src,
+                                  double *__restrict__ dst, int64_t ld_dst, int64_t n) {
+    const int64_t row = blockIdx.y;
+    const S *s = src + row * ld_src;
+    double *d = dst + row * ld_dst;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) d[i] = (double)s[i];
+}
+
+template <typename S>
+static int launch_widen_rows(const S *src, int64_t ld_src, double *dst, int64_t ld_dst,
+                             int64_t rows, int64_t n, void *stream) {
+    if (rows <= 0 || n <= 0) return OSZ_OK;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "widen: more than 65535 rows per call");
+    int bx = (int)((n + 255) / 256);
+    const int cap = (sm_count() * 16 + (int)rows - 1) / (int)rows;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    widen_rows_kernel<S><<<dim3((unsigned)bx, (unsigned)rows), 256, 0, as_stream(stream)>>>(
+        src, ld_src, dst, ld_dst, n);
+    OSZ_LAUNCHED("widen_rows");
+    return OSZ_OK;
+}
+
 template <typename T, bool PACK>
 static int launch_transpose(const T *src, T *dst, int64_t outer, int64_t n, int64_t inner,
                             int64_t ld, void *stream) {
@@ -193,6 +218,15 @@ int osz_widen_i16_f64(const int16_t *src, double *dst, int64_t count, void *stre
     widen_kernel<int16_t><<<blocks, 256, 0, as_stream(stream)>>>(src, dst, count);
     OSZ_LAUNCHED("widen_i16");
     return OSZ_OK;
+}
+
+int osz_widen_rows_f32_f64(const float *src, int64_t ld_src, double *dst, int64_t ld_dst,
+                           int64_t rows, int64_t n, void *stream) {
+    return launch_widen_rows<float>(src, ld_src, dst, ld_dst, rows, n, stream);
+}
+int osz_widen_rows_i16_f64(const int16_t *src, int64_t ld_src, double *dst, int64_t ld_dst,
+                           int64_t rows, int64_t n, void *stream) {
+    return launch_widen_rows<int16_t>(src, ld_src, dst, ld_dst, rows, n, stream);
 }
 
 }  // extern "C"

@@ -89,6 +89,24 @@ def fir_oracle_sweep():
             close(got, ref)
 
 
+def narrow_input_dtypes():
+    """float32 / int16 chunks (EDF samples) travel narrow and come back float64
+    (reference dtype rule)."""
+    rng = np.random.default_rng(4)
+    filt = Kaiser(fpass=500, fstop=600, fs=5000)
+    for dtype in (np.float32, np.int16):
+        x = (rng.standard_normal((3, 20000)) * 1000).astype(dtype)
+        y = filt(producer(x, 6000, -1), 6000, axis=-1, mode="same").to_array()
+        assert y.dtype == np.float64
+        ref = np.concatenate(oracle.oaconvolve(x.astype(np.float64), filt.coeffs, 6000, -1,
+                                               "same"), -1)
+        close(y, ref)
+        cnt, f, p = psd(x, 1024, resolution=1.0)
+        rc, rf, rp = oracle.welch_psd(x.astype(np.float64), 1024, -1, 1.0)
+        assert cnt == rc
+        close(p, rp)
+
+
 # ------------------------------------------------------------------ IIR ----
 def iir_golden():
     g = golden("iir_butter8")

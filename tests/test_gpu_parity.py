@@ -42,6 +42,10 @@ def test_fir_oracle_sweep():
     pc.fir_oracle_sweep()
 
 
+def test_narrow_input_dtypes():
+    pc.narrow_input_dtypes()
+
+
 @pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("ntaps", [1, 2, 15, 16, 31, 113, 400, 671, 1025])
 def test_fir_kernels_vs_numpy(dv, algo, ntaps):
@@ -65,6 +69,18 @@ def test_fir_long_taps_block8192(dv):
     plan = dv.FirPlan(taps, 2)
     x = rng.standard_normal((2, 30000 + 1499))
     y = plan.run(_dev(dv, x), 30000).cpu().numpy()
+    ref = np.stack([np.convolve(r, taps, "valid") for r in x])
+    assert relerr(y, ref) < 1e-12
+
+
+def test_fir_partitioned_taps(dv):
+    """More than 2049 taps: the taps are partitioned and the partial
+    convolutions accumulated."""
+    rng = np.random.default_rng(6)
+    taps = rng.standard_normal(5000)
+    plan = dv.FirPlan(taps)
+    x = rng.standard_normal((2, 20000 + 4999))
+    y = plan.run(_dev(dv, x), 20000).cpu().numpy()
     ref = np.stack([np.convolve(r, taps, "valid") for r in x])
     assert relerr(y, ref) < 1e-12
 

@@ -18,6 +18,7 @@ from tests import parity_cases as pc
 
 
 def test_fir(fake_gpu):
+    pc.narrow_input_dtypes()
     pc.fir_golden()
     pc.fir_long_golden()
     pc.fir_oracle_sweep()
