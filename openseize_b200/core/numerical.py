@@ -506,6 +506,108 @@ def _resample_taps(L, M, fs, fir, kwargs):
     return np.asarray(fir(fpass, fstop, fs, gpass, gstop).coeffs, dtype=np.float64)
 
 
+class _Resampler:
+    """Computes output samples [o_lo, o_hi) of ``resample_poly(x, L, M, window=h)``
+    from a window of the input held on the device."""
+
+    def __init__(self, pro, h, L, M, axis):
+        self.source, self.nsamp_in = pro, pro.shape[axis]
+        self.plan = dv.UpfirdnPlan.cached(h, L, M)
+        self.reach = len(h)                        # taps of the filter the input sees
+        self.center = (len(h) - 1) // 2
+
+    def compute(self, window, w_first, o_lo, o_hi, out):
+        return self.plan.run(window, w_first, o_lo, o_hi - o_lo, out=out)
+
+
+class _FusedFirDecimator(_Resampler):
+    """``downsample(FIR(x))`` as ONE decimating filter.
+
+    An FIR stage in mode 'same' followed by decimation by M is, away from the
+    recording's ends, a single FIR with taps c = h_fir * h_antialias evaluated
+    at every M-th sample: K/M multiply-adds per input sample instead of a full
+    rate FIR plus a decimator, and the full-rate intermediate (2 x 8 bytes per
+    sample of HBM traffic) is never written.  The first and last few outputs
+    see the 'same'-mode truncation of the intermediate signal; they are
+    computed with the two unfused kernels on the edge samples only, so the
+    result equals the two-stage result everywhere (to rounding)."""
+
+    def __init__(self, fir_pro, fir_taps, h, M, axis):
+        inner = fir_pro.data.args[0]
+        self.source, self.nsamp_in = inner, inner.shape[axis]
+        self.k1, self.k2, self.M = len(fir_taps), len(h), M
+        self.left = (self.k1 - 1) // 2             # 'same' cuts of the FIR stage
+        self.right = self.k1 - 1 - self.left
+        self.half2 = (self.k2 - 1) // 2
+        self.ny = self.nsamp_in                    # 'same': FIR output length
+        fused = np.convolve(np.asarray(h, dtype=np.float64), fir_taps)
+        self.plan = dv.UpfirdnPlan.cached(fused, 1, M)
+        self.fir_plan = dv.FirPlan.cached(fir_taps)
+        self.dec_plan = dv.UpfirdnPlan.cached(h, 1, M)
+        self.reach = len(fused)
+        self.center = (len(fused) - 1) // 2
+        assert self.center == self.half2 + self.left
+        # outputs j_lo .. j_hi see an untruncated intermediate signal
+        self.j_lo = dv.ceil_div(self.k2 - 1 - self.half2, M)
+        self.j_hi = (self.ny - 1 - self.half2) // M
+
+    def _fir_span(self, window, w_first, u0, u1):
+        """FIR 'same' output samples [u0, u1) from the input window."""
+        rows = window.shape[0]
+        lo = u0 + self.left - (self.k1 - 1)        # first input sample needed
+        hi = u1 + self.left                        # exclusive
+        zl, zr = max(0, -lo), max(0, hi - self.nsamp_in)
+        core = window[:, max(lo, 0) - w_first:min(hi, self.nsamp_in) - w_first]
+        buf = dv.cat_time([dv.zeros_rows(rows, zl) if zl else None, core,
+                           dv.zeros_rows(rows, zr) if zr else None])
+        return self.fir_plan.run(buf, u1 - u0)
+
+    def compute(self, window, w_first, o_lo, o_hi, out):
+        if out is None:
+            out = dv.empty((window.shape[0], o_hi - o_lo))
+        a, b = max(o_lo, self.j_lo), min(o_hi, self.j_hi + 1)
+        if b > a:
+            self.plan.run(window, w_first, a, b - a, out=out[:, a - o_lo:b - o_lo])
+        if o_lo < self.j_lo:                       # left edge of the recording
+            e = min(o_hi, self.j_lo)
+            u1 = (e - 1) * self.M + self.half2 + 1
+            y = self._fir_span(window, w_first, 0, u1)
+            self.dec_plan.run(y, 0, o_lo, e - o_lo, out=out[:, :e - o_lo])
+        if o_hi > self.j_hi + 1:                   # right edge
+            s0 = max(o_lo, self.j_hi + 1)
+            u0 = max(0, s0 * self.M + self.half2 - (self.k2 - 1))
+            y = self._fir_span(window, w_first, u0, self.ny)
+            self.dec_plan.run(y, u0, s0, o_hi - s0, out=out[:, s0 - o_lo:])
+        return out
+
+
+def _fusable_fir(pro, L, M, ntaps2, axis):
+    """The (fir taps) of ``pro`` when it is an openseize_b200 FIR stage that can
+    be folded into the decimator that consumes it, else None."""
+    import os
+
+    if L != 1 or M < 2 or os.environ.get("OSZ_FUSE", "1") == "0":
+        return None
+    if not isinstance(pro, GenProducer) or pro.kwargs:
+        return None
+    func = pro.data
+    if not isinstance(func, functools.partial) or func.func is not oaconvolve:
+        return None
+    args, kw = func.args, func.keywords or {}
+    if len(args) != 4 or set(kw) - {"nfft_factor"}:
+        return None
+    inner, taps, fir_axis, mode = args
+    taps = np.asarray(taps, dtype=np.float64)
+    nd = len(pro.shape)
+    if mode != "same" or normalize_axis(fir_axis, nd) != normalize_axis(axis, nd):
+        return None
+    if len(taps) % 2 == 0 or ntaps2 % 2 == 0:      # centres must add up exactly
+        return None
+    if not isinstance(inner, Producer) or inner.shape[axis] < 4 * (len(taps) + ntaps2 + M):
+        return None
+    return taps
+
+
 def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs):
     dv.require_cuda()
     nsamp = pro.shape[axis]
@@ -514,53 +616,57 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs
                          .format(M, axis, nsamp))
     nsamp, csize, nchunks = _resample_geometry(pro, L, M, axis)
     h = _resample_taps(L, M, fs, fir, kwargs)
-    plan = dv.UpfirdnPlan.cached(h, L, M)
-    ntaps = len(h)
-    half = (ntaps - 1) // 2
     total_out = dv.ceil_div(nsamp * L, M)
     per_chunk = csize * L // M
     rows = _layout_of(pro, axis).rows
 
     src = producer(pro, csize, axis)               # same mutation as numerical.py:590
+    fir_taps = _fusable_fir(src, L, M, len(h), axis)
+    stage = (_FusedFirDecimator(src, fir_taps, h, M, axis) if fir_taps is not None
+             else _Resampler(src, h, L, M, axis))
+    n_in, center, reach = stage.nsamp_in, stage.center, stage.reach
     ring = _TimeRing(rows)                         # input window and its first global index
     w_first = 0
     emitted = 0                                    # yields done (the reference makes nchunks-1)
+    done = 0                                       # outputs already yielded (free mode)
     seen = 0                                       # input samples received
+
+    def trim(o_next):
+        # oldest input sample output o_next touches (2 samples of slack)
+        nonlocal w_first
+        keep_from = max((o_next * M + center - (reach - 1)) // L - 2, w_first)
+        ring.drop(keep_from - w_first)
+        w_first = keep_from
+
     # The values do not depend on the input blocking (one global resample_poly,
     # SURVEY 8a5), only the yield boundaries do: take upstream blocks as they come.
-    done = 0                                       # outputs already yielded (free mode)
-    for chunk in device_chunks(src, axis, regrid=False, alloc=ring):
+    for chunk in device_chunks(stage.source, axis, regrid=False, alloc=ring):
         ring.push(chunk)
         seen += chunk.shape[1]
         if _free:
             # A device consumer takes blocks of any size: emit every output whose
             # input support has arrived, so the ring only ever holds the filter's
             # reach instead of waiting for the reference's chunk boundary.
-            o_hi = total_out if seen >= nsamp else min(total_out, max(
-                done, ((seen - 1) * L - half) // M + 1))
+            o_hi = total_out if seen >= n_in else min(total_out, max(
+                done, ((seen - 1) * L - center) // M + 1))
             if o_hi > done:
                 out = _new_rows(_out, rows, o_hi - done)
-                yield plan.run(ring.window(), w_first, done, o_hi - done, out=out)
+                yield stage.compute(ring.window(), w_first, done, o_hi, out)
                 done = o_hi
-                keep_from = max((o_hi * M + half - (ntaps - 1)) // L - 2, w_first)
-                ring.drop(keep_from - w_first)
-                w_first = keep_from
+                trim(o_hi)
             continue
         while emitted < nchunks - 1:
             last_yield = emitted == nchunks - 2
             o_lo = emitted * per_chunk
             o_hi = total_out if last_yield else (emitted + 1) * per_chunk
             # newest input sample output o_hi-1 touches
-            need_hi = nsamp if last_yield else min(nsamp, ((o_hi - 1) * M + half) // L + 1)
+            need_hi = n_in if last_yield else min(n_in, ((o_hi - 1) * M + center) // L + 1)
             if seen < need_hi:
                 break
             out = _new_rows(_out, rows, o_hi - o_lo)
-            yield plan.run(ring.window(), w_first, o_lo, o_hi - o_lo, out=out)
+            yield stage.compute(ring.window(), w_first, o_lo, o_hi, out)
             emitted += 1
-            # oldest input sample the next yield touches (2 samples of slack)
-            keep_from = max((o_hi * M + half - (ntaps - 1)) // L - 2, w_first)
-            ring.drop(keep_from - w_first)
-            w_first = keep_from
+            trim(o_hi)
 
 
 def _polyphase_layout(pro, L, M, fs, fir, axis, **kwargs):

@@ -283,6 +283,43 @@ def spectra_oracle_sweep(fs=1024, resolutions=(1.0, 2.0, 4.0)):
     close(np.stack(list(Xp), -1), oracle.stft(x, fs, -1, resolutions[0])[2])
 
 
+def fused_fir_decimate():
+    """downsample(FIR(x)) is run as one decimating filter with the edges done by
+    the two unfused kernels: it must equal the reference's two stages on every
+    sample, for ragged lengths, chunk sizes and factors; OSZ_FUSE=0 (unfused
+    device chain) gives the same."""
+    import os
+
+    rng = np.random.default_rng(12)
+    fs = 5000
+    kais = Kaiser(fpass=500, fstop=600, fs=fs)                 # 113 taps
+    for n, cs, M in ((30011, 7000, 4), (52345, 10000, 10), (20000, 3333, 3), (41000, 41000, 5)):
+        x = rng.standard_normal((3, n)) + 2.0
+        r1 = np.concatenate(oracle.oaconvolve(x, kais.coeffs, cs, -1, "same"), -1)
+        ref_blocks = oracle.polyphase_resample(r1, 1, M, fs, cs, -1)
+        ref = np.concatenate(ref_blocks, -1)
+        for fuse in ("1", "0"):
+            os.environ["OSZ_FUSE"] = fuse
+            try:
+                pro = downsample(kais(producer(x, cs, -1), cs, axis=-1), M, fs, cs, axis=-1)
+                got_blocks = [np.array(b) for b in pro]
+            finally:
+                os.environ.pop("OSZ_FUSE", None)
+            got = np.concatenate(got_blocks, -1)
+            assert got.shape == ref.shape == pro.shape, (fuse, got.shape, ref.shape)
+            close(got, ref, tol=1e-12)
+            # the edges are where the fused filter alone would be wrong
+            close(got[:, :200], ref[:, :200], tol=1e-12)
+            close(got[:, -200:], ref[:, -200:], tol=1e-12)
+    # not fusable (mode 'valid'): plain device chain
+    x = rng.standard_normal((2, 30000))
+    r1 = np.concatenate(oracle.oaconvolve(x, kais.coeffs, 7000, -1, "valid"), -1)
+    ref = np.concatenate(oracle.polyphase_resample(r1, 1, 4, fs, 7000, -1), -1)
+    got = downsample(kais(producer(x, 7000, -1), 7000, axis=-1, mode="valid"), 4, fs, 7000,
+                     axis=-1).to_array()
+    close(got, ref, tol=1e-12)
+
+
 # ------------------------------------------------------------- pipeline ----
 def pipeline_chain():
     """Notch -> Kaiser FIR -> downsample -> psd, composed through producers

@@ -233,6 +233,10 @@ def test_pipeline_chain_on_device():
     pc.pipeline_chain()
 
 
+def test_fused_fir_decimate():
+    pc.fused_fir_decimate()
+
+
 def test_full_size_properties(dv):
     """BASELINE-sized chunk (64 rows x 1e6): size-independent properties --
     impulse response reproduces the taps, linearity, filter-then-PSD of a sine

@@ -43,6 +43,7 @@ def test_spectra(fake_gpu):
 
 def test_pipeline_chain(fake_gpu):
     pc.pipeline_chain()
+    pc.fused_fir_decimate()
 
 
 def test_no_cpu_fallback():
