@@ -21,6 +21,8 @@
 // after the last sample is written back, exactly as the reference carries `z`
 // between chunks.  All per-filter tables ride in the kernel parameter block
 // (constant bank), so concurrent plans never share mutable device state.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -29,9 +31,7 @@ namespace osz {
 
 constexpr int SOS_NT = 256;
 constexpr int SOS_T = 32;
-constexpr int SOS_BLK = SOS_NT * SOS_T;   // 8192
 constexpr int SOS_MAXSEC = 16;
-constexpr int SOS_LD = SOS_T + 1;         // padded smem row
 
 struct SosSec {
     double b0, b1, b2, a1, a2;
@@ -39,6 +39,7 @@ struct SosSec {
     double P[5][4];     // M^(2^k), row major
     double Q[4];        // M^32 (one warp)
     double A8[4];       // A^8: state transition over one 8-sample sub-piece
+    double A16[4];      // A^16: thread transition of the T = 16 kernel
 };
 struct SosParams {
     int nsec;
@@ -55,12 +56,21 @@ __device__ __forceinline__ void mat_apply(const double (&m)[4], double a0, doubl
     o1 = fma(m[2], a0, m[3] * a1);
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(SOS_NT, 2)
+// T = samples per thread: 32 for long cascades (less scan work per sample), 16
+// for one or two sections, where the kernel is bound by memory latency and the
+// smaller footprint (32 registers of samples, 35 KB of shared memory) lets four
+// CTAs share an SM instead of two.
+template <bool WRITE, int T>
+__global__ void __launch_bounds__(SOS_NT, (T == 32 ? 2 : 4))
 sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
                 int64_t n, int reverse, double *__restrict__ state, double *__restrict__ y,
-                int64_t ldy, const double *__restrict__ lanepow /* [sec][32][4] */) {
-    extern __shared__ __align__(16) double buf[];   // SOS_NT * SOS_LD
+                int64_t ldy, const double *__restrict__ lanepow /* [sec][32][4]: A^(T*(lane+1)) */) {
+    constexpr int BLK = SOS_NT * T;        // samples per CTA iteration
+    constexpr int LD = T + 1;              // padded shared-memory row
+    constexpr int LOGT = T == 32 ? 5 : 4;
+    constexpr int NCH = T / 8;             // independent 8-sample chains per thread
+    static_assert(T == 32 || T == 16, "T");
+    extern __shared__ __align__(16) double buf[];   // SOS_NT * LD
     __shared__ double wtot[SOS_NT / 32][2];
     __shared__ double carry[SOS_MAXSEC][2];
 
@@ -73,55 +83,57 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
 
     if (tid < nsec * 2) carry[tid >> 1][tid & 1] = st[tid];
 
-    const int64_t nblk = (n + SOS_BLK - 1) / SOS_BLK;
-    const int64_t first_len = n - (nblk - 1) * SOS_BLK;
+    const int64_t nblk = (n + BLK - 1) / BLK;
+    const int64_t first_len = n - (nblk - 1) * BLK;
 
     for (int64_t blk = 0; blk < nblk; ++blk) {
-        // The first block is the short one and sits at the END of the 8192
+        // The first block is the short one and sits at the END of the BLK
         // slots, behind `off` virtual zero samples that keep a zero state.
-        const int off = blk == 0 ? (int)(SOS_BLK - first_len) : 0;
-        const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * SOS_BLK;
+        const int off = blk == 0 ? (int)(BLK - first_len) : 0;
+        const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * BLK;
         __syncthreads();   // carry[] visible / buf free
         if (blk != 0) {
-            // full block: 32 independent coalesced loads in flight per thread
+            // full block: T independent coalesced loads in flight per thread
             const double *src = reverse ? xr + (n - 1 - pos0) - tid : xr + pos0 + tid;
-            double tmp[SOS_T];
+            double tmp[T];
 #pragma unroll
-            for (int it = 0; it < SOS_T; ++it)
+            for (int it = 0; it < T; ++it)
                 tmp[it] = ld_stream(reverse ? src - it * SOS_NT : src + it * SOS_NT);
 #pragma unroll
-            for (int it = 0; it < SOS_T; ++it) {
+            for (int it = 0; it < T; ++it) {
                 const int e = tid + it * SOS_NT;
-                buf[(e >> 5) * SOS_LD + (e & 31)] = tmp[it];
+                buf[(e >> LOGT) * LD + (e & (T - 1))] = tmp[it];
             }
         } else {
 #pragma unroll 8
-            for (int e = tid; e < SOS_BLK; e += SOS_NT) {
+            for (int e = tid; e < BLK; e += SOS_NT) {
                 double val = 0.0;
                 if (e >= off) {
                     const int64_t s = pos0 + (e - off);
                     val = ld_stream(xr + (reverse ? n - 1 - s : s));
                 }
-                buf[(e >> 5) * SOS_LD + (e & 31)] = val;
+                buf[(e >> LOGT) * LD + (e & (T - 1))] = val;
             }
         }
         __syncthreads();
-        double v[SOS_T];
+        double v[T];
 #pragma unroll
-        for (int i = 0; i < SOS_T; ++i) v[i] = buf[tid * SOS_LD + i];
+        for (int i = 0; i < T; ++i) v[i] = buf[tid * LD + i];
 
-        const int pstar = off >> 5, ioff = off & 31;
+        const int pstar = off >> LOGT, ioff = off & (T - 1);
         for (int s = 0; s < nsec; ++s) {
             const SosSec &c = prm.sec[s];
             const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
             double z0 = 0.0, z1 = 0.0;
             if (blk != 0) {
-                // Four independent 8-sample chains per thread (the single
-                // 32-sample chain left the FP64 pipe 2/3 idle waiting on its own
-                // results): sub-piece 0 starts from the thread's entering state
-                // (the carry for thread 0, else zero), sub-pieces 1..3 from zero
-                // and are fixed up in-thread with the same zero-input tables.
-                double za0[4] = {0.0, 0.0, 0.0, 0.0}, za1[4] = {0.0, 0.0, 0.0, 0.0};
+                // NCH independent 8-sample chains per thread (a single chain left
+                // the FP64 pipe 2/3 idle waiting on its own results): sub-piece 0
+                // starts from the thread's entering state (the carry for thread
+                // 0, else zero), the others from zero and are fixed up in-thread
+                // with the same zero-input tables.
+                double za0[NCH], za1[NCH];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) za0[j] = za1[j] = 0.0;
                 if (tid == 0) {
                     za0[0] = carry[s][0];
                     za1[0] = carry[s][1];
@@ -129,7 +141,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < NCH; ++j) {
                         const double xi = v[8 * j + i];
                         const double yi = fma(b0, xi, za0[j]);
                         za0[j] = fma(na1, yi, fma(b1, xi, za1[j]));
@@ -139,7 +151,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 }
                 double e0 = za0[0], e1 = za1[0];           // state at the end of sub-piece 0
 #pragma unroll
-                for (int j = 1; j < 4; ++j) {
+                for (int j = 1; j < NCH; ++j) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         v[8 * j + i] = fma(c.g0[i], e0, fma(c.g1[i], e1, v[8 * j + i]));
@@ -154,7 +166,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 const bool inj = tid == pstar;
                 const double c0 = carry[s][0], c1 = carry[s][1];
 #pragma unroll
-                for (int i = 0; i < SOS_T; ++i) {
+                for (int i = 0; i < T; ++i) {
                     if (inj && i == ioff) {
                         z0 = c0;
                         z1 = c1;
@@ -166,15 +178,17 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                     v[i] = yi;
                 }
             }
-            // ---- warp-inclusive scan of e_p = M e_{p-1} + f_p
+            // ---- warp-inclusive scan of e_p = M e_{p-1} + f_p, M = A^T:
+            //      M^(2^k) is P[k] for T = 32 and {A16, P[0..3]} for T = 16
             double f0 = z0, f1 = z1;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
+                const double *pm = T == 32 ? c.P[k] : (k == 0 ? c.A16 : c.P[k - 1]);
                 const double g0 = __shfl_up_sync(0xffffffffu, f0, 1 << k);
                 const double g1 = __shfl_up_sync(0xffffffffu, f1, 1 << k);
                 if (lane >= (1 << k)) {
-                    f0 += fma(c.P[k][0], g0, c.P[k][1] * g1);
-                    f1 += fma(c.P[k][2], g0, c.P[k][3] * g1);
+                    f0 += fma(pm[0], g0, pm[1] * g1);
+                    f1 += fma(pm[2], g0, pm[3] * g1);
                 }
             }
             if (lane == 31) {
@@ -182,11 +196,12 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 wtot[warp][1] = f1;
             }
             __syncthreads();
-            // ---- state entering this warp
+            // ---- state entering this warp (transition over one warp: M^32)
+            const double *qm = T == 32 ? c.Q : c.P[4];
             double cw0 = 0.0, cw1 = 0.0;
             for (int u = 0; u < warp; ++u) {
-                const double t0 = fma(c.Q[0], cw0, c.Q[1] * cw1) + wtot[u][0];
-                const double t1 = fma(c.Q[2], cw0, c.Q[3] * cw1) + wtot[u][1];
+                const double t0 = fma(qm[0], cw0, qm[1] * cw1) + wtot[u][0];
+                const double t1 = fma(qm[2], cw0, qm[3] * cw1) + wtot[u][1];
                 cw0 = t0;
                 cw1 = t1;
             }
@@ -204,7 +219,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             // zero-input response of the entering state (it is exactly zero for
             // every thread up to and including the one that injected the carry)
 #pragma unroll
-            for (int i = 0; i < SOS_T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
+            for (int i = 0; i < T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
             if (tid == SOS_NT - 1) {
                 carry[s][0] = e0;
                 carry[s][1] = e1;
@@ -213,13 +228,24 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
         }
         if (WRITE) {
 #pragma unroll
-            for (int i = 0; i < SOS_T; ++i) buf[tid * SOS_LD + i] = v[i];
+            for (int i = 0; i < T; ++i) buf[tid * LD + i] = v[i];
             __syncthreads();
+            if (blk != 0) {
+                double *dst = reverse ? yr + (n - 1 - pos0) - tid : yr + pos0 + tid;
+#pragma unroll
+                for (int it = 0; it < T; ++it) {
+                    const int e = tid + it * SOS_NT;
+                    st_stream(reverse ? dst - it * SOS_NT : dst + it * SOS_NT,
+                              buf[(e >> LOGT) * LD + (e & (T - 1))]);
+                }
+            } else {
 #pragma unroll 4
-            for (int e = tid; e < SOS_BLK; e += SOS_NT) {
-                if (e >= off) {
-                    const int64_t s = pos0 + (e - off);
-                    st_stream(yr + (reverse ? n - 1 - s : s), buf[(e >> 5) * SOS_LD + (e & 31)]);
+                for (int e = tid; e < BLK; e += SOS_NT) {
+                    if (e >= off) {
+                        const int64_t s = pos0 + (e - off);
+                        st_stream(yr + (reverse ? n - 1 - s : s),
+                                  buf[(e >> LOGT) * LD + (e & (T - 1))]);
+                    }
                 }
             }
         }
@@ -244,7 +270,8 @@ using namespace osz;
 
 struct osz_sos_plan {
     SosParams prm;
-    double *d_lanepow = nullptr;
+    int T = 32;                     // samples per thread of the kernel this plan uses
+    double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
 };
 
 namespace {
@@ -267,6 +294,12 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
     osz_sos_plan *p = new osz_sos_plan();
     p->prm.nsec = nsec;
     p->prm.pad_ = 0;
+    {
+        // OSZ_SOS_T=16|32 overrides the choice (tuning / tests)
+        const char *e = getenv("OSZ_SOS_T");
+        p->T = e ? atoi(e) : (nsec <= 2 ? 16 : 32);
+        if (p->T != 16 && p->T != 32) p->T = 32;
+    }
     std::vector<double> lanepow((size_t)nsec * 32 * 4);
     for (int s = 0; s < nsec; ++s) {
         const double *r = sos + 6 * s;
@@ -284,6 +317,12 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         const M2 A = {-(long double)c.a1, 1.0L, -(long double)c.a2, 0.0L};
         M2 pw = {1.0L, 0.0L, 0.0L, 1.0L};   // A^i
         for (int i = 0; i < SOS_T; ++i) {
+            if (i == 16) {
+                c.A16[0] = (double)pw.a;
+                c.A16[1] = (double)pw.b;
+                c.A16[2] = (double)pw.c;
+                c.A16[3] = (double)pw.d;
+            }
             if (i == 8) {
                 c.A8[0] = (double)pw.a;
                 c.A8[1] = (double)pw.b;
@@ -307,14 +346,16 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         c.Q[1] = (double)q.b;
         c.Q[2] = (double)q.c;
         c.Q[3] = (double)q.d;
-        M2 lp = M;                           // M^(lane+1)
+        M2 Mt = M;                           // thread transition A^T
+        if (p->T == 16) Mt = {c.A16[0], c.A16[1], c.A16[2], c.A16[3]};
+        M2 lp = Mt;                          // Mt^(lane+1)
         for (int l = 0; l < 32; ++l) {
             double *d = &lanepow[((size_t)s * 32 + l) * 4];
             d[0] = (double)lp.a;
             d[1] = (double)lp.b;
             d[2] = (double)lp.c;
             d[3] = (double)lp.d;
-            lp = mul(M, lp);
+            lp = mul(Mt, lp);
         }
     }
     for (int s = nsec; s < SOS_MAXSEC; ++s) p->prm.sec[s] = SosSec{};
@@ -340,19 +381,20 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_exec_f64: null argument");
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
-    const int smem = SOS_NT * SOS_LD * 8;
+    const int smem = SOS_NT * (p->T + 1) * 8;
+#define OSZ_SOS_LAUNCH(W, TT)                                                                   \
+    do {                                                                                        \
+        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+        sos_scan_kernel<W, TT><<<(unsigned)rows, SOS_NT, smem, st>>>(                           \
+            p->prm, x, ldx, n, reverse, state, y, ldy, p->d_lanepow);                           \
+    } while (0)
     if (y) {
-        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        sos_scan_kernel<true><<<(unsigned)rows, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse,
-                                                                    state, y, ldy, p->d_lanepow);
+        if (p->T == 16) OSZ_SOS_LAUNCH(true, 16); else OSZ_SOS_LAUNCH(true, 32);
     } else {
-        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        sos_scan_kernel<false><<<(unsigned)rows, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse,
-                                                                     state, nullptr, 0,
-                                                                     p->d_lanepow);
+        if (p->T == 16) OSZ_SOS_LAUNCH(false, 16); else OSZ_SOS_LAUNCH(false, 32);
     }
+#undef OSZ_SOS_LAUNCH
     OSZ_LAUNCHED("sos_scan_kernel");
     return OSZ_OK;
 }

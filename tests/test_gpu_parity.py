@@ -93,13 +93,23 @@ def test_iir_oracle_sweep():
     pc.iir_oracle_sweep()
 
 
-@pytest.mark.parametrize("n", [1, 31, 32, 33, 8191, 8192, 8193, 16384, 50001])
-def test_sos_kernel_vs_scipy(dv, n):
+@pytest.mark.parametrize("kind", ["butter8", "notch", "lowpass2"])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 8191, 8192, 8193,
+                               16384, 50001])
+def test_sos_kernel_vs_scipy(dv, n, kind):
     """Scan kernel vs the sequential DF2T recurrence: forward and reversed,
-    random initial state, output and final state; C2's 8-section band-pass whose
-    poles sit at radius 0.99978 (hard part 2)."""
+    random initial state, output and final state.  butter8 is C2's 8-section
+    band-pass whose poles sit at radius 0.99978 (hard part 2) and runs
+    the 32-samples-per-thread kernel; the one- and two-section filters run the
+    16-samples-per-thread kernel."""
     rng = np.random.default_rng(n)
-    sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+    if kind == "butter8":
+        sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+    elif kind == "notch":
+        b, a = sps.iirnotch(60, 10, fs=30000)
+        sos = np.concatenate([b, a])[None]
+    else:
+        sos = sps.butter(4, 300, fs=5000, output="sos")
     plan = dv.SosPlan(sos)
     rows = 3
     x = rng.standard_normal((rows, n)) + 1.0
