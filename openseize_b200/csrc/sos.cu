@@ -21,6 +21,7 @@
 // after the last sample is written back, exactly as the reference carries `z`
 // between chunks.  All per-filter tables ride in the kernel parameter block
 // (constant bank), so concurrent plans never share mutable device state.
+#include <math.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -63,8 +64,10 @@ __device__ __forceinline__ void mat_apply(const double (&m)[4], double a0, doubl
 template <bool WRITE, int T>
 __global__ void __launch_bounds__(SOS_NT, (T == 32 ? 2 : 4))
 sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
-                int64_t n, int reverse, double *__restrict__ state, double *__restrict__ y,
-                int64_t ldy, const double *__restrict__ lanepow /* [sec][32][4]: A^(T*(lane+1)) */) {
+                int64_t n_total, int reverse, const double *__restrict__ state_in,
+                double *__restrict__ state, double *__restrict__ y, int64_t ldy,
+                const double *__restrict__ lanepow /* [sec][32][4]: A^(T*(lane+1)) */,
+                int64_t span_len, int64_t settle) {
     constexpr int BLK = SOS_NT * T;        // samples per CTA iteration
     constexpr int LD = T + 1;              // padded shared-memory row
     constexpr int LOGT = T == 32 ? 5 : 4;
@@ -77,11 +80,26 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t row = blockIdx.x;
     const int nsec = prm.nsec;
-    const double *xr = x + row * ldx;
-    double *yr = WRITE ? y + row * ldy : nullptr;
     double *st = state + row * nsec * 2;
 
-    if (tid < nsec * 2) carry[tid >> 1][tid & 1] = st[tid];
+    // Time split: span k of a row covers logical samples [a, b).  Spans after
+    // the first warm the filter up from a zero state over the `settle` samples
+    // before `a` (a stable cascade has forgotten its starting state by then, to
+    // ~1e-24 relative) and store nothing for them.  Span 0 starts from the
+    // carried state; the last span writes the state that is carried on.
+    const int64_t span = blockIdx.y;
+    const int64_t a = span * span_len;
+    int64_t b = a + span_len;
+    if (b > n_total) b = n_total;
+    const int64_t w0 = span == 0 ? 0 : a - settle;      // first logical sample processed
+    const int64_t n = b - w0;                           // samples this CTA runs through
+    const int64_t keep = a - w0;                        // local index of the first stored sample
+    // logical sample s (local) <-> global index: forward w0 + s, reverse n_total-1-(w0+s)
+    const double *xr = x + row * ldx + (reverse ? n_total - 1 - w0 : w0);
+    double *yr = WRITE ? y + row * ldy + (reverse ? n_total - 1 - w0 : w0) : nullptr;
+
+    if (tid < nsec * 2)
+        carry[tid >> 1][tid & 1] = span == 0 ? state_in[row * nsec * 2 + tid] : 0.0;
 
     const int64_t nblk = (n + BLK - 1) / BLK;
     const int64_t first_len = n - (nblk - 1) * BLK;
@@ -94,7 +112,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
         __syncthreads();   // carry[] visible / buf free
         if (blk != 0) {
             // full block: T independent coalesced loads in flight per thread
-            const double *src = reverse ? xr + (n - 1 - pos0) - tid : xr + pos0 + tid;
+            const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
             double tmp[T];
 #pragma unroll
             for (int it = 0; it < T; ++it)
@@ -110,7 +128,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 double val = 0.0;
                 if (e >= off) {
                     const int64_t s = pos0 + (e - off);
-                    val = ld_stream(xr + (reverse ? n - 1 - s : s));
+                    val = ld_stream(reverse ? xr - s : xr + s);
                 }
                 buf[(e >> LOGT) * LD + (e & (T - 1))] = val;
             }
@@ -226,12 +244,12 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             }
             __syncthreads();   // wtot reusable, carry[s] published
         }
-        if (WRITE) {
+        if (WRITE && pos0 + (BLK - off) > keep) {       // block holds samples to store
 #pragma unroll
             for (int i = 0; i < T; ++i) buf[tid * LD + i] = v[i];
             __syncthreads();
-            if (blk != 0) {
-                double *dst = reverse ? yr + (n - 1 - pos0) - tid : yr + pos0 + tid;
+            if (blk != 0 && pos0 >= keep) {
+                double *dst = reverse ? yr - pos0 - tid : yr + pos0 + tid;
 #pragma unroll
                 for (int it = 0; it < T; ++it) {
                     const int e = tid + it * SOS_NT;
@@ -241,17 +259,21 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             } else {
 #pragma unroll 4
                 for (int e = tid; e < BLK; e += SOS_NT) {
-                    if (e >= off) {
-                        const int64_t s = pos0 + (e - off);
-                        st_stream(yr + (reverse ? n - 1 - s : s),
-                                  buf[(e >> LOGT) * LD + (e & (T - 1))]);
-                    }
+                    const int64_t s = pos0 + (e - off);
+                    if (e >= off && s >= keep)
+                        st_stream(reverse ? yr - s : yr + s, buf[(e >> LOGT) * LD + (e & (T - 1))]);
                 }
             }
         }
     }
     __syncthreads();
-    if (tid < nsec * 2) st[tid] = carry[tid >> 1][tid & 1];
+    if (span == gridDim.y - 1 && tid < nsec * 2) st[tid] = carry[tid >> 1][tid & 1];
+}
+
+__global__ void sos_copy_state_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                      int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[i];
 }
 
 __global__ void sos_state_from_sample_kernel(SosZi zi, int nsec, const double *__restrict__ x,
@@ -271,6 +293,7 @@ using namespace osz;
 struct osz_sos_plan {
     SosParams prm;
     int T = 32;                     // samples per thread of the kernel this plan uses
+    int64_t settle = -1;            // samples after which the start state is forgotten (-1: never)
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
 };
 
@@ -295,13 +318,29 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
     p->prm.nsec = nsec;
     p->prm.pad_ = 0;
     {
-        // OSZ_SOS_T=16|32 overrides the choice (tuning / tests)
+        // One CTA per row: with rows CTAs in the grid the smaller footprint of
+        // T = 16 buys no extra residency, and it measured slower (notch, 256 rows:
+        // 1.02 ms vs 0.92 ms; 8 sections: 3.67 vs 2.74 ms).  T = 32 is the default;
+        // OSZ_SOS_T=16 selects the other build (tests exercise both).
         const char *e = getenv("OSZ_SOS_T");
-        p->T = e ? atoi(e) : (nsec <= 2 ? 16 : 32);
+        p->T = e ? atoi(e) : 32;
         if (p->T != 16 && p->T != 32) p->T = 32;
     }
     std::vector<double> lanepow((size_t)nsec * 32 * 4);
+    double rmax = 0.0;              // largest pole radius of the cascade
     for (int s = 0; s < nsec; ++s) {
+        {
+            const double a0 = sos[6 * s + 3], a1 = sos[6 * s + 4] / a0, a2 = sos[6 * s + 5] / a0;
+            const double disc = a1 * a1 - 4.0 * a2;
+            double r;
+            if (disc < 0.0) {
+                r = sqrt(a2);
+            } else {
+                const double sq = sqrt(disc);
+                r = fmax(fabs((-a1 + sq) * 0.5), fabs((-a1 - sq) * 0.5));
+            }
+            if (r > rmax) rmax = r;
+        }
         const double *r = sos + 6 * s;
         const long double a0 = r[3];
         if (a0 == 0.0L) {
@@ -359,6 +398,9 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         }
     }
     for (int s = nsec; s < SOS_MAXSEC; ++s) p->prm.sec[s] = SosSec{};
+    if (rmax < 1.0)
+        p->settle = rmax <= 0.0 ? 2 * nsec
+                                : (int64_t)ceil(log(1e-24) / log(rmax)) + 64 * (int64_t)nsec;
     if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
             cudaSuccess) {
@@ -382,12 +424,40 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
     const int smem = SOS_NT * (p->T + 1) * 8;
+    // Spans per row: enough CTAs for ~4 waves, each span at least two settle
+    // lengths long so the warm-up stays a fraction of the work.  OSZ_SOS_SPLIT
+    // forces a count (1 = off).
+    int64_t nspan = 1;
+    if (p->settle > 0 && y) {       // a state-only pass wants the last span only
+        static const int forced = [] {
+            const char *e = getenv("OSZ_SOS_SPLIT");
+            return e ? atoi(e) : 0;
+        }();
+        const int64_t by_len = n / (2 * p->settle);
+        int64_t want = forced > 0 ? forced : (4 * (int64_t)sm_count() + rows - 1) / rows;
+        if (want > by_len) want = by_len;
+        if (want > 65535) want = 65535;
+        if (want > 1) nspan = want;
+    }
+    const int64_t span_len = (n + nspan - 1) / nspan;
+    const double *state_in = state;
+    double *tmp = nullptr;
+    if (nspan > 1) {
+        // the last span writes the carried state while span 0 may still read it
+        const int64_t count = rows * p->prm.nsec * 2;
+        OSZ_CUDA(cudaMallocAsync(&tmp, (size_t)count * 8, st));
+        sos_copy_state_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(state, tmp, count);
+        OSZ_LAUNCHED("sos_copy_state_kernel");
+        state_in = tmp;
+    }
+    const dim3 grid((unsigned)rows, (unsigned)nspan);
 #define OSZ_SOS_LAUNCH(W, TT)                                                                   \
     do {                                                                                        \
         OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-        sos_scan_kernel<W, TT><<<(unsigned)rows, SOS_NT, smem, st>>>(                           \
-            p->prm, x, ldx, n, reverse, state, y, ldy, p->d_lanepow);                           \
+        sos_scan_kernel<W, TT><<<grid, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse, state_in, \
+                                                           state, y, ldy, p->d_lanepow,         \
+                                                           span_len, p->settle);                \
     } while (0)
     if (y) {
         if (p->T == 16) OSZ_SOS_LAUNCH(true, 16); else OSZ_SOS_LAUNCH(true, 32);
@@ -395,6 +465,7 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         if (p->T == 16) OSZ_SOS_LAUNCH(false, 16); else OSZ_SOS_LAUNCH(false, 32);
     }
 #undef OSZ_SOS_LAUNCH
+    if (tmp) OSZ_CUDA(cudaFreeAsync(tmp, st));
     OSZ_LAUNCHED("sos_scan_kernel");
     return OSZ_OK;
 }
