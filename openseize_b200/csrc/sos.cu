@@ -294,6 +294,11 @@ struct osz_sos_plan {
     SosParams prm;
     int T = 32;                     // samples per thread of the kernel this plan uses
     int64_t settle = -1;            // samples after which the start state is forgotten (-1: never)
+    // Time-split launches read the initial state from a copy (the last span writes
+    // the carried state while span 0 may not have read it yet).  The copy lives in
+    // this plan-owned scratch, so a plan must not run on two streams at once.
+    mutable double *d_scratch = nullptr;
+    mutable int64_t scratch_count = 0;
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
 };
 
@@ -414,6 +419,7 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
 int osz_sos_plan_destroy(osz_sos_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_lanepow);
+    cudaFree(p->d_scratch);
     delete p;
     return OSZ_OK;
 }
@@ -424,9 +430,10 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
     const int smem = SOS_NT * (p->T + 1) * 8;
-    // Spans per row: enough CTAs for ~4 waves, each span at least two settle
-    // lengths long so the warm-up stays a fraction of the work.  OSZ_SOS_SPLIT
-    // forces a count (1 = off).
+    // Spans per row.  Splitting pays only while one CTA per row leaves SMs idle
+    // (rows <= SM count): 64 rows x 8 sections 1.83 -> 1.32 ms with 2 spans, but
+    // 256 rows 2.76 -> 3.27 ms (the warm-up is extra work on a full GPU).  Each
+    // span is at least two settle lengths long.  OSZ_SOS_SPLIT forces a count.
     int64_t nspan = 1;
     if (p->settle > 0 && y) {       // a state-only pass wants the last span only
         static const int forced = [] {
@@ -434,7 +441,11 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
             return e ? atoi(e) : 0;
         }();
         const int64_t by_len = n / (2 * p->settle);
-        int64_t want = forced > 0 ? forced : (4 * (int64_t)sm_count() + rows - 1) / rows;
+        int64_t want = 1;
+        if (forced > 0)
+            want = forced;
+        else if (rows <= sm_count())
+            want = (2 * (int64_t)sm_count() + rows - 1) / rows;
         if (want > by_len) want = by_len;
         if (want > 65535) want = 65535;
         if (want > 1) nspan = want;
@@ -445,7 +456,14 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (nspan > 1) {
         // the last span writes the carried state while span 0 may still read it
         const int64_t count = rows * p->prm.nsec * 2;
-        OSZ_CUDA(cudaMallocAsync(&tmp, (size_t)count * 8, st));
+        if (p->scratch_count < count) {
+            if (p->d_scratch) OSZ_CUDA(cudaFree(p->d_scratch));
+            p->d_scratch = nullptr;
+            p->scratch_count = 0;
+            OSZ_CUDA(cudaMalloc(&p->d_scratch, (size_t)count * 8));
+            p->scratch_count = count;
+        }
+        tmp = p->d_scratch;
         sos_copy_state_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(state, tmp, count);
         OSZ_LAUNCHED("sos_copy_state_kernel");
         state_in = tmp;
@@ -465,7 +483,6 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         if (p->T == 16) OSZ_SOS_LAUNCH(false, 16); else OSZ_SOS_LAUNCH(false, 32);
     }
 #undef OSZ_SOS_LAUNCH
-    if (tmp) OSZ_CUDA(cudaFreeAsync(tmp, st));
     OSZ_LAUNCHED("sos_scan_kernel");
     return OSZ_OK;
 }
