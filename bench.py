@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-named", action="store_true",
+                    help="skip the stand-alone FIR / Welch kernel timings")
     return ap.parse_args()
 
 
@@ -151,6 +153,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None      # wall-clock bounds of the timed region
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -165,7 +174,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc:
@@ -178,7 +187,12 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for stamp, line in self.lines:
+            # samples taken while the timed region ran (the sampler itself is
+            # started before the warm-up: nvidia-smi needs ~0.1 s to come up)
+            if self.t0 is not None and self.t1 is not None and not (
+                    self.t0 - 0.02 <= stamp <= self.t1 + 0.02):
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -278,6 +292,59 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def named_kernels(rows, chunk, hbm_peak):
+    """The two kernels BASELINE.json's north_star names (Kaiser-FIR oaconvolve
+    and Welch PSD), timed alone on an HBM-resident 256 x 1e6 chunk (2 GB, >> L2)
+    with CUDA events: 3 warm-up + 5 timed launches each."""
+    import scipy.signal as sps
+    import torch
+
+    from openseize_b200.core import device as dv
+    from openseize_b200.filtering.fir import Kaiser
+
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.mean(ms))
+
+    def entry(ms, ch_samples, bytes_per):
+        gbs = ch_samples * bytes_per / (ms * 1e-3) / 1e9
+        return {"ms": ms, "channel_samples_per_s": ch_samples / (ms * 1e-3),
+                "alg_bytes_per_sample": bytes_per, "achieved_GBps": gbs, "frac": gbs / hbm_peak}
+
+    for fs, label in ((30000, "fir_oaconvolve_kaiser671"), (5000, "fir_oaconvolve_kaiser113")):
+        taps = Kaiser(fpass=500, fstop=600, fs=fs).coeffs
+        plan = dv.FirPlan(taps)
+        x = torch.randn((rows, chunk + len(taps) - 1), dtype=torch.float64, device="cuda",
+                        generator=gen)
+        y = torch.empty((rows, chunk), dtype=torch.float64, device="cuda")
+        out[label] = entry(timed(lambda: plan.run(x, chunk, out=y)), rows * chunk, 16)
+        out[label]["taps"] = int(len(taps))
+        del x, y
+    w = sps.get_window("hann", NFFT)
+    plan = dv.SpecPlan(NFFT, NFFT // 2, w, "constant", 1.0 / (FS * float(np.sum(w ** 2))))
+    x = torch.randn((rows, chunk), dtype=torch.float64, device="cuda", generator=gen)
+    nseg = plan.nseg_available(chunk)
+    acc = dv.zeros((rows, NFFT // 2 + 1))
+    out["welch_psd_nfft4096"] = entry(timed(lambda: plan.welch_accum(x, nseg, acc)),
+                                      rows * nseg * plan.stride, 8)
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
@@ -334,7 +401,8 @@ def run_ours(args):
     marks = Marks(W, K, barrier)
     sampler = ClockSampler(local)
     launches = {}
-    marks.on_start = lambda: (sampler.start(), launches.__setitem__("a", _abi.launch_count()),
+    sampler.start()
+    marks.on_start = lambda: (sampler.mark_start(), launches.__setitem__("a", _abi.launch_count()),
                               setattr(dv, "TIMERS", {}))
     timers = {}
 
@@ -342,12 +410,13 @@ def run_ours(args):
         launches["b"] = _abi.launch_count()
         timers.update(dv.TIMERS or {})
         dv.TIMERS = None
-        sampler.stop()
+        sampler.mark_stop()
 
     marks.on_stop = on_stop
     src = device_source(pool, rows, chunk, nchunks, marks)
     cnt, freqs, est = run_psd(build_pipeline(src, chunk))
     torch.cuda.synchronize()
+    sampler.stop()
     secs = max_over_ranks(marks.seconds())
     value = world * K * rows * chunk / secs
     assert np.all(np.isfinite(est)) and est.shape == (rows, NFFT // 2 + 1)
@@ -375,6 +444,7 @@ def run_ours(args):
                     "share_of_step": kernels[dom]["ms_total"] / (secs * 1e3)}
     del pool, src
     torch.cuda.empty_cache()
+    named = named_kernels(rows, chunk, hbm_peak) if rank == 0 and not args.no_named else None
 
     # ---- e2e: pinned host chunks through the public API ----------------------
     e2e = None
@@ -414,6 +484,8 @@ def run_ours(args):
         }
         if roofline:
             line["roofline"] = roofline
+        if named:
+            line["named_kernels"] = named
         if e2e:
             line["e2e"] = e2e
         if cpu_line:
