@@ -72,10 +72,17 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                "openseize_b200: %s is missing -- build it with "
-                "`python -m openseize_b200.csrc.build` (or __graft_entry__.build()). "
-                "There is no CPU fallback." % LIB_PATH)
+            # Not a fallback: the only thing tried is compiling the CUDA library
+            # itself (nvcc, sm_100a).  Without nvcc the operators cannot run.
+            try:
+                from openseize_b200.csrc import build as _build
+
+                _build.build()
+            except Exception as exc:
+                raise RuntimeError(
+                    "openseize_b200: %s is missing and could not be built (%s) -- build it "
+                    "with `python -m openseize_b200.csrc.build` (or __graft_entry__.build()). "
+                    "There is no CPU fallback." % (LIB_PATH, exc))
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

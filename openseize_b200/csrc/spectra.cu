@@ -142,6 +142,14 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
 
     for (int64_t p = p0; p < p1; ++p) {
         double2 v[16];
+        if (p + 1 < p1) {
+            // pull the next pair's samples towards L2 while this pair is transformed
+            // (the loads below otherwise wait on DRAM: long_scoreboard was the top stall)
+            const double *nx = xr + 2 * (p + 1) * stride;
+            const int64_t span_elems = stride + N;              // samples the next pair reads
+            for (int64_t e = (int64_t)tid * 16; e < span_elems; e += (int64_t)NT * 16)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + e));
+        }
         load_pair<LOG2N, DETREND>(v, xr + 2 * p * stride, 2 * p + 1 < nseg, stride, win, red, tid);
         fft_r2r<LOG2N>(v, sm, ftw, tid);
 #pragma unroll
