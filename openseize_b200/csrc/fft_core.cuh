@@ -166,22 +166,42 @@ __device__ __forceinline__ double2 csqr(double2 a) {
     return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y);
 }
 
-// v[r] *= w^r for r = 1 .. R-1, powers from a depth-4 product tree.
+// High powers of a base twiddle: they only depend on the table entry, so a
+// ping-pong group computes them BEFORE it takes the FP64 token (this keeps the
+// serial squaring chain off the token's critical path).
+struct TwPre {
+    double2 w4, w8, w12;
+};
 template <int R>
-__device__ __forceinline__ void twiddle_pow(double2 *v, double2 w1) {
+__device__ __forceinline__ TwPre twiddle_pre(double2 w1) {
+    TwPre p;
+    p.w4 = p.w8 = p.w12 = make_double2(1.0, 0.0);
+    if constexpr (R >= 8) {
+        p.w4 = csqr(csqr(w1));
+        if constexpr (R >= 16) {
+            p.w8 = csqr(p.w4);
+            p.w12 = cmul(p.w8, p.w4);
+        }
+    }
+    return p;
+}
+
+// v[r] *= w^r for r = 1 .. R-1, powers from a shallow product tree.
+template <int R>
+__device__ __forceinline__ void twiddle_pow(double2 *v, double2 w1, const TwPre &pre) {
     if constexpr (R >= 2) v[1] = cmul(v[1], w1);
     if constexpr (R >= 4) {
         const double2 w2 = csqr(w1), w3 = cmul(w2, w1);
         v[2] = cmul(v[2], w2);
         v[3] = cmul(v[3], w3);
         if constexpr (R >= 8) {
-            const double2 w4 = csqr(w2);
+            const double2 w4 = pre.w4;
             v[4] = cmul(v[4], w4);
             v[5] = cmul(v[5], cmul(w4, w1));
             v[6] = cmul(v[6], cmul(w4, w2));
             v[7] = cmul(v[7], cmul(w4, w3));
             if constexpr (R >= 16) {
-                const double2 w8 = csqr(w4), w12 = cmul(w8, w4);
+                const double2 w8 = pre.w8, w12 = pre.w12;
                 v[8] = cmul(v[8], w8);
                 v[9] = cmul(v[9], cmul(w8, w1));
                 v[10] = cmul(v[10], cmul(w8, w2));
@@ -210,12 +230,107 @@ __device__ __forceinline__ FftTw fft_load_tw(const double2 *__restrict__ tw, int
     return t;
 }
 
-// One middle pass (radix R, sub-transform length Ns) over the CTA's N points,
-// in place in shared memory: every thread reads all its inputs, the CTA
+// ---- synchronisation policies ------------------------------------------------
+// The transform alternates FP64 phases (twiddle + butterfly, registers only)
+// with exchange phases (shared-memory stores/loads around a barrier).  Two
+// CTAs that merely share an SM fall into lock step -- both in an FP64 phase,
+// then both in an exchange phase, because the pipes are shared round-robin --
+// and each pipe idles half of the time (profiles/r01_ncu_summary.md: FP64
+// 50 % + LSU 55 %).  SyncPingPong runs TWO transforms in one CTA, one per
+// thread group, and passes an FP64 token between the groups with named
+// barriers, so that one group's twiddled butterflies overlap the other's
+// exchange.  ptxas moves arithmetic freely across BAR instructions, so the
+// token is tied to the data flow: the pass's base twiddle is read from shared
+// memory AFTER the acquiring barrier (every product of the pass depends on it),
+// and the releasing barrier's id is computed from the butterfly results.
+struct SyncCta {
+    FftTw t;
+    __device__ __forceinline__ void group() const { __syncthreads(); }
+    __device__ __forceinline__ double2 peek_m1() const { return t.m1; }
+    __device__ __forceinline__ double2 peek_m2() const { return t.m2; }
+    __device__ __forceinline__ double2 peek_last() const { return t.last; }
+    __device__ __forceinline__ double2 acquire(double2 peeked) const { return peeked; }
+    __device__ __forceinline__ void acquire_first(double2 (&)[16]) const {}
+    __device__ __forceinline__ void release(double2 (&)[16]) const {}
+};
+
+// Two groups of N/16 threads; barrier ids: 1+g group-local, 3+g "group g may
+// compute".  Group 1 calls prime() once before the main loop, group 0 drain()
+// once after it, and both groups execute the same number of acquire/release
+// pairs.  `tw_sm` is the CTA's shared-memory copy of the base-twiddle table,
+// `zero` an opaque 0 (a kernel argument the compiler cannot fold).
+template <int LOG2N>
+struct SyncPingPong {
+    using C = FftCfg<LOG2N>;
+    static constexpr int GT = C::NT;
+    int g, tid, zero;
+    const double2 *tw_sm;
+    __device__ __forceinline__ void group() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
+    }
+    // Wait for the token; returns an opaque 0 that exists only after the wait (a
+    // clock read masked by `zero`).  XOR-ing it into an operand of the phase's
+    // arithmetic is the data dependency that keeps ptxas from hoisting that
+    // arithmetic above the barrier.  (A shared-memory read after the barrier
+    // would do the same, but it queues behind the other group's exchange
+    // traffic: 180 cycles per phase in the first version.)
+    __device__ __forceinline__ int take() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "n"(2 * GT) : "memory");
+        int c;
+        asm volatile("mov.u32 %0, %%clock;" : "=r"(c)::"memory");
+        return c & zero;
+    }
+    static __device__ __forceinline__ double tie(double a, int t) {
+        return __hiloint2double(__double2hiint(a) ^ t, __double2loint(a));
+    }
+    __device__ __forceinline__ double2 taken(double2 w) const {
+        const int t = take();
+        return make_double2(tie(w.x, t), tie(w.y, t));
+    }
+    __device__ __forceinline__ double2 peek_m1() const { return tw_sm[C::OFF_M1 + (tid & 15)]; }
+    __device__ __forceinline__ double2 peek_m2() const {
+        return tw_sm[C::OFF_M2 + (tid & (16 * C::R1 - 1))];
+    }
+    __device__ __forceinline__ double2 peek_last() const { return tw_sm[C::OFF_L + tid]; }
+    __device__ __forceinline__ double2 acquire(double2 peeked) const { return taken(peeked); }
+    // Token for the twiddle-free first pass: tie the four values every
+    // first-stage butterfly starts from.
+    __device__ __forceinline__ void acquire_first(double2 (&v)[16]) const {
+        const int t = take();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = make_double2(tie(v[r].x, t), tie(v[r].y, t));
+    }
+    // Pass the token on.  The barrier id is computed from the results of the
+    // last butterfly stage (two outputs of each final 4-point butterfly), so the
+    // arrive cannot be scheduled ahead of the arithmetic.
+    __device__ __forceinline__ void release(double2 (&v)[16]) const {
+        int t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            t[q] = __double2hiint(v[q].x) | __double2hiint(v[q].y) | __double2hiint(v[q + 4].x) |
+                   __double2hiint(v[q + 4].y);
+        const int u = ((t[0] | t[1]) | (t[2] | t[3])) & zero;
+        asm volatile("bar.arrive %0, %1;" ::"r"(4 - g + u), "n"(2 * GT) : "memory");
+    }
+    // a turn without work: shifts this group's phase sequence against the other's
+    __device__ __forceinline__ void idle_turn() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "n"(2 * GT) : "memory");
+        asm volatile("bar.arrive %0, %1;" ::"r"(4 - g), "n"(2 * GT) : "memory");
+    }
+    __device__ __forceinline__ void prime() const {
+        if (g == 1) asm volatile("bar.arrive 3, %0;" ::"n"(2 * GT) : "memory");
+    }
+    __device__ __forceinline__ void drain() const {
+        if (g == 0) asm volatile("bar.sync 3, %0;" ::"n"(2 * GT) : "memory");
+    }
+};
+
+// One middle pass (radix R, sub-transform length Ns) over the group's N points,
+// in place in shared memory: every thread reads all its inputs, the group
 // synchronises, then butterflies are written to their Stockham positions.
 // All of a thread's butterflies share k = tid mod Ns, hence one base twiddle.
-template <int N, int R, int NS>
-__device__ __forceinline__ void fft_mid_pass(double2 *sm, double2 w1, int tid) {
+template <int N, int R, int NS, bool FIRST_MID, class Sync>
+__device__ __forceinline__ void fft_mid_pass(double2 *sm, int tid, const Sync &sync) {
     constexpr int NT = N / 16;
     constexpr int PER = 16 / R;  // butterflies per thread
     static_assert(NT % NS == 0, "k must not depend on the butterfly index");
@@ -227,45 +342,77 @@ __device__ __forceinline__ void fft_mid_pass(double2 *sm, double2 w1, int tid) {
 #pragma unroll
         for (int r = 0; r < R; ++r) v[q * R + r] = src[fft_pad16(q * NT + r * (N / R))];
     }
-    __syncthreads();
+    const double2 wp = FIRST_MID ? sync.peek_m1() : sync.peek_m2();
+    const TwPre pre = twiddle_pre<R>(wp);
+    sync.group();
+    const double2 w1 = sync.acquire(wp);
     const int k = tid & (NS - 1);
     double2 *dst = sm + fft_phys((tid - k) * R + k);
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
-        twiddle_pow<R>(v + q * R, w1);
+        twiddle_pow<R>(v + q * R, w1, pre);
         bfly<R>(v + q * R);
+    }
+    sync.release(v);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
 #pragma unroll
         for (int r = 0; r < R; ++r) dst[fft_pad16(q * NT * R + r * NS)] = v[q * R + r];
     }
-    __syncthreads();
+    sync.group();
 }
 
 // Forward FFT, registers to registers (see file header).  `sm` must hold
-// FftCfg<LOG2N>::SMEM_ELEMS double2.  Contains its own leading barrier, so it
-// can be called back to back.
-template <int LOG2N>
-__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm, const FftTw &tw, int tid) {
+// FftCfg<LOG2N>::SMEM_ELEMS double2 (per group); `tid` is the index within the
+// group.  Contains its own leading barrier, so it can be called back to back.
+// The first pass (no twiddles) runs outside the FP64 token.  REL = false: the
+// caller continues with FP64 work after the last pass and calls
+// sync.release(v) itself.
+struct FftNoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `after_loads()` runs once the last pass has read its inputs: from then on the
+// transform no longer touches `sm` (callers refill it for the next item there).
+template <int LOG2N, class Sync, bool REL = true, class Hook = FftNoHook>
+__device__ __forceinline__ void fft_r2r_tail(double2 (&v)[16], double2 *sm, int tid,
+                                             const Sync &sync, const Hook &after_loads = Hook()) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT;
-    // pass 1: radix 16, Ns = 1, no twiddles
-    bfly<16>(v);
-    __syncthreads();  // previous users of sm are done
+    // (pass 1, a twiddle-free bfly<16>(v), has been done by the caller)
+    sync.group();  // previous users of sm are done
     {
         double2 *dst = sm + 17 * tid;     // fft_phys(16 * tid + r) = 17 * tid + r
 #pragma unroll
         for (int r = 0; r < 16; ++r) dst[r] = v[r];
     }
-    __syncthreads();
-    if constexpr (C::R1 > 1) fft_mid_pass<N, C::R1, 16>(sm, tw.m1, tid);
-    if constexpr (C::R2 > 1) fft_mid_pass<N, C::R2, 16 * C::R1>(sm, tw.m2, tid);
+    sync.group();
+    if constexpr (C::R1 > 1) fft_mid_pass<N, C::R1, 16, true>(sm, tid, sync);
+    if constexpr (C::R2 > 1) fft_mid_pass<N, C::R2, 16 * C::R1, false>(sm, tid, sync);
     // last pass: radix 16, Ns = N/16, k = tid, output index tid + r*NT
     {
         const double2 *src = sm + fft_phys(tid);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = src[fft_pad16(r * NT)];
     }
-    twiddle_pow<16>(v, tw.last);
+    const double2 wp = sync.peek_last();
+    const TwPre pre = twiddle_pre<16>(wp);
+    after_loads();
+    const double2 wl = sync.acquire(wp);
+    twiddle_pow<16>(v, wl, pre);
     bfly<16>(v);
+    if (REL) sync.release(v);
+}
+
+template <int LOG2N, class Sync, bool REL = true>
+__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm, int tid, const Sync &sync) {
+    bfly<16>(v);   // pass 1: radix 16, Ns = 1, no twiddles
+    fft_r2r_tail<LOG2N, Sync, REL>(v, sm, tid, sync);
+}
+
+template <int LOG2N>
+__device__ __forceinline__ void fft_r2r(double2 (&v)[16], double2 *sm, const FftTw &tw, int tid) {
+    fft_r2r<LOG2N, SyncCta>(v, sm, tid, SyncCta{tw});
 }
 
 // Host: base-twiddle tables for FftCfg<log2n>, as (re, im) pairs.

@@ -162,6 +162,208 @@ fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int nta
     }
 }
 
+// Ping-pong variant (N = 4096): one persistent CTA per SM, two thread groups,
+// each transforming its own pair of blocks; the groups alternate on the FP64
+// pipe (fft_core.cuh SyncPingPong) so one group's butterflies overlap the other
+// group's shared-memory exchanges and global traffic.  Work item w =
+// row * npairs + pair; group g of CTA c takes w = 2c + g, then strides by
+// 2 * gridDim.x.  Every group runs the same number of iterations (the token
+// protocol needs matching acquire/release counts); items past the end compute
+// on zeros and store nothing.
+//
+// The item's input span (both blocks: step + N contiguous samples) is fetched
+// by ONE 1-D TMA bulk copy into the group's own exchange buffer, issued as
+// soon as the previous item's last pass has read its inputs, so the DRAM
+// latency hides behind that item's last butterflies and its stores.  H is kept
+// as a half table in shared memory (real taps: H[N-k] = conj H[k]).
+template <int LOG2N>
+struct FirPP {
+    using C = FftCfg<LOG2N>;
+    static constexpr int NH = C::N / 2 + 1;
+    static constexpr int OFF_H = C::TW_TOTAL * 16;
+    static constexpr int OFF_BAR = OFF_H + NH * 16;
+    static constexpr int OFF_X = (OFF_BAR + 16 + 127) & ~127;
+    static constexpr int SMEM = OFF_X + 2 * C::SMEM_BYTES;
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+template <int LOG2N, bool ACC, int POLICY>
+__global__ void __launch_bounds__(2 * FftCfg<LOG2N>::NT, 1)
+fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
+                  const double2 *__restrict__ H, const double2 *__restrict__ tw,
+                  double *__restrict__ y, int64_t ldy, int64_t npairs, int64_t nwork, int iters,
+                  int lag, int zero) {
+    using C = FftCfg<LOG2N>;
+    using L = FirPP<LOG2N>;
+    using Sync = SyncPingPong<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g = threadIdx.x / NT;
+    const int tid = threadIdx.x - g * NT;
+    double2 *tw_sm = reinterpret_cast<double2 *>(smem_raw);
+    double2 *h_sm = reinterpret_cast<double2 *>(smem_raw + L::OFF_H);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR) + g;
+    double2 *sm = reinterpret_cast<double2 *>(smem_raw + L::OFF_X) + g * C::SMEM_ELEMS;
+    double *sx = reinterpret_cast<double *>(sm);      // the exchange buffer as the item's input span
+
+    for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
+    for (int i = threadIdx.x; i < L::NH; i += 2 * NT) h_sm[i] = ldg(H + i);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const Sync sync{g, tid, zero, tw_sm};
+
+    const int64_t step = N - ntaps + 1;
+    const int64_t span = n_out + ntaps - 1;
+    const int k1 = ntaps - 1;
+    const int64_t dw = 2 * (int64_t)gridDim.x;
+    const int64_t drow = dw / npairs, dpair = dw - drow * npairs;
+    int64_t w = 2 * (int64_t)blockIdx.x + g;
+    int64_t row = w / npairs, pair = w - row * npairs;
+
+    // thread 0 of the group: fetch the span of item (w_, row_, pair_) into sx
+    auto issue = [&](int64_t w_, int64_t row_, int64_t pair_) {
+        if (w_ >= nwork) return;
+        const double *src = x + row_ * ldx + pair_ * 2 * step;
+        const int64_t left = span - pair_ * 2 * step;           // samples readable from src
+        const int64_t need = left < step + N ? left : step + N;
+        const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+        int64_t cnt = need + mis;                               // from the 16-byte aligned src - mis
+        if (cnt & 1) {   // bulk copies move multiples of 16 bytes: odd tail by hand
+            sx[cnt - 1] = src[need - 1];
+            cnt -= 1;
+        }
+        mbar_expect_tx(bar, (uint32_t)cnt * 8u);                // (release: publishes the tail)
+        if (cnt > 0) tma_load_1d(sx, src - mis, (uint32_t)cnt * 8u, bar);
+    };
+    if (tid == 0) issue(w, row, pair);
+    sync.prime();
+    // Group 1 runs two turns behind group 0, so that a group's longest stretch
+    // without FP64 work (stores of one item + input of the next) coincides with
+    // the other group's longest FP64 phase (last pass + H + first inverse pass).
+    if (g == 1)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+
+    for (int it = 0; it < iters; ++it) {
+        const bool live = w < nwork;
+        const int64_t base_a = pair * 2 * step;
+        const int64_t left = span - base_a;
+        int64_t wn = w + dw, rown = row + drow, pairn = pair + dpair;
+        if (pairn >= npairs) {
+            pairn -= npairs;
+            ++rown;
+        }
+
+        double2 v[16];
+        if (live) {
+            const int mis = (int)((reinterpret_cast<uintptr_t>(x + row * ldx + base_a) >> 3) & 1);
+            const double *xa = sx + mis + tid, *xb = xa + step;
+            while (!mbar_try_wait(bar, it & 1)) {
+            }
+            if (left >= step + N) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = make_double2(xa[r * NT], xb[r * NT]);
+            } else {
+                const int lim_a = (int)(left > N ? N : left);
+                const int lim_b = (int)(left - step > N ? N : (left < step ? 0 : left - step));
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int i = tid + r * NT;
+                    v[r].x = i < lim_a ? xa[r * NT] : 0.0;
+                    v[r].y = i < lim_b ? xb[r * NT] : 0.0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = make_double2(0.0, 0.0);
+        }
+        if (POLICY & 1) sync.acquire_first(v);
+        bfly<16>(v);
+        if (POLICY & 1) sync.release(v);
+        fft_r2r_tail<LOG2N, Sync, (POLICY & 2) == 0>(v, sm, tid, sync);
+        // still holding the token: multiply by H and run the inverse transform's
+        // first (twiddle-free) pass
+        {
+            const double2 *hlo = h_sm + tid, *hhi = h_sm + 8 * NT - tid;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 p = cmul(v[r], hlo[r * NT]);
+                v[r] = make_double2(p.y, p.x);  // swap: inverse transform via the forward kernel
+            }
+#pragma unroll
+            for (int r = 8; r < 16; ++r) {
+                const double2 h = hhi[(8 - r) * NT];    // H[k] = conj H[N - k], N - k = (16-r) NT - tid
+                const double2 a = v[r];
+                v[r] = make_double2(fma(a.y, h.x, -a.x * h.y), fma(a.x, h.x, a.y * h.y));
+            }
+        }
+        bfly<16>(v);
+        if (POLICY & 2) sync.release(v);
+        fft_r2r_tail<LOG2N, Sync, true>(v, sm, tid, sync, [&]() {
+            sync.group();                 // every thread of the group has read its inputs
+            if (tid == 0) {
+                fence_proxy_async();
+                issue(wn, rown, pairn);
+            }
+        });
+
+        if (live) {
+            double *ya = y + row * ldy + base_a + tid - k1;
+            double *yb = ya + step;
+            const int64_t oa = n_out - base_a + k1, ob = oa - step;
+            // after the swap back: real part = v.y, imaginary part = v.x
+            if (ob >= N) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    if (tid + r * NT >= k1) {
+                        if (ACC) {   // a later partition of a filter longer than one block
+                            ya[r * NT] += v[r].y;
+                            yb[r * NT] += v[r].x;
+                        } else {
+                            st_stream(ya + r * NT, v[r].y);
+                            st_stream(yb + r * NT, v[r].x);
+                        }
+                    }
+                }
+            } else {
+                const int out_a = (int)(oa > N ? N : oa), out_b = (int)(ob < 0 ? 0 : ob);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int i = tid + r * NT;
+                    if (i >= k1) {
+                        if (ACC) {
+                            if (i < out_a) ya[r * NT] += v[r].y;
+                            if (i < out_b) yb[r * NT] += v[r].x;
+                        } else {
+                            if (i < out_a) st_stream(ya + r * NT, v[r].y);
+                            if (i < out_b) st_stream(yb + r * NT, v[r].x);
+                        }
+                    }
+                }
+            }
+        }
+        w = wn;
+        row = rown;
+        pair = pairn;
+    }
+    if (g == 0)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+    sync.drain();
+}
+
 }  // namespace osz
 
 using namespace osz;
@@ -195,6 +397,46 @@ static int launch_fir_fft(const osz_fir_plan *p, const double *x, int64_t ldx, i
         x, ldx, n_out, p->ntaps, p->d_H, p->d_tw, y, ldy, accumulate);
     OSZ_LAUNCHED("fir_fft_kernel");
     return OSZ_OK;
+}
+
+template <int LOG2N, bool ACC, int POLICY>
+static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                             int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
+    using C = FftCfg<LOG2N>;
+    constexpr int SMEM = FirPP<LOG2N>::SMEM;
+    OSZ_CUDA(cudaFuncSetAttribute(fir_fft_pp_kernel<LOG2N, ACC, POLICY>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int64_t step = C::N - p->ntaps + 1;
+    const int64_t nblocks = (n_out + step - 1) / step;
+    const int64_t npairs = (nblocks + 1) / 2;
+    const int64_t nwork = npairs * rows;
+    int64_t grid = (nwork + 1) / 2;
+    if (grid > sm_count()) grid = sm_count();
+    const int iters = (int)((nwork + 2 * grid - 1) / (2 * grid));
+    static const int lag = [] {
+        const char *e = getenv("OSZ_PP_LAG");
+        return e ? atoi(e) : 2;
+    }();
+    fir_fft_pp_kernel<LOG2N, ACC, POLICY><<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
+        x, ldx, n_out, p->ntaps, p->d_H, p->d_tw, y, ldy, npairs, nwork, iters, lag, 0);
+    OSZ_LAUNCHED("fir_fft_pp_kernel");
+    return OSZ_OK;
+}
+
+template <int LOG2N, bool ACC>
+static int launch_fir_fft_pp_policy(const osz_fir_plan *p, const double *x, int64_t ldx,
+                                    int64_t rows, int64_t n_out, double *y, int64_t ldy,
+                                    cudaStream_t st) {
+    static const int policy = [] {
+        const char *e = getenv("OSZ_PP_POLICY");
+        return e ? atoi(e) : 3;
+    }();
+    switch (policy) {
+        case 0: return launch_fir_fft_pp<LOG2N, ACC, 0>(p, x, ldx, rows, n_out, y, ldy, st);
+        case 1: return launch_fir_fft_pp<LOG2N, ACC, 1>(p, x, ldx, rows, n_out, y, ldy, st);
+        case 2: return launch_fir_fft_pp<LOG2N, ACC, 2>(p, x, ldx, rows, n_out, y, ldy, st);
+        default: return launch_fir_fft_pp<LOG2N, ACC, 3>(p, x, ldx, rows, n_out, y, ldy, st);
+    }
 }
 
 extern "C" {
@@ -329,6 +571,14 @@ static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t
             const char *e = getenv("OSZ_FIR_MINB");
             return e ? atoi(e) : 2;
         }();
+        static const int pp = [] {
+            const char *e = getenv("OSZ_FIR_PP");
+            return e ? atoi(e) : 1;
+        }();
+        if (pp)
+            return accumulate
+                       ? launch_fir_fft_pp_policy<12, true>(p, x, ldx, rows, n_out, y, ldy, st)
+                       : launch_fir_fft_pp_policy<12, false>(p, x, ldx, rows, n_out, y, ldy, st);
         if (minb == 3) return launch_fir_fft<12, 3>(p, x, ldx, rows, n_out, y, ldy, st, accumulate);
         return launch_fir_fft<12, 2>(p, x, ldx, rows, n_out, y, ldy, st, accumulate);
     }
