@@ -100,4 +100,39 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
         : "memory");
 }
 
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+// One thread: fetch `need` (> 0) contiguous doubles starting at `src` into the
+// shared buffer `dst` (16-byte aligned) with one bulk copy that completes on
+// `bar` (one arrival).  Bulk copies move multiples of 16 bytes between 16-byte
+// aligned addresses, so the copy starts at the aligned address at or below
+// `src` -- element i of the span lands at dst[span_mis(src) + i] -- and an odd
+// tail element is copied by hand before the (releasing) arrive.  Reading the
+// element below an unaligned `src` is safe: allocations start 256-byte aligned,
+// so it belongs to the same allocation.
+__device__ __forceinline__ int span_mis(const double *src) {
+    return (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+}
+__device__ __forceinline__ void tma_fetch_span(double *dst, const double *src, int64_t need,
+                                               uint64_t *bar) {
+    const int mis = span_mis(src);
+    int64_t cnt = need + mis;
+    if (cnt & 1) {
+        dst[cnt - 1] = src[need - 1];
+        cnt -= 1;
+    }
+    mbar_expect_tx(bar, (uint32_t)cnt * 8u);
+    if (cnt > 0) tma_load_1d(dst, src - mis, (uint32_t)cnt * 8u, bar);
+}
+
 }  // namespace osz

@@ -186,18 +186,6 @@ struct FirPP {
     static constexpr int SMEM = OFF_X + 2 * C::SMEM_BYTES;
 };
 
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    return ok != 0;
-}
-
 template <int LOG2N, bool ACC, int POLICY>
 __global__ void __launch_bounds__(2 * FftCfg<LOG2N>::NT, 1)
 fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
@@ -239,15 +227,7 @@ fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int 
         if (w_ >= nwork) return;
         const double *src = x + row_ * ldx + pair_ * 2 * step;
         const int64_t left = span - pair_ * 2 * step;           // samples readable from src
-        const int64_t need = left < step + N ? left : step + N;
-        const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
-        int64_t cnt = need + mis;                               // from the 16-byte aligned src - mis
-        if (cnt & 1) {   // bulk copies move multiples of 16 bytes: odd tail by hand
-            sx[cnt - 1] = src[need - 1];
-            cnt -= 1;
-        }
-        mbar_expect_tx(bar, (uint32_t)cnt * 8u);                // (release: publishes the tail)
-        if (cnt > 0) tma_load_1d(sx, src - mis, (uint32_t)cnt * 8u, bar);
+        tma_fetch_span(sx, src, left < step + N ? left : step + N, bar);
     };
     if (tid == 0) issue(w, row, pair);
     sync.prime();
@@ -269,8 +249,7 @@ fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int 
 
         double2 v[16];
         if (live) {
-            const int mis = (int)((reinterpret_cast<uintptr_t>(x + row * ldx + base_a) >> 3) & 1);
-            const double *xa = sx + mis + tid, *xb = xa + step;
+            const double *xa = sx + span_mis(x + row * ldx + base_a) + tid, *xb = xa + step;
             while (!mbar_try_wait(bar, it & 1)) {
             }
             if (left >= step + N) {

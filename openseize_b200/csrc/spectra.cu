@@ -15,6 +15,8 @@
 //
 // Other nfft (not a power of two, or outside 256..8192) use the generic path
 // in spectra_generic.cu.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -168,6 +170,207 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
     }
 }
 
+// Ping-pong Welch (256 <= nfft <= 4096): one persistent CTA per SM, two thread
+// groups, each walking its own contiguous run of segment pairs (row-major over
+// (row, pair)); the groups alternate on the FP64 pipe (fft_core.cuh
+// SyncPingPong), so one group's butterflies overlap the other's shared-memory
+// exchanges.  A pair's samples (stride + nfft contiguous doubles) arrive by one
+// TMA bulk copy into the group's exchange buffer, issued as soon as the previous
+// pair's last pass has read its inputs.  |Z|^2 accumulates in shared memory and
+// is folded into psd_sum whenever the run crosses into another row.
+template <int LOG2N>
+struct WelchPP {
+    using C = FftCfg<LOG2N>;
+    static constexpr int OFF_BAR = C::TW_TOTAL * 16;
+    static constexpr int OFF_RED = OFF_BAR + 16;                       // [group][parity][2][8 warps]
+    static constexpr int OFF_G = (OFF_RED + 2 * 2 * 2 * 8 * 8 + 127) & ~127;
+    static constexpr int GROUP_BYTES = C::SMEM_BYTES + C::N * 8;      // exchange + accumulators
+    static constexpr int SMEM = OFF_G + 2 * GROUP_BYTES;
+    static constexpr int CTAS_PER_SM = 4096 / C::N;                   // 512 threads per SM
+};
+
+template <int LOG2N, int DETREND>
+__global__ void __launch_bounds__(2 * FftCfg<LOG2N>::NT, WelchPP<LOG2N>::CTAS_PER_SM)
+welch_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
+                const double *__restrict__ win, const double2 *__restrict__ tw, double norm,
+                double *__restrict__ psd_sum, int64_t ldp, int64_t npairs, int64_t nwork,
+                int64_t per_group, int lag, int zero) {
+    using C = FftCfg<LOG2N>;
+    using L = WelchPP<LOG2N>;
+    using Sync = SyncPingPong<LOG2N>;
+    constexpr int N = C::N, NT = C::NT, NW = NT / 32 > 0 ? NT / 32 : 1;
+    static_assert(NT >= 32, "ping-pong Welch needs whole warps per group");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g = threadIdx.x / NT;
+    const int tid = threadIdx.x - g * NT;
+    double2 *tw_sm = reinterpret_cast<double2 *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR) + g;
+    double *red = reinterpret_cast<double *>(smem_raw + L::OFF_RED) + g * 32;
+    double2 *sm = reinterpret_cast<double2 *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES);
+    double *sx = reinterpret_cast<double *>(sm);
+    double *accs = reinterpret_cast<double *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES +
+                                              C::SMEM_BYTES);
+
+    for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) accs[r * NT + tid] = 0.0;
+    __syncthreads();
+    const Sync sync{g, tid, zero, tw_sm};
+
+    // this group's run of work items [w0, w1); item w = row * npairs + pair
+    const int64_t w0 = ((int64_t)blockIdx.x * 2 + g) * per_group;
+    int64_t w1 = w0 + per_group;
+    if (w1 > nwork) w1 = nwork;
+    int64_t row = w0 < nwork ? w0 / npairs : 0;
+    int64_t pair = w0 < nwork ? w0 - row * npairs : 0;
+
+    auto issue = [&](int64_t w_, int64_t row_, int64_t pair_) {
+        if (w_ >= w1) return;
+        const int64_t need = 2 * pair_ + 1 < nseg ? stride + N : N;
+        tma_fetch_span(sx, x + row_ * ldx + 2 * pair_ * stride, need, bar);
+    };
+    auto flush = [&](int64_t row_) {
+        // fold k and N-k:  psd[k] += norm * (A[k] + A[N-k]) for 0 < k < N/2 (the
+        // one-sided doubling), psd[0] += norm * A[0], psd[N/2] += norm * A[N/2]
+        double *out = psd_sum + row_ * ldp;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int idx = tid + r * NT;
+            const int bin = idx <= N / 2 ? idx : N - idx;
+            atomicAdd(out + bin, accs[r * NT + tid] * norm);
+            accs[r * NT + tid] = 0.0;
+        }
+    };
+    if (tid == 0) issue(w0, row, pair);
+    sync.prime();
+    if (g == 1)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+
+    for (int64_t it = 0; it < per_group; ++it) {
+        const int64_t w = w0 + it;
+        const bool live = w < w1;
+        int64_t rown = row, pairn = pair + 1;
+        if (pairn >= npairs) {
+            pairn = 0;
+            ++rown;
+        }
+        double2 v[16];
+        double wv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) wv[r] = ldg(win + tid + r * NT);
+        if (live) {
+            const double *xa = sx + span_mis(x + row * ldx + 2 * pair * stride) + tid;
+            const double *xb = xa + stride;
+            while (!mbar_try_wait(bar, (uint32_t)(it & 1))) {
+            }
+            if (2 * pair + 1 < nseg) {
+                if (stride == N / 2) {
+                    // 50 % overlap: the second segment's first half is the first one's second
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) v[r].x = xa[r * NT];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r].y = v[r + 8].x;
+#pragma unroll
+                    for (int r = 8; r < 16; ++r) v[r].y = xa[(r + 8) * NT];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) v[r] = make_double2(xa[r * NT], xb[r * NT]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = make_double2(xa[r * NT], 0.0);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = make_double2(0.0, 0.0);
+        }
+        if (DETREND != OSZ_DETREND_NONE) {
+            // segment sums: per thread, per warp (shuffles), per group (shared memory)
+            constexpr int NV = DETREND == OSZ_DETREND_LINEAR ? 4 : 2;
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            const double tbar = 0.5 * (N - 1);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                s[0] += v[r].x;
+                s[1] += v[r].y;
+                if (DETREND == OSZ_DETREND_LINEAR) {
+                    const double tc = (double)(tid + r * NT) - tbar;
+                    s[2] = fma(tc, v[r].x, s[2]);
+                    s[3] = fma(tc, v[r].y, s[3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            }
+            double *rd = red + (it & 1) * 16 * 0;   // (single buffer: see the barrier below)
+            if ((tid & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) rd[i * 8 + (tid >> 5)] = s[i];
+            }
+            sync.group();
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < NW; ++q) t += rd[i * 8 + q];   // same order in every thread
+                s[i] = t;
+            }
+            // (the next write to `red` comes after this item's exchange barriers)
+            const int tk = sync.take();
+            const double ma = Sync::tie(s[0] / N, tk), mb = Sync::tie(s[1] / N, tk);
+            if (DETREND == OSZ_DETREND_CONSTANT) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    v[r].x = (v[r].x - ma) * wv[r];
+                    v[r].y = (v[r].y - mb) * wv[r];
+                }
+            } else {
+                // least-squares line over t = 0..N-1 (scipy.signal.detrend type='linear')
+                const double stt = (double)N * ((double)N * N - 1.0) / 12.0;   // sum (t - tbar)^2
+                const double ka = s[2] / stt, kb = s[3] / stt;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double tc = (double)(tid + r * NT) - tbar;
+                    v[r].x = (v[r].x - fma(ka, tc, ma)) * wv[r];
+                    v[r].y = (v[r].y - fma(kb, tc, mb)) * wv[r];
+                }
+            }
+        } else {
+            const int tk = sync.take();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const double w_ = Sync::tie(wv[r], tk);
+                v[r].x *= w_;
+                v[r].y *= w_;
+            }
+        }
+        bfly<16>(v);
+        sync.release(v);
+        fft_r2r_tail<LOG2N, Sync, true>(v, sm, tid, sync, [&]() {
+            sync.group();                 // every thread of the group has read its inputs
+            if (tid == 0) {
+                fence_proxy_async();
+                issue(w + 1, rown, pairn);
+            }
+        });
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            accs[r * NT + tid] = fma(v[r].x, v[r].x, fma(v[r].y, v[r].y, accs[r * NT + tid]));
+        if (live && (rown != row || w + 1 >= w1)) flush(row);
+        row = rown;
+        pair = pairn;
+    }
+    if (g == 0)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+    sync.drain();
+}
+
 // Per-segment outputs: one CTA per (segment pair, row).
 template <int LOG2N, int DETREND, int MODE>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
@@ -264,6 +467,29 @@ static int launch_welch(const osz_spec_plan *p, const double *x, int64_t ldx, in
     return OSZ_OK;
 }
 
+template <int LOG2N, int DETREND>
+static int launch_welch_pp(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                           int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
+    using C = FftCfg<LOG2N>;
+    using L = WelchPP<LOG2N>;
+    OSZ_CUDA(cudaFuncSetAttribute(welch_pp_kernel<LOG2N, DETREND>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    const int64_t npairs = (nseg + 1) / 2;
+    const int64_t nwork = npairs * rows;
+    int64_t grid = (nwork + 1) / 2;
+    if (grid > (int64_t)sm_count() * L::CTAS_PER_SM) grid = (int64_t)sm_count() * L::CTAS_PER_SM;
+    const int64_t per_group = (nwork + 2 * grid - 1) / (2 * grid);
+    static const int lag = [] {
+        const char *e = getenv("OSZ_WELCH_LAG");
+        return e ? atoi(e) : 0;
+    }();
+    welch_pp_kernel<LOG2N, DETREND><<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
+        x, ldx, nseg, p->stride, p->d_win, p->d_tw, p->norm, psd, ldp, npairs, nwork, per_group,
+        lag, 0);
+    OSZ_LAUNCHED("welch_pp_kernel");
+    return OSZ_OK;
+}
+
 template <int LOG2N, int DETREND, int MODE>
 static int launch_segments(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                            int64_t nseg, double *out, cudaStream_t st) {
@@ -280,7 +506,16 @@ static int launch_segments(const osz_spec_plan *p, const double *x, int64_t ldx,
 template <int LOG2N, int DETREND>
 static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
                          int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st) {
-    if (mode == SPEC_ACCUM) return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+    if (mode == SPEC_ACCUM) {
+        static const int pp = [] {
+            const char *e = getenv("OSZ_WELCH_PP");
+            return e ? atoi(e) : 1;
+        }();
+        if constexpr (LOG2N >= 9 && LOG2N <= 12) {
+            if (pp) return launch_welch_pp<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+        }
+        return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+    }
     if (mode == SPEC_PGRAM)
         return launch_segments<LOG2N, DETREND, SPEC_PGRAM>(p, x, ldx, rows, nseg, out, st);
     return launch_segments<LOG2N, DETREND, SPEC_STFT>(p, x, ldx, rows, nseg, out, st);

@@ -14,6 +14,8 @@
 //     warps of a CTA split the (phase, tap) work of the same 32*R outputs and
 //     reduce through shared memory.
 // upfirdn_general_kernel   any up/down; one thread per output sample.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -167,6 +169,189 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
     }
 }
 
+// ---- double-buffered decimator -------------------------------------------------
+// Same arithmetic as upfirdn_dec_kernel, reorganised so the FP64 pipe never
+// waits for staging (the first kernel alternated a memory-bound staging phase
+// and an FP64-bound FIR phase per tile, and two co-resident CTAs drift into
+// lock step: FP64 pipe 29-45 %, profiles/r01_ncu_summary.md):
+//   * one persistent 512-thread CTA per SM walks tiles of 32*R outputs;
+//   * the next tile is scattered phase-major into the second shared-memory
+//     buffer by 8-byte cp.async (LDGSTS, zero-fill outside the supplied window)
+//     while the 16 warps run the FIR of the current tile; every thread's
+//     scatter offsets are the same for every tile and live in registers;
+//   * the (phase, tap) work is split between warps in blocks of R taps, so a
+//     run always starts on a window boundary (no per-load pointer select) and
+//     taps are read two at a time (LDS.128, broadcast).
+// Instruction mix of the inner loop: 64 DFMA per 4 + 8 loads.
+constexpr int UFD2_NT = 512;
+constexpr int UFD2_NW = UFD2_NT / 32;
+constexpr int UFD2_MAXE = 26;            // staged elements per thread and tile (register table)
+// Taps of the double-buffered kernel live in constant memory, one slot per plan
+// (first fit, released when the plan is destroyed; plans that find no room use
+// the first kernel).  [M][QB*R] reversed taps by phase, zero padded.
+constexpr int UFD2_CONST_DOUBLES = 7168;   // 56 KB of the 64 KB constant bank
+__constant__ double c_ufd_taps[UFD2_CONST_DOUBLES];
+
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst_smem, const void *src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(UFD2_NT, 1)
+upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, int64_t x_len,
+                    int64_t out_first, int64_t n_out, int K, int M, int QB /* R-tap blocks per phase */,
+                    int ldm /* doubles per phase row, odd */, int half,
+                    const double *__restrict__ gphase /* [M][QB*R] reversed taps, zero padded */,
+                    double *__restrict__ y, int64_t ldy, int tiles_per_row, int64_t ntiles,
+                    int tap_slot /* offset into c_ufd_taps */) {
+    constexpr int TO = 32 * R;
+    constexpr int LDR = 32 * (R + 1);
+    extern __shared__ __align__(16) double smem[];
+    const int Qp = QB * R;
+    double *red = smem;                                       // [NW][32 lanes][R + 1]
+    double *bufs = red + UFD2_NW * LDR;                       // 2 x [M][ldm]
+    const int tile_elems = M * ldm;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+    const int n_in = (TO + Qp) * M;
+
+    // byte offset (within a buffer) of staged element tid + k * NT: phase e % M,
+    // decimated index e / M
+    uint32_t off[UFD2_MAXE];
+#pragma unroll
+    for (int k = 0; k < UFD2_MAXE; ++k) {
+        const int e = tid + k * UFD2_NT;
+        const int pe = e % M, me = e / M;
+        off[k] = (uint32_t)(pe * ldm + ufd_phys<R>(me)) * 8u;
+    }
+    const uint32_t sbase = smem_u32(bufs);
+
+    auto stage = [&](int64_t t, int which) {
+        if (t >= ntiles) return;
+        const int64_t row = t / tiles_per_row;
+        const int64_t o0 = (t - row * tiles_per_row) * TO;
+        const int64_t rel0 = (out_first + o0) * M + half - (K - 1) - x_first;
+        const double *xr = x + row * ldx;
+        const uint32_t dst = sbase + (uint32_t)which * (uint32_t)tile_elems * 8u;
+        if (rel0 >= 0 && rel0 + n_in <= x_len) {
+            const double *src = xr + rel0 + tid;
+#pragma unroll
+            for (int k = 0; k < UFD2_MAXE; ++k)
+                if (tid + k * UFD2_NT < n_in) cp_async8_zfill(dst + off[k], src + k * UFD2_NT, true);
+        } else {
+#pragma unroll
+            for (int k = 0; k < UFD2_MAXE; ++k) {
+                const int e = tid + k * UFD2_NT;
+                const int64_t gi = rel0 + e;
+                const bool ok = gi >= 0 && gi < x_len;
+                if (e < n_in) cp_async8_zfill(dst + off[k], ok ? xr + gi : xr, ok);
+            }
+        }
+    };
+
+    // Taps come from constant memory through the
+    // UNIFORM datapath: a DFMA whose multiplier is a uniform register reads two
+    // vector operands instead of three, and three-vector-operand DFMA streams
+    // sustain only ~46 of 64 lanes/clk/SM on B200 (tools/microbench/fp64_rate.cu).
+    // every warp runs the same number of (phase, R-tap block) units, so the
+    // control flow below is warp- AND block-uniform
+    const int units = M * QB;
+    const int upw = (units + UFD2_NW - 1) / UFD2_NW;
+    const int ubase = __shfl_sync(0xffffffffu, warp * upw, 0);
+    const int p_first = ubase / QB, b_first = ubase - p_first * QB;
+
+    stage(blockIdx.x, 0);
+    cp_async_commit();
+    int parity = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, parity ^= 1) {
+        const double *xs = bufs + (size_t)parity * tile_elems;
+        stage(t + gridDim.x, parity ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+        // Two register windows alternate: while the taps of one block run against
+        // (wa | wb), the block after it is already loading into the other set.
+        // Window element d of block b, lane l, phase p: xs[p*ldm + (l + b)*(R+1) + d].
+        {
+            double wa[R], wb[R];
+            int pcur = p_first, bcur = b_first;
+            const double *gp = c_ufd_taps + tap_slot + ubase * R;
+            for (int i = 0; i < upw; i += 2) {
+                if (ubase + i >= units) break;
+                {
+                    const double *px = xs + pcur * ldm + (lane + bcur) * (R + 1);
+                    if (i == 0 || bcur == 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) wa[r] = px[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) wb[r] = px[R + 1 + r];
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const double g = gp[u];
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            acc[r] = fma(g, r + u < R ? wa[(r + u) % R] : wb[(r + u) % R], acc[r]);
+                    }
+                    if (++bcur == QB) {
+                        bcur = 0;
+                        ++pcur;
+                    }
+                }
+                if (i + 1 >= upw || ubase + i + 1 >= units) break;
+                {
+                    const double *px = xs + pcur * ldm + (lane + bcur) * (R + 1);
+                    if (bcur == 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) wb[r] = px[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) wa[r] = px[R + 1 + r];
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const double g = gp[R + u];
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            acc[r] = fma(g, r + u < R ? wb[(r + u) % R] : wa[(r + u) % R], acc[r]);
+                    }
+                    if (++bcur == QB) {
+                        bcur = 0;
+                        ++pcur;
+                    }
+                }
+                gp += 2 * R;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) red[warp * LDR + lane * (R + 1) + r] = acc[r];
+        __syncthreads();
+        const int64_t row = t / tiles_per_row;
+        const int64_t o0 = (t - row * tiles_per_row) * TO;
+        for (int o = tid; o < TO; o += UFD2_NT) {
+            const int idx = (o / R) * (R + 1) + (o % R);
+            double sum = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < UFD2_NW; ++w8) sum += red[w8 * LDR + idx];
+            if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
+        }
+        // (the next iteration's barrier orders these reads before red is rewritten;
+        //  this tile's buffer is refilled only after that barrier as well)
+    }
+    cp_async_wait<0>();
+}
+
 __global__ void upfirdn_general_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first,
                                        int64_t x_len, int64_t out_first, int64_t n_out, int K,
                                        int L, int M, int half,
@@ -201,6 +386,12 @@ struct osz_upfirdn_plan {
     size_t smem = 0;
     double *d_h = nullptr;         // h * up
     double *d_gphase = nullptr;    // [down][Q]
+    // double-buffered kernel
+    bool dec2 = false;
+    int ldm2 = 0, QB = 0;
+    size_t smem2 = 0;
+    double *d_gphase2 = nullptr;   // [down][QB*8], zero padded
+    int tap_slot = -1, tap_len = 0; // the same taps in constant memory (c_ufd_taps)
 };
 
 template <int R>
@@ -214,6 +405,48 @@ static int launch_dec(const osz_upfirdn_plan *p, const double *x, int64_t ldx, i
                                                          p->K, p->down, p->Q, p->ldm, p->half,
                                                          p->d_gphase, y, ldy);
     OSZ_LAUNCHED("upfirdn_dec_kernel");
+    return OSZ_OK;
+}
+
+// first-fit allocator over c_ufd_taps (a handful of live plans at most)
+#include <mutex>
+static std::mutex g_slot_mu;
+static std::vector<std::pair<int, int>> g_slots;   // (offset, length), sorted by offset
+static int ufd_slot_alloc(int len) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    len = (len + 1) & ~1;
+    int at = 0;
+    size_t i = 0;
+    for (; i < g_slots.size(); ++i) {
+        if (g_slots[i].first - at >= len) break;
+        at = g_slots[i].first + g_slots[i].second;
+    }
+    if (at + len > UFD2_CONST_DOUBLES) return -1;
+    g_slots.insert(g_slots.begin() + i, std::make_pair(at, len));
+    return at;
+}
+static void ufd_slot_free(int off, int) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (size_t i = 0; i < g_slots.size(); ++i)
+        if (g_slots[i].first == off) {
+            g_slots.erase(g_slots.begin() + i);
+            return;
+        }
+}
+
+template <int R>
+static int launch_dec2(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
+                       int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out, double *y,
+                       int64_t ldy, cudaStream_t st) {
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec2_kernel<R>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem2));
+    const int64_t tiles_per_row = (n_out + 32 * R - 1) / (32 * R);
+    const int64_t ntiles = tiles_per_row * rows;
+    int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
+    upfirdn_dec2_kernel<R><<<(unsigned)grid, UFD2_NT, p->smem2, st>>>(
+        x, ldx, x_first, x_len, out_first, n_out, p->K, p->down, p->QB, p->ldm2, p->half,
+        p->d_gphase2, y, ldy, (int)tiles_per_row, ntiles, p->tap_slot);
+    OSZ_LAUNCHED("upfirdn_dec2_kernel");
     return OSZ_OK;
 }
 
@@ -262,6 +495,33 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
             ok = cudaMalloc(&p->d_gphase, gp.size() * 8) == cudaSuccess &&
                  cudaMemcpy(p->d_gphase, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice) ==
                      cudaSuccess;
+            // double-buffered kernel: R = 8, taps padded to whole blocks of R per phase
+            if (ok) {
+                constexpr int R2 = 8, TO2 = 32 * R2;
+                const int QB = (p->Q + R2 - 1) / R2, Qp = QB * R2;
+                const int cols = TO2 + Qp + R2;                 // decimated samples per phase row
+                int ldm2 = cols + cols / R2 + 1;
+                if ((ldm2 & 1) == 0) ++ldm2;
+                const size_t smem2 = (2 * (size_t)M * ldm2 + (size_t)UFD2_NW * 32 * (R2 + 1)) * 8;
+                const int per_thread = ((TO2 + Qp) * M + UFD2_NT - 1) / UFD2_NT;
+                const int slot = smem2 <= 225 * 1024 && per_thread <= UFD2_MAXE
+                                     ? ufd_slot_alloc(M * Qp) : -1;
+                if (slot >= 0) {
+                    std::vector<double> gp2((size_t)M * Qp, 0.0);
+                    for (int j = 0; j < K; ++j) gp2[(size_t)(j % M) * Qp + j / M] = hs[K - 1 - j];
+                    ok = cudaMalloc(&p->d_gphase2, gp2.size() * 8) == cudaSuccess &&
+                         cudaMemcpy(p->d_gphase2, gp2.data(), gp2.size() * 8,
+                                    cudaMemcpyHostToDevice) == cudaSuccess;
+                    p->tap_slot = slot;
+                    p->tap_len = M * Qp;
+                    ok = ok && cudaMemcpyToSymbol(c_ufd_taps, gp2.data(), gp2.size() * 8,
+                                                  (size_t)slot * 8) == cudaSuccess;
+                    p->dec2 = ok;
+                    p->ldm2 = ldm2;
+                    p->QB = QB;
+                    p->smem2 = smem2;
+                }
+            }
         }
     }
     if (!ok) {
@@ -276,6 +536,8 @@ int osz_upfirdn_plan_destroy(osz_upfirdn_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_h);
     cudaFree(p->d_gphase);
+    cudaFree(p->d_gphase2);
+    if (p->tap_slot >= 0) ufd_slot_free(p->tap_slot, p->tap_len);
     delete p;
     return OSZ_OK;
 }
@@ -287,6 +549,15 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
     if (rows <= 0 || n_out <= 0) return OSZ_OK;
     if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "upfirdn: more than 65535 rows per call");
     cudaStream_t st = as_stream(stream);
+    static const int use_dec2 = [] {
+        // measured on B200 (256 x 1e6, profiles/r01_kernel_bench.md): 158.6 vs 164.9 G
+        // samples/s for the fused 1231-tap filter, 255 vs 268 at 561 taps -- the
+        // double-buffered kernel stays opt-in until its tap delivery is uniform
+        const char *e = getenv("OSZ_UFD_DEC2");
+        return e ? atoi(e) : 0;
+    }();
+    if (p->dec2 && use_dec2)
+        return launch_dec2<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
     switch (p->R) {
         case 16: return launch_dec<16>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
         case 8: return launch_dec<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
