@@ -381,12 +381,18 @@ def sosfilt(pro, sos, axis, zi=None):
     from chunk to chunk (reference numerical.py:301-335)."""
 
 
-def _filtfilt_device(pro, cascade, zi, axis, _out=None):
+def _filtfilt_device(pro, cascade, zi, axis, _out=None, _fwd_states=None, _drop_last=False):
     """Shared forward-backward driver (reference numerical.py:338-411,449-520):
     one global forward pass; each chunk's backward pass starts from the state
     left by filtering the NEXT forward chunk backwards from zi * its last
-    sample; the last chunk starts from zi * its own last sample."""
-    fwd_states, prev = None, None
+    sample; the last chunk starts from zi * its own last sample.
+
+    Time shards (sharding.iir_time_sharded) run this on a span of the recording:
+    ``_fwd_states`` is the forward state entering the span (instead of
+    zi * first sample) and ``_drop_last`` marks the span's last chunk as the
+    look-ahead chunk borrowed from the next span -- it is filtered forward but
+    its own backward pass belongs to the next rank."""
+    fwd_states, prev = _fwd_states, None
     for chunk in device_chunks(pro, axis):
         if fwd_states is None:
             fwd_states = cascade.state_from_sample(zi, chunk, 0)
@@ -404,7 +410,7 @@ def _filtfilt_device(pro, cascade, zi, axis, _out=None):
             cascade.run(fwd[:, :m], look, reverse=True, want_output=False)
             yield cascade.run(prev, look, reverse=True, out=_out)
         prev = fwd
-    if prev is not None:
+    if prev is not None and not _drop_last:
         last = cascade.state_from_sample(zi, prev, prev.shape[1] - 1)
         yield cascade.run(prev, last, reverse=True, out=_out)
 

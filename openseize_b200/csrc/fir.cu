@@ -99,7 +99,7 @@ fir_fft_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int nta
                double *__restrict__ y, int64_t ldy, int accumulate) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sm = reinterpret_cast<double2 *>(smem_raw);
 
     const int tid = threadIdx.x;

@@ -122,7 +122,7 @@ welch_accum_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int6
                    double *__restrict__ psd_sum, int64_t ldp, int64_t pairs_per_cta) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sm = reinterpret_cast<double2 *>(smem_raw);
     // per-thread |Z|^2 accumulators live in shared memory ([r][tid], conflict
     // free): in registers they pushed the FFT over the 128-register budget of
@@ -379,7 +379,7 @@ spec_segments_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, in
                      const double2 *__restrict__ tw, double norm, double *__restrict__ out) {
     using C = FftCfg<LOG2N>;
     constexpr int N = C::N, NT = C::NT, NF = N / 2 + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sm = reinterpret_cast<double2 *>(smem_raw);
     __shared__ double red[4 * 32];
 

@@ -12,10 +12,20 @@ sample axis and needs only a bounded carry along time:
   segments and all-reduces its partial periodogram SUM and segment count (the
   only collective on the path: NCCL over NVLink, a (rows, nfft//2+1) float64
   message -- 4 MB for 256 x 2049 -- so it is latency bound, not bandwidth
-  bound).
+  bound);
+* time sharding of FIR filtering and resampling -- each rank reads its span of
+  the recording plus a filter-length halo straight from the host array (no
+  GPU-to-GPU traffic) and keeps the outputs of its own span;
+* time sharding of the IIR filters -- the recurrence carries state through
+  time, so every rank first reduces its span to the state it would leave when
+  entered at rest, the (rows, nsec, 2) summaries are all-gathered (kilobytes)
+  and composed with the cascade's zero-input transition matrix, and each rank
+  then filters its span from its true entering state.  The forward-backward
+  filters additionally borrow the next span's first chunk, because the
+  reference's backward pass looks one chunk ahead (numerical.py:394-403).
 
-Everything here is host-side planning plus one ``all_reduce``; the arithmetic
-is the same GPU kernels (``numerical.welch_sum``).
+Everything here is host-side planning plus small collectives; the arithmetic
+is the same GPU kernels.
 """
 
 import numpy as np
@@ -137,3 +147,238 @@ def psd_time_sharded(data, fs, axis=-1, resolution=0.5, window="hann", overlap=0
     summed = packed[:-1].reshape(layout.rows, nfft // 2 + 1)
     estimate = np.array(dv.download(summed, layout).get()) / total
     return total, np.fft.rfftfreq(nfft, 1 / fs), estimate
+
+
+# ---------------------------------------------------------------------------
+# time sharding of the filters (few-channel recordings)
+# ---------------------------------------------------------------------------
+def _in_memory(data):
+    if isinstance(data, ArrayProducer):
+        data = data.data
+    if not isinstance(data, np.ndarray):
+        raise TypeError("time sharding slices in-memory data")
+    return data
+
+
+def time_spans(n, size, align=1):
+    """``size`` contiguous spans covering range(n) whose interior boundaries are
+    multiples of ``align`` (the chunk grid for the chunk-dependent filters)."""
+    units = -(-int(n) // int(align))
+    return [(min(a * align, n), min(b * align, n)) for a, b in split_range(units, size)]
+
+
+def gather_time(local, axis, group=None):
+    """Concatenate every rank's span along ``axis`` (host side; every rank gets
+    the whole result).  ``local`` may be None for a rank with an empty span."""
+    rank, size = world(group)
+    if size == 1:
+        return local
+    parts = [None] * size
+    _dist().all_gather_object(parts, local, group=group)
+    return np.concatenate([p for p in parts if p is not None], axis=axis)
+
+
+def fir_time_sharded(data, window, chunksize, axis=-1, mode="same", group=None, gather=True):
+    """``nm.oaconvolve`` of one recording with the OUTPUT's time axis split over
+    the ranks.  Rank r convolves samples [o0 - (K-1), o1) of the input (zeros
+    outside the recording, as numpy's convolution modes imply) and keeps outputs
+    [o0, o1); the halo comes from the host array.  Returns the whole result
+    (``gather``) or ``((o0, o1), this rank's span)``."""
+    data = _in_memory(data)
+    axis = normalize_axis(axis, data.ndim)
+    window = np.asarray(window, dtype=np.float64)
+    k, n = len(window), data.shape[axis]
+    if n < k:
+        raise ValueError("oaconvolve: data length {} along axis is shorter than the {} taps"
+                         .format(n, k))
+    left, right = nm._mode_cuts(k, mode)
+    total = n + k - 1 - left - right                  # output samples of this mode
+    rank, size = world(group)
+    o0, o1 = split_range(total, size)[rank]
+    local = None
+    if o1 > o0:
+        f0, f1 = left + o0, left + o1                 # full-convolution indices wanted
+        in_lo, in_hi = max(f0 - (k - 1), 0), min(f1, n)
+        if in_hi - in_lo < k:                         # a sliver: widen the halo to K samples
+            in_lo = max(in_hi - k, 0)
+            in_hi = min(in_lo + k, n)
+        sub = slice_along_axis(data, in_lo, in_hi, axis=axis)
+        blocks = list(nm.oaconvolve(producer(sub, chunksize, axis), window, axis, "full"))
+        full = np.concatenate(blocks, axis=axis)      # full[j] is full-convolution index in_lo + j
+        local = slice_along_axis(full, f0 - in_lo, f1 - in_lo, axis=axis)
+    if not gather:
+        return (o0, o1), local
+    return gather_time(local, axis, group)
+
+
+def resample_time_sharded(data, L, M, fs, chunksize, axis=-1, group=None, gather=True, **kwargs):
+    """``nm.polyphase_resample`` with the output's time axis split over the
+    ranks.  The reference's chunked resampler equals one global
+    ``scipy.signal.resample_poly`` call for every chunking, so a
+    rank resamples its input span widened by the filter reach on both sides,
+    aligned to the decimation grid, and keeps exactly its outputs."""
+    from math import gcd
+
+    from openseize_b200.filtering.fir import Kaiser
+
+    data = _in_memory(data)
+    axis = normalize_axis(axis, data.ndim)
+    n = data.shape[axis]
+    g = gcd(int(L), int(M))
+    up, down = int(L) // g, int(M) // g
+    total = -(-n * up // down)                        # ceil(N L / M), resampling.py:90-92
+    h = nm._resample_taps(L, M, fs, Kaiser, kwargs)
+    reach = -(-(len(h) - 1) // (2 * up)) + 1           # input samples a tap can reach either side
+    rank, size = world(group)
+    o0, o1 = split_range(total, size)[rank]
+    local = None
+    if o1 > o0:
+        in_lo = max((o0 * down) // up - reach, 0)
+        in_lo -= in_lo % down                         # output index in_lo*up/down is an integer
+        in_hi = min(-(-(o1 * down) // up) + reach + down, n)
+        # the sub-recording must satisfy the reference's own size rules (numerical.py:569-576)
+        in_hi = min(max(in_hi, in_lo + 3 * down + len(h)), n)
+        in_lo = max(min(in_lo, in_hi - 3 * down - len(h)), 0)
+        in_lo -= in_lo % down
+        sub = slice_along_axis(data, in_lo, in_hi, axis=axis)
+        sub_pro = producer(sub, chunksize, axis)
+        blocks = list(nm.polyphase_resample(sub_pro, L, M, fs, Kaiser, axis, **kwargs))
+        y = np.concatenate(blocks, axis=axis)
+        first = in_lo * up // down                    # global index of y's first sample
+        local = slice_along_axis(y, o0 - first, o1 - first, axis=axis)
+        assert local.shape[axis] == o1 - o0, (local.shape, o0, o1, first)
+    if not gather:
+        return (o0, o1), local
+    return gather_time(local, axis, group)
+
+
+def cascade_transition(sos):
+    """One-step zero-input state transition of a DF2T biquad cascade: the
+    (2 nsec, 2 nsec) matrix T with state' = T state when the input sample is 0.
+    State order is scipy's: (z0, z1) of section 0, then section 1, ...  Derived
+    from the recurrence of SURVEY.md 8a2 (y = b0 x + z0; z0' = b1 x - a1 y + z1;
+    z1' = b2 x - a2 y; the next section's x is this section's y)."""
+    sos = np.atleast_2d(np.asarray(sos, dtype=np.longdouble))
+    sos = sos / sos[:, 3:4]
+    nsec = sos.shape[0]
+    T = np.zeros((2 * nsec, 2 * nsec), dtype=np.longdouble)
+    for j in range(2 * nsec):
+        state = np.zeros((nsec, 2), dtype=np.longdouble)
+        state.reshape(-1)[j] = 1
+        x = np.longdouble(0)
+        nxt = np.zeros_like(state)
+        for s in range(nsec):
+            b0, b1, b2, _, a1, a2 = sos[s]
+            y = b0 * x + state[s, 0]
+            nxt[s, 0] = b1 * x - a1 * y + state[s, 1]
+            nxt[s, 1] = b2 * x - a2 * y
+            x = y
+        T[:, j] = nxt.reshape(-1)
+    return T
+
+
+def _matrix_power(T, n):
+    out = np.eye(T.shape[0], dtype=T.dtype)
+    base = T.copy()
+    n = int(n)
+    while n:
+        if n & 1:
+            out = base @ out
+        base = base @ base
+        n >>= 1
+    return out
+
+
+def _states_to_host(states):
+    t = dv.torch()
+    return t.cat([s for s in states], dim=1).cpu().numpy().astype(np.float64)
+
+
+def _entering_states(cascade, data, spans, rank, axis, chunksize, first_state, group):
+    """Forward state entering this rank's span.  Every rank filters its own span
+    from rest and keeps only the final state f_r; with Phi_r = T^(span length),
+    s_0 = first_state and s_(r+1) = Phi_r s_r + f_r  (superposition of the
+    zero-state and zero-input responses)."""
+    layout = dv.Layout(data.shape, axis)
+    a, b = spans[rank]
+    size = len(spans)
+    f = np.zeros((layout.rows, cascade.nsec, 2))
+    if size > 1 and b > a and rank < size - 1:
+        states = cascade.zero_state(layout.rows)
+        sub = slice_along_axis(data, a, b, axis=axis)
+        for chunk in nm.device_chunks(producer(sub, chunksize, axis), axis, regrid=False):
+            cascade.run(chunk, states, want_output=False)
+        f = _states_to_host(states)
+    finals = [f]
+    if size > 1:
+        finals = [None] * size
+        _dist().all_gather_object(finals, f, group=group)
+    T = cascade_transition(cascade.sos)
+    s = np.asarray(first_state, dtype=np.longdouble).reshape(layout.rows, -1)
+    for q in range(rank):
+        qa, qb = spans[q]
+        if qb > qa:
+            phi = _matrix_power(T, qb - qa)
+            s = s @ phi.T + finals[q].reshape(layout.rows, -1)
+    return np.ascontiguousarray(s.astype(np.float64)).reshape(layout.rows, cascade.nsec, 2)
+
+
+def iir_time_sharded(data, coeffs, chunksize, axis=-1, dephase=True, zi=None, fmt="sos",
+                     group=None, gather=True):
+    """``IIR.__call__`` semantics (filtering/bases.py:153-213) for one recording
+    with its time axis split over the ranks on the chunk grid of ``chunksize``:
+    ``nm.sosfiltfilt`` / ``nm.filtfilt`` when ``dephase`` else ``nm.sosfilt`` /
+    ``nm.lfilter`` (``fmt`` 'sos' or 'ba'; (b, a) of second order at most).
+    Results equal the single-process ones to rounding: the forward-backward
+    filters keep the reference's dependence on the chunk grid."""
+    import scipy.signal as sps
+
+    data = _in_memory(data)
+    axis = normalize_axis(axis, data.ndim)
+    n = data.shape[axis]
+    chunksize = int(chunksize)
+    layout = dv.Layout(data.shape, axis)
+    if fmt == "sos":
+        sos = np.atleast_2d(np.asarray(coeffs, dtype=np.float64))
+        zi_ss = sps.sosfilt_zi(sos)
+    else:
+        sos = nm._ba_to_sos(coeffs)
+        z = np.atleast_1d(sps.lfilter_zi(*coeffs))
+        zi_ss = np.zeros((1, 2))
+        zi_ss[0, :len(z)] = z
+    cascade = nm._Cascade(sos)
+    rank, size = world(group)
+    spans = time_spans(n, size, chunksize)
+    a, b = spans[rank]
+
+    # state entering the recording
+    if dephase:
+        x0 = np.moveaxis(slice_along_axis(data, 0, 1, axis=axis).reshape(
+            layout.outer, 1, layout.inner), 1, 2).reshape(layout.rows)
+        first = zi_ss[None, :, :] * x0[:, None, None]            # zi * x0, numerical.py:385
+    elif zi is None:
+        first = np.zeros((layout.rows, cascade.nsec, 2))
+    elif fmt == "sos":
+        first = nm._zi_to_rows(zi, layout, cascade.nsec).cpu().numpy()
+    else:
+        first = nm._lfilter_zi_rows(coeffs, zi, layout).cpu().numpy()
+    entering = _entering_states(cascade, data, spans, rank, axis, chunksize, first, group)
+
+    local = None
+    if b > a:
+        states = cascade.split_state(dv.from_host(entering))
+        if dephase:
+            stop = min(b + chunksize, n)                          # borrow the look-ahead chunk
+            sub = slice_along_axis(data, a, stop, axis=axis)
+            gen = nm._filtfilt_device(producer(sub, chunksize, axis), cascade, zi_ss, axis,
+                                      _fwd_states=states, _drop_last=stop > b)
+        else:
+            sub = slice_along_axis(data, a, b, axis=axis)
+            gen = (cascade.run(chunk, states)
+                   for chunk in nm.device_chunks(producer(sub, chunksize, axis), axis,
+                                                 regrid=False))
+        local = np.concatenate(list(nm._to_host(gen, layout)), axis=axis)
+        assert local.shape[axis] == b - a
+    if not gather:
+        return (a, b), local
+    return gather_time(local, axis, group)

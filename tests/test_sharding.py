@@ -65,8 +65,22 @@ def _worker(rank, size, port, out):
         c2, f2, p2 = psd(filt(mine, 9000), fs, resolution=1.0)
         gathered = [None] * size
         dist.all_gather_object(gathered, p2)
+        # (3) time-sharded filters: halos from the host array; the IIR state crosses
+        #     ranks as an all-gather of (rows, nsec, 2) summaries
+        import scipy.signal as sps
+
+        xt = rng.standard_normal((3, 50000)) + 0.5
+        fir_same = sharding.fir_time_sharded(xt, filt.coeffs, 7000, mode="same")
+        fir_valid = sharding.fir_time_sharded(xt, filt.coeffs, 7000, mode="valid")
+        rs = sharding.resample_time_sharded(xt, 3, 7, fs, 6000)
+        sos = sps.butter(4, [5, 60], btype="bandpass", fs=fs, output="sos")
+        ff = sharding.iir_time_sharded(xt, sos, 8000, dephase=True)
+        fw = sharding.iir_time_sharded(xt, sos, 8000, dephase=False)
+        ba = sps.iirnotch(60, 10, fs=fs)
+        nf = sharding.iir_time_sharded(xt, ba, 8000, dephase=True, fmt="ba")
         if rank == 0:
-            out.put((cnt, f, p, c2, np.concatenate(gathered, 0)))
+            out.put((cnt, f, p, c2, np.concatenate(gathered, 0),
+                     dict(fir_same=fir_same, fir_valid=fir_valid, rs=rs, ff=ff, fw=fw, nf=nf)))
     finally:
         dist.destroy_process_group()
 
@@ -81,7 +95,7 @@ def test_two_ranks_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    cnt, f, p, c2, p2 = out.get(timeout=240)
+    cnt, f, p, c2, p2, sharded = out.get(timeout=240)
     for pr in procs:
         pr.join(60)
         assert pr.exitcode == 0
@@ -97,3 +111,69 @@ def test_two_ranks_gloo():
     rc2, _, rp2 = oracle.welch_psd(y, 1024, -1, 1.0)
     assert c2 == rc2
     assert np.max(np.abs(p2 - rp2)) / np.max(np.abs(rp2)) < 1e-12
+
+    # time-sharded filters against the single-process oracle
+    import scipy.signal as sps
+
+    xt = rng.standard_normal((3, 50000)) + 0.5
+    for mode in ("same", "valid"):
+        ref = np.concatenate(oracle.oaconvolve(xt, taps, 7000, -1, mode), -1)
+        got = sharded["fir_" + mode]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+    ref = np.concatenate(oracle.polyphase_resample(xt, 3, 7, 1024, 6000, -1), -1)
+    assert sharded["rs"].shape == ref.shape
+    assert np.max(np.abs(sharded["rs"] - ref)) / np.max(np.abs(ref)) < 1e-12
+    sos = sps.butter(4, [5, 60], btype="bandpass", fs=1024, output="sos")
+    ref = np.concatenate(oracle.sosfiltfilt(xt, sos, 8000, -1), -1)
+    assert np.max(np.abs(sharded["ff"] - ref)) / np.max(np.abs(ref)) < 1e-9
+    ref = np.concatenate(oracle.sosfilt(xt, sos, 8000, -1)[0], -1)
+    assert np.max(np.abs(sharded["fw"] - ref)) / np.max(np.abs(ref)) < 1e-9
+    ref = np.concatenate(oracle.filtfilt(xt, sps.iirnotch(60, 10, fs=1024), 8000, -1), -1)
+    assert np.max(np.abs(sharded["nf"] - ref)) / np.max(np.abs(ref)) < 1e-9
+
+
+def test_time_shards_simulated(fake_gpu, monkeypatch):
+    """FIR and resampling time shards need no collective: emulate 1, 3 and 5
+    ranks in one process and stitch the spans."""
+    import oracle
+    from oracle.chunked import _kaiser_lowpass
+
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 3, 41000))
+    taps = _kaiser_lowpass(100, 150, 1024, 1.0, 40.0)
+    for size in (1, 3, 5):
+        for mode in ("full", "same", "valid"):
+            parts = []
+            for r in range(size):
+                monkeypatch.setattr(sharding, "world", lambda group=None, r=r: (r, size))
+                (o0, o1), loc = sharding.fir_time_sharded(x, taps, 5000, mode=mode, gather=False)
+                assert loc.shape[-1] == o1 - o0
+                parts.append(loc)
+            got = np.concatenate(parts, -1)
+            ref = np.concatenate(oracle.oaconvolve(x, taps, 5000, -1, mode), -1)
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+        for (L, M) in ((1, 4), (3, 2), (5, 3)):
+            parts = []
+            for r in range(size):
+                monkeypatch.setattr(sharding, "world", lambda group=None, r=r: (r, size))
+                (o0, o1), loc = sharding.resample_time_sharded(x, L, M, 1024, 4000, gather=False)
+                parts.append(loc)
+            got = np.concatenate(parts, -1)
+            ref = np.concatenate(oracle.polyphase_resample(x, L, M, 1024, 4000, -1), -1)
+            assert got.shape == ref.shape, (got.shape, ref.shape, L, M, size)
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+def test_cascade_transition_matches_recurrence():
+    import scipy.signal as sps
+
+    sos = sps.butter(3, [5, 60], btype="bandpass", fs=1024, output="sos")
+    T = sharding.cascade_transition(sos).astype(np.float64)
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((sos.shape[0], 2))
+    n = 37
+    _, zf = sps.sosfilt(sos, np.zeros(n), zi=z)
+    got = (np.linalg.matrix_power(T, n) @ z.reshape(-1)).reshape(-1, 2)
+    assert np.allclose(got, zf, rtol=1e-10, atol=1e-14)
