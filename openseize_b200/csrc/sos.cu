@@ -110,15 +110,6 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
         const int off = blk == 0 ? (int)(BLK - first_len) : 0;
         const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * BLK;
         __syncthreads();   // carry[] visible / buf free
-        if (blk + 1 < nblk) {
-            // pull the next block towards L2 while this one is loaded and scanned: a
-            // CTA walks its row block by block, so its loads otherwise pay the full
-            // DRAM latency once per block
-            const int64_t np = first_len + blk * BLK;          // pos0 of block blk + 1
-            const double *nx = reverse ? xr - np - (BLK - 1) : xr + np;
-            for (int e = tid * 16; e < BLK; e += SOS_NT * 16)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + e));
-        }
         if (blk != 0) {
             // full block: T independent coalesced loads in flight per thread
             const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;

@@ -287,7 +287,7 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
         {
             double wa[R], wb[R];
             int pcur = p_first, bcur = b_first;
-            const double *gp = c_ufd_taps + tap_slot + ubase * R;
+            const int gidx = tap_slot + ubase * R;        // warp-uniform tap index
             for (int i = 0; i < upw; i += 2) {
                 if (ubase + i >= units) break;
                 {
@@ -300,7 +300,7 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
                     for (int r = 0; r < R; ++r) wb[r] = px[R + 1 + r];
 #pragma unroll
                     for (int u = 0; u < R; ++u) {
-                        const double g = gp[u];
+                        const double g = c_ufd_taps[gidx + i * R + u];
 #pragma unroll
                         for (int r = 0; r < R; ++r)
                             acc[r] = fma(g, r + u < R ? wa[(r + u) % R] : wb[(r + u) % R], acc[r]);
@@ -321,7 +321,7 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
                     for (int r = 0; r < R; ++r) wa[r] = px[R + 1 + r];
 #pragma unroll
                     for (int u = 0; u < R; ++u) {
-                        const double g = gp[R + u];
+                        const double g = c_ufd_taps[gidx + (i + 1) * R + u];
 #pragma unroll
                         for (int r = 0; r < R; ++r)
                             acc[r] = fma(g, r + u < R ? wb[(r + u) % R] : wa[(r + u) % R], acc[r]);
@@ -331,7 +331,6 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
                         ++pcur;
                     }
                 }
-                gp += 2 * R;
             }
         }
 #pragma unroll
