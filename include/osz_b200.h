@@ -131,6 +131,28 @@ int osz_sos_state_from_sample_f64(const osz_sos_plan *plan, const double *zi_hos
                                   const double *x_dev, int64_t ldx, int64_t rows,
                                   int64_t sample, double *state_dev, void *stream);
 
+/* ---- transfer-function IIR of any order: replaces scipy.signal.lfilter as
+ *      called by nm.lfilter / nm.filtfilt (core/numerical.py:445,508,511,519)
+ *      when max(len a, len b) > 3 (second order rides the biquad scan) ------ */
+typedef struct osz_tf_plan osz_tf_plan;
+/* b, a as handed to scipy.signal.lfilter (normalised by a[0] like scipy). */
+int osz_tf_plan_create(osz_tf_plan **plan, const double *b_host, int nb, const double *a_host,
+                       int na);
+int osz_tf_plan_destroy(osz_tf_plan *plan);
+int osz_tf_plan_states(const osz_tf_plan *plan);   /* max(nb, na) - 1 */
+/* Transposed direct form II, evaluated in scipy's order.  state_dev is
+ * (rows, states) delay registers: initial condition in, final condition out
+ * (the reference's `z`, numerical.py:439-446).  reverse / y_dev == NULL as for
+ * osz_sos_exec_f64. */
+int osz_tf_exec_f64(const osz_tf_plan *plan, const double *x_dev, int64_t ldx, int64_t rows,
+                    int64_t n, int reverse, double *state_dev, double *y_dev, int64_t ldy,
+                    void *stream);
+/* state[r][j] = zi[j] * x[r][sample]: zi_host is scipy.signal.lfilter_zi(b, a)
+ * (numerical.py:487-496,508,519). */
+int osz_tf_state_from_sample_f64(const osz_tf_plan *plan, const double *zi_host,
+                                 const double *x_dev, int64_t ldx, int64_t rows, int64_t sample,
+                                 double *state_dev, void *stream);
+
 /* ---- polyphase resampling: replaces scipy.signal.resample_poly/upfirdn as
  *      called by nm.polyphase_resample (core/numerical.py:610,631) -------- */
 typedef struct osz_upfirdn_plan osz_upfirdn_plan;
@@ -173,6 +195,14 @@ int osz_periodogram_f64(const osz_spec_plan *plan, const double *x_dev, int64_t 
                         int64_t rows, int64_t nseg, double *out_dev, void *stream);
 int osz_stft_f64(const osz_spec_plan *plan, const double *x_dev, int64_t ldx,
                  int64_t rows, int64_t nseg, double *out_dev, void *stream);
+/* One zero-padded segment per row, for periodogram / modified_dft calls with
+ * nfft > n (numerical.py:688-699): out[r][i] = (x[r][i] - trend_r(i)) * w[i]
+ * for i < n and 0 for n <= i < nfft; trend per `detrend` over the n samples,
+ * w = get_window(window, n) already on the device.  The transform then runs
+ * on `out` with a unit window and no detrending. */
+int osz_spec_prepare_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t n,
+                         int64_t nfft, const double *window_dev, int detrend,
+                         double *out_dev, int64_t ldo, void *stream);
 
 #ifdef __cplusplus
 }

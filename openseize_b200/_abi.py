@@ -52,6 +52,11 @@ SIGNATURES = {
     "osz_sos_plan_destroy": (c_int, [_vp]),
     "osz_sos_exec_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, _i64, _vp]),
     "osz_sos_state_from_sample_f64": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "osz_tf_plan_create": (c_int, [POINTER(_vp), _dp, c_int, _dp, c_int]),
+    "osz_tf_plan_destroy": (c_int, [_vp]),
+    "osz_tf_plan_states": (c_int, [_vp]),
+    "osz_tf_exec_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, _i64, _vp]),
+    "osz_tf_state_from_sample_f64": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_upfirdn_plan_create": (c_int, [POINTER(_vp), _dp, c_int, c_int, c_int]),
     "osz_upfirdn_plan_destroy": (c_int, [_vp]),
     "osz_upfirdn_exec_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64,
@@ -62,6 +67,7 @@ SIGNATURES = {
     "osz_welch_accum_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "osz_periodogram_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_stft_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "osz_spec_prepare_f64": (c_int, [_vp, _i64, _i64, _i64, _i64, _vp, c_int, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -376,6 +376,56 @@ class SosPlan(_Plan):
         return state
 
 
+class TfPlan(_Plan):
+    """(b, a) filter of any order, transposed direct form II like scipy's lfilter."""
+    _destroy = "osz_tf_plan_destroy"
+
+    def __init__(self, b, a):
+        super().__init__()
+        require_cuda()
+        barr, bptr = _abi.as_double_array(np.atleast_1d(b))
+        aarr, aptr = _abi.as_double_array(np.atleast_1d(a))
+        rc = _abi.load().osz_tf_plan_create(ctypes.byref(self.handle), bptr, len(barr), aptr,
+                                            len(aarr))
+        _abi.check(rc, "tf_plan_create")
+        self.nstate = int(max(len(barr), len(aarr)) - 1)
+
+    @staticmethod
+    def cached(b, a):
+        b = np.ascontiguousarray(np.atleast_1d(b), dtype=np.float64)
+        a = np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)
+        return _plans.get(("tf", b.tobytes(), a.tobytes()), lambda: TfPlan(b, a))
+
+    def run(self, x, state, reverse=False, want_output=True, out=None):
+        """Filter x (rows, n); ``state`` (rows, nstate) is updated in place."""
+        rows, n = x.shape
+        assert state.shape == (rows, self.nstate) and state.is_contiguous()
+        xp, ldx = _rows_ptr(x)
+        if want_output:
+            if out is None:
+                out = empty((rows, n))
+            yp, ldy = _rows_ptr(out)
+        else:
+            out, yp, ldy = None, _vp(0), 0
+        rc = _launch("tf", 16 * rows * n, _abi.load().osz_tf_exec_f64, self.handle, xp, ldx, rows,
+                     n, int(bool(reverse)), _vp(state.data_ptr()), yp, ldy, _cur_stream())
+        _abi.check(rc, "tf_exec")
+        return out
+
+    def state_from_sample(self, zi, x, sample):
+        """state[r, :] = zi * x[r, sample]."""
+        rows = x.shape[0]
+        zarr, zptr = _abi.as_double_array(zi)
+        assert zarr.shape == (self.nstate,)
+        state = empty((rows, self.nstate))
+        xp, ldx = _rows_ptr(x)
+        rc = _abi.load().osz_tf_state_from_sample_f64(self.handle, zptr, xp, ldx, rows,
+                                                      int(sample), _vp(state.data_ptr()),
+                                                      _cur_stream())
+        _abi.check(rc, "tf_state_from_sample")
+        return state
+
+
 class UpfirdnPlan(_Plan):
     _destroy = "osz_upfirdn_plan_destroy"
 
@@ -454,6 +504,20 @@ class SpecPlan(_Plan):
         rc = fn(self.handle, xp, ldx, rows, int(nseg), _vp(out.data_ptr()), _cur_stream())
         _abi.check(rc, "stft" if complex_ else "periodogram")
         return out
+
+
+def spec_prepare(x, n, nfft, window, detrend):
+    """(rows, nfft) device rows: the first n samples of x detrended and
+    windowed, then zeros (periodogram / modified_dft with nfft > n)."""
+    rows = x.shape[0]
+    w = from_host(np.ascontiguousarray(window, dtype=np.float64))
+    out = empty((rows, int(nfft)))
+    xp, ldx = _rows_ptr(x)
+    op, ldo = _rows_ptr(out)
+    rc = _abi.load().osz_spec_prepare_f64(xp, ldx, rows, int(n), int(nfft), _vp(w.data_ptr()),
+                                          _abi.DETREND[detrend], op, ldo, _cur_stream())
+    _abi.check(rc, "spec_prepare")
+    return out
 
 
 def ceil_div(a, b):

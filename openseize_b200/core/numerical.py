@@ -429,17 +429,57 @@ def sosfiltfilt(pro, sos, axis):
     exactly as the reference's does."""
 
 
+def _ba_order(coeffs):
+    b, a = coeffs
+    return int(max(len(np.atleast_1d(b)), len(np.atleast_1d(a))) - 1)
+
+
 def _ba_to_sos(coeffs):
     """(b, a) of order <= 2 as one DF2T biquad -- scipy's lfilter recurrence for
     order 2 is the sosfilt section recurrence."""
     b, a = (np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in coeffs)
     if max(len(b), len(a)) > 3:
-        raise NotImplementedError(
-            "transfer-function (b, a) filters above second order are not on the GPU path "
-            "yet; design the filter with fmt='sos'")
+        raise ValueError("_ba_to_sos: order above 2")
     b = np.pad(b, (0, 3 - len(b)))
     a = np.pad(a, (0, 3 - len(a)))
     return np.concatenate([b, a])[None, :]
+
+
+class _TfFilter:
+    """A (b, a) filter above second order behind the interface the shared
+    drivers use of `_Cascade` (run / state_from_sample / zero_state / settle).
+    The state of a row is scipy's lfilter `zi` vector (order,)."""
+
+    def __init__(self, coeffs):
+        b, a = (np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in coeffs)
+        self.plan = dv.TfPlan.cached(b, a)
+        self.nstate = self.plan.nstate
+        poles = np.roots(a) if len(a) > 1 else np.zeros(0)
+        rmax = float(np.max(np.abs(poles))) if len(poles) else 0.0
+        if rmax >= 1.0:
+            self.settle = None
+        elif rmax == 0.0:
+            self.settle = 2 * self.nstate
+        else:
+            self.settle = int(np.ceil(np.log(1e-24) / np.log(rmax))) + 64 * self.nstate
+
+    def zero_state(self, rows):
+        return dv.zeros((rows, self.nstate))
+
+    def state_from_sample(self, zi, x, sample):
+        return self.plan.state_from_sample(zi, x, sample)
+
+    def run(self, x, state, reverse=False, want_output=True, out=None):
+        dst = _new_rows(out, x.shape[0], x.shape[1]) if want_output else None
+        return self.plan.run(x, state, reverse=reverse, want_output=want_output, out=dst)
+
+
+def _tf_zi_rows(coeffs, zi, layout):
+    """Reference lfilter zi layout (..., K-1, ...) -> (rows, K-1) state rows."""
+    k = _ba_order(coeffs)
+    zi = np.broadcast_to(np.asarray(zi, dtype=np.float64), layout.host_shape(k))
+    zi = np.moveaxis(zi.reshape(layout.outer, k, layout.inner), 1, 2)
+    return dv.from_host(np.ascontiguousarray(zi).reshape(layout.rows, k))
 
 
 def _lfilter_zi_rows(coeffs, zi, layout):
@@ -457,6 +497,12 @@ def _lfilter_zi_rows(coeffs, zi, layout):
 def _lfilter_device(pro, coeffs, axis, zi=None, _out=None, _free=False):
     dv.require_cuda()
     layout = _layout_of(pro, axis)
+    if _ba_order(coeffs) > 2:
+        filt = _TfFilter(coeffs)
+        states = filt.zero_state(layout.rows) if zi is None else _tf_zi_rows(coeffs, zi, layout)
+        for chunk in device_chunks(pro, axis, regrid=False):
+            yield filt.run(chunk, states, out=_out)
+        return
     cascade = _Cascade(_ba_to_sos(coeffs))
     if zi is None:
         states = cascade.zero_state(layout.rows)
@@ -468,14 +514,18 @@ def _lfilter_device(pro, coeffs, axis, zi=None, _out=None, _free=False):
 
 @_gpu_genfunc(_lfilter_device, _same_layout)
 def lfilter(pro, coeffs, axis, zi=None):
-    """Forward (b, a) filter with carried state (reference numerical.py:414-446);
-    second order and below (``Notch`` always is, filtering/iir.py:391)."""
+    """Forward (b, a) filter with carried state (reference numerical.py:414-446).
+    Second order and below (``Notch`` always is, filtering/iir.py:391) runs on
+    the time-parallel biquad scan, higher orders on the sequential DF2T kernel."""
 
 
 def _filtfilt_ba_device(pro, coeffs, axis, _out=None, _free=False):
     dv.require_cuda()
-    cascade = _Cascade(_ba_to_sos(coeffs))
     z = np.atleast_1d(sps.lfilter_zi(*coeffs))        # numerical.py:487
+    if _ba_order(coeffs) > 2:
+        yield from _filtfilt_device(pro, _TfFilter(coeffs), z, axis, _out)
+        return
+    cascade = _Cascade(_ba_to_sos(coeffs))
     zi = np.zeros((1, 2))
     zi[0, :len(z)] = z
     yield from _filtfilt_device(pro, cascade, zi, axis, _out)
@@ -756,10 +806,17 @@ def _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_):
     nsamp = arr.shape[axis]
     if nsamp == 0:
         raise ValueError("cannot estimate the spectrum of an empty array")
-    if nsamp != nfft:
-        raise NotImplementedError(
-            "zero-padded DFTs (nfft > samples) are not on the GPU path; openseize's "
-            "estimators always use nfft-long segments")
+    if nsamp < nfft:
+        # zero-padded transform (reference numerical.py:688-699): detrend and
+        # window the nsamp samples, pad with zeros, transform with a unit window
+        layout = dv.Layout(arr.shape, axis)
+        coeffs = sps.get_window(window, nsamp)
+        padded = dv.spec_prepare(dv.upload(arr, layout), nsamp, nfft, coeffs, detrend)
+        plan = dv.SpecPlan.cached(nfft, nfft, np.ones(nfft), None,
+                                  _spec_norm(coeffs, fs, scaling))
+        out = plan.segments(padded, 1, complex_)[0]
+        res = dv.download(out, layout, complex_).get()
+        return np.fft.rfftfreq(nfft, d=1 / fs), np.array(res)
     layout = dv.Layout(arr.shape, axis)
     coeffs = sps.get_window(window, nsamp)
     plan = dv.SpecPlan.cached(nfft, nfft, coeffs, detrend, _spec_norm(coeffs, fs, scaling))

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libosz_b200.so")
-SOURCES = ["runtime.cu", "fir.cu", "sos.cu", "upfirdn.cu", "spectra.cu", "spectra_generic.cu"]
+SOURCES = ["runtime.cu", "fir.cu", "sos.cu", "tf.cu", "upfirdn.cu", "spectra.cu",
+           "spectra_generic.cu"]
 HEADERS = ["common.cuh", "fft_core.cuh", os.path.join("..", "..", "include", "osz_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

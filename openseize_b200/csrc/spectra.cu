@@ -420,6 +420,45 @@ spec_segments_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, in
     }
 }
 
+// One zero-padded segment per row (periodogram / modified_dft with nfft > n,
+// reference numerical.py:688-699): out[r][i] = (x[r][i] - trend_r(i)) * win[i]
+// for i < n, 0 for n <= i < nfft.  One CTA per row; the transform itself then
+// runs with a unit window and no detrending.
+__global__ void __launch_bounds__(256)
+spec_prepare_kernel(const double *__restrict__ x, int64_t ldx, int64_t n, int64_t nfft,
+                    const double *__restrict__ win, int detrend, double *__restrict__ out,
+                    int64_t ldo) {
+    __shared__ double red[4 * 32];
+    const int tid = threadIdx.x;
+    const double *xr = x + (int64_t)blockIdx.x * ldx;
+    double *orow = out + (int64_t)blockIdx.x * ldo;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const double tbar = 0.5 * (double)(n - 1);
+    if (detrend != OSZ_DETREND_NONE) {
+        for (int64_t i = tid; i < n; i += 256) {
+            const double v = xr[i];
+            s[0] += v;
+            s[2] = fma((double)i - tbar, v, s[2]);
+        }
+        block_sum<4, 256>(s, red, tid);
+    }
+    const double mean = s[0] / (double)n;
+    double slope = 0.0;
+    if (detrend == OSZ_DETREND_LINEAR && n > 1) {
+        const double dn = (double)n;
+        slope = s[2] / (dn * (dn * dn - 1.0) / 12.0);
+    }
+    for (int64_t i = tid; i < nfft; i += 256) {
+        double v = 0.0;
+        if (i < n) {
+            v = xr[i];
+            if (detrend != OSZ_DETREND_NONE) v -= fma(slope, (double)i - tbar, mean);
+            v *= win[i];
+        }
+        orow[i] = v;
+    }
+}
+
 }  // namespace osz
 
 using namespace osz;
@@ -613,6 +652,19 @@ int osz_welch_accum_f64(const osz_spec_plan *p, const double *x, int64_t ldx, in
 int osz_periodogram_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                         int64_t nseg, double *out, void *stream) {
     return spec_exec(p, SPEC_PGRAM, x, ldx, rows, nseg, out, 0, stream);
+}
+int osz_spec_prepare_f64(const double *x, int64_t ldx, int64_t rows, int64_t n, int64_t nfft,
+                         const double *window_dev, int detrend, double *out, int64_t ldo,
+                         void *stream) {
+    if (!x || !window_dev || !out || n < 1 || nfft < n)
+        return fail(OSZ_ERR_ARG, "osz_spec_prepare_f64: bad arguments");
+    if (detrend < OSZ_DETREND_NONE || detrend > OSZ_DETREND_LINEAR)
+        return fail(OSZ_ERR_ARG, "osz_spec_prepare_f64: unknown detrend");
+    if (rows <= 0) return OSZ_OK;
+    spec_prepare_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, ldx, n, nfft, window_dev,
+                                                                      detrend, out, ldo);
+    OSZ_LAUNCHED("spec_prepare_kernel");
+    return OSZ_OK;
 }
 int osz_stft_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t nseg,
                  double *out, void *stream) {

@@ -59,6 +59,25 @@ class FakeSos:
         return _t(zi[None, :, :] * x.numpy()[:, sample][:, None, None])
 
 
+class FakeTf:
+    def __init__(self, b, a):
+        self.b, self.a = np.atleast_1d(b).astype(float), np.atleast_1d(a).astype(float)
+        self.nstate = max(len(self.b), len(self.a)) - 1
+
+    def run(self, x, state, reverse=False, want_output=True, out=None):
+        xn = x.numpy()
+        if reverse:
+            xn = xn[:, ::-1]
+        y, zf = sps.lfilter(self.b, self.a, xn, axis=-1, zi=state.numpy())
+        state.copy_(_t(zf))
+        if not want_output:
+            return None
+        return _ret(y[:, ::-1] if reverse else y, out)
+
+    def state_from_sample(self, zi, x, sample):
+        return _t(np.asarray(zi, dtype=float)[None, :] * x.numpy()[:, sample][:, None])
+
+
 class FakeUpfirdn:
     def __init__(self, h, up, down):
         self.h = np.asarray(h, dtype=np.float64) * up
@@ -143,13 +162,24 @@ def _download(dev, layout, complex_=False):
     return _Now(np.ascontiguousarray(a).reshape(layout.host_shape(n)))
 
 
+def _spec_prepare(x, n, nfft, window, detrend):
+    seg = x.numpy()[:, :n]
+    if detrend in ("constant", "linear"):
+        seg = sps.detrend(seg, axis=-1, type=detrend)
+    out = np.zeros((seg.shape[0], nfft))
+    out[:, :n] = seg * np.asarray(window)
+    return _t(out)
+
+
 def install(mp):
     mp.setattr(dv, "DEVICE", "cpu")
     mp.setattr(dv, "require_cuda", lambda: torch)
     mp.setattr(dv, "upload", _upload)
     mp.setattr(dv, "download", _download)
+    mp.setattr(dv, "spec_prepare", _spec_prepare)
     mp.setattr(dv.FirPlan, "cached", staticmethod(lambda taps, algo=0: FakeFir(taps, algo)))
     mp.setattr(dv.SosPlan, "cached", staticmethod(lambda sos: FakeSos(sos)))
+    mp.setattr(dv.TfPlan, "cached", staticmethod(lambda b, a: FakeTf(b, a)))
     mp.setattr(dv.UpfirdnPlan, "cached",
                staticmethod(lambda h, up, down: FakeUpfirdn(h, up, down)))
     mp.setattr(dv.SpecPlan, "cached",

@@ -155,6 +155,20 @@ def iir_oracle_sweep():
     close(got, np.concatenate(oracle.lfilter(x, (b, a), 6000, -1, zi)[0], -1))
     got = np.concatenate(list(nm.filtfilt(producer(x, 6000, -1), (b, a), -1)), -1)
     close(got, np.concatenate(oracle.filtfilt(x, (b, a), 6000, -1), -1))
+    # transfer-function filters above second order (sequential DF2T kernel)
+    for coeffs in (sps.butter(4, [0.05, 0.3], btype="bandpass"), sps.cheby1(5, 1, 0.25),
+                   sps.butter(3, 0.2)):
+        k = max(len(coeffs[0]), len(coeffs[1])) - 1
+        x = rng.standard_normal((3, 21013)) + 1.0
+        zi = rng.standard_normal((3, k))
+        got = np.concatenate(list(nm.lfilter(producer(x, 6000, -1), coeffs, -1, zi)), -1)
+        close(got, np.concatenate(oracle.lfilter(x, coeffs, 6000, -1, zi)[0], -1))
+        got = np.concatenate(list(nm.filtfilt(producer(x, 6000, -1), coeffs, -1)), -1)
+        close(got, np.concatenate(oracle.filtfilt(x, coeffs, 6000, -1), -1))
+    xm = rng.standard_normal((2, 9001, 2))
+    coeffs = sps.butter(4, 0.3)
+    got = np.concatenate(list(nm.filtfilt(producer(xm, 4000, 1), coeffs, 1)), 1)
+    close(got, np.concatenate(oracle.filtfilt(xm, coeffs, 4000, 1), 1))
     # chunks longer than the cascade's settle length: the look-ahead pass of the
     # forward-backward filters is cut to the samples that still matter
     x = rng.standard_normal((2, 130001)) + 5.0
@@ -281,6 +295,20 @@ def spectra_oracle_sweep(fs=1024, resolutions=(1.0, 2.0, 4.0)):
     f, t, Xp = stft(producer(x, 9000, -1), fs, resolution=resolutions[0], asarray=False)
     assert not isinstance(Xp, np.ndarray)
     close(np.stack(list(Xp), -1), oracle.stft(x, fs, -1, resolutions[0])[2])
+    # single in-memory segments, zero padded (nfft > samples) and cropped
+    # (reference tests/test_spectra.py:16-139)
+    seg = rng.standard_normal((3, 700)) + 1.5
+    for nfft in (700, 1024, 1500, 512):
+        for det in ("constant", "linear"):
+            for scaling in ("density", "spectrum"):
+                f, p = nm.periodogram(seg, fs, nfft=nfft, window="hann", axis=-1, detrend=det,
+                                      scaling=scaling)
+                rf, rp = oracle.periodogram(seg, fs, nfft, "hann", -1, det, scaling)
+                assert np.array_equal(f, rf)
+                close(p, rp)
+    f, X = nm.modified_dft(seg.T.copy(), fs, 1024, "hamming", 0, "constant", "density")
+    rf, rX = oracle.modified_dft(seg.T.copy(), fs, 1024, "hamming", 0, "constant", "density")
+    close(X, rX)
 
 
 def fused_fir_decimate():
