@@ -104,9 +104,11 @@ def main(which):
                timeit(lambda: plan.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
         del x
     if not which or "welch" in which:
-        for nfft in (1024, 4096, 8192):
+        for nfft in (1024, 4096, 8192) + ((2400, 10000, 60000) if "generic" in which else ()):
             w = sps.get_window("hann", nfft)
             plan = dv.SpecPlan(nfft, nfft // 2, w, "constant", 1.0 / (30000 * np.sum(w ** 2)))
+            if nfft > 8192:
+                rows = 64
             x = rnd(rows, n)
             nseg = plan.nseg_available(n)
             acc = dv.zeros((rows, nfft // 2 + 1))
