@@ -67,7 +67,9 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 int64_t n_total, int reverse, const double *__restrict__ state_in,
                 double *__restrict__ state, double *__restrict__ y, int64_t ldy,
                 const double *__restrict__ lanepow /* [sec][32][4]: A^(T*(lane+1)) */,
-                int64_t span_len, int64_t settle) {
+                int64_t span_len, int64_t settle,
+                const double *__restrict__ span_in /* exact split, pass 2: entering states */,
+                double *__restrict__ span_out /* exact split, pass 1: final states */) {
     constexpr int BLK = SOS_NT * T;        // samples per CTA iteration
     constexpr int LD = T + 1;              // padded shared-memory row
     constexpr int LOGT = T == 32 ? 5 : 4;
@@ -87,19 +89,30 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     // before `a` (a stable cascade has forgotten its starting state by then, to
     // ~1e-24 relative) and store nothing for them.  Span 0 starts from the
     // carried state; the last span writes the state that is carried on.
+    // Exact split (span_in / span_out): no warm-up; pass 1 runs every span from
+    // rest (span 0 from the carried state) and publishes its final state, the
+    // host-launched combine kernel turns those into entering states, pass 2
+    // starts every span from its true entering state.
+    const bool exact = span_in != nullptr || span_out != nullptr;
     const int64_t span = blockIdx.y;
     const int64_t a = span * span_len;
     int64_t b = a + span_len;
     if (b > n_total) b = n_total;
-    const int64_t w0 = span == 0 ? 0 : a - settle;      // first logical sample processed
+    const int64_t w0 = (span == 0 || exact) ? a : a - settle;   // first logical sample processed
     const int64_t n = b - w0;                           // samples this CTA runs through
     const int64_t keep = a - w0;                        // local index of the first stored sample
     // logical sample s (local) <-> global index: forward w0 + s, reverse n_total-1-(w0+s)
     const double *xr = x + row * ldx + (reverse ? n_total - 1 - w0 : w0);
     double *yr = WRITE ? y + row * ldy + (reverse ? n_total - 1 - w0 : w0) : nullptr;
 
-    if (tid < nsec * 2)
-        carry[tid >> 1][tid & 1] = span == 0 ? state_in[row * nsec * 2 + tid] : 0.0;
+    if (tid < nsec * 2) {
+        double c0 = 0.0;
+        if (span == 0)
+            c0 = state_in[row * nsec * 2 + tid];
+        else if (span_in)
+            c0 = span_in[(row * gridDim.y + span) * nsec * 2 + tid];
+        carry[tid >> 1][tid & 1] = c0;
+    }
 
     const int64_t nblk = (n + BLK - 1) / BLK;
     const int64_t first_len = n - (nblk - 1) * BLK;
@@ -267,7 +280,36 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
         }
     }
     __syncthreads();
-    if (span == gridDim.y - 1 && tid < nsec * 2) st[tid] = carry[tid >> 1][tid & 1];
+    if (tid < nsec * 2) {
+        if (span_out)
+            span_out[(row * gridDim.y + span) * nsec * 2 + tid] = carry[tid >> 1][tid & 1];
+        else if (span == gridDim.y - 1)
+            st[tid] = carry[tid >> 1][tid & 1];
+    }
+}
+
+// Exact split, between the passes: entering state of span k+1 = Phi e_k + f_k,
+// Phi = (zero-input transition of the whole cascade)^(span length); span 0 ran
+// from the true carried state, so f_0 is already the state entering span 1.
+__global__ void sos_combine_kernel(const double *__restrict__ phi /* ns2 x ns2 */,
+                                   const double *__restrict__ f, double *__restrict__ e,
+                                   int64_t rows, int nspan, int ns2) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    double cur[2 * SOS_MAXSEC], nxt[2 * SOS_MAXSEC];
+    const double *fr = f + row * nspan * ns2;
+    double *er = e + row * nspan * ns2;
+    for (int i = 0; i < ns2; ++i) cur[i] = fr[i];
+    for (int k = 1; k < nspan; ++k) {
+        for (int i = 0; i < ns2; ++i) er[k * ns2 + i] = cur[i];
+        if (k + 1 == nspan) break;
+        for (int i = 0; i < ns2; ++i) {
+            double acc = fr[k * ns2 + i];
+            for (int j = 0; j < ns2; ++j) acc = fma(phi[i * ns2 + j], cur[j], acc);
+            nxt[i] = acc;
+        }
+        for (int i = 0; i < ns2; ++i) cur[i] = nxt[i];
+    }
 }
 
 __global__ void sos_copy_state_kernel(const double *__restrict__ src, double *__restrict__ dst,
@@ -300,6 +342,12 @@ struct osz_sos_plan {
     mutable double *d_scratch = nullptr;
     mutable int64_t scratch_count = 0;
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
+    // exact time split: per-span states (pass 1 finals | pass 2 entering) and Phi
+    mutable double *d_span = nullptr;
+    mutable int64_t span_count = 0;
+    mutable double *d_phi = nullptr;
+    mutable int64_t phi_len = -1;   // span length d_phi was built for
+    std::vector<long double> Tmat;  // (2 nsec)^2 one-step zero-input transition, row major
 };
 
 namespace {
@@ -403,6 +451,26 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         }
     }
     for (int s = nsec; s < SOS_MAXSEC; ++s) p->prm.sec[s] = SosSec{};
+    {
+        // one-step zero-input transition of the whole cascade (the next section's
+        // input is this section's output): column j = step(unit state j, x = 0)
+        const int ns2 = 2 * nsec;
+        p->Tmat.assign((size_t)ns2 * ns2, 0.0L);
+        for (int j = 0; j < ns2; ++j) {
+            long double xin = 0.0L;
+            for (int s2 = 0; s2 < nsec; ++s2) {
+                const SosSec &c = p->prm.sec[s2];
+                const long double z0 = (j == 2 * s2) ? 1.0L : 0.0L;
+                const long double z1 = (j == 2 * s2 + 1) ? 1.0L : 0.0L;
+                const long double yv = (long double)c.b0 * xin + z0;
+                p->Tmat[(size_t)(2 * s2) * ns2 + j] =
+                    (long double)c.b1 * xin - (long double)c.a1 * yv + z1;
+                p->Tmat[(size_t)(2 * s2 + 1) * ns2 + j] =
+                    (long double)c.b2 * xin - (long double)c.a2 * yv;
+                xin = yv;
+            }
+        }
+    }
     if (rmax < 1.0)
         p->settle = rmax <= 0.0 ? 2 * nsec
                                 : (int64_t)ceil(log(1e-24) / log(rmax)) + 64 * (int64_t)nsec;
@@ -420,6 +488,8 @@ int osz_sos_plan_destroy(osz_sos_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_lanepow);
     cudaFree(p->d_scratch);
+    cudaFree(p->d_span);
+    cudaFree(p->d_phi);
     delete p;
     return OSZ_OK;
 }
@@ -430,32 +500,90 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
     const int smem = SOS_NT * (p->T + 1) * 8;
+    const int64_t BLK = (int64_t)SOS_NT * p->T;
+    const int ns2 = 2 * p->prm.nsec;
     // Spans per row.  Splitting pays only while one CTA per row leaves SMs idle
-    // (rows <= SM count): 64 rows x 8 sections 1.83 -> 1.32 ms with 2 spans, but
-    // 256 rows 2.76 -> 3.27 ms (the warm-up is extra work on a full GPU).  Each
-    // span is at least two settle lengths long.  OSZ_SOS_SPLIT forces a count.
+    // (rows <= SM count).  Two ways to cut a row:
+    //   warm-up: every later span re-filters the `settle` samples before it from
+    //            rest (cost n/k + settle per CTA); 64 rows x 8 sections 1.83 -> 1.32 ms
+    //            with 2 spans, but useless on a full GPU (256 rows 2.76 -> 3.27 ms)
+    //            and impossible when the filter decays slowly (settle ~ n);
+    //   exact:   pass 1 reduces every span to its final state from rest, a combine
+    //            kernel composes them with Phi = T^(span length), pass 2 filters
+    //            every span from its true entering state (cost ~2.1 n/k).
+    // OSZ_SOS_SPLIT / OSZ_SOS_EXACT force a span count of either kind.
     int64_t nspan = 1;
-    if (p->settle > 0 && y) {       // a state-only pass wants the last span only
+    bool exact = false;
+    if (y) {                        // a state-only pass wants the last span only
         static const int forced = [] {
             const char *e = getenv("OSZ_SOS_SPLIT");
             return e ? atoi(e) : 0;
         }();
-        const int64_t by_len = n / (2 * p->settle);
-        int64_t want = 1;
-        if (forced > 0)
-            want = forced;
-        else if (rows <= sm_count())
-            want = (2 * (int64_t)sm_count() + rows - 1) / rows;
-        if (want > by_len) want = by_len;
-        if (want > 65535) want = 65535;
-        if (want > 1) nspan = want;
+        static const int forced_exact = [] {
+            const char *e = getenv("OSZ_SOS_EXACT");
+            return e ? atoi(e) : 0;
+        }();
+        // Predicted time of a launch, in units of "samples one CTA filters alone":
+        // per-CTA work times the slow-down once CTAs outnumber the SMs (a second
+        // co-resident CTA adds ~35 %; fitted on B200 to 4...128 rows x {1, 8} sections,
+        // profiles/r01_kernel_bench.md).
+        const double sms = (double)sm_count();
+        auto slowdown = [&](double ctas) {
+            if (ctas <= sms) return 1.0;
+            const double resident = ctas < 2 * sms ? ctas : 2 * sms;   // two CTAs per SM fit
+            const double waves = ceil(ctas / (2 * sms));
+            return waves * resident / (sms + 0.35 * (resident - sms));
+        };
+        // fixed cost of the exact split (two extra launches, the combine loop), in samples
+        const double ms_per_msample = 0.36 + 0.172 * p->prm.nsec;
+        int64_t kmax_warm = p->settle > 0 ? n / (2 * p->settle) : 0;
+        int64_t kmax_exact = n / (8 * BLK);          // spans of at least eight blocks
+        if (forced > 0) {
+            kmax_exact = 0;
+            kmax_warm = kmax_warm < forced ? kmax_warm : forced;
+        } else if (forced_exact > 0) {
+            kmax_warm = 0;
+            kmax_exact = kmax_exact < forced_exact ? kmax_exact : forced_exact;
+        }
+        if (kmax_warm > 64) kmax_warm = 64;
+        if (kmax_exact > 64) kmax_exact = 64;
+        if (forced > 0) {
+            if (kmax_warm >= 2) nspan = kmax_warm;
+        } else if (forced_exact > 0) {
+            if (kmax_exact >= 2) {
+                nspan = kmax_exact;
+                exact = true;
+            }
+        } else {
+            double best = (double)n * slowdown((double)rows);
+            const int64_t kmax = kmax_warm > kmax_exact ? kmax_warm : kmax_exact;
+            for (int64_t k = 2; k <= kmax; ++k) {
+                const double slow = slowdown((double)rows * k);
+                if (k <= kmax_warm) {
+                    const double t = ((double)n / k + (double)p->settle) * slow;
+                    if (t < best) {
+                        best = t;
+                        nspan = k;
+                        exact = false;
+                    }
+                }
+                if (k <= kmax_exact) {
+                    const double fixed = (0.06 + 4e-6 * k * ns2 * ns2) / ms_per_msample * 1e6;
+                    const double t = 2.1 * (double)n / k * slow + fixed;
+                    if (t < best) {
+                        best = t;
+                        nspan = k;
+                        exact = true;
+                    }
+                }
+            }
+        }
     }
     const int64_t span_len = (n + nspan - 1) / nspan;
     const double *state_in = state;
-    double *tmp = nullptr;
     if (nspan > 1) {
         // the last span writes the carried state while span 0 may still read it
-        const int64_t count = rows * p->prm.nsec * 2;
+        const int64_t count = rows * ns2;
         if (p->scratch_count < count) {
             if (p->d_scratch) OSZ_CUDA(cudaFree(p->d_scratch));
             p->d_scratch = nullptr;
@@ -463,27 +591,81 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
             OSZ_CUDA(cudaMalloc(&p->d_scratch, (size_t)count * 8));
             p->scratch_count = count;
         }
-        tmp = p->d_scratch;
-        sos_copy_state_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(state, tmp, count);
+        sos_copy_state_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(state, p->d_scratch,
+                                                                             count);
         OSZ_LAUNCHED("sos_copy_state_kernel");
-        state_in = tmp;
+        state_in = p->d_scratch;
+    }
+    double *span_f = nullptr, *span_e = nullptr;
+    if (exact) {
+        const int64_t count = rows * nspan * ns2;
+        if (p->span_count < 2 * count) {
+            if (p->d_span) OSZ_CUDA(cudaFree(p->d_span));
+            p->d_span = nullptr;
+            p->span_count = 0;
+            OSZ_CUDA(cudaMalloc(&p->d_span, (size_t)(2 * count) * 8));
+            p->span_count = 2 * count;
+        }
+        span_f = p->d_span;
+        span_e = p->d_span + count;
+        if (p->phi_len != span_len) {
+            // Phi = T^span_len by repeated squaring in long double
+            const size_t nn = (size_t)ns2 * ns2;
+            std::vector<long double> acc(nn, 0.0L), base(p->Tmat), tmp(nn);
+            for (int i = 0; i < ns2; ++i) acc[(size_t)i * ns2 + i] = 1.0L;
+            auto matmul = [&](const std::vector<long double> &A, const std::vector<long double> &B,
+                              std::vector<long double> &C) {
+                for (int i = 0; i < ns2; ++i)
+                    for (int j = 0; j < ns2; ++j) {
+                        long double sum = 0.0L;
+                        for (int k = 0; k < ns2; ++k)
+                            sum += A[(size_t)i * ns2 + k] * B[(size_t)k * ns2 + j];
+                        C[(size_t)i * ns2 + j] = sum;
+                    }
+            };
+            for (int64_t e = span_len; e; e >>= 1) {
+                if (e & 1) {
+                    matmul(base, acc, tmp);
+                    acc.swap(tmp);
+                }
+                matmul(base, base, tmp);
+                base.swap(tmp);
+            }
+            std::vector<double> phi(nn);
+            for (size_t i = 0; i < nn; ++i) phi[i] = (double)acc[i];
+            if (!p->d_phi) OSZ_CUDA(cudaMalloc(&p->d_phi, (size_t)4 * SOS_MAXSEC * SOS_MAXSEC * 8));
+            // (stream-ordered with the kernels below; pageable source: synchronous on return)
+            OSZ_CUDA(cudaMemcpyAsync(p->d_phi, phi.data(), nn * 8, cudaMemcpyHostToDevice, st));
+            OSZ_CUDA(cudaStreamSynchronize(st));
+            p->phi_len = span_len;
+        }
     }
     const dim3 grid((unsigned)rows, (unsigned)nspan);
-#define OSZ_SOS_LAUNCH(W, TT)                                                                   \
+#define OSZ_SOS_LAUNCH(W, TT, YY, SIN, SOUT)                                                    \
     do {                                                                                        \
         OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
         sos_scan_kernel<W, TT><<<grid, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse, state_in, \
-                                                           state, y, ldy, p->d_lanepow,         \
-                                                           span_len, p->settle);                \
+                                                           state, YY, ldy, p->d_lanepow,        \
+                                                           span_len, p->settle, SIN, SOUT);     \
+        OSZ_LAUNCHED("sos_scan_kernel");                                                        \
     } while (0)
-    if (y) {
-        if (p->T == 16) OSZ_SOS_LAUNCH(true, 16); else OSZ_SOS_LAUNCH(true, 32);
+    if (exact) {
+        if (p->T == 16) OSZ_SOS_LAUNCH(false, 16, nullptr, nullptr, span_f);
+        else OSZ_SOS_LAUNCH(false, 32, nullptr, nullptr, span_f);
+        sos_combine_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>(p->d_phi, span_f, span_e,
+                                                                       rows, (int)nspan, ns2);
+        OSZ_LAUNCHED("sos_combine_kernel");
+        if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, span_e, nullptr);
+        else OSZ_SOS_LAUNCH(true, 32, y, span_e, nullptr);
+    } else if (y) {
+        if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, nullptr, nullptr);
+        else OSZ_SOS_LAUNCH(true, 32, y, nullptr, nullptr);
     } else {
-        if (p->T == 16) OSZ_SOS_LAUNCH(false, 16); else OSZ_SOS_LAUNCH(false, 32);
+        if (p->T == 16) OSZ_SOS_LAUNCH(false, 16, nullptr, nullptr, nullptr);
+        else OSZ_SOS_LAUNCH(false, 32, nullptr, nullptr, nullptr);
     }
 #undef OSZ_SOS_LAUNCH
-    OSZ_LAUNCHED("sos_scan_kernel");
     return OSZ_OK;
 }
 
