@@ -469,6 +469,7 @@ struct osz_spec_plan {
     double *d_win = nullptr;
     double2 *d_tw = nullptr;
     void *generic = nullptr;    // spectra_generic.cu state
+    void *mixed = nullptr;      // spectra_mixed.cu state (shared-memory mixed radix), may be null
 };
 
 // generic path (spectra_generic.cu)
@@ -476,6 +477,12 @@ int osz_generic_create(void **state, int nfft);
 void osz_generic_destroy(void *state);
 int osz_generic_exec(void *state, const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
                      int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st);
+// shared-memory mixed-radix path (spectra_mixed.cu)
+int osz_mixed_create(void **state, int nfft);
+void osz_mixed_destroy(void *state);
+int osz_mixed_can(void *state, int mode);
+int osz_mixed_exec(void *state, const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
+                   int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st);
 // accessors used by the generic path
 int osz_spec_plan_nfft(const osz_spec_plan *p) { return p->nfft; }
 int osz_spec_plan_stride(const osz_spec_plan *p) { return p->stride; }
@@ -582,7 +589,15 @@ static int spec_exec(const osz_spec_plan *p, int mode, const double *x, int64_t 
     if (rows <= 0 || nseg <= 0) return OSZ_OK;
     if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "spectra: more than 65535 rows per call");
     cudaStream_t st = as_stream(stream);
-    if (p->path == 2) return osz_generic_exec(p->generic, p, mode, x, ldx, rows, nseg, out, ldp, st);
+    if (p->path == 2) {
+        static const int use_mixed = [] {
+            const char *e = getenv("OSZ_SPEC_MIXED");
+            return e ? atoi(e) : 1;
+        }();
+        if (use_mixed && p->mixed && osz_mixed_can(p->mixed, mode))
+            return osz_mixed_exec(p->mixed, p, mode, x, ldx, rows, nseg, out, ldp, st);
+        return osz_generic_exec(p->generic, p, mode, x, ldx, rows, nseg, out, ldp, st);
+    }
     switch (p->log2n) {
         case 8: return dispatch_detrend<8>(p, mode, x, ldx, rows, nseg, out, ldp, st);
         case 9: return dispatch_detrend<9>(p, mode, x, ldx, rows, nseg, out, ldp, st);
@@ -621,6 +636,7 @@ int osz_spec_plan_create(osz_spec_plan **out, int nfft, int stride, const double
     } else if (ok) {
         p->path = 2;
         int rc = osz_generic_create(&p->generic, nfft);
+        if (rc == OSZ_OK) rc = osz_mixed_create(&p->mixed, nfft);
         if (rc != OSZ_OK) {
             osz_spec_plan_destroy(p);
             return rc;
@@ -639,6 +655,7 @@ int osz_spec_plan_destroy(osz_spec_plan *p) {
     cudaFree(p->d_win);
     cudaFree(p->d_tw);
     if (p->generic) osz_generic_destroy(p->generic);
+    if (p->mixed) osz_mixed_destroy(p->mixed);
     delete p;
     return OSZ_OK;
 }
