@@ -91,6 +91,19 @@ int osz_widen_rows_f32_f64(const float *src_dev, int64_t ld_src, double *dst_dev
                            int64_t rows, int64_t n, void *stream);
 int osz_widen_rows_i16_f64(const int16_t *src_dev, int64_t ld_src, double *dst_dev,
                            int64_t ld_dst, int64_t rows, int64_t n, void *stream);
+/* EDF ingest fused into the upload (the reference's Reader._records / _read_array
+ * / _decipher, file_io/edf.py:382-419,452-556).  rec_dev holds whole data records as
+ * they sit in the file, per_record int16 each, every selected channel with spr
+ * samples per record at chan_off[c] inside a record; row c of dst receives samples
+ * skip .. skip+n-1 (counted from the first record in rec_dev):
+ *   dst[c][i] = rec[(skip+i)/spr][chan_off[c] + (skip+i)%spr] * slope[c] + offset[c]
+ * multiply and add rounded separately like numpy's `arr * slopes; result += offsets`.
+ * The records cross PCIe as int16: a quarter of the float64 width, and no host-side
+ * de-interleaving. */
+int osz_decode_edf_records_f64(const int16_t *rec_dev, int64_t per_record, int64_t spr,
+                               const int *chan_off_dev, const double *slope_dev,
+                               const double *offset_dev, int64_t skip, double *dst_dev,
+                               int64_t ld_dst, int64_t rows, int64_t n, void *stream);
 
 /* ---- FIR: replaces _cconvolve + overlap-add of nm.oaconvolve
  *      (core/numerical.py:229-269) --------------------------------------- */

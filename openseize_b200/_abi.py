@@ -44,6 +44,8 @@ SIGNATURES = {
     "osz_widen_i16_f64": (c_int, [_vp, _vp, _i64, _vp]),
     "osz_widen_rows_f32_f64": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "osz_widen_rows_i16_f64": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "osz_decode_edf_records_f64": (c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
+                                           _i64, _vp]),
     "osz_fir_plan_create": (c_int, [POINTER(_vp), _dp, c_int, c_int]),
     "osz_fir_plan_destroy": (c_int, [_vp]),
     "osz_fir_plan_algo": (c_int, [_vp]),

@@ -93,6 +93,56 @@ class Layout:
         return self.lead + (int(n),) + self.trail
 
 
+_calib_cache = {}
+
+
+def _calibration(chunk):
+    """Device copies of an EDF chunk's (channel offsets, slopes, offsets), cached
+    per value (they are the same for every chunk of a reader)."""
+    t = torch()
+    key = (chunk.chan_off.tobytes(), chunk.slopes.tobytes(), chunk.offsets.tobytes())
+    hit = _calib_cache.get(key)
+    if hit is None:
+        if len(_calib_cache) > 64:
+            _calib_cache.clear()
+        hit = (t.from_numpy(chunk.chan_off.copy()).to("cuda"), from_host(chunk.slopes),
+               from_host(chunk.offsets))
+        _calib_cache[key] = hit
+    return hit
+
+
+def _upload_edf(chunk, layout, alloc=None):
+    """EDF records -> device rows: the int16 records cross PCIe as they are (one
+    contiguous copy from pinned memory on the side stream), a kernel
+    de-interleaves and calibrates them into float64 rows."""
+    t = require_cuda()
+    rows, n = chunk.shape
+    dev = alloc(rows, n) if alloc is not None else t.empty((rows, n), dtype=t.float64,
+                                                           device="cuda")
+    if n == 0 or rows == 0:
+        return dev
+    h2d, _ = _Streams.get()
+    cur = t.cuda.current_stream()
+    off, sl, of = _calibration(chunk)
+    with t.cuda.stream(h2d):
+        raw = t.empty(chunk.records.shape, dtype=t.int16, device="cuda")
+        src = t.from_numpy(chunk.records)
+        if not src.is_pinned():
+            stage = t.empty(chunk.records.shape, dtype=t.int16, pin_memory=True)
+            stage.copy_(src)
+            src = stage
+        raw.copy_(src, non_blocking=True)
+        raw._osz_keepalive = src
+    cur.wait_stream(h2d)
+    raw.record_stream(cur)
+    ldd = dev.stride(0) if rows > 1 else n
+    _abi.check(_abi.load().osz_decode_edf_records_f64(
+        _vp(raw.data_ptr()), chunk.records.shape[1], chunk.spr, _vp(off.data_ptr()),
+        _vp(sl.data_ptr()), _vp(of.data_ptr()), chunk.skip, _vp(dev.data_ptr()), ldd, rows, n,
+        _cur_stream()), "decode_edf")
+    return dev
+
+
 def upload(arr, layout, alloc=None):
     """Host chunk -> device rows ``(rows, n)`` float64 on the current stream.
     ``alloc(rows, n)`` places the rows in the consumer's staging ring.
@@ -102,6 +152,12 @@ def upload(arr, layout, alloc=None):
     caching host allocator) so it overlaps the kernels of the previous chunk.
     """
     t = require_cuda()
+    if hasattr(arr, "records") and hasattr(arr, "chan_off"):
+        # an EDF RawChunk (file_io/edf.py): whole int16 records + calibration
+        if layout.inner != 1 or layout.outer != arr.shape[0]:
+            arr = arr.decode()
+        else:
+            return _upload_edf(arr, layout, alloc)
     a = np.asarray(arr)
     narrow = a.dtype in (np.float32, np.int16) and layout.inner == 1
     if a.dtype != np.float64 and not narrow:
@@ -129,8 +185,8 @@ def upload(arr, layout, alloc=None):
         dev = alloc(layout.outer, n) if alloc is not None else t.empty(
             (layout.outer, n), dtype=t.float64, device="cuda")
         lib = _abi.load()
-        fn = lib.osz_widen_rows_f32_f64 if a.dtype == np.float32 else lib.osz_widen_rows_i16_f64
         ldd = dev.stride(0) if layout.outer > 1 else n
+        fn = lib.osz_widen_rows_f32_f64 if a.dtype == np.float32 else lib.osz_widen_rows_i16_f64
         _abi.check(fn(_vp(raw.data_ptr()), n, _vp(dev.data_ptr()), ldd, layout.outer, n,
                       _cur_stream()), "widen")
         return dev

@@ -129,6 +129,23 @@ class ReaderProducer(Producer):
         for a in range(self.start, self.stop, self.chunksize):
             yield self.data.read(a, min(a + self.chunksize, self.stop), **self.kwargs)
 
+    def iter_raw(self):
+        """Chunks as the reader's raw records (``file_io.edf.RawChunk``: int16
+        samples + calibration) for consumers that decode on the GPU; None when
+        the reader cannot provide them (no ``read_raw``, mixed sample rates, a
+        sample axis other than the last, extra ``read`` arguments)."""
+        reader = self.data
+        if (not hasattr(reader, "read_raw") or self.kwargs or len(reader.shape) != 2
+                or self.axis not in (1, -1) or not getattr(reader, "uniform_rate", False)):
+            return None
+
+        def chunks():
+            reader.open()
+            for a in range(self.start, self.stop, self.chunksize):
+                yield reader.read_raw(a, min(a + self.chunksize, self.stop))
+
+        return chunks()
+
 
 class GenProducer(Producer):
     """Re-chunks whatever a generating function yields to ``chunksize``."""

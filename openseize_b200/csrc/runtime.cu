@@ -76,6 +76,32 @@ __global__ void widen_rows_kernel(const S *__restrict__ src, int64_t ld_src,
     for (; i < n; i += step) d[i] = (double)s[i];
 }
 
+// EDF ingest on the device.  `rec` holds whole data records exactly as they sit
+// in the file: record r = [ch0: spr samples | ch1: spr samples | ...] (per_record
+// int16 each).  Row c of the output is channel chan_off[c] (its offset inside a
+// record), samples skip .. skip+n-1 counted from the first record:
+//     dst[c][i] = rec[(skip+i) / spr][chan_off[c] + (skip+i) % spr] * slope[c] + offset[c]
+// with a separate multiply and add (two roundings), so the rows are bit-identical
+// to the reference's `arr * slopes; result += offsets` (file_io/edf.py:412-419).
+__global__ void decode_edf_records_kernel(const int16_t *__restrict__ rec, int64_t per_record,
+                                          int64_t spr, const int *__restrict__ chan_off,
+                                          const double *__restrict__ slope,
+                                          const double *__restrict__ offset, int64_t skip,
+                                          double *__restrict__ dst, int64_t ld_dst, int64_t n) {
+    const int64_t row = blockIdx.y;
+    double *d = dst + row * ld_dst;
+    const double a = slope[row], b = offset[row];
+    const int16_t *base = rec + chan_off[row];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        const int64_t t = skip + i;
+        const int64_t r = t / spr;
+        const int16_t v = base[r * per_record + (t - r * spr)];
+        d[i] = __dadd_rn(__dmul_rn((double)v, a), b);
+    }
+}
+
 template <typename S>
 static int launch_widen_rows(const S *src, int64_t ld_src, double *dst, int64_t ld_dst,
                              int64_t rows, int64_t n, void *stream) {
@@ -227,6 +253,22 @@ int osz_widen_rows_f32_f64(const float *src, int64_t ld_src, double *dst, int64_
 int osz_widen_rows_i16_f64(const int16_t *src, int64_t ld_src, double *dst, int64_t ld_dst,
                            int64_t rows, int64_t n, void *stream) {
     return launch_widen_rows<int16_t>(src, ld_src, dst, ld_dst, rows, n, stream);
+}
+int osz_decode_edf_records_f64(const int16_t *rec, int64_t per_record, int64_t spr,
+                               const int *chan_off_dev, const double *slope_dev,
+                               const double *offset_dev, int64_t skip, double *dst, int64_t ld_dst,
+                               int64_t rows, int64_t n, void *stream) {
+    if (!rec || !chan_off_dev || !slope_dev || !offset_dev || !dst || spr < 1 || per_record < spr)
+        return fail(OSZ_ERR_ARG, "osz_decode_edf_records_f64: bad arguments");
+    if (rows <= 0 || n <= 0) return OSZ_OK;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "decode: more than 65535 rows per call");
+    int bx = (int)((n + 255) / 256);
+    const int cap = (sm_count() * 16 + (int)rows - 1) / (int)rows;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    decode_edf_records_kernel<<<dim3((unsigned)bx, (unsigned)rows), 256, 0, as_stream(stream)>>>(
+        rec, per_record, spr, chan_off_dev, slope_dev, offset_dev, skip, dst, ld_dst, n);
+    OSZ_LAUNCHED("decode_edf_records");
+    return OSZ_OK;
 }
 
 }  // extern "C"

@@ -147,6 +147,8 @@ class _Now:
 
 
 def _upload(arr, layout, alloc=None):
+    if hasattr(arr, "records") and hasattr(arr, "chan_off"):
+        arr = arr.decode()                      # EDF RawChunk (decoded on the GPU in the product)
     a = np.asarray(arr, dtype=np.float64)
     n = a.shape[layout.axis]
     a = np.moveaxis(a.reshape(layout.outer, n, layout.inner), 1, 2)
