@@ -9,6 +9,7 @@ outer * inner`` and row ``o * inner + i`` holds ``chunk[o, :, i]``.
 """
 
 import ctypes
+import os
 import math
 from collections import OrderedDict
 
@@ -94,6 +95,30 @@ class Layout:
 
 
 _calib_cache = {}
+_copy_pool = None
+
+
+def _staged_copy(dst, src):
+    """Copy a host chunk into its pinned staging block.  One memcpy thread moves
+    ~10 GB/s, a fifth of what the PCIe link takes (measured: 1.0 G channel-samples/s
+    of pageable float64 into psd); large chunks are split over a few threads
+    (numpy releases the GIL while it copies)."""
+    global _copy_pool
+    if src.nbytes < (8 << 20) or src.ndim != 2 or src.shape[1] < 4096:
+        np.copyto(dst, src)
+        return
+    import concurrent.futures as cf
+
+    if _copy_pool is None:
+        _copy_pool = cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1),
+                                           thread_name_prefix="osz-stage")
+    parts = _copy_pool._max_workers
+    n = src.shape[1]
+    step = -(-n // parts)
+    futs = [_copy_pool.submit(np.copyto, dst[:, a:a + step], src[:, a:a + step])
+            for a in range(0, n, step)]
+    for f in futs:
+        f.result()
 
 
 def _calibration(chunk):
@@ -227,7 +252,7 @@ def upload(arr, layout, alloc=None):
                 dev._osz_keepalive = a2
             else:
                 stage = t.empty((layout.outer, n), dtype=t.float64, pin_memory=True)
-                np.copyto(stage.numpy(), a2)
+                _staged_copy(stage.numpy(), a2)
                 dev.copy_(stage, non_blocking=True)
         cur.wait_stream(h2d)
         dev.record_stream(cur)

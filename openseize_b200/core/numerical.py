@@ -95,6 +95,9 @@ def _device_twin(pro):
     return (twin, args, kwargs) if twin is not None else None
 
 
+_HOST_BLOCK_BYTES = 32 << 20
+
+
 def device_chunks(pro, axis, regrid=True, alloc=None):
     """Yield ``pro``'s chunks as device rows ``(rows, chunk)``.
 
@@ -116,10 +119,20 @@ def device_chunks(pro, axis, regrid=True, alloc=None):
     else:
         twin = _device_twin(pro)
         if twin is None:
+            # A consumer that does not depend on the chunk grid (regrid=False) takes
+            # arrays and readers in blocks of >= ~32 MB: psd pulls fs-sized chunks
+            # (spectra/estimators.py:141), and a thousand 2 MB uploads cost more in
+            # launches than in PCIe time.  Results do not change.
+            step = int(pro.chunksize)
+            if not regrid and hasattr(pro, "blocks"):
+                per_chunk = max(layout.rows * step * 8, 1)
+                step *= max(1, -(-_HOST_BLOCK_BYTES // per_chunk))
             # EDF readers hand over their int16 records: a quarter of the PCIe
             # traffic, calibrated on the device (file_io/edf.py)
-            raw = pro.iter_raw() if hasattr(pro, "iter_raw") else None
-            for arr in (raw if raw is not None else pro):
+            raw = pro.iter_raw(step) if hasattr(pro, "iter_raw") else None
+            if raw is None:
+                raw = pro.blocks(step) if hasattr(pro, "blocks") else pro
+            for arr in raw:
                 yield dv.upload(arr, layout, alloc)
             return
         func, args, kwargs = twin

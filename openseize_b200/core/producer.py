@@ -101,10 +101,14 @@ class ArrayProducer(Producer):
         return self.data.shape
 
     def __iter__(self):
+        yield from self.blocks(self.chunksize)
+
+    def blocks(self, step):
+        """Views of ``step`` samples (a multiple of chunksize for consumers that
+        do not depend on the chunk grid and want fewer, larger uploads)."""
         n = self.data.shape[self.axis]
-        for start in range(0, n, self.chunksize):
-            yield slice_along_axis(self.data, start, min(start + self.chunksize, n),
-                                   axis=self.axis)
+        for start in range(0, n, step):
+            yield slice_along_axis(self.data, start, min(start + step, n), axis=self.axis)
 
 
 class ReaderProducer(Producer):
@@ -125,11 +129,14 @@ class ReaderProducer(Producer):
         return tuple(s)
 
     def __iter__(self):
-        self.data.open()
-        for a in range(self.start, self.stop, self.chunksize):
-            yield self.data.read(a, min(a + self.chunksize, self.stop), **self.kwargs)
+        yield from self.blocks(self.chunksize)
 
-    def iter_raw(self):
+    def blocks(self, step):
+        self.data.open()
+        for a in range(self.start, self.stop, step):
+            yield self.data.read(a, min(a + step, self.stop), **self.kwargs)
+
+    def iter_raw(self, step=None):
         """Chunks as the reader's raw records (``file_io.edf.RawChunk``: int16
         samples + calibration) for consumers that decode on the GPU; None when
         the reader cannot provide them (no ``read_raw``, mixed sample rates, a
@@ -139,10 +146,12 @@ class ReaderProducer(Producer):
                 or self.axis not in (1, -1) or not getattr(reader, "uniform_rate", False)):
             return None
 
+        step = int(step or self.chunksize)
+
         def chunks():
             reader.open()
-            for a in range(self.start, self.stop, self.chunksize):
-                yield reader.read_raw(a, min(a + self.chunksize, self.stop))
+            for a in range(self.start, self.stop, step):
+                yield reader.read_raw(a, min(a + step, self.stop))
 
         return chunks()
 
