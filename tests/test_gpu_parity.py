@@ -223,6 +223,36 @@ def test_fft_sizes_vs_numpy(dv, nfft, detrend):
     assert relerr(psd_sum.cpu().numpy(), ref_sum) < 1e-12
 
 
+@pytest.mark.parametrize("nfft,stride", [(4096, 2048), (4096, 3687), (4096, 1024), (1024, 333),
+                                         (512, 512), (2048, 1), (2400, 1200), (1000, 77),
+                                         (10000, 5000)])
+def test_welch_unaligned_and_strides(dv, nfft, stride):
+    """Welch on rows that start at odd elements with an odd leading dimension
+    (the TMA span fetch copies from the aligned address below and patches odd
+    tails), strides other than nfft/2, and 1 .. 41 segments: the ping-pong
+    kernel (powers of two), the mixed-radix kernel (2400, 1000, 10000)."""
+    rng = np.random.default_rng(nfft + stride)
+    w = sps.get_window("hamming", nfft)
+    norm = 1.0 / (1000.0 * np.sum(w ** 2))
+    plan = dv.SpecPlan(nfft, stride, w, "constant", norm)
+    for rows, nseg in ((1, 1), (5, 2), (2, 3), (3, 8), (2, 41)):
+        if stride == 1 and nseg > 8:
+            continue
+        n = (nseg - 1) * stride + nfft
+        x = rng.standard_normal((rows, n)) + 2.0
+        buf = dv.zeros((rows, n + 5))
+        buf[:, 3:3 + n] = _dev(dv, x)
+        psd_sum = dv.zeros((rows, nfft // 2 + 1))
+        plan.welch_accum(buf[:, 3:3 + n], nseg, psd_sum)
+        ref = 0
+        for k in range(nseg):
+            seg = sps.detrend(x[:, k * stride:k * stride + nfft], axis=-1, type="constant")
+            p = np.abs(np.fft.rfft(seg * w, axis=-1)) ** 2 * norm
+            p[:, 1:-1] *= 2
+            ref = ref + p
+        assert relerr(psd_sum.cpu().numpy(), ref) < 1e-11, (nfft, stride, rows, nseg)
+
+
 @pytest.mark.parametrize("nfft", [2, 3, 60, 97, 250, 1001, 1009, 2000, 10000, 16384])
 def test_generic_nfft_vs_numpy(dv, nfft):
     """Mixed-radix (2..16, 3, 5, 7, 11, 13) and Bluestein (97, 1009) lengths,
