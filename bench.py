@@ -358,6 +358,11 @@ def named_kernels(rows, chunk, hbm_peak):
         y = torch.empty((rows, chunk), dtype=torch.float64, device="cuda")
         out[label] = entry(timed(lambda: plan.run(x, chunk, out=y)), rows * chunk, 16)
         out[label]["taps"] = int(len(taps))
+        # opt-in float32 arithmetic (float64 in and out, ~5e-7 of the output peak)
+        plan32 = dv.FirPlan(taps, 3)
+        out[label + "_f32compute"] = entry(timed(lambda: plan32.run(x, chunk, out=y)),
+                                           rows * chunk, 16)
+        out[label + "_f32compute"]["taps"] = int(len(taps))
         del x, y
     w = sps.get_window("hann", NFFT)
     plan = dv.SpecPlan(NFFT, NFFT // 2, w, "constant", 1.0 / (FS * float(np.sum(w ** 2))))

@@ -108,7 +108,14 @@ int osz_decode_edf_records_f64(const int16_t *rec_dev, int64_t per_record, int64
 /* ---- FIR: replaces _cconvolve + overlap-add of nm.oaconvolve
  *      (core/numerical.py:229-269) --------------------------------------- */
 typedef struct osz_fir_plan osz_fir_plan;
-enum { OSZ_FIR_AUTO = 0, OSZ_FIR_DIRECT = 1, OSZ_FIR_FFT = 2 };
+enum {
+    OSZ_FIR_AUTO = 0,
+    OSZ_FIR_DIRECT = 1,
+    OSZ_FIR_FFT = 2,
+    /* overlap-save FFT evaluated in float32, float64 samples in and out: opt-in
+     * (the reference is float64); differs by ~1e-6 of the output peak */
+    OSZ_FIR_FFT_F32 = 3
+};
 /* taps: the window the reference passes to oaconvolve (numerical.py:158). */
 int osz_fir_plan_create(osz_fir_plan **plan, const double *taps_host, int ntaps, int algo);
 int osz_fir_plan_destroy(osz_fir_plan *plan);

@@ -16,3 +16,12 @@ library is present (there is no CPU fallback).
 from openseize_b200.core.producer import producer  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def set_compute(kind):
+    """Arithmetic of the FFT-based FIR path: "float64" (default, the reference's) or
+    "float32" (opt-in: float64 samples in and out, transforms in float32; results
+    within ~1e-6 of the output peak).  Also settable with OSZ_COMPUTE=float32."""
+    from openseize_b200.core import device
+
+    device.set_compute(kind)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libosz_b200.so")
 
 OSZ_OK, OSZ_ERR_ARG, OSZ_ERR_CUDA, OSZ_ERR_UNSUPPORTED, OSZ_ERR_ALLOC = 0, -1, -2, -3, -4
-FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
+FIR_AUTO, FIR_DIRECT, FIR_FFT, FIR_FFT_F32 = 0, 1, 2, 3
 DETREND = {None: 0, False: 0, "none": 0, "constant": 1, "linear": 2}
 
 _i64, _dp, _vp = c_int64, POINTER(c_double), c_void_p

@@ -374,6 +374,20 @@ class _Cache:
 _plans = _Cache()
 
 
+# Arithmetic of the FIR overlap-save transforms: "float64" (default: the reference
+# computes and returns float64) or "float32" (opt-in: float64 samples in and out,
+# FFTs in float32, ~1e-6 of the output peak; north_star's float32 tolerance is 1e-5).
+COMPUTE = os.environ.get("OSZ_COMPUTE", "float64")
+
+
+def set_compute(kind):
+    """Select the arithmetic of the FFT-based FIR path: "float64" | "float32"."""
+    global COMPUTE
+    if kind not in ("float64", "float32"):
+        raise ValueError("compute must be 'float64' or 'float32'")
+    COMPUTE = kind
+
+
 class FirPlan(_Plan):
     _destroy = "osz_fir_plan_destroy"
 
@@ -389,6 +403,8 @@ class FirPlan(_Plan):
     @staticmethod
     def cached(taps, algo=_abi.FIR_AUTO):
         arr = np.ascontiguousarray(taps, dtype=np.float64)
+        if algo == _abi.FIR_AUTO and COMPUTE == "float32" and 24 < arr.size <= 1025:
+            algo = _abi.FIR_FFT_F32
         return _plans.get(("fir", arr.tobytes(), int(algo)), lambda: FirPlan(arr, algo))
 
     def run(self, xbuf, n_out, out=None):

@@ -343,6 +343,163 @@ fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int 
     sync.drain();
 }
 
+// float32-compute variant of the ping-pong kernel (opt-in, OSZ_FIR_FFT_F32):
+// float64 samples in and out, both transforms and the H product in float32
+// (namespace oszf of fft_core.cuh).  The FP32 pipe issues at twice the FP64 rate
+// and the exchange buffers halve, so the kernel becomes HBM bound at the
+// float64 roofline's 16 bytes per sample; the result differs from the float64
+// path by ~1e-6 of the output peak (north_star's float32 tolerance is 1e-5).
+// The input span has its own staging buffer here (the float2 exchange buffer is
+// too small for it), so the next item's TMA copy is issued as soon as this
+// item's samples are in registers and has the whole item to land.
+template <int LOG2N>
+struct FirPPC32 {
+    using C = oszf::FftCfg<LOG2N>;
+    static constexpr int NH = C::N / 2 + 1;
+    static constexpr int OFF_H = C::TW_TOTAL * 8;
+    static constexpr int OFF_BAR = (OFF_H + NH * 8 + 15) & ~15;
+    static constexpr int OFF_X = (OFF_BAR + 16 + 127) & ~127;
+    static constexpr int STAGE_BYTES = 2 * C::N * 8;                  // step + N doubles at most
+    static constexpr int GROUP_BYTES = C::SMEM_BYTES + STAGE_BYTES;
+    static constexpr int SMEM = OFF_X + 2 * GROUP_BYTES;
+};
+
+template <int LOG2N, bool ACC>
+__global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, 1)
+fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
+                      const float2 *__restrict__ H, const float2 *__restrict__ tw,
+                      double *__restrict__ y, int64_t ldy, int64_t npairs, int64_t nwork,
+                      int iters, int lag, int zero) {
+    using C = oszf::FftCfg<LOG2N>;
+    using L = FirPPC32<LOG2N>;
+    using Sync = oszf::SyncPingPong<LOG2N>;
+    constexpr int N = C::N, NT = C::NT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g = threadIdx.x / NT;
+    const int tid = threadIdx.x - g * NT;
+    float2 *tw_sm = reinterpret_cast<float2 *>(smem_raw);
+    float2 *h_sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_H);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR) + g;
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_X + g * L::GROUP_BYTES);
+    double *sx = reinterpret_cast<double *>(smem_raw + L::OFF_X + g * L::GROUP_BYTES +
+                                            C::SMEM_BYTES);
+
+    for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
+    for (int i = threadIdx.x; i < L::NH; i += 2 * NT) h_sm[i] = ldg(H + i);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const Sync sync{g, tid, zero, tw_sm};
+
+    const int64_t step = N - ntaps + 1;
+    const int64_t span = n_out + ntaps - 1;
+    const int k1 = ntaps - 1;
+    const int64_t dw = 2 * (int64_t)gridDim.x;
+    const int64_t drow = dw / npairs, dpair = dw - drow * npairs;
+    int64_t w = 2 * (int64_t)blockIdx.x + g;
+    int64_t row = w / npairs, pair = w - row * npairs;
+
+    auto issue = [&](int64_t w_, int64_t row_, int64_t pair_) {
+        if (w_ >= nwork) return;
+        const double *src = x + row_ * ldx + pair_ * 2 * step;
+        const int64_t left = span - pair_ * 2 * step;
+        tma_fetch_span(sx, src, left < step + N ? left : step + N, bar);
+    };
+    if (tid == 0) issue(w, row, pair);
+    sync.prime();
+    if (g == 1)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+
+    for (int it = 0; it < iters; ++it) {
+        const bool live = w < nwork;
+        const int64_t base_a = pair * 2 * step;
+        const int64_t left = span - base_a;
+        int64_t wn = w + dw, rown = row + drow, pairn = pair + dpair;
+        if (pairn >= npairs) {
+            pairn -= npairs;
+            ++rown;
+        }
+        float2 v[16];
+        if (live) {
+            const double *xa = sx + span_mis(x + row * ldx + base_a) + tid, *xb = xa + step;
+            while (!mbar_try_wait(bar, it & 1)) {
+            }
+            if (left >= step + N) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    v[r] = make_float2((float)xa[r * NT], (float)xb[r * NT]);
+            } else {
+                const int lim_a = (int)(left > N ? N : left);
+                const int lim_b = (int)(left - step > N ? N : (left < step ? 0 : left - step));
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int i = tid + r * NT;
+                    v[r].x = i < lim_a ? (float)xa[r * NT] : 0.0f;
+                    v[r].y = i < lim_b ? (float)xb[r * NT] : 0.0f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = make_float2(0.0f, 0.0f);
+        }
+        // the staging buffer is free once every thread of the group holds its samples
+        sync.group();
+        if (tid == 0) {
+            fence_proxy_async();
+            issue(wn, rown, pairn);
+        }
+        sync.acquire_first(v);
+        oszf::bfly<16>(v);
+        sync.release(v);
+        oszf::fft_r2r_tail<LOG2N, Sync, false>(v, sm, tid, sync);
+        {
+            const float2 *hlo = h_sm + tid, *hhi = h_sm + 8 * NT - tid;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float2 p = oszf::cmul(v[r], hlo[r * NT]);
+                v[r] = make_float2(p.y, p.x);
+            }
+#pragma unroll
+            for (int r = 8; r < 16; ++r) {
+                const float2 h = hhi[(8 - r) * NT];
+                const float2 a = v[r];
+                v[r] = make_float2(fmaf(a.y, h.x, -a.x * h.y), fmaf(a.x, h.x, a.y * h.y));
+            }
+        }
+        oszf::bfly<16>(v);
+        sync.release(v);
+        oszf::fft_r2r_tail<LOG2N, Sync, true>(v, sm, tid, sync);
+
+        if (live) {
+            double *ya = y + row * ldy + base_a + tid - k1;
+            double *yb = ya + step;
+            const int64_t oa = n_out - base_a + k1, ob = oa - step;
+            const int out_a = (int)(oa > N ? N : oa), out_b = (int)(ob < 0 ? 0 : (ob > N ? N : ob));
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int i = tid + r * NT;
+                if (i >= k1) {
+                    if (ACC) {
+                        if (i < out_a) ya[r * NT] += (double)v[r].y;
+                        if (i < out_b) yb[r * NT] += (double)v[r].x;
+                    } else {
+                        if (i < out_a) st_stream(ya + r * NT, (double)v[r].y);
+                        if (i < out_b) st_stream(yb + r * NT, (double)v[r].x);
+                    }
+                }
+            }
+        }
+        w = wn;
+        row = rown;
+        pair = pairn;
+    }
+    if (g == 0)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+    sync.drain();
+}
+
 }  // namespace osz
 
 using namespace osz;
@@ -359,6 +516,8 @@ struct osz_fir_plan {
     double *d_taps_rev = nullptr;   // direct
     double2 *d_H = nullptr;         // fft
     double2 *d_tw = nullptr;
+    float2 *d_Hf = nullptr;         // float32-compute fft (OSZ_FIR_FFT_F32)
+    float2 *d_twf = nullptr;
 };
 
 template <int LOG2N, int MINB>
@@ -403,6 +562,27 @@ static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx
 }
 
 template <int LOG2N, bool ACC>
+static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
+                                 int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
+    using C = oszf::FftCfg<LOG2N>;
+    constexpr int SMEM = FirPPC32<LOG2N>::SMEM;
+    static_assert(SMEM <= 227 * 1024, "float32-compute FIR: shared memory");
+    OSZ_CUDA(cudaFuncSetAttribute(fir_fft_pp_c32_kernel<LOG2N, ACC>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int64_t step = C::N - p->ntaps + 1;
+    const int64_t nblocks = (n_out + step - 1) / step;
+    const int64_t npairs = (nblocks + 1) / 2;
+    const int64_t nwork = npairs * rows;
+    int64_t grid = (nwork + 1) / 2;
+    if (grid > sm_count()) grid = sm_count();
+    const int iters = (int)((nwork + 2 * grid - 1) / (2 * grid));
+    fir_fft_pp_c32_kernel<LOG2N, ACC><<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
+        x, ldx, n_out, p->ntaps, p->d_Hf, p->d_twf, y, ldy, npairs, nwork, iters, 2, 0);
+    OSZ_LAUNCHED("fir_fft_pp_c32_kernel");
+    return OSZ_OK;
+}
+
+template <int LOG2N, bool ACC>
 static int launch_fir_fft_pp_policy(const osz_fir_plan *p, const double *x, int64_t ldx,
                                     int64_t rows, int64_t n_out, double *y, int64_t ldy,
                                     cudaStream_t st) {
@@ -422,6 +602,12 @@ extern "C" {
 
 int osz_fir_plan_create(osz_fir_plan **out, const double *taps, int ntaps, int algo) {
     if (!out || !taps || ntaps < 1) return fail(OSZ_ERR_ARG, "osz_fir_plan_create: bad arguments");
+    bool c32 = false;
+    if (algo == OSZ_FIR_FFT_F32) {
+        // float32 compute exists for one N = 4096 block; longer filters stay in float64
+        c32 = ntaps <= 1025;
+        algo = OSZ_FIR_FFT;
+    }
     if (algo == OSZ_FIR_AUTO) algo = ntaps <= 24 ? OSZ_FIR_DIRECT : OSZ_FIR_FFT;
     if (algo == OSZ_FIR_DIRECT && ntaps > FIR_DIRECT_MAX_TAPS) algo = OSZ_FIR_FFT;
     osz_fir_plan *p = new osz_fir_plan();
@@ -478,6 +664,20 @@ int osz_fir_plan_create(osz_fir_plan **out, const double *taps, int ntaps, int a
             H[2 * k] = (double)(re / N);
             H[2 * k + 1] = (double)(im / N);
         }
+        if (c32 && p->log2n == 12) {
+            std::vector<float> Hf(H.size()), twf = oszf::make_fft_twiddles(12);
+            for (size_t i = 0; i < H.size(); ++i) Hf[i] = (float)H[i];
+            if (cudaMalloc(&p->d_Hf, Hf.size() * 4) != cudaSuccess ||
+                cudaMemcpy(p->d_Hf, Hf.data(), Hf.size() * 4, cudaMemcpyHostToDevice) !=
+                    cudaSuccess ||
+                cudaMalloc(&p->d_twf, twf.size() * 4) != cudaSuccess ||
+                cudaMemcpy(p->d_twf, twf.data(), twf.size() * 4, cudaMemcpyHostToDevice) !=
+                    cudaSuccess) {
+                osz_fir_plan_destroy(p);
+                return fail(OSZ_ERR_CUDA, "osz_fir_plan_create: device upload failed");
+            }
+            p->algo = OSZ_FIR_FFT_F32;
+        }
         std::vector<double> tw = make_fft_twiddles(p->log2n);
         if (cudaMalloc(&p->d_H, H.size() * 8) != cudaSuccess ||
             cudaMemcpy(p->d_H, H.data(), H.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -500,6 +700,8 @@ int osz_fir_plan_destroy(osz_fir_plan *p) {
     cudaFree(p->d_taps_rev);
     cudaFree(p->d_H);
     cudaFree(p->d_tw);
+    cudaFree(p->d_Hf);
+    cudaFree(p->d_twf);
     delete p;
     return OSZ_OK;
 }
@@ -542,6 +744,9 @@ static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t
         OSZ_LAUNCHED("fir_direct_kernel");
         return OSZ_OK;
     }
+    if (p->algo == OSZ_FIR_FFT_F32 && p->log2n == 12)
+        return accumulate ? launch_fir_fft_pp_c32<12, true>(p, x, ldx, rows, n_out, y, ldy, st)
+                          : launch_fir_fft_pp_c32<12, false>(p, x, ldx, rows, n_out, y, ldy, st);
     if (p->log2n == 12) {
         // Two CTAs per SM at 128 registers beat three at 80 (104 B of spills):
         // 217 vs 184 G samples/s at 113 taps (profiles/r01_kernel_bench.md).

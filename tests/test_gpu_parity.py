@@ -6,6 +6,9 @@ import numpy as np
 import pytest
 import scipy.signal as sps
 
+import oracle
+from openseize_b200 import producer
+
 from tests import parity_cases as pc
 from tests.conftest import has_cuda, relerr
 
@@ -61,6 +64,39 @@ def test_fir_kernels_vs_numpy(dv, algo, ntaps):
         y = plan.run(buf[:, 1:1 + x.shape[1]], n_out).cpu().numpy()
         ref = np.stack([np.convolve(r, taps, "valid") for r in x])
         assert relerr(y, ref) < 1e-12, (algo, ntaps, rows, n_out)
+
+
+def test_fir_float32_compute(dv):
+    """Opt-in float32 arithmetic of the overlap-save FIR (float64 in and out):
+    within north_star's float32 tolerance, 1e-5 of the output peak, of the
+    float64 oracle -- through the kernel and through the public operator."""
+    import openseize_b200
+    from openseize_b200.filtering.fir import Kaiser
+
+    rng = np.random.default_rng(21)
+    for fs in (5000, 30000):
+        taps = Kaiser(500, 600, fs).coeffs
+        plan = dv.FirPlan(taps, 3)
+        assert plan.algo == 3
+        for rows, n_out in ((1, 1), (3, 1919), (2, 40001)):
+            x = rng.standard_normal((rows, n_out + len(taps) - 1)) + 0.5
+            buf = dv.zeros((rows, x.shape[1] + 3))
+            buf[:, 1:1 + x.shape[1]] = _dev(dv, x)
+            y = plan.run(buf[:, 1:1 + x.shape[1]], n_out).cpu().numpy()
+            ref = np.stack([np.convolve(r, taps, "valid") for r in x])
+            assert relerr(y, ref) < 1e-5, (fs, rows, n_out)
+    x = rng.standard_normal((4, 120000)) + 2.0
+    filt = Kaiser(500, 600, 5000)
+    ref = np.concatenate(oracle.oaconvolve(x, filt.coeffs, 30000, -1, "same"), -1)
+    openseize_b200.set_compute("float32")
+    try:
+        y32 = filt(producer(x, 30000, -1), 30000, axis=-1).to_array()
+    finally:
+        openseize_b200.set_compute("float64")
+    y64 = filt(producer(x, 30000, -1), 30000, axis=-1).to_array()
+    assert y32.dtype == np.float64 and y32.shape == ref.shape
+    assert 1e-9 < relerr(y32, ref) < 1e-5          # really float32 arithmetic, within tolerance
+    assert relerr(y64, ref) < 1e-12
 
 
 def test_fir_long_taps_block8192(dv):
