@@ -168,16 +168,24 @@ def host_source(pool, rows, chunk, nchunks, marks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs, read through NVML
+    in a background thread (the same counters `nvidia-smi --query-gpu=clocks.sm,
+    clocks_event_reasons.*` prints).  An `nvidia-smi -lms 20` subprocess was used
+    first: every one of its samples stalled the GPU work for ~3 ms (64.5 instead of
+    74.5 G channel-samples/s over a 140 ms timed region), eight of them at N = 8
+    stretched the step from 3.5 to 5.6 ms, and its ~0.5 s start-up stalls launches
+    too.  In-process NVML queries cost microseconds."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
 
     def __init__(self, index, enabled=True, period_ms=20):
-        self.index, self.proc, self.lines = index, None, []
-        self.enabled, self.period_ms = enabled, int(period_ms)
+        self.index, self.enabled, self.period = index, enabled, period_ms / 1e3
+        self.samples, self.thread, self._stop = [], None, threading.Event()
         self.t0 = self.t1 = None      # wall-clock bounds of the timed region
+        self.ready = False
 
     def mark_start(self):
         self.t0 = time.time()
@@ -189,51 +197,60 @@ class ClockSampler:
         if not self.enabled:
             return
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # LOCAL_RANK indexes CUDA devices; honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle,
+                                                                 pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.enabled = False
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.time(), sm, mask))
+                self.ready = True
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for stamp, line in self.lines:
-            # samples taken while the timed region ran (the sampler itself is
-            # started before the warm-up: nvidia-smi needs ~0.1 s to come up)
+        sm, reasons = [], set()
+        for stamp, clock, mask in self.samples:
             if self.t0 is not None and self.t1 is not None and not (
                     self.t0 - 0.02 <= stamp <= self.t1 + 0.02):
                 continue
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val == "Active":
+            sm.append(clock)
+            for name, _, bit in self.REASONS:
+                if mask & bit:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
 
 
 # ---------------------------------------------------------------------------
@@ -450,23 +467,25 @@ def run_ours(args):
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     pool = [torch.randn((rows, chunk), dtype=torch.float64, device="cuda", generator=gen)
             for _ in range(2)]
+    marks = Marks(W, K, barrier)
+    sampler = ClockSampler(local, enabled=rank == 0 and os.environ.get("OSZ_BENCH_CLOCKS", "1") == "1",
+                           period_ms=25 if world == 1 else 50)
+    launches = {}
+    sampler.start()
     # Untimed pre-warm, then a barrier: a fresh box pages the CUDA libraries in and
     # ramps its clocks during the first second, and with one rank per GPU the ranks
-    # reach steady state at different moments (one N = 8 run on a box that had been
-    # up for a minute measured 9.1 ms per step instead of 3.6).  The contract's W
-    # warm-up steps and K timed steps follow unchanged.
-    t_end = time.perf_counter() + 0.4
-    while time.perf_counter() < t_end:
+    # reach steady state at different moments.  The contract's W warm-up steps and K
+    # timed steps follow unchanged.
+    # (N = 1 needs none -- the W warm-up steps do -- and measured 3.9 instead of 3.54 ms
+    # per step when a pre-warm was combined with the clock poller.)
+    prewarm = float(os.environ.get("OSZ_BENCH_PREWARM", "0.4" if world > 1 else "0"))
+    t_min, t_max = time.perf_counter() + prewarm, time.perf_counter() + (3.0 if prewarm else 0.0)
+    while time.perf_counter() < t_min or (sampler.enabled and not sampler.ready
+                                          and time.perf_counter() < t_max):
         pre = DeviceSourceOnce(pool, rows, chunk, 4)
         run_psd(build_pipeline(pre.producer(), chunk))
         torch.cuda.synchronize()
     barrier()
-    marks = Marks(W, K, barrier)
-    # One poller per box: every nvidia-smi query takes a driver-wide lock, and eight
-    # ranks polling at 50 Hz stretched the step from 3.5 to 5.6 ms at N = 8.
-    sampler = ClockSampler(local, enabled=rank == 0, period_ms=20 if world == 1 else 100)
-    launches = {}
-    sampler.start()
     marks.on_start = lambda: (sampler.mark_start(), launches.__setitem__("a", _abi.launch_count()),
                               setattr(dv, "TIMERS", {}))
     timers = {}
