@@ -27,7 +27,9 @@ def bench_md():
     for title, name in (("N = 1, `python bench.py` (defaults: 40 steps, 5 warm-up)", "bench_full.log"),
                         ("N = 1, `python bench.py --impl reference --steps 3 --warmup 1`", "bench_ref.log"),
                         ("N = 2, `torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 20 --warmup 5`",
-                         "bench_2gpu.log")):
+                         "bench_2gpu.log"),
+                        ("N = 8, `torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 20 --warmup 5`",
+                         "bench_8gpu.log")):
         d = last_json(os.path.join(GP, name))
         if d is None:
             continue
@@ -44,6 +46,9 @@ def bench_md():
                       (d["e2e"]["value"] / 1e9, d["e2e"]["value"] * 8 / 1e9 / d["n_gpus"]),
                       "* our kernels launched in the timed region: %d; clocks %s" %
                       (d["gpu_launches"], json.dumps(d["clocks"]))]
+            if d.get("per_rank"):
+                lines += ["* per rank: own ms/step %s; sum of kernel times per step %s" %
+                          (d["per_rank"]["ms_per_step"], d["per_rank"]["kernel_ms_per_step"])]
             if "cpu_baseline" in d:
                 lines += ["* cpu_baseline (oracle port, %d cores): %.1f M channel-samples/s" %
                           (d["cpu_baseline"]["cores"], d["cpu_baseline"]["value"] / 1e6)]
@@ -97,7 +102,7 @@ def launches_md():
         cnt[name] += 1
     total = sum(tot.values())
     lines = ["# Round 1 — ncu launch list of the bench command", "",
-             "    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \\",
+             "    ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \\",
              "        --log-file gpurun_out/r01_launches.csv \\",
              "        python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-named", "",
              "(after the same command exited 0 without ncu).  Per-launch times under ncu are cold",
