@@ -83,6 +83,17 @@ class _DeviceFifo:
         return out
 
 
+def _regrid_device(blocks, cs):
+    """Re-block a stream of device rows to ``cs`` samples (last one shorter)."""
+    fifo = _DeviceFifo()
+    for block in blocks:
+        fifo.put(block)
+        while fifo.size >= cs:
+            yield fifo.get(cs)
+    if fifo.size:
+        yield fifo.get(cs)
+
+
 def _device_twin(pro):
     """(device generating function, args, kwargs) if ``pro`` is a producer over
     one of this module's GPU generating functions, else None."""
@@ -235,15 +246,27 @@ def _to_host(device_gen, layout, complex_=False):
         yield pending.get()
 
 
-def _gpu_genfunc(device_func, out_layout):
+def _gpu_genfunc(device_func, out_layout, regrid=False):
     """Build the host generating function of a device generating function.
-    ``out_layout(*args, **kwargs)`` gives the Layout of the yielded arrays."""
+    ``out_layout(*args, **kwargs)`` gives the Layout of the yielded arrays.
+    ``regrid``: cut the yielded blocks to the input producer's chunk grid (only
+    for functions whose raw yield lengths are not part of the reference's contract)."""
 
     def decorate(host_stub):
         @functools.wraps(host_stub)
         def genfunc(*args, **kwargs):
             layout = out_layout(*args, **kwargs)
-            yield from _to_host(device_func(*args, **kwargs), layout)
+            blocks = device_func(*args, **kwargs)
+            # The host consumer (GenProducer) re-chunks what we yield to the chunk size
+            # of the operator call, which is the input producer's chunk size.  Cutting
+            # the blocks to that grid on the DEVICE (HBM copies) lets them pass through
+            # the host FIFO without the per-chunk np.concatenate that a stream of
+            # off-grid blocks costs (FIR 'same' shortens its first block by the left cut,
+            # so every later block would straddle: 4 ms per 32 MB chunk).
+            cs = int(getattr(args[0], "chunksize", 0) or 0) if args else 0
+            if regrid and cs > 0:
+                blocks = _regrid_device(blocks, cs)
+            yield from _to_host(blocks, layout)
 
         genfunc.device = device_func
         return genfunc
@@ -292,7 +315,7 @@ def _oaconvolve_layout(pro, window, axis, mode, nfft_factor=32):
     return _layout_of(pro, axis)
 
 
-@_gpu_genfunc(_oaconvolve_device, _oaconvolve_layout)
+@_gpu_genfunc(_oaconvolve_device, _oaconvolve_layout, regrid=True)
 def oaconvolve(pro, window, axis, mode, nfft_factor=32):
     """Convolve every 1-D slice of a producer along ``axis`` with ``window``;
     numpy convolve modes.  ``nfft_factor`` is accepted for signature parity and
