@@ -292,6 +292,32 @@ class Pending:
         return out.reshape(self._shape)
 
 
+class _PendingBlock:
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def get(self):
+        self._event.synchronize()
+        return self._host.numpy()
+
+
+def download_block(dev):
+    """A contiguous device tensor -> pinned host ndarray of the same shape, copied
+    on the download stream; ``get()`` waits for it."""
+    t = require_cuda()
+    cur = t.cuda.current_stream()
+    _, d2h = _Streams.get()
+    dev = dev.contiguous()
+    host = t.empty(tuple(dev.shape), dtype=dev.dtype, pin_memory=True)
+    d2h.wait_stream(cur)
+    with t.cuda.stream(d2h):
+        host.copy_(dev, non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record(d2h)
+    dev.record_stream(d2h)
+    return _PendingBlock(host, ev)
+
+
 def download(dev, layout, complex_=False):
     """Device rows ``(rows, n)`` (float64, or complex128 stored as (rows, n, 2))
     -> :class:`Pending` host array of shape ``layout.host_shape(n)``."""

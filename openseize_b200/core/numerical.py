@@ -871,11 +871,18 @@ def _estimatives_device(pro, fs, nfft, window, overlap, axis, detrend, scaling, 
     complex_ = func is modified_dft
     if func is not modified_dft and func is not periodogram:
         raise TypeError("func must be numerical.periodogram or numerical.modified_dft")
-    plan = _spec_plan(fs, nfft, window, overlap, detrend, scaling)
-    for buf, nseg in _segment_batches(pro, axis, plan, pad_left, pad_right):
-        out = plan.segments(buf, nseg, complex_)
+    for out, nseg in _estimatives_batches(pro, fs, nfft, window, overlap, axis, detrend, scaling,
+                                          complex_, pad_left, pad_right):
         for k in range(nseg):
             yield out[k]
+
+
+def _estimatives_batches(pro, fs, nfft, window, overlap, axis, detrend, scaling, complex_,
+                         pad_left=0, pad_right=0):
+    """(device tensor (nseg, rows, nfreq[, 2]), nseg) per batch of windows."""
+    plan = _spec_plan(fs, nfft, window, overlap, detrend, scaling)
+    for buf, nseg in _segment_batches(pro, axis, plan, pad_left, pad_right):
+        yield plan.segments(buf, nseg, complex_), nseg
 
 
 def _spectra_estimatives(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
@@ -885,9 +892,34 @@ def _spectra_estimatives(pro, fs, nfft, window, overlap, axis, detrend, scaling,
     ``pad_right`` are zeros put around the recording (STFT boundary/padded)."""
     complex_ = func is modified_dft
     layout = _layout_of(pro, axis)
+    if layout.inner == 1 and (func is modified_dft or func is periodogram):
+        # sample axis last: a batch of windows is one contiguous device block
+        # (nseg, rows, nfreq[, 2]) -- ONE device-to-host copy per batch instead of one
+        # per window (a thousand 1 MB copies cost more in launches than in PCIe time),
+        # handed to the consumer one batch behind the kernels
+        pending = None
+        for out, nseg in _estimatives_batches(pro, fs, nfft, window, overlap, axis, detrend,
+                                              scaling, complex_, pad_left, pad_right):
+            nxt = (dv.download_block(out), nseg)
+            if pending is not None:
+                yield from _split_windows(pending, layout, complex_)
+            pending = nxt
+        if pending is not None:
+            yield from _split_windows(pending, layout, complex_)
+        return
     gen = _estimatives_device(pro, fs, nfft, window, overlap, axis, detrend, scaling, func,
                               pad_left, pad_right)
     yield from _to_host(gen, layout, complex_)
+
+
+def _split_windows(pending, layout, complex_):
+    block, nseg = pending
+    host = block.get()                      # (nseg, rows, nfreq[, 2]) float64, pinned
+    if complex_:
+        host = host.view(np.complex128)[..., 0]
+    nfreq = host.shape[2]
+    for k in range(nseg):
+        yield host[k].reshape(layout.host_shape(nfreq))
 
 
 _spectra_estimatives.device = _estimatives_device

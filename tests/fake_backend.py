@@ -173,12 +173,17 @@ def _spec_prepare(x, n, nfft, window, detrend):
     return _t(out)
 
 
+def _download_block(dev):
+    return _Now(np.array(dev.numpy(), copy=True))
+
+
 def install(mp):
     mp.setattr(dv, "DEVICE", "cpu")
     mp.setattr(dv, "require_cuda", lambda: torch)
     mp.setattr(dv, "upload", _upload)
     mp.setattr(dv, "download", _download)
     mp.setattr(dv, "spec_prepare", _spec_prepare)
+    mp.setattr(dv, "download_block", _download_block)
     mp.setattr(dv.FirPlan, "cached", staticmethod(lambda taps, algo=0: FakeFir(taps, algo)))
     mp.setattr(dv.SosPlan, "cached", staticmethod(lambda sos: FakeSos(sos)))
     mp.setattr(dv.TfPlan, "cached", staticmethod(lambda b, a: FakeTf(b, a)))
