@@ -388,6 +388,12 @@ def named_kernels(rows, chunk, hbm_peak):
     acc = dv.zeros((rows, NFFT // 2 + 1))
     out["welch_psd_nfft4096"] = entry(timed(lambda: plan.welch_accum(x, nseg, acc)),
                                       rows * nseg * plan.stride, 8)
+    # opt-in float32 arithmetic (float64 samples in, float64 sums out)
+    plan32 = dv.SpecPlan(NFFT, NFFT // 2, w, "constant", 1.0 / (FS * float(np.sum(w ** 2))),
+                         "float32")
+    acc.zero_()
+    out["welch_psd_nfft4096_f32compute"] = entry(
+        timed(lambda: plan32.welch_accum(x, nseg, acc)), rows * nseg * plan.stride, 8)
     del x
     torch.cuda.empty_cache()
     return out

@@ -202,6 +202,16 @@ int osz_spec_plan_create(osz_spec_plan **plan, int nfft, int stride,
                          const double *window_host, int detrend, double norm);
 int osz_spec_plan_destroy(osz_spec_plan *plan);
 int osz_spec_plan_path(const osz_spec_plan *plan); /* 1 = shared-memory pow2, 2 = generic */
+/* Arithmetic of the plan's transforms.  OSZ_COMPUTE_F64 (default) is the
+ * reference's; OSZ_COMPUTE_F32 is the opt-in float32 mode (float64 samples in,
+ * float64 sums out; samples are centred in float64, then window product and
+ * FFT run in float32 -- within north_star's float32 tolerance, 1e-5 of the
+ * largest bin).  It exists for osz_welch_accum_f64 at nfft = 512 .. 4096;
+ * other plans / entry points keep float64 (osz_spec_plan_compute tells).
+ * window_host: the same coefficients given to osz_spec_plan_create. */
+enum { OSZ_COMPUTE_F64 = 0, OSZ_COMPUTE_F32 = 1 };
+int osz_spec_plan_set_compute(osz_spec_plan *plan, int compute, const double *window_host);
+int osz_spec_plan_compute(const osz_spec_plan *plan);
 /* Fused Welch accumulate: for each row adds the one-sided periodograms of
  * segments s = 0..nseg-1 (segment s = x[r][s*stride .. s*stride+nfft)) into
  * psd_sum_dev[r*ldp + k], k <= nfft/2.  The caller divides by the segment

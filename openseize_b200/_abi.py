@@ -66,6 +66,8 @@ SIGNATURES = {
     "osz_spec_plan_create": (c_int, [POINTER(_vp), c_int, c_int, _dp, c_int, c_double]),
     "osz_spec_plan_destroy": (c_int, [_vp]),
     "osz_spec_plan_path": (c_int, [_vp]),
+    "osz_spec_plan_set_compute": (c_int, [_vp, c_int, _dp]),
+    "osz_spec_plan_compute": (c_int, [_vp]),
     "osz_welch_accum_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "osz_periodogram_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_stft_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -400,14 +400,16 @@ class _Cache:
 _plans = _Cache()
 
 
-# Arithmetic of the FIR overlap-save transforms: "float64" (default: the reference
-# computes and returns float64) or "float32" (opt-in: float64 samples in and out,
-# FFTs in float32, ~1e-6 of the output peak; north_star's float32 tolerance is 1e-5).
+# Arithmetic of the FIR overlap-save transforms and of the Welch accumulation:
+# "float64" (default: the reference computes and returns float64) or "float32"
+# (opt-in: float64 samples in and out, FFTs in float32, ~1e-6 of the output peak;
+# north_star's float32 tolerance is 1e-5).
 COMPUTE = os.environ.get("OSZ_COMPUTE", "float64")
 
 
 def set_compute(kind):
-    """Select the arithmetic of the FFT-based FIR path: "float64" | "float32"."""
+    """Select the arithmetic of the FFT-based FIR path and of the Welch
+    accumulation: "float64" | "float32"."""
     global COMPUTE
     if kind not in ("float64", "float32"):
         raise ValueError("compute must be 'float64' or 'float32'")
@@ -585,7 +587,7 @@ class UpfirdnPlan(_Plan):
 class SpecPlan(_Plan):
     _destroy = "osz_spec_plan_destroy"
 
-    def __init__(self, nfft, stride, window, detrend, norm):
+    def __init__(self, nfft, stride, window, detrend, norm, compute="float64"):
         super().__init__()
         require_cuda()
         arr, ptr = _abi.as_double_array(window)
@@ -595,12 +597,18 @@ class SpecPlan(_Plan):
                                               ptr, _abi.DETREND[detrend], float(norm))
         _abi.check(rc, "spec_plan_create")
         self.path = _abi.load().osz_spec_plan_path(self.handle)
+        if compute == "float32":
+            rc = _abi.load().osz_spec_plan_set_compute(self.handle, 1, ptr)
+            _abi.check(rc, "spec_plan_set_compute")
+        # what the plan's Welch accumulation really computes in (float32 exists for
+        # power-of-two nfft 512 .. 4096 only)
+        self.compute = ("float64", "float32")[_abi.load().osz_spec_plan_compute(self.handle)]
 
     @staticmethod
     def cached(nfft, stride, window, detrend, norm):
         arr = np.ascontiguousarray(window, dtype=np.float64)
-        key = ("spec", int(nfft), int(stride), arr.tobytes(), str(detrend), float(norm))
-        return _plans.get(key, lambda: SpecPlan(nfft, stride, arr, detrend, norm))
+        key = ("spec", int(nfft), int(stride), arr.tobytes(), str(detrend), float(norm), COMPUTE)
+        return _plans.get(key, lambda: SpecPlan(nfft, stride, arr, detrend, norm, COMPUTE))
 
     def nseg_available(self, width):
         return (width - self.nfft) // self.stride + 1 if width >= self.nfft else 0

@@ -371,6 +371,233 @@ welch_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t
     sync.drain();
 }
 
+// float32-compute variant of the ping-pong Welch kernel (opt-in, the plan's
+// compute mode): float64 samples in, float64 sums out, window product and
+// transform in float32 (namespace oszf of fft_core.cuh).  The float64 kernel is
+// bound by the FP64 pipe at ~25 % of the 8-bytes-per-sample HBM roofline; the
+// FP32 pipe issues at twice that rate and the exchange buffers halve.
+//   * Samples are centred in float64 BEFORE they are narrowed: d = x - c with c
+//     the first sample of the pair's span, so a DC offset far above the signal's
+//     fluctuation costs no float32 precision.  The detrend sums run in float64
+//     over the d (exact input to the float32 stage), the fitted mean / line is
+//     then removed in float32.
+//   * |Z|^2 is formed in float32 and accumulated in float64 REGISTERS (the
+//     float32 transform leaves room for them), folded into psd_sum whenever the
+//     run crosses into another row.
+//   * The span has its own staging buffer, so the next pair's TMA copy is issued
+//     as soon as this pair's samples are in registers.
+template <int LOG2N>
+struct WelchPPC32 {
+    using C = oszf::FftCfg<LOG2N>;
+    static constexpr int OFF_BAR = C::TW_TOTAL * 8;
+    static constexpr int OFF_RED = OFF_BAR + 16;                       // [group][4][8 warps]
+    static constexpr int OFF_WIN = (OFF_RED + 2 * 4 * 8 * 8 + 127) & ~127;
+    static constexpr int OFF_G = (OFF_WIN + C::N * 4 + 127) & ~127;
+    static constexpr int STAGE_BYTES = ((2 * C::N + 2) * 8 + 127) & ~127;   // stride + N (+ misalignment)
+    static constexpr int GROUP_BYTES = C::SMEM_BYTES + STAGE_BYTES;
+    static constexpr int SMEM = OFF_G + 2 * GROUP_BYTES;
+    // 512 threads per SM where shared memory allows (it does down to nfft 1024)
+    static constexpr int FIT = (228 * 1024) / (SMEM + 1024);
+    static constexpr int CTAS_PER_SM = 4096 / C::N < FIT ? 4096 / C::N : FIT;
+};
+
+template <int LOG2N, int DETREND>
+__global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, WelchPPC32<LOG2N>::CTAS_PER_SM)
+welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
+                    const float *__restrict__ win, const float2 *__restrict__ tw, double norm,
+                    double *__restrict__ psd_sum, int64_t ldp, int64_t npairs, int64_t nwork,
+                    int64_t per_group, int lag, int zero) {
+    using C = oszf::FftCfg<LOG2N>;
+    using L = WelchPPC32<LOG2N>;
+    using Sync = oszf::SyncPingPong<LOG2N>;
+    constexpr int N = C::N, NT = C::NT, NW = NT / 32;
+    static_assert(NT >= 32, "ping-pong Welch needs whole warps per group");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g = threadIdx.x / NT;
+    const int tid = threadIdx.x - g * NT;
+    float2 *tw_sm = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR) + g;
+    double *red = reinterpret_cast<double *>(smem_raw + L::OFF_RED) + g * 32;
+    float *win_sm = reinterpret_cast<float *>(smem_raw + L::OFF_WIN);
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES);
+    double *sx = reinterpret_cast<double *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES +
+                                            C::SMEM_BYTES);
+
+    for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
+    for (int i = threadIdx.x; i < N; i += 2 * NT) win_sm[i] = ldg(win + i);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const Sync sync{g, tid, zero, tw_sm};
+    double acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+
+    // this group's run of work items [w0, w1); item w = row * npairs + pair
+    const int64_t w0 = ((int64_t)blockIdx.x * 2 + g) * per_group;
+    int64_t w1 = w0 + per_group;
+    if (w1 > nwork) w1 = nwork;
+    int64_t row = w0 < nwork ? w0 / npairs : 0;
+    int64_t pair = w0 < nwork ? w0 - row * npairs : 0;
+
+    auto issue = [&](int64_t w_, int64_t row_, int64_t pair_) {
+        if (w_ >= w1) return;
+        const int64_t need = 2 * pair_ + 1 < nseg ? stride + N : N;
+        tma_fetch_span(sx, x + row_ * ldx + 2 * pair_ * stride, need, bar);
+    };
+    auto flush = [&](int64_t row_) {
+        // fold k and N-k:  psd[k] += norm * (A[k] + A[N-k]) for 0 < k < N/2 (the
+        // one-sided doubling), psd[0] += norm * A[0], psd[N/2] += norm * A[N/2]
+        double *out = psd_sum + row_ * ldp;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int idx = tid + r * NT;
+            const int bin = idx <= N / 2 ? idx : N - idx;
+            atomicAdd(out + bin, acc[r] * norm);
+            acc[r] = 0.0;
+        }
+    };
+    if (tid == 0) issue(w0, row, pair);
+    sync.prime();
+    if (g == 1)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+
+    for (int64_t it = 0; it < per_group; ++it) {
+        const int64_t w = w0 + it;
+        const bool live = w < w1;
+        int64_t rown = row, pairn = pair + 1;
+        if (pairn >= npairs) {
+            pairn = 0;
+            ++rown;
+        }
+        float2 v[16];
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        constexpr double tbar = 0.5 * (N - 1);
+        if (live) {
+            const double *x0 = sx + span_mis(x + row * ldx + 2 * pair * stride);
+            const double *xa = x0 + tid;
+            const double *xb = xa + stride;
+            while (!mbar_try_wait(bar, (uint32_t)(it & 1))) {
+            }
+            const double c = DETREND != OSZ_DETREND_NONE ? x0[0] : 0.0;
+            const bool has_b = 2 * pair + 1 < nseg;
+            if (has_b && stride == N / 2) {
+                // 50 % overlap: the second segment's first half is the first one's second
+                double d[24];
+#pragma unroll
+                for (int r = 0; r < 24; ++r) d[r] = xa[r * NT] - c;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = make_float2((float)d[r], (float)d[r + 8]);
+                if (DETREND != OSZ_DETREND_NONE) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        s[0] += d[r];
+                        s[1] += d[r + 8];
+                        if (DETREND == OSZ_DETREND_LINEAR) {
+                            const double tc = (double)(tid + r * NT) - tbar;
+                            s[2] = fma(tc, d[r], s[2]);
+                            s[3] = fma(tc, d[r + 8], s[3]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double da = xa[r * NT] - c;
+                    const double db = has_b ? xb[r * NT] - c : 0.0;
+                    v[r] = make_float2((float)da, (float)db);
+                    if (DETREND != OSZ_DETREND_NONE) {
+                        s[0] += da;
+                        s[1] += db;
+                        if (DETREND == OSZ_DETREND_LINEAR) {
+                            const double tc = (double)(tid + r * NT) - tbar;
+                            s[2] = fma(tc, da, s[2]);
+                            s[3] = fma(tc, db, s[3]);
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = make_float2(0.0f, 0.0f);
+        }
+        if (DETREND != OSZ_DETREND_NONE) {
+            // segment sums: per warp (shuffles), per group (shared memory)
+            constexpr int NV = DETREND == OSZ_DETREND_LINEAR ? 4 : 2;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            }
+            if ((tid & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) red[i * 8 + (tid >> 5)] = s[i];
+            }
+        }
+        // every thread of the group holds its samples: the staging buffer is free
+        // for the next pair (and `red` is complete)
+        sync.group();
+        if (tid == 0) {
+            fence_proxy_async();
+            issue(w + 1, rown, pairn);
+        }
+        if (DETREND != OSZ_DETREND_NONE) {
+            constexpr int NV = DETREND == OSZ_DETREND_LINEAR ? 4 : 2;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < NW; ++q) t += red[i * 8 + q];   // same order in every thread
+                s[i] = t;
+            }
+            // (the next write to `red` comes after this item's exchange barriers)
+            const float ma0 = (float)(s[0] / N), mb0 = (float)(s[1] / N);
+            const int tk = sync.take();
+            const float ma = Sync::tie(ma0, tk), mb = Sync::tie(mb0, tk);
+            if (DETREND == OSZ_DETREND_CONSTANT) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float wv = win_sm[tid + r * NT];
+                    v[r].x = (v[r].x - ma) * wv;
+                    v[r].y = (v[r].y - mb) * wv;
+                }
+            } else {
+                // least-squares line over t = 0..N-1 (scipy.signal.detrend type='linear')
+                constexpr double stt = (double)N * ((double)N * N - 1.0) / 12.0;   // sum (t - tbar)^2
+                const float ka = (float)(s[2] / stt), kb = (float)(s[3] / stt);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float tc = (float)(tid + r * NT) - (float)tbar;
+                    const float wv = win_sm[tid + r * NT];
+                    v[r].x = (v[r].x - fmaf(ka, tc, ma)) * wv;
+                    v[r].y = (v[r].y - fmaf(kb, tc, mb)) * wv;
+                }
+            }
+        } else {
+            const int tk = sync.take();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const float w_ = Sync::tie(win_sm[tid + r * NT], tk);
+                v[r].x *= w_;
+                v[r].y *= w_;
+            }
+        }
+        oszf::bfly<16>(v);
+        sync.release(v);
+        oszf::fft_r2r_tail<LOG2N, Sync, true>(v, sm, tid, sync);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] += (double)fmaf(v[r].x, v[r].x, v[r].y * v[r].y);
+        if (live && (rown != row || w + 1 >= w1)) flush(row);
+        row = rown;
+        pair = pairn;
+    }
+    if (g == 0)
+        for (int i = 0; i < lag; ++i) sync.idle_turn();
+    sync.drain();
+}
+
 // Per-segment outputs: one CTA per (segment pair, row).
 template <int LOG2N, int DETREND, int MODE>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::NT, (LOG2N <= 12 ? 2 : 1))
@@ -465,9 +692,12 @@ using namespace osz;
 
 struct osz_spec_plan {
     int nfft = 0, stride = 0, detrend = 0, path = 0, log2n = 0;
+    int compute = OSZ_COMPUTE_F64;
     double norm = 0.0;
     double *d_win = nullptr;
     double2 *d_tw = nullptr;
+    float *d_winf = nullptr;    // float32 compute (osz_spec_plan_set_compute)
+    float2 *d_twf = nullptr;
     void *generic = nullptr;    // spectra_generic.cu state
     void *mixed = nullptr;      // spectra_mixed.cu state (shared-memory mixed radix), may be null
 };
@@ -536,6 +766,31 @@ static int launch_welch_pp(const osz_spec_plan *p, const double *x, int64_t ldx,
     return OSZ_OK;
 }
 
+template <int LOG2N, int DETREND>
+static int launch_welch_pp_c32(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                               int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
+    using C = oszf::FftCfg<LOG2N>;
+    using L = WelchPPC32<LOG2N>;
+    static_assert(L::SMEM * L::CTAS_PER_SM + 1024 * L::CTAS_PER_SM <= 228 * 1024,
+                  "float32-compute Welch: shared memory");
+    OSZ_CUDA(cudaFuncSetAttribute(welch_pp_c32_kernel<LOG2N, DETREND>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    const int64_t npairs = (nseg + 1) / 2;
+    const int64_t nwork = npairs * rows;
+    int64_t grid = (nwork + 1) / 2;
+    if (grid > (int64_t)sm_count() * L::CTAS_PER_SM) grid = (int64_t)sm_count() * L::CTAS_PER_SM;
+    const int64_t per_group = (nwork + 2 * grid - 1) / (2 * grid);
+    static const int lag = [] {
+        const char *e = getenv("OSZ_WELCH_LAG");
+        return e ? atoi(e) : 0;
+    }();
+    welch_pp_c32_kernel<LOG2N, DETREND><<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
+        x, ldx, nseg, p->stride, p->d_winf, p->d_twf, p->norm, psd, ldp, npairs, nwork, per_group,
+        lag, 0);
+    OSZ_LAUNCHED("welch_pp_c32_kernel");
+    return OSZ_OK;
+}
+
 template <int LOG2N, int DETREND, int MODE>
 static int launch_segments(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                            int64_t nseg, double *out, cudaStream_t st) {
@@ -558,6 +813,8 @@ static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int6
             return e ? atoi(e) : 1;
         }();
         if constexpr (LOG2N >= 9 && LOG2N <= 12) {
+            if (p->compute == OSZ_COMPUTE_F32 && p->d_winf && p->d_twf)
+                return launch_welch_pp_c32<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
             if (pp) return launch_welch_pp<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
         }
         return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
@@ -654,6 +911,8 @@ int osz_spec_plan_destroy(osz_spec_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_win);
     cudaFree(p->d_tw);
+    cudaFree(p->d_winf);
+    cudaFree(p->d_twf);
     if (p->generic) osz_generic_destroy(p->generic);
     if (p->mixed) osz_mixed_destroy(p->mixed);
     delete p;
@@ -661,6 +920,33 @@ int osz_spec_plan_destroy(osz_spec_plan *p) {
 }
 
 int osz_spec_plan_path(const osz_spec_plan *p) { return p ? p->path : 0; }
+
+int osz_spec_plan_set_compute(osz_spec_plan *p, int compute, const double *window) {
+    if (!p || (compute != OSZ_COMPUTE_F64 && compute != OSZ_COMPUTE_F32))
+        return fail(OSZ_ERR_ARG, "osz_spec_plan_set_compute: bad arguments");
+    if (compute == OSZ_COMPUTE_F64) {
+        p->compute = OSZ_COMPUTE_F64;
+        return OSZ_OK;
+    }
+    // float32 arithmetic exists for the Welch accumulation at nfft = 512 .. 4096;
+    // every other plan keeps computing in float64
+    if (p->path != 1 || p->log2n < 9 || p->log2n > 12) return OSZ_OK;
+    if (!p->d_winf) {
+        if (!window) return fail(OSZ_ERR_ARG, "osz_spec_plan_set_compute: window needed");
+        std::vector<float> wf((size_t)p->nfft);
+        for (int i = 0; i < p->nfft; ++i) wf[(size_t)i] = (float)window[i];
+        std::vector<float> twf = oszf::make_fft_twiddles(p->log2n);
+        const bool ok =
+            cudaMalloc(&p->d_winf, wf.size() * 4) == cudaSuccess &&
+            cudaMemcpy(p->d_winf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&p->d_twf, twf.size() * 4) == cudaSuccess &&
+            cudaMemcpy(p->d_twf, twf.data(), twf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) return fail(OSZ_ERR_CUDA, "osz_spec_plan_set_compute: device upload failed");
+    }
+    p->compute = OSZ_COMPUTE_F32;
+    return OSZ_OK;
+}
+int osz_spec_plan_compute(const osz_spec_plan *p) { return p ? p->compute : 0; }
 
 int osz_welch_accum_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                         int64_t nseg, double *psd_sum, int64_t ldp, void *stream) {

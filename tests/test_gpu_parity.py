@@ -289,6 +289,68 @@ def test_welch_unaligned_and_strides(dv, nfft, stride):
         assert relerr(psd_sum.cpu().numpy(), ref) < 1e-11, (nfft, stride, rows, nseg)
 
 
+@pytest.mark.parametrize("nfft,stride", [(4096, 2048), (4096, 3687), (2048, 1024), (1024, 333),
+                                         (512, 512), (1024, 512), (512, 256)])
+@pytest.mark.parametrize("detrend", ["constant", "linear", None])
+def test_welch_float32_compute(dv, nfft, stride, detrend):
+    """Opt-in float32 arithmetic of the Welch accumulation (float64 samples in,
+    float64 sums out): within north_star's float32 tolerance, 1e-5 of the
+    largest bin, of the float64 result -- with a DC offset 1000x the signal
+    (samples are centred in float64 before they are narrowed), a drift,
+    unaligned rows and 1 .. 41 segments."""
+    rng = np.random.default_rng(nfft + stride)
+    w = sps.get_window("hann", nfft)
+    norm = 1.0 / (1000.0 * np.sum(w ** 2))
+    plan = dv.SpecPlan(nfft, stride, w, detrend, norm, "float32")
+    assert plan.compute == "float32"
+    for rows, nseg in ((1, 1), (5, 2), (2, 3), (3, 8), (2, 41)):
+        n = (nseg - 1) * stride + nfft
+        x = rng.standard_normal((rows, n)) + 3 * np.sin(2 * np.pi * 0.01 * np.arange(n))
+        if detrend:
+            x = x + 1000.0 + (np.arange(n) * (2.0 / nfft) if detrend == "linear" else 0.0)
+        buf = dv.zeros((rows, n + 5))
+        buf[:, 3:3 + n] = _dev(dv, x)
+        psd_sum = dv.zeros((rows, nfft // 2 + 1))
+        plan.welch_accum(buf[:, 3:3 + n], nseg, psd_sum)
+        ref = 0
+        for k in range(nseg):
+            seg = x[:, k * stride:k * stride + nfft]
+            if detrend:
+                seg = sps.detrend(seg, axis=-1, type=detrend)
+            p = np.abs(np.fft.rfft(seg * w, axis=-1)) ** 2 * norm
+            p[:, 1:-1] *= 2
+            ref = ref + p
+        got = psd_sum.cpu().numpy()
+        err = np.max(np.abs(got - ref), axis=-1) / np.max(ref, axis=-1)    # per channel
+        assert np.all(err < 1e-5), (nfft, stride, detrend, rows, nseg, err)
+
+
+def test_psd_float32_compute(dv):
+    """psd() under set_compute("float32"): really float32 arithmetic, within tolerance."""
+    import openseize_b200
+    from openseize_b200.spectra.estimators import psd
+
+    rng = np.random.default_rng(77)
+    fs = 4096.0
+    t = np.arange(400000) / fs
+    x = rng.standard_normal((3, t.size)) + 20 * np.sin(2 * np.pi * 60 * t) + 500.0
+    cnt_o, f_o, ref = oracle.welch_psd(x, fs, -1, fs / 4096)
+    openseize_b200.set_compute("float32")
+    try:
+        cnt32, f32, p32 = psd(producer(x, 100000, -1), fs, resolution=fs / 4096)
+    finally:
+        openseize_b200.set_compute("float64")
+    cnt64, f64, p64 = psd(producer(x, 100000, -1), fs, resolution=fs / 4096)
+    assert cnt32 == cnt64 == cnt_o and np.array_equal(f32, f_o)
+    e32 = np.max(np.abs(p32 - ref), axis=-1) / np.max(ref, axis=-1)
+    e64 = np.max(np.abs(p64 - ref), axis=-1) / np.max(ref, axis=-1)
+    assert np.all(e64 < 1e-11)
+    assert np.all(e32 < 1e-5) and np.any(e32 > 1e-11)
+    # plans outside the float32 kernel's range keep float64 and say so
+    w = sps.get_window("hann", 2000)
+    assert dv.SpecPlan(2000, 1000, w, "constant", 1.0, "float32").compute == "float64"
+
+
 @pytest.mark.parametrize("nfft", [2, 3, 60, 97, 250, 1001, 1009, 2000, 10000, 16384])
 def test_generic_nfft_vs_numpy(dv, nfft):
     """Mixed-radix (2..16, 3, 5, 7, 11, 13) and Bluestein (97, 1009) lengths,

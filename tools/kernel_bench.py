@@ -114,6 +114,11 @@ def main(which):
             acc = dv.zeros((rows, nfft // 2 + 1))
             report("welch nfft=%d" % nfft, timeit(lambda: plan.welch_accum(x, nseg, acc)),
                    rows * nseg * plan.stride, 8)
+            if nfft <= 4096 and not nfft & (nfft - 1):
+                p32 = dv.SpecPlan(nfft, nfft // 2, w, "constant",
+                                  1.0 / (30000 * np.sum(w ** 2)), "float32")
+                report("welch nfft=%d float32 compute" % nfft,
+                       timeit(lambda: p32.welch_accum(x, nseg, acc)), rows * nseg * plan.stride, 8)
             if nfft == 4096:
                 xs = rnd(32, n)
                 ns = plan.nseg_available(n)
