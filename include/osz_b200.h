@@ -234,6 +234,34 @@ int osz_spec_prepare_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t
                          int64_t nfft, const double *window_dev, int detrend,
                          double *out_dev, int64_t ldo, void *stream);
 
+/* ---- producer tools on device-resident chunks ---------------
+ * Mask compaction of MaskedProducer (core/producer.py:427-444: np.take of the
+ * kept samples along the sample axis): y[r][j] = x[r][idx[j]], idx_dev the
+ * ascending int64 positions np.flatnonzero(mask chunk) on the device. */
+int osz_take_cols_f64(const double *x_dev, int64_t ldx, int64_t rows, const int64_t *idx_dev,
+                      int64_t nkeep, double *y_dev, int64_t ldy, void *stream);
+/* protools.mean / protools.std along the production axis (core/protools.py:
+ * 529-536, 580-590), one call per chunk:  acc[r] += (n * mean_chunk[r],
+ * n * mean(chunk^2)[r], n), mean over the values that are not NaN when
+ * ignore_nan (np.nanmean) -- the reference's chunk-weighted combination.
+ * acc_dev: rows x 3 (zeroed by the caller before the first chunk);
+ * scratch_dev: rows x osz_row_moments_slots() x 3 doubles. */
+int osz_row_moments_slots(void);
+int osz_row_moments_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t n,
+                        int ignore_nan, double *acc_dev, double *scratch_dev, void *stream);
+/* protools.standardize along the production axis (:659-662):
+ * y[r][i] = (x[r][i] - mean[r]) / std[r]. */
+int osz_row_standardize_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t n,
+                            const double *mean_dev, const double *std_dev, double *y_dev,
+                            int64_t ldy, void *stream);
+/* The same three for an axis that is NOT the production axis (:538-543, 592-595,
+ * 663-668): per sample i the np.(nan)mean / np.(nan)std over the rows of the
+ * chunk; any of mean_out (n), std_out (n), y (rows x n standardized) may be
+ * null. */
+int osz_col_moments_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t n,
+                        int ignore_nan, double *mean_out_dev, double *std_out_dev,
+                        double *y_dev, int64_t ldy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

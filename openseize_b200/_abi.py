@@ -72,6 +72,11 @@ SIGNATURES = {
     "osz_periodogram_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_stft_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_spec_prepare_f64": (c_int, [_vp, _i64, _i64, _i64, _i64, _vp, c_int, _vp, _i64, _vp]),
+    "osz_take_cols_f64": (c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "osz_row_moments_slots": (c_int, []),
+    "osz_row_moments_f64": (c_int, [_vp, _i64, _i64, _i64, c_int, _vp, _vp, _vp]),
+    "osz_row_standardize_f64": (c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "osz_col_moments_f64": (c_int, [_vp, _i64, _i64, _i64, c_int, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

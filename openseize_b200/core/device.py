@@ -651,6 +651,89 @@ def spec_prepare(x, n, nfft, window, detrend):
     return out
 
 
+# --------------------------------------------------------------------------
+# producer tools (csrc/protools.cu)
+# --------------------------------------------------------------------------
+def take_cols(x, idx):
+    """x[:, idx] for device rows ``(rows, n)`` and ascending host int64 positions
+    ``idx`` (np.flatnonzero of a mask chunk): the device compaction of
+    MaskedProducer (reference core/producer.py:436-437)."""
+    t = require_cuda()
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    rows = x.shape[0]
+    out = empty((rows, int(idx.size)))
+    if idx.size == 0 or rows == 0:
+        return out
+    if int(idx[0]) < 0 or int(idx[-1]) >= x.shape[1]:
+        # np.take's error for a mask that is True beyond the end of the data
+        raise IndexError("index {} is out of bounds for axis with size {}".format(
+            int(idx[-1]), x.shape[1]))
+    idx_dev = t.from_numpy(idx).to(DEVICE)
+    xp, ldx = _rows_ptr(x)
+    yp, ldy = _rows_ptr(out)
+    rc = _launch("take_cols", 16 * rows * int(idx.size), _abi.load().osz_take_cols_f64, xp, ldx,
+                 rows, _vp(idx_dev.data_ptr()), int(idx.size), yp, ldy, _cur_stream())
+    _abi.check(rc, "take_cols")
+    idx_dev.record_stream(t.cuda.current_stream())
+    return out
+
+
+class RowMoments:
+    """Running per-row sums for protools.mean / protools.std along the
+    production axis: ``add`` folds one chunk in on the device, ``result`` brings
+    back (sum of n * chunk mean, sum of n * chunk mean of squares, sum of n)."""
+
+    def __init__(self, rows, ignore_nan=True):
+        require_cuda()
+        self.rows, self.ignore_nan = int(rows), bool(ignore_nan)
+        self.acc = zeros((self.rows, 3))
+        self.scratch = empty((self.rows, _abi.load().osz_row_moments_slots() * 3))
+
+    def add(self, x):
+        assert x.shape[0] == self.rows
+        xp, ldx = _rows_ptr(x)
+        rc = _launch("row_moments", 8 * self.rows * x.shape[1], _abi.load().osz_row_moments_f64,
+                     xp, ldx, self.rows, int(x.shape[1]), int(self.ignore_nan),
+                     _vp(self.acc.data_ptr()), _vp(self.scratch.data_ptr()), _cur_stream())
+        _abi.check(rc, "row_moments")
+
+    def result(self):
+        return self.acc.cpu().numpy()
+
+
+def row_standardize(x, mean_dev, std_dev, out=None):
+    """(x - mean[r]) / std[r] per device row (protools.standardize, production axis)."""
+    rows, n = x.shape
+    if out is None:
+        out = empty((rows, n))
+    xp, ldx = _rows_ptr(x)
+    yp, ldy = _rows_ptr(out)
+    rc = _launch("standardize", 16 * rows * n, _abi.load().osz_row_standardize_f64, xp, ldx, rows,
+                 int(n), _vp(mean_dev.data_ptr()), _vp(std_dev.data_ptr()), yp, ldy, _cur_stream())
+    _abi.check(rc, "row_standardize")
+    return out
+
+
+def col_moments(x, ignore_nan=True, want="mean"):
+    """Per-sample statistics ACROSS the rows of a device chunk: ``want`` =
+    "mean" | "std" -> (1, n) rows, "standardize" -> (rows, n)."""
+    rows, n = x.shape
+    xp, ldx = _rows_ptr(x)
+    null = _vp(0)
+    if want == "standardize":
+        out = empty((rows, n))
+        yp, ldy = _rows_ptr(out)
+        args = (null, null, yp, ldy)
+    else:
+        out = empty((1, n))
+        args = ((_vp(out.data_ptr()), null) if want == "mean" else (null, _vp(out.data_ptr()))) \
+            + (null, 0)
+    rc = _launch("col_moments", 8 * rows * n, _abi.load().osz_col_moments_f64, xp, ldx, rows,
+                 int(n), int(bool(ignore_nan)), *args, _cur_stream())
+    _abi.check(rc, "col_moments")
+    return out
+
+
 def ceil_div(a, b):
     return -(-int(a) // int(b))
 

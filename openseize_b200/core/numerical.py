@@ -22,7 +22,8 @@ import scipy.signal as sps
 
 from openseize_b200.core import device as dv
 from openseize_b200.core.arraytools import normalize_axis
-from openseize_b200.core.producer import DeviceProducer, GenProducer, Producer, producer
+from openseize_b200.core.producer import (DeviceProducer, GenProducer, MaskedProducer, Producer,
+                                           producer)
 
 # ---------------------------------------------------------------------------
 # shape helpers (pure index arithmetic, reference core/numerical.py:19-155)
@@ -127,6 +128,8 @@ def device_chunks(pro, axis, regrid=True, alloc=None):
     layout = dv.Layout(pro.shape, axis)
     if isinstance(pro, DeviceProducer):
         source = pro.device_iter()
+    elif isinstance(pro, MaskedProducer) and pro.axis == layout.axis:
+        source = _masked_device(pro)
     else:
         twin = _device_twin(pro)
         if twin is None:
@@ -160,6 +163,20 @@ def device_chunks(pro, axis, regrid=True, alloc=None):
             yield fifo.get(cs)
     if fifo.size:
         yield fifo.get(cs)
+
+
+def _masked_device(pro):
+    """MaskedProducer on the device (reference core/producer.py:427-444): the
+    inner producer's chunks -- uploaded, or handed over in HBM when it is a chain
+    of GPU operators -- are compacted by ``take_cols`` with the positions of the
+    mask chunk that pairs with them; chunks without a kept sample are skipped and
+    production stops when the producer or the mask runs out (``zip``).  The
+    caller re-blocks the stream to the chunk size as the reference's FIFO does."""
+    inner = pro.data
+    for block, keep in zip(device_chunks(inner, pro.axis, regrid=True), pro.mask):
+        idx = np.flatnonzero(keep)
+        if idx.size:
+            yield dv.take_cols(block, idx)
 
 
 def _new_rows(out, rows, n):

@@ -14,7 +14,7 @@ PKG = os.path.dirname(HERE)
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libosz_b200.so")
 SOURCES = ["runtime.cu", "fir.cu", "sos.cu", "tf.cu", "upfirdn.cu", "spectra.cu",
-           "spectra_generic.cu", "spectra_mixed.cu"]
+           "spectra_generic.cu", "spectra_mixed.cu", "protools.cu"]
 HEADERS = ["common.cuh", "fft_core.cuh", "fft_core_body.inc", os.path.join("..", "..", "include", "osz_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

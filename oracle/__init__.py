@@ -49,4 +49,8 @@ from oracle.chunked import (  # noqa: F401
     segments,
     welch_psd,
     stft,
+    masked,
+    pro_mean,
+    pro_std,
+    standardize,
 )

@@ -399,3 +399,77 @@ def stft(x, fs, axis=-1, resolution=0.5, window="hann", overlap=0.5,
         _, X = modified_dft(seg, fs, nfft, window, axis, detrend, scaling)
         cols.append(X)
     return freqs, time, np.stack(cols, axis=-1)
+
+
+# --------------------------------------------------------------------------
+# producer tools: masked producers and reductions
+# --------------------------------------------------------------------------
+def masked(x, mask, chunksize, axis=-1):
+    """Arrays yielded by ``producer(x, chunksize, axis, mask=mask)``
+    (core/producer.py:427-444): chunk k of the data is paired with chunk k of
+    the mask (``zip``: production stops when either runs out), chunks without a
+    kept sample are skipped, the kept samples (``np.take`` of ``flatnonzero``)
+    are re-chunked to ``chunksize`` by a FIFO."""
+    x = np.asarray(x)
+    mask = np.asarray(mask)
+    fifo, out = _Fifo(int(chunksize), axis), []
+    for arr, keep in zip(split_chunks(x, chunksize, axis), split_chunks(mask, chunksize, 0)):
+        if not np.any(keep):                                    # :432-433
+            continue
+        fifo.put(np.take(arr, np.flatnonzero(keep), axis=axis))  # :436-437
+        while fifo.qsize() >= fifo.size:                        # :439-441
+            out.append(fifo.get())
+    if fifo.qsize() > 0:                                        # :444-446
+        out.append(fifo.get())
+    return out
+
+
+def pro_mean(chunks, pro_axis, axis=-1, ignore_nan=True, keepdims=False):
+    """``protools.mean`` (core/protools.py:500-543) over the list of arrays a
+    producer yields along ``pro_axis``."""
+    averager = np.nanmean if ignore_nan else np.mean
+    ndim = chunks[0].ndim
+    ax = int(np.arange(ndim)[axis])
+    if ax == int(np.arange(ndim)[pro_axis]):
+        sums, cnts = 0, 0
+        for arr in chunks:                                      # :531-534
+            cnts += arr.shape[axis]
+            sums += arr.shape[axis] * averager(arr, axis=axis, keepdims=keepdims)
+        return sums / cnts                                      # :536
+    avgs = [averager(a, axis=ax, keepdims=True) for a in chunks]   # :539
+    result = np.concatenate(avgs, axis=pro_axis)
+    return result if keepdims else np.squeeze(result, ax)
+
+
+def pro_std(chunks, pro_axis, axis=-1, ignore_nan=True, keepdims=False):
+    """``protools.std`` (core/protools.py:546-595): sqrt(E[x^2] - E[x]^2) with
+    the chunk-weighted means of ``pro_mean``."""
+    averager = np.nanmean if ignore_nan else np.mean
+    dev = np.nanstd if ignore_nan else np.std
+    ndim = chunks[0].ndim
+    ax = int(np.arange(ndim)[axis])
+    if ax == int(np.arange(ndim)[pro_axis]):
+        expected_squared = pro_mean(chunks, pro_axis, ax, ignore_nan, keepdims) ** 2   # :580
+        sum_squares, cnts = 0, 0
+        for arr in chunks:                                      # :582-587
+            cnts += arr.shape[axis]
+            sum_squares += arr.shape[axis] * averager(arr ** 2, axis=axis, keepdims=keepdims)
+        return np.sqrt(sum_squares / cnts - expected_squared)   # :590
+    stds = [dev(a, axis=ax, keepdims=True) for a in chunks]     # :593
+    result = np.concatenate(stds, axis=pro_axis)
+    return result if keepdims else np.squeeze(result, ax)
+
+
+def standardize(chunks, pro_axis, axis=-1, ignore_nan=True):
+    """Arrays yielded by ``protools.standardize`` (core/protools.py:598-668)."""
+    means = pro_mean(chunks, pro_axis, axis, ignore_nan, keepdims=True)    # :633
+    stds = pro_std(chunks, pro_axis, axis, ignore_nan, keepdims=True)      # :634
+    ndim = chunks[0].ndim
+    if int(np.arange(ndim)[axis]) == int(np.arange(ndim)[pro_axis]):
+        return [(arr - means) / stds for arr in chunks]         # :659-662
+    out, pos = [], 0
+    for arr in chunks:                                          # :664-668
+        n = arr.shape[pro_axis]
+        out.append((arr - _ax(means, pos, pos + n, pro_axis)) / _ax(stds, pos, pos + n, pro_axis))
+        pos += n
+    return out

@@ -64,12 +64,68 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
+def protools_golden(report):
+    """Masked producers (core/producer.py:379-444) and protools.mean / std /
+    standardize (core/protools.py:500-668): SURVEY 8f, N3."""
+    import oracle
+    from openseize import producer
+    from openseize.core import protools
+
+    fs = 500
+    x = signal(51, 3, 4500, fs) + 40.0
+    rng = np.random.default_rng(52)
+    # a "sleep state" mask: runs of kept / dropped samples, some chunks fully dropped
+    mask = np.repeat(rng.random(45) < 0.55, 100)
+    mask[1000:2100] = False
+    gold = {"seed": 51, "rows": 3, "n": 4500, "fs": fs, "offset": 40.0, "x_sum": x.sum(),
+            "mask": mask, "chunksize": 500}
+    for name, arr, axis in (("ax1", x, -1), ("ax0", np.ascontiguousarray(x.T), 0)):
+        mpro = producer(arr, 500, axis, mask=mask)
+        ref_list = [np.array(a) for a in mpro]
+        mine_list = oracle.masked(arr, mask, 500, axis)
+        assert [a.shape for a in ref_list] == [a.shape for a in mine_list]
+        assert all(np.array_equal(a, b) for a, b in zip(ref_list, mine_list))
+        gold["masked_lengths_" + name] = np.array([a.shape[axis] for a in ref_list])
+        gold["masked_" + name] = np.concatenate(ref_list, axis)
+        chunks = oracle.split_chunks(arr, 500, axis)
+        for ax in (0, 1):
+            for keep in (False, True):
+                m = protools.mean(producer(arr, 500, axis), ax, keepdims=keep)
+                s = protools.std(producer(arr, 500, axis), ax, keepdims=keep)
+                om = oracle.pro_mean(chunks, axis, ax, keepdims=keep)
+                osd = oracle.pro_std(chunks, axis, ax, keepdims=keep)
+                assert np.array_equal(m, om) and np.array_equal(s, osd), (name, ax, keep)
+                gold["mean_%s_axis%d_keep%d" % (name, ax, keep)] = m
+                gold["std_%s_axis%d_keep%d" % (name, ax, keep)] = s
+            z = protools.standardize(producer(arr, 500, axis), ax).to_array()
+            oz = np.concatenate(oracle.standardize(chunks, axis, ax), axis)
+            assert np.array_equal(z, oz), (name, ax)
+            gold["standardized_%s_axis%d" % (name, ax)] = z
+    # NaNs: the chunk-weighted nanmean of the reference (n * nanmean per chunk)
+    xn = x.copy()
+    xn[0, 100:160] = np.nan
+    xn[2, 2500:3400] = np.nan
+    chunks = oracle.split_chunks(xn, 500, -1)
+    m = protools.mean(producer(xn, 500, -1), -1)
+    s = protools.std(producer(xn, 500, -1), -1)
+    assert np.array_equal(m, oracle.pro_mean(chunks, -1, -1), equal_nan=True)
+    assert np.array_equal(s, oracle.pro_std(chunks, -1, -1), equal_nan=True)
+    gold["nan_spans"] = np.array([[0, 100, 160], [2, 2500, 3400]])
+    gold["mean_nan"], gold["std_nan"] = m, s
+    np.savez_compressed(os.path.join(GOLD, "protools.npz"), **gold)
+    report.append(("protools", "bit-exact vs reference (masked producer, mean, std, standardize)"))
+
+
 def main():
     sys.path.insert(0, ROOT)
     import oracle
     producer, nm, fir, iir, resampling, estimators = _import_reference()
     os.makedirs(GOLD, exist_ok=True)
     report = []
+    if sys.argv[1:] == ["protools"]:          # only the fixture added last
+        protools_golden(report)
+        print(report)
+        return
 
     # ---------------- FIR: Kaiser 113 taps, all modes, both axes -----------
     fs = 5000
@@ -208,6 +264,8 @@ def main():
                 gold[key + "_X"] = X[..., idx]
         np.savez_compressed(os.path.join(GOLD, "spectra_%s.npz" % name), **gold)
         report.append(("spectra_" + name, "bit-exact vs reference"))
+
+    protools_golden(report)
 
     for name, status in report:
         print("%-18s %s" % (name, status))

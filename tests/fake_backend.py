@@ -177,6 +177,49 @@ def _download_block(dev):
     return _Now(np.array(dev.numpy(), copy=True))
 
 
+def _take_cols(x, idx):
+    idx = np.asarray(idx, dtype=np.int64)
+    if idx.size and (idx[0] < 0 or idx[-1] >= x.shape[1]):
+        raise IndexError("index out of bounds")
+    return _t(x.numpy()[:, idx])
+
+
+class FakeRowMoments:
+    """Contract of osz_row_moments_f64 (include/osz_b200.h)."""
+
+    def __init__(self, rows, ignore_nan=True):
+        self.acc, self.ignore_nan = np.zeros((rows, 3)), ignore_nan
+        self.avg = np.nanmean if ignore_nan else np.mean
+
+    def add(self, x):
+        import warnings
+
+        a, n = x.numpy(), x.shape[1]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.acc[:, 0] += n * self.avg(a, axis=1)
+            self.acc[:, 1] += n * self.avg(a ** 2, axis=1)
+        self.acc[:, 2] += n
+
+    def result(self):
+        return self.acc.copy()
+
+
+def _row_standardize(x, mean_dev, std_dev, out=None):
+    y = (x.numpy() - mean_dev.numpy()[:, None]) / std_dev.numpy()[:, None]
+    return _ret(y, out)
+
+
+def _col_moments(x, ignore_nan=True, want="mean"):
+    a = x.numpy()
+    avg, dev = (np.nanmean, np.nanstd) if ignore_nan else (np.mean, np.std)
+    if want == "mean":
+        return _t(avg(a, axis=0, keepdims=True))
+    if want == "std":
+        return _t(dev(a, axis=0, keepdims=True))
+    return _t((a - avg(a, axis=0, keepdims=True)) / dev(a, axis=0, keepdims=True))
+
+
 def install(mp):
     mp.setattr(dv, "DEVICE", "cpu")
     mp.setattr(dv, "require_cuda", lambda: torch)
@@ -184,6 +227,10 @@ def install(mp):
     mp.setattr(dv, "download", _download)
     mp.setattr(dv, "spec_prepare", _spec_prepare)
     mp.setattr(dv, "download_block", _download_block)
+    mp.setattr(dv, "take_cols", _take_cols)
+    mp.setattr(dv, "RowMoments", FakeRowMoments)
+    mp.setattr(dv, "row_standardize", _row_standardize)
+    mp.setattr(dv, "col_moments", _col_moments)
     mp.setattr(dv.FirPlan, "cached", staticmethod(lambda taps, algo=0: FakeFir(taps, algo)))
     mp.setattr(dv.SosPlan, "cached", staticmethod(lambda sos: FakeSos(sos)))
     mp.setattr(dv.TfPlan, "cached", staticmethod(lambda b, a: FakeTf(b, a)))

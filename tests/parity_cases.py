@@ -371,3 +371,73 @@ def pipeline_chain():
     close(p, rp)
     # and the intermediate producer is still iterable on the host
     close(kais(notch(producer(x, cs, -1), cs, axis=-1), cs, axis=-1).to_array(), r2)
+
+
+# ------------------------------------------------- producer tools (N3) ----
+def protools_golden():
+    """Masked producers consumed by GPU operators and protools.mean / std /
+    standardize against the real reference's outputs (tests/golden/protools.npz)."""
+    from openseize_b200.core import protools
+
+    g = golden("protools")
+    fs, cs, mask = int(g["fs"]), int(g["chunksize"]), g["mask"]
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs) + float(g["offset"])
+    assert x.sum() == float(g["x_sum"])
+    for name, arr, axis in (("ax1", x, -1), ("ax0", np.ascontiguousarray(x.T), 0)):
+        # host iteration of the masked producer: the reference's yields, bit for bit
+        mpro = producer(arr, cs, axis, mask=mask)
+        got = list(mpro)
+        assert [a.shape[axis] for a in got] == list(g["masked_lengths_" + name])
+        assert np.array_equal(np.concatenate(got, axis), g["masked_" + name])
+        assert mpro.shape[axis] == g["masked_" + name].shape[axis]
+        # the device compaction (what a GPU operator downstream consumes): same samples
+        layout_axis = axis % arr.ndim
+        blocks = list(nm._to_host(nm.device_chunks(producer(arr, cs, axis, mask=mask), axis),
+                                  nm._layout_of(mpro, layout_axis)))
+        assert [a.shape[axis] for a in blocks] == list(g["masked_lengths_" + name])
+        assert np.array_equal(np.concatenate(blocks, axis), g["masked_" + name])
+        for ax in (0, 1):
+            for keep in (0, 1):
+                m = protools.mean(producer(arr, cs, axis), ax, keepdims=bool(keep))
+                s = protools.std(producer(arr, cs, axis), ax, keepdims=bool(keep))
+                close(m, g["mean_%s_axis%d_keep%d" % (name, ax, keep)], 1e-12)
+                close(s, g["std_%s_axis%d_keep%d" % (name, ax, keep)], 1e-9)
+            z = protools.standardize(producer(arr, cs, axis), ax)
+            assert z.shape == arr.shape and z.chunksize == cs
+            close(z.to_array(), g["standardized_%s_axis%d" % (name, ax)], 1e-9)
+    # NaNs are skipped per chunk; a chunk of nothing but NaNs makes the row NaN
+    # (the reference's n * nanmean(chunk) weighting, protools.py:531-536)
+    xn = x.copy()
+    for r, a, b in g["nan_spans"]:
+        xn[r, a:b] = np.nan
+    m = protools.mean(producer(xn, cs, -1), -1)
+    s = protools.std(producer(xn, cs, -1), -1)
+    assert np.array_equal(np.isnan(m), np.isnan(g["mean_nan"]))
+    ok = ~np.isnan(m)
+    close(m[ok], g["mean_nan"][ok], 1e-12)
+    close(s[ok], g["std_nan"][ok], 1e-9)
+
+
+def masked_chain():
+    """The quickstart workflow: filter -> state mask ->
+    standardize -> PSD, every stage handing its chunks over on the device;
+    against the oracle run stage by stage."""
+    from openseize_b200.core import protools
+
+    fs, cs = 1000, 4000
+    rng = np.random.default_rng(61)
+    x = signal(62, 3, 30000, fs) + 7.0
+    mask = np.repeat(rng.random(60) < 0.6, 500)
+    filt = Notch(fstop=60, width=6, fs=fs)
+    y = filt(producer(x, cs, -1), cs, axis=-1, dephase=False)
+    masked = producer(y, cs, -1, mask=mask)
+    z = protools.standardize(masked, -1)
+    cnt, freqs, est = psd(z, fs, resolution=fs / 1024)
+    b, a = filt.coeffs
+    oy = np.concatenate(oracle.lfilter(x, (b, a), cs, -1)[0], -1)
+    om = oracle.masked(oy, mask, cs, -1)
+    oz = np.concatenate(oracle.standardize(om, -1, -1), -1)
+    ocnt, ofreqs, oest = oracle.welch_psd(oz, fs, -1, fs / 1024)
+    assert cnt == ocnt and np.array_equal(freqs, ofreqs)
+    close(est, oest)
+    close(z.to_array(), oz)

@@ -221,6 +221,11 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps):
     assert relerr(y, ref[:, o_lo:o_hi]) < 1e-12
 
 
+def test_producer_tools_golden():
+    pc.protools_golden()
+    pc.masked_chain()
+
+
 def test_spectra_golden():
     pc.spectra_golden("pow2")
     pc.spectra_golden("nonpow2")          # nfft = 2000: generic mixed-radix path

@@ -46,6 +46,11 @@ def test_pipeline_chain(fake_gpu):
     pc.fused_fir_decimate()
 
 
+def test_producer_tools(fake_gpu):
+    pc.protools_golden()
+    pc.masked_chain()
+
+
 def test_no_cpu_fallback():
     """Without a GPU (and without the test stand-ins) the operators raise."""
     import torch

@@ -93,3 +93,34 @@ def test_oracle_matches_scipy_global_calls():
     cnt, f, p = oracle.welch_psd(x, 1000, -1, 0.5)
     rf, rp = sps.welch(x, fs=1000, nperseg=2000, noverlap=1000, window="hann", axis=-1)
     assert np.allclose(p, rp) and np.allclose(f, rf)
+
+
+def test_protools_golden_bit_exact():
+    """Masked producer + protools.mean / std / standardize."""
+    g = golden("protools")
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), int(g["fs"])) + float(g["offset"])
+    assert x.sum() == float(g["x_sum"])
+    cs, mask = int(g["chunksize"]), g["mask"]
+    for name, arr, axis in (("ax1", x, -1), ("ax0", np.ascontiguousarray(x.T), 0)):
+        blocks = oracle.masked(arr, mask, cs, axis)
+        assert [b.shape[axis] for b in blocks] == list(g["masked_lengths_" + name])
+        assert np.array_equal(np.concatenate(blocks, axis), g["masked_" + name])
+        chunks = oracle.split_chunks(arr, cs, axis)
+        for ax in (0, 1):
+            for keep in (0, 1):
+                assert np.array_equal(oracle.pro_mean(chunks, axis, ax, keepdims=bool(keep)),
+                                      g["mean_%s_axis%d_keep%d" % (name, ax, keep)])
+                assert np.array_equal(oracle.pro_std(chunks, axis, ax, keepdims=bool(keep)),
+                                      g["std_%s_axis%d_keep%d" % (name, ax, keep)])
+            assert np.array_equal(np.concatenate(oracle.standardize(chunks, axis, ax), axis),
+                                  g["standardized_%s_axis%d" % (name, ax)])
+    xn = x.copy()
+    for r, a, b in g["nan_spans"]:
+        xn[r, a:b] = np.nan
+    chunks = oracle.split_chunks(xn, cs, -1)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert np.array_equal(oracle.pro_mean(chunks, -1, -1), g["mean_nan"], equal_nan=True)
+            assert np.array_equal(oracle.pro_std(chunks, -1, -1), g["std_nan"], equal_nan=True)

@@ -127,9 +127,31 @@ def main(which):
             del x
 
 
+def protools_bench():
+    """Producer tools: mask compaction, moments, standardize."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rows, n = 256, 1_000_000
+    x = torch.randn((rows, n), dtype=torch.float64, device="cuda", generator=g)
+    mask = np.repeat(np.random.default_rng(0).random(n // 500) < 0.6, 500)
+    idx = np.flatnonzero(mask)
+    report("take_cols (60 %% kept, runs of 500)", timeit(lambda: dv.take_cols(x, idx)),
+           rows * idx.size, 16)
+    mom = dv.RowMoments(rows)
+    report("row_moments", timeit(lambda: mom.add(x)), rows * n, 8)
+    mu, sd = dv.zeros((rows,)), dv.zeros((rows,)) + 1.0
+    y = torch.empty_like(x)
+    report("row_standardize", timeit(lambda: dv.row_standardize(x, mu, sd, out=y)), rows * n, 16)
+    report("col_moments standardize", timeit(lambda: dv.col_moments(x, True, "standardize")),
+           rows * n, 16)
+
+
 if __name__ == "__main__":
     argv = sys.argv[1:]
     if "--once" in argv:
         ONCE = True
         argv.remove("--once")
-    main(argv)
+    if argv == ["protools"]:
+        dv.require_cuda()
+        protools_bench()
+    else:
+        main(argv)
