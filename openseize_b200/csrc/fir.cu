@@ -17,6 +17,7 @@
 // Both compute  y[r][i] = sum_k taps[k] * x[r][i + K-1-k]  (header contract).
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -364,7 +365,7 @@ struct FirPPC32 {
     static constexpr int SMEM = OFF_X + 2 * GROUP_BYTES;
 };
 
-template <int LOG2N, bool ACC>
+template <int LOG2N, bool ACC, bool TOKEN>
 __global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, 1)
 fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
                       const float2 *__restrict__ H, const float2 *__restrict__ tw,
@@ -372,7 +373,8 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
                       int iters, int lag, int zero) {
     using C = oszf::FftCfg<LOG2N>;
     using L = FirPPC32<LOG2N>;
-    using Sync = oszf::SyncPingPong<LOG2N>;
+    using Sync = typename std::conditional<TOKEN, oszf::SyncPingPong<LOG2N>,
+                                           oszf::SyncGroups<LOG2N>>::type;
     constexpr int N = C::N, NT = C::NT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g = threadIdx.x / NT;
@@ -567,8 +569,13 @@ static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const double *x, int64_t
     using C = oszf::FftCfg<LOG2N>;
     constexpr int SMEM = FirPPC32<LOG2N>::SMEM;
     static_assert(SMEM <= 227 * 1024, "float32-compute FIR: shared memory");
-    OSZ_CUDA(cudaFuncSetAttribute(fir_fft_pp_c32_kernel<LOG2N, ACC>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    static const int token = [] {
+        const char *e = getenv("OSZ_FIR32_TOKEN");
+        return e ? atoi(e) : 0;
+    }();
+    auto kern = token ? fir_fft_pp_c32_kernel<LOG2N, ACC, true>
+                      : fir_fft_pp_c32_kernel<LOG2N, ACC, false>;
+    OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int64_t step = C::N - p->ntaps + 1;
     const int64_t nblocks = (n_out + step - 1) / step;
     const int64_t npairs = (nblocks + 1) / 2;
@@ -576,7 +583,7 @@ static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const double *x, int64_t
     int64_t grid = (nwork + 1) / 2;
     if (grid > sm_count()) grid = sm_count();
     const int iters = (int)((nwork + 2 * grid - 1) / (2 * grid));
-    fir_fft_pp_c32_kernel<LOG2N, ACC><<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
+    kern<<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
         x, ldx, n_out, p->ntaps, p->d_Hf, p->d_twf, y, ldy, npairs, nwork, iters, 2, 0);
     OSZ_LAUNCHED("fir_fft_pp_c32_kernel");
     return OSZ_OK;

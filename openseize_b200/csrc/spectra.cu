@@ -17,6 +17,7 @@
 // in spectra_generic.cu.
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -401,7 +402,7 @@ struct WelchPPC32 {
     static constexpr int CTAS_PER_SM = 4096 / C::N < FIT ? 4096 / C::N : FIT;
 };
 
-template <int LOG2N, int DETREND>
+template <int LOG2N, int DETREND, bool TOKEN>
 __global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, WelchPPC32<LOG2N>::CTAS_PER_SM)
 welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
                     const float *__restrict__ win, const float2 *__restrict__ tw, double norm,
@@ -409,7 +410,8 @@ welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int
                     int64_t per_group, int lag, int zero) {
     using C = oszf::FftCfg<LOG2N>;
     using L = WelchPPC32<LOG2N>;
-    using Sync = oszf::SyncPingPong<LOG2N>;
+    using Sync = typename std::conditional<TOKEN, oszf::SyncPingPong<LOG2N>,
+                                           oszf::SyncGroups<LOG2N>>::type;
     constexpr int N = C::N, NT = C::NT, NW = NT / 32;
     static_assert(NT >= 32, "ping-pong Welch needs whole warps per group");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -773,8 +775,13 @@ static int launch_welch_pp_c32(const osz_spec_plan *p, const double *x, int64_t 
     using L = WelchPPC32<LOG2N>;
     static_assert(L::SMEM * L::CTAS_PER_SM + 1024 * L::CTAS_PER_SM <= 228 * 1024,
                   "float32-compute Welch: shared memory");
-    OSZ_CUDA(cudaFuncSetAttribute(welch_pp_c32_kernel<LOG2N, DETREND>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    static const int token = [] {
+        const char *e = getenv("OSZ_WELCH32_TOKEN");
+        return e ? atoi(e) : 0;
+    }();
+    auto kern = token ? welch_pp_c32_kernel<LOG2N, DETREND, true>
+                      : welch_pp_c32_kernel<LOG2N, DETREND, false>;
+    OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     const int64_t npairs = (nseg + 1) / 2;
     const int64_t nwork = npairs * rows;
     int64_t grid = (nwork + 1) / 2;
@@ -784,7 +791,7 @@ static int launch_welch_pp_c32(const osz_spec_plan *p, const double *x, int64_t 
         const char *e = getenv("OSZ_WELCH_LAG");
         return e ? atoi(e) : 0;
     }();
-    welch_pp_c32_kernel<LOG2N, DETREND><<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
+    kern<<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
         x, ldx, nseg, p->stride, p->d_winf, p->d_twf, p->norm, psd, ldp, npairs, nwork, per_group,
         lag, 0);
     OSZ_LAUNCHED("welch_pp_c32_kernel");

@@ -60,7 +60,7 @@ def main(which):
             taps = Kaiser(500, 600, fs).coeffs
             x = rnd(rows, n + len(taps) - 1)
             y = torch.empty((rows, n), dtype=torch.float64, device="cuda")
-            for algo, an in ((1, "direct"), (2, "fft")):
+            for algo, an in ((1, "direct"), (2, "fft"), (3, "fft float32 compute")):
                 if algo == 1 and len(taps) > 200:
                     continue
                 plan = dv.FirPlan(taps, algo)
