@@ -187,7 +187,7 @@ struct FirPP {
     static constexpr int SMEM = OFF_X + 2 * C::SMEM_BYTES;
 };
 
-template <int LOG2N, bool ACC, int POLICY>
+template <int LOG2N, bool ACC, int POLICY, bool TOKEN = true>
 __global__ void __launch_bounds__(2 * FftCfg<LOG2N>::NT, 1)
 fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
                   const double2 *__restrict__ H, const double2 *__restrict__ tw,
@@ -195,7 +195,7 @@ fir_fft_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int 
                   int lag, int zero) {
     using C = FftCfg<LOG2N>;
     using L = FirPP<LOG2N>;
-    using Sync = SyncPingPong<LOG2N>;
+    using Sync = typename std::conditional<TOKEN, SyncPingPong<LOG2N>, SyncGroups<LOG2N>>::type;
     constexpr int N = C::N, NT = C::NT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g = threadIdx.x / NT;
@@ -544,8 +544,13 @@ static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx
                              int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
     using C = FftCfg<LOG2N>;
     constexpr int SMEM = FirPP<LOG2N>::SMEM;
-    OSZ_CUDA(cudaFuncSetAttribute(fir_fft_pp_kernel<LOG2N, ACC, POLICY>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    static const int token = [] {
+        const char *e = getenv("OSZ_FIR64_TOKEN");
+        return e ? atoi(e) : 1;
+    }();
+    auto kern = token ? fir_fft_pp_kernel<LOG2N, ACC, POLICY, true>
+                      : fir_fft_pp_kernel<LOG2N, ACC, POLICY, false>;
+    OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int64_t step = C::N - p->ntaps + 1;
     const int64_t nblocks = (n_out + step - 1) / step;
     const int64_t npairs = (nblocks + 1) / 2;
@@ -557,7 +562,7 @@ static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx
         const char *e = getenv("OSZ_PP_LAG");
         return e ? atoi(e) : 2;
     }();
-    fir_fft_pp_kernel<LOG2N, ACC, POLICY><<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
+    kern<<<(unsigned)grid, 2 * C::NT, SMEM, st>>>(
         x, ldx, n_out, p->ntaps, p->d_H, p->d_tw, y, ldy, npairs, nwork, iters, lag, 0);
     OSZ_LAUNCHED("fir_fft_pp_kernel");
     return OSZ_OK;

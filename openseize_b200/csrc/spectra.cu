@@ -190,7 +190,7 @@ struct WelchPP {
     static constexpr int CTAS_PER_SM = 4096 / C::N;                   // 512 threads per SM
 };
 
-template <int LOG2N, int DETREND>
+template <int LOG2N, int DETREND, bool TOKEN = true>
 __global__ void __launch_bounds__(2 * FftCfg<LOG2N>::NT, WelchPP<LOG2N>::CTAS_PER_SM)
 welch_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
                 const double *__restrict__ win, const double2 *__restrict__ tw, double norm,
@@ -198,7 +198,7 @@ welch_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t
                 int64_t per_group, int lag, int zero) {
     using C = FftCfg<LOG2N>;
     using L = WelchPP<LOG2N>;
-    using Sync = SyncPingPong<LOG2N>;
+    using Sync = typename std::conditional<TOKEN, SyncPingPong<LOG2N>, SyncGroups<LOG2N>>::type;
     constexpr int N = C::N, NT = C::NT, NW = NT / 32 > 0 ? NT / 32 : 1;
     static_assert(NT >= 32, "ping-pong Welch needs whole warps per group");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -750,8 +750,14 @@ static int launch_welch_pp(const osz_spec_plan *p, const double *x, int64_t ldx,
                            int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
     using C = FftCfg<LOG2N>;
     using L = WelchPP<LOG2N>;
-    OSZ_CUDA(cudaFuncSetAttribute(welch_pp_kernel<LOG2N, DETREND>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    static const int token = [] {
+        // measured (256 x 1e6): nfft 4096 206 G samples/s with the token, 200 without;
+        // nfft 1024 (four CTAs per SM) 209 with, 227 without
+        const char *e = getenv("OSZ_WELCH64_TOKEN");
+        return e ? atoi(e) : (LOG2N >= 11 ? 1 : 0);
+    }();
+    auto kern = token ? welch_pp_kernel<LOG2N, DETREND, true> : welch_pp_kernel<LOG2N, DETREND, false>;
+    OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     const int64_t npairs = (nseg + 1) / 2;
     const int64_t nwork = npairs * rows;
     int64_t grid = (nwork + 1) / 2;
@@ -761,7 +767,7 @@ static int launch_welch_pp(const osz_spec_plan *p, const double *x, int64_t ldx,
         const char *e = getenv("OSZ_WELCH_LAG");
         return e ? atoi(e) : 0;
     }();
-    welch_pp_kernel<LOG2N, DETREND><<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
+    kern<<<(unsigned)grid, 2 * C::NT, L::SMEM, st>>>(
         x, ldx, nseg, p->stride, p->d_win, p->d_tw, p->norm, psd, ldp, npairs, nwork, per_group,
         lag, 0);
     OSZ_LAUNCHED("welch_pp_kernel");
