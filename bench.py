@@ -98,9 +98,22 @@ class Marks:
         self.torch, self.w, self.k, self.barrier = torch, warmup, steps, barrier
         self.ev = {}
         self.wall = {}
+        self.host = []           # host clock at every chunk hand-out (diagnostic)
         self.on_start, self.on_stop = None, None
 
+    def host_pace(self):
+        """How fast the host enqueues: ms between consecutive chunk hand-outs inside
+        the timed region.  A median near the device's ms per step means the host
+        cannot run ahead of the GPU and every host hiccup lands in the step time."""
+        t = [b - a for (i, a), (j, b) in zip(self.host, self.host[1:])
+             if self.w < i and j < self.w + self.k]
+        if not t:
+            return None
+        return {"median_ms": round(1e3 * float(np.median(t)), 3),
+                "max_ms": round(1e3 * float(np.max(t)), 3)}
+
     def at(self, i):
+        self.host.append((i, time.perf_counter()))
         if i not in (self.w, self.w + self.k):
             return
         t = self.torch
@@ -475,7 +488,7 @@ def run_ours(args):
             for _ in range(2)]
     marks = Marks(W, K, barrier)
     sampler = ClockSampler(local, enabled=rank == 0 and os.environ.get("OSZ_BENCH_CLOCKS", "1") == "1",
-                           period_ms=25 if world == 1 else 50)
+                           period_ms=45 if world == 1 else 50)
     launches = {}
     sampler.start()
     # Untimed pre-warm, then a barrier: a fresh box pages the CUDA libraries in and
@@ -581,6 +594,7 @@ def run_ours(args):
                        "l2": "each step reads a 2 GB chunk (>> 126 MB L2); pool of 2 chunks"},
             "gpu_launches": int(launches.get("b", 0) - launches.get("a", 0)),
             "clocks": sampler.summary(), "kernels": kernels,
+            "host_enqueue": marks.host_pace(),
         }
         if per_rank:
             line["per_rank"] = per_rank
