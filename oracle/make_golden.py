@@ -116,14 +116,33 @@ def protools_golden(report):
     report.append(("protools", "bit-exact vs reference (masked producer, mean, std, standardize)"))
 
 
+def hilbert_golden(report):
+    """Type III FIR Hilbert transformer (filtering/special.py:16-133)."""
+    import oracle
+    from openseize import producer
+    from openseize.filtering.special import Hilbert
+
+    fs = 500
+    x = signal(71, 2, 6000, fs)
+    hil = Hilbert(width=12, fs=fs)
+    ref = hil(producer(x, 1500, -1), 1500, axis=-1).to_array()
+    mine = np.concatenate(oracle.oaconvolve(x, hil.coeffs, 1500, -1, "same"), -1)
+    assert np.array_equal(ref, mine)
+    np.savez_compressed(os.path.join(GOLD, "hilbert.npz"), seed=71, rows=2, n=6000, fs=fs,
+                        width=12, taps=hil.coeffs, chunksize=1500, x_sum=x.sum(), y=ref)
+    report.append(("hilbert", "bit-exact vs reference"))
+
+
 def main():
     sys.path.insert(0, ROOT)
     import oracle
     producer, nm, fir, iir, resampling, estimators = _import_reference()
     os.makedirs(GOLD, exist_ok=True)
     report = []
-    if sys.argv[1:] == ["protools"]:          # only the fixture added last
-        protools_golden(report)
+    only = {"protools": protools_golden, "hilbert": hilbert_golden}
+    if sys.argv[1:] and all(a in only for a in sys.argv[1:]):   # only the named fixtures
+        for a in sys.argv[1:]:
+            only[a](report)
         print(report)
         return
 
@@ -266,6 +285,7 @@ def main():
         report.append(("spectra_" + name, "bit-exact vs reference"))
 
     protools_golden(report)
+    hilbert_golden(report)
 
     for name, status in report:
         print("%-18s %s" % (name, status))

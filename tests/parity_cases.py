@@ -373,6 +373,19 @@ def pipeline_chain():
     close(kais(notch(producer(x, cs, -1), cs, axis=-1), cs, axis=-1).to_array(), r2)
 
 
+def hilbert_golden():
+    """Type III Hilbert transformer (reference filtering/special.py): design
+    bit-identical, application within tolerance of the reference's output."""
+    from openseize_b200.filtering.special import Hilbert
+
+    g = golden("hilbert")
+    fs, cs = int(g["fs"]), int(g["chunksize"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    hil = Hilbert(width=float(g["width"]), fs=fs)
+    assert np.array_equal(hil.coeffs, g["taps"])
+    close(hil(producer(x, cs, -1), cs, axis=-1).to_array(), g["y"])
+
+
 # ------------------------------------------------- producer tools (N3) ----
 def protools_golden():
     """Masked producers consumed by GPU operators and protools.mean / std /

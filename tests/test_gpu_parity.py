@@ -39,6 +39,7 @@ def test_native_library_is_what_runs(dv):
 def test_fir_golden():
     pc.fir_golden()
     pc.fir_long_golden()
+    pc.hilbert_golden()
 
 
 def test_fir_oracle_sweep():

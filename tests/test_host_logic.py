@@ -21,6 +21,7 @@ def test_fir(fake_gpu):
     pc.narrow_input_dtypes()
     pc.fir_golden()
     pc.fir_long_golden()
+    pc.hilbert_golden()
     pc.fir_oracle_sweep()
 
 

@@ -124,3 +124,10 @@ def test_protools_golden_bit_exact():
             warnings.simplefilter("ignore")
             assert np.array_equal(oracle.pro_mean(chunks, -1, -1), g["mean_nan"], equal_nan=True)
             assert np.array_equal(oracle.pro_std(chunks, -1, -1), g["std_nan"], equal_nan=True)
+
+
+def test_hilbert_golden_bit_exact():
+    g = golden("hilbert")
+    x = _x(g)
+    got = np.concatenate(oracle.oaconvolve(x, g["taps"], int(g["chunksize"]), -1, "same"), -1)
+    assert np.array_equal(got, g["y"])
