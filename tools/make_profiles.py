@@ -46,6 +46,18 @@ def bench_md():
                       (d["e2e"]["value"] / 1e9, d["e2e"]["value"] * 8 / 1e9 / d["n_gpus"]),
                       "* our kernels launched in the timed region: %d; clocks %s" %
                       (d["gpu_launches"], json.dumps(d["clocks"]))]
+            nar = (d.get("e2e") or {}).get("narrow_inputs")
+            if nar:
+                lines += ["* e2e with narrower samples (widened on the device; extra, not the "
+                          "contract's e2e): " + ", ".join(
+                              "%s **%.2f G/s** (%.1f GB/s over PCIe)" %
+                              (k, v["value"] / 1e9,
+                               v["value"] / (d["config"]["rows_per_gpu"] * d["config"]["chunk"])
+                               * v["h2d_bytes_per_step"] / 1e9 / d["n_gpus"])
+                              for k, v in nar.items())]
+            if d.get("host_enqueue"):
+                lines += ["* host enqueue pace inside the timed region: %s" %
+                          json.dumps(d["host_enqueue"])]
             if d.get("per_rank"):
                 lines += ["* per rank: own ms/step %s; sum of kernel times per step %s" %
                           (d["per_rank"]["ms_per_step"], d["per_rank"]["kernel_ms_per_step"])]
