@@ -544,12 +544,9 @@ static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx
                              int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
     using C = FftCfg<LOG2N>;
     constexpr int SMEM = FirPP<LOG2N>::SMEM;
-    static const int token = [] {
-        const char *e = getenv("OSZ_FIR64_TOKEN");
-        return e ? atoi(e) : 1;
-    }();
-    auto kern = token ? fir_fft_pp_kernel<LOG2N, ACC, POLICY, true>
-                      : fir_fft_pp_kernel<LOG2N, ACC, POLICY, false>;
+    // (the token-free build measured slower in float64: 223 vs 257 G samples/s at 113 taps,
+    // 201 vs 222 at 671 -- profiles/r01_ncu_summary.md D -- and is not instantiated)
+    auto kern = fir_fft_pp_kernel<LOG2N, ACC, POLICY, true>;
     OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int64_t step = C::N - p->ntaps + 1;
     const int64_t nblocks = (n_out + step - 1) / step;

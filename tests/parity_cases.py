@@ -454,3 +454,37 @@ def masked_chain():
     assert cnt == ocnt and np.array_equal(freqs, ofreqs)
     close(est, oest)
     close(z.to_array(), oz)
+
+
+def protools_edges():
+    """Masks shorter than the data, masked producers straight into psd and into a
+    FIR, scalar results for 1-D producers, 3-D producers, pickling."""
+    import pickle
+
+    from openseize_b200.core import protools
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 20000)) + 5
+    mask = rng.random(12000) < 0.5                      # production stops with the mask
+    ref = np.concatenate(oracle.masked(x, mask, 3000, -1), -1)
+    mpro = producer(x, 3000, -1, mask=mask)
+    got = np.concatenate(list(nm._to_host(nm.device_chunks(mpro, -1), nm._layout_of(mpro, -1))), -1)
+    assert np.array_equal(ref, got)
+    cnt, _, p = psd(producer(x, 3000, -1, mask=mask), 1000.0, resolution=1000 / 512)
+    ocnt, _, op = oracle.welch_psd(ref, 1000.0, -1, 1000 / 512)
+    assert cnt == ocnt
+    close(p, op)
+    filt = Kaiser(100, 150, 1000)
+    y = filt(producer(x, 3000, -1, mask=mask), 3000, axis=-1).to_array()
+    close(y, np.concatenate(oracle.oaconvolve(ref, filt.coeffs, 3000, -1, "same"), -1))
+    m = protools.mean(producer(x[0], 3000, -1), -1)
+    s = protools.std(producer(x[0], 3000, -1), -1)
+    assert np.ndim(m) == 0 and abs(m - x[0].mean()) < 1e-12 and abs(s - x[0].std()) < 1e-10
+    x3 = rng.standard_normal((2, 3, 7000))
+    m3 = protools.mean(producer(x3, 2000, -1), -1)
+    assert m3.shape == (2, 3)
+    close(m3, x3.mean(-1), 1e-12)
+    z3 = protools.standardize(producer(x3, 2000, -1), -1).to_array()
+    close(z3, (x3 - x3.mean(-1, keepdims=True)) / x3.std(-1, keepdims=True))
+    zp = protools.standardize(producer(x, 3000, -1), -1)
+    assert np.array_equal(pickle.loads(pickle.dumps(zp)).to_array(), zp.to_array())

@@ -225,6 +225,7 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps):
 def test_producer_tools_golden():
     pc.protools_golden()
     pc.masked_chain()
+    pc.protools_edges()
 
 
 def test_spectra_golden():

@@ -50,6 +50,7 @@ def test_pipeline_chain(fake_gpu):
 def test_producer_tools(fake_gpu):
     pc.protools_golden()
     pc.masked_chain()
+    pc.protools_edges()
 
 
 def test_no_cpu_fallback():
