@@ -442,3 +442,42 @@ def test_full_size_properties(dv):
     two = dv.cat_time([h1, h2])
     assert float((whole - two).abs().max()) / float(whole.abs().max()) < 1e-10
     assert relerr(st2.cpu().numpy(), st.cpu().numpy()) < 1e-9
+
+
+def test_baseline_configs_full_length():
+    """BASELINE.json configs 1-4 at their FULL recording length against the
+    oracle, on as many channels as the oracle finishes in seconds (channels are
+    independent): C1 complete (4 x 18 000 000, the reference's own
+    CPU-runnable case), C2 on 2 of 64 channels, C3 and C4 on one channel."""
+    from openseize_b200.filtering.fir import Kaiser
+    from openseize_b200.filtering.iir import Butter
+    from openseize_b200.resampling.resampling import downsample
+    from openseize_b200.spectra.estimators import psd
+
+    cs = 1_000_000
+    rng = np.random.default_rng([1, 0])
+    # C1: Kaiser 500/600 @ 5 kHz, 113 taps, mode 'same', chunksize 1e6
+    x = rng.standard_normal((4, 18_000_000))
+    filt = Kaiser(fpass=500, fstop=600, fs=5000)
+    y = filt(producer(x, cs, -1), cs, axis=-1, mode="same").to_array()
+    ref = np.concatenate(oracle.oaconvolve(x, filt.coeffs, cs, -1, "same"), -1)
+    assert y.shape == ref.shape == x.shape and relerr(y, ref) < 1e-9
+    # C2: Butterworth band-pass 1-100 Hz (8 sections), forward-backward, 18 chunks
+    butter = Butter(fpass=[1, 100], fstop=[0.5, 200], fs=5000, gpass=1, gstop=40)
+    z = butter(producer(x[:2], cs, -1), cs, axis=-1, dephase=True).to_array()
+    ref = np.concatenate(oracle.sosfiltfilt(x[:2], butter.coeffs, cs, -1), -1)
+    assert z.shape == ref.shape and relerr(z, ref) < 1e-9
+    del y, z, ref
+    # C3: downsample 5000 -> 250 Hz, 108 000 000 samples: lengths exact, values 1e-9
+    x1 = np.random.default_rng([1, 1]).standard_normal((1, 108_000_000))
+    d = downsample(producer(x1, cs, -1), M=20, fs=5000, chunksize=cs, axis=-1)
+    got = list(d)
+    refl = oracle.polyphase_resample(x1, 1, 20, 5000, cs, -1)
+    assert d.shape == (1, 5_400_000) and sum(a.shape[-1] for a in got) == 5_400_000
+    assert relerr(np.concatenate(got, -1), np.concatenate(refl, -1)) < 1e-9
+    del got, refl, d
+    # C4: Welch PSD nfft 4096, 50 % overlap, Hann @ 30 kHz: 52 733 segments
+    cnt, freqs, est = psd(producer(x1, cs, -1), fs=30000, resolution=30000 / 4096)
+    ocnt, ofreqs, oest = oracle.welch_psd(x1, 30000, -1, 30000 / 4096)
+    assert cnt == ocnt == 52733 and np.array_equal(freqs, ofreqs)
+    assert relerr(est, oest) < 1e-9
