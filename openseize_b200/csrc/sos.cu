@@ -156,6 +156,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             const SosSec &c = prm.sec[s];
             const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
             double z0 = 0.0, z1 = 0.0;
+            double zs0[NCH - 1], zs1[NCH - 1];     // zero-state finals of sub-pieces 0 .. NCH-2
             if (blk != 0) {
                 // NCH independent 8-sample chains per thread (a single chain left
                 // the FP64 pipe 2/3 idle waiting on its own results): sub-piece 0
@@ -180,12 +181,13 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                         v[8 * j + i] = yi;
                     }
                 }
-                double e0 = za0[0], e1 = za1[0];           // state at the end of sub-piece 0
+                // thread-final state for a zero entering state: the sub-pieces' final
+                // states chained through A^8.  Their OUTPUTS are not fixed up here: every
+                // sub-piece gets one zero-input correction below, from its true entering
+                // state, once the scan has delivered the thread's.
+                double e0 = za0[0], e1 = za1[0];
 #pragma unroll
                 for (int j = 1; j < NCH; ++j) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[8 * j + i] = fma(c.g0[i], e0, fma(c.g1[i], e1, v[8 * j + i]));
                     const double t0 = fma(c.A8[0], e0, c.A8[1] * e1) + za0[j];
                     const double t1 = fma(c.A8[2], e0, c.A8[3] * e1) + za1[j];
                     e0 = t0;
@@ -193,6 +195,11 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 }
                 z0 = e0;
                 z1 = e1;
+#pragma unroll
+                for (int j = 0; j < NCH - 1; ++j) {
+                    zs0[j] = za0[j];
+                    zs1[j] = za1[j];
+                }
             } else {
                 const bool inj = tid == pstar;
                 const double c0 = carry[s][0], c1 = carry[s][1];
@@ -249,8 +256,26 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             }
             // zero-input response of the entering state (it is exactly zero for
             // every thread up to and including the one that injected the carry)
+            if (blk != 0) {
+                // sub-piece j enters with E_j: E_0 = the thread's entering state,
+                // E_(j+1) = A^8 E_j + (zero-state final of sub-piece j)
+                double q0 = s0, q1 = s1;
 #pragma unroll
-            for (int i = 0; i < T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
+                for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[8 * j + i] = fma(c.g0[i], q0, fma(c.g1[i], q1, v[8 * j + i]));
+                    if (j + 1 < NCH) {
+                        const double t0 = fma(c.A8[0], q0, c.A8[1] * q1) + zs0[j];
+                        const double t1 = fma(c.A8[2], q0, c.A8[3] * q1) + zs1[j];
+                        q0 = t0;
+                        q1 = t1;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
+            }
             if (tid == SOS_NT - 1) {
                 carry[s][0] = e0;
                 carry[s][1] = e1;
