@@ -76,7 +76,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     constexpr int NCH = T / 8;             // independent 8-sample chains per thread
     static_assert(T == 32 || T == 16, "T");
     extern __shared__ __align__(16) double buf[];   // SOS_NT * LD
-    __shared__ double wtot[SOS_NT / 32][2];
+    __shared__ double wtot[2][SOS_NT / 32][2];   // double-buffered by section parity
     __shared__ double carry[SOS_MAXSEC][2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,17 +229,18 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                     f1 += fma(pm[2], g0, pm[3] * g1);
                 }
             }
+            double (*wt)[2] = wtot[s & 1];
             if (lane == 31) {
-                wtot[warp][0] = f0;
-                wtot[warp][1] = f1;
+                wt[warp][0] = f0;
+                wt[warp][1] = f1;
             }
             __syncthreads();
             // ---- state entering this warp (transition over one warp: M^32)
             const double *qm = T == 32 ? c.Q : c.P[4];
             double cw0 = 0.0, cw1 = 0.0;
             for (int u = 0; u < warp; ++u) {
-                const double t0 = fma(qm[0], cw0, qm[1] * cw1) + wtot[u][0];
-                const double t1 = fma(qm[2], cw0, qm[3] * cw1) + wtot[u][1];
+                const double t0 = fma(qm[0], cw0, qm[1] * cw1) + wt[u][0];
+                const double t1 = fma(qm[2], cw0, qm[3] * cw1) + wt[u][1];
                 cw0 = t0;
                 cw1 = t1;
             }
@@ -280,7 +281,10 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 carry[s][0] = e0;
                 carry[s][1] = e1;
             }
-            __syncthreads();   // wtot reusable, carry[s] published
+            // No barrier here: the other wtot buffer takes section s+1's totals, and a
+            // warp can only write this one again (section s+2) after every warp has
+            // passed section s+1's barrier, i.e. has finished reading it.  carry[s] is
+            // next read by thread 0 in the NEXT block, behind that block's barriers.
         }
         if (WRITE && pos0 + (BLK - off) > keep) {       // block holds samples to store
 #pragma unroll
