@@ -28,6 +28,8 @@ def bench_md():
                         ("N = 1, `python bench.py --impl reference --steps 3 --warmup 1`", "bench_ref.log"),
                         ("N = 2, `torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 20 --warmup 5`",
                          "bench_2gpu.log"),
+                        ("N = 4, `torchrun --nproc-per-node 4 bench.py --gpus 4 --steps 20 --warmup 5`",
+                         "bench_4gpu.log"),
                         ("N = 8, `torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 20 --warmup 5`",
                          "bench_8gpu.log")):
         d = last_json(os.path.join(GP, name))
