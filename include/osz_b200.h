@@ -105,6 +105,11 @@ int osz_decode_edf_records_f64(const int16_t *rec_dev, int64_t per_record, int64
                                const double *offset_dev, int64_t skip, double *dst_dev,
                                int64_t ld_dst, int64_t rows, int64_t n, void *stream);
 
+/* Arithmetic of a plan (osz_*_plan_set_compute): the reference's float64, or the
+ * opt-in float32 mode -- float64 samples in and out, the kernel's arithmetic in
+ * float32, within north_star's float32 tolerance (1e-5 of the output peak). */
+enum { OSZ_COMPUTE_F64 = 0, OSZ_COMPUTE_F32 = 1 };
+
 /* ---- FIR: replaces _cconvolve + overlap-add of nm.oaconvolve
  *      (core/numerical.py:229-269) --------------------------------------- */
 typedef struct osz_fir_plan osz_fir_plan;
@@ -181,6 +186,11 @@ typedef struct osz_upfirdn_plan osz_upfirdn_plan;
 int osz_upfirdn_plan_create(osz_upfirdn_plan **plan, const double *h_host, int ntaps,
                             int up, int down);
 int osz_upfirdn_plan_destroy(osz_upfirdn_plan *plan);
+/* OSZ_COMPUTE_F32: the decimating kernel (up == 1) narrows the samples when it
+ * stages a tile and runs taps, windows and sums in float32; other plans keep
+ * float64 (osz_upfirdn_plan_compute tells). */
+int osz_upfirdn_plan_set_compute(osz_upfirdn_plan *plan, int compute);
+int osz_upfirdn_plan_compute(const osz_upfirdn_plan *plan);
 /* Global output sample j of the resampled recording is
  *   y[j] = sum_k h'[j*down + half - k*up] * x[k],  half = (ntaps-1)/2
  * (scipy's resample_poly after its pre-pad/pre-remove bookkeeping).  This call
@@ -209,7 +219,6 @@ int osz_spec_plan_path(const osz_spec_plan *plan); /* 1 = shared-memory pow2, 2 
  * largest bin).  It exists for osz_welch_accum_f64 at nfft = 512 .. 4096;
  * other plans / entry points keep float64 (osz_spec_plan_compute tells).
  * window_host: the same coefficients given to osz_spec_plan_create. */
-enum { OSZ_COMPUTE_F64 = 0, OSZ_COMPUTE_F32 = 1 };
 int osz_spec_plan_set_compute(osz_spec_plan *plan, int compute, const double *window_host);
 int osz_spec_plan_compute(const osz_spec_plan *plan);
 /* Fused Welch accumulate: for each row adds the one-sided periodograms of

@@ -63,6 +63,8 @@ SIGNATURES = {
     "osz_upfirdn_plan_destroy": (c_int, [_vp]),
     "osz_upfirdn_exec_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64,
                                      _vp]),
+    "osz_upfirdn_plan_set_compute": (c_int, [_vp, c_int]),
+    "osz_upfirdn_plan_compute": (c_int, [_vp]),
     "osz_spec_plan_create": (c_int, [POINTER(_vp), c_int, c_int, _dp, c_int, c_double]),
     "osz_spec_plan_destroy": (c_int, [_vp]),
     "osz_spec_plan_path": (c_int, [_vp]),

@@ -400,7 +400,8 @@ class _Cache:
 _plans = _Cache()
 
 
-# Arithmetic of the FIR overlap-save transforms and of the Welch accumulation:
+# Arithmetic of the FIR overlap-save transforms, the decimating polyphase filter
+# and the Welch accumulation:
 # "float64" (default: the reference computes and returns float64) or "float32"
 # (opt-in: float64 samples in and out, FFTs in float32, ~1e-6 of the output peak;
 # north_star's float32 tolerance is 1e-5).
@@ -554,7 +555,7 @@ class TfPlan(_Plan):
 class UpfirdnPlan(_Plan):
     _destroy = "osz_upfirdn_plan_destroy"
 
-    def __init__(self, h, up, down):
+    def __init__(self, h, up, down, compute="float64"):
         super().__init__()
         require_cuda()
         arr, ptr = _abi.as_double_array(h)
@@ -562,12 +563,17 @@ class UpfirdnPlan(_Plan):
         rc = _abi.load().osz_upfirdn_plan_create(ctypes.byref(self.handle), ptr, self.ntaps,
                                                  self.up, self.down)
         _abi.check(rc, "upfirdn_plan_create")
+        if compute == "float32":
+            _abi.check(_abi.load().osz_upfirdn_plan_set_compute(self.handle, 1),
+                       "upfirdn_plan_set_compute")
+        # float32 exists for the decimating kernel (up == 1) only
+        self.compute = ("float64", "float32")[_abi.load().osz_upfirdn_plan_compute(self.handle)]
 
     @staticmethod
     def cached(h, up, down):
         arr = np.ascontiguousarray(h, dtype=np.float64)
-        return _plans.get(("ufd", arr.tobytes(), int(up), int(down)),
-                          lambda: UpfirdnPlan(arr, up, down))
+        return _plans.get(("ufd", arr.tobytes(), int(up), int(down), COMPUTE),
+                          lambda: UpfirdnPlan(arr, up, down, COMPUTE))
 
     def run(self, x, x_first, out_first, n_out, out=None):
         """x: (rows, m) holding global input samples x_first .. x_first+m-1.

@@ -30,18 +30,22 @@ __device__ __forceinline__ int ufd_phys(int m) {
     return m + m / R;
 }
 
-// R outputs per lane; tile = 32*R outputs per CTA.
-template <int R>
+// R outputs per lane; tile = 32*R outputs per CTA.  T = double, or float for the
+// opt-in float32 arithmetic (float64 samples in and out: they are narrowed when the
+// tile is staged, taps, windows and partial sums are float32, the result is widened
+// when it is stored; half the shared memory, twice the FMA rate).
+template <int R, typename T>
 __global__ void __launch_bounds__(UFD_NT, 2)
 upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, int64_t x_len,
                    int64_t out_first, int64_t n_out, int K, int M, int Q /* taps per phase */,
                    int ldm /* smem row length, odd */, int half,
-                   const double *__restrict__ gphase /* [M][Q] reversed taps by phase */,
+                   const T *__restrict__ gphase /* [M][Q] reversed taps by phase */,
                    double *__restrict__ y, int64_t ldy) {
     constexpr int TO = 32 * R;
-    extern __shared__ __align__(16) double smem[];
-    double *xs = smem;                       // [M][ldm]
-    double *gs = smem + (size_t)M * ldm;     // [M][Q]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *smem = reinterpret_cast<T *>(smem_raw);
+    T *xs = smem;                            // [M][ldm]
+    T *gs = smem + (size_t)M * ldm;          // [M][Q]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t row = blockIdx.y;
@@ -69,7 +73,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
                 for (int u = 0; u < U; ++u) val[u] = ld_stream(src + u * UFD_NT);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    xs[p * ldm + ufd_phys<R>(m)] = val[u];
+                    xs[p * ldm + ufd_phys<R>(m)] = (T)val[u];
                     p += dp;
                     m += dm;
                     if (p >= M) {
@@ -86,7 +90,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (e0 + u * UFD_NT < n_in) xs[p * ldm + ufd_phys<R>(m)] = val[u];
+                    if (e0 + u * UFD_NT < n_in) xs[p * ldm + ufd_phys<R>(m)] = (T)val[u];
                     p += dp;
                     m += dm;
                     if (p >= M) {
@@ -105,9 +109,9 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
     const int s_lo = (int)(((int64_t)slots * warp) / UFD_NW);
     const int s_hi = (int)(((int64_t)slots * (warp + 1)) / UFD_NW);
 
-    double acc[R];
+    T acc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    for (int r = 0; r < R; ++r) acc[r] = (T)0;
 
     // Shared-memory position of window element i of lane l is
     //   l*(R+1) + T(i),  T(i) = i + i/R   (ufd_phys of l*R + i, R a power of two).
@@ -119,22 +123,22 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
         const int p = s / Q, q0 = s - p * Q;
         int q1 = Q;
         if (p * Q + q1 > s_hi) q1 = s_hi - p * Q;
-        const double *gp = gs + p * Q;
+        const T *gp = gs + p * Q;
         const unsigned uq = (unsigned)q0;
         const unsigned rem = uq % R;
-        const double *pa = xs + p * ldm + lane * (R + 1) + (uq + uq / R);   // T(q0), crossing not passed
-        const double *pb = pa + 1;                                          // crossing passed
+        const T *pa = xs + p * ldm + lane * (R + 1) + (uq + uq / R);   // T(q0), crossing not passed
+        const T *pb = pa + 1;                                          // crossing passed
         bool c[R];
 #pragma unroll
         for (int u = 0; u < R; ++u) c[u] = rem + u >= R;
-        double w[R];
+        T w[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) w[r] = (c[r] ? pb : pa)[r];
         int q = q0;
         for (; q + R <= q1; q += R) {
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                const double g = gp[q + u];
+                const T g = gp[q + u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(g, w[(r + u) % R], acc[r]);
                 w[u] = (c[u] ? pb : pa)[u + R + 1];
@@ -146,7 +150,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
 #pragma unroll
         for (int u = 0; u < R; ++u) {
             if (q + u < q1) {
-                const double g = gp[q + u];
+                const T g = gp[q + u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(g, w[(r + u) % R], acc[r]);
                 w[u] = (c[u] ? pb : pa)[u + R + 1];
@@ -155,17 +159,17 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
         s = p * Q + q1;
     }
     __syncthreads();   // tile no longer needed: reuse it for the cross-warp sum
-    double *red = smem;   // [NW][32 lanes][R + 1]: the +1 keeps the stride-R stores conflict free
+    T *red = smem;   // [NW][32 lanes][R + 1]: the +1 keeps the stride-R stores conflict free
     constexpr int LDR = 32 * (R + 1);
 #pragma unroll
     for (int r = 0; r < R; ++r) red[warp * LDR + lane * (R + 1) + r] = acc[r];
     __syncthreads();
     for (int o = tid; o < TO; o += UFD_NT) {
         const int idx = (o / R) * (R + 1) + (o % R);
-        double sum = 0.0;
+        T sum = (T)0;
 #pragma unroll
         for (int w8 = 0; w8 < UFD_NW; ++w8) sum += red[w8 * LDR + idx];
-        if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
+        if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, (double)sum);
     }
 }
 
@@ -385,6 +389,10 @@ struct osz_upfirdn_plan {
     size_t smem = 0;
     double *d_h = nullptr;         // h * up
     double *d_gphase = nullptr;    // [down][Q]
+    float *d_gphasef = nullptr;    // the same taps in float32 (osz_upfirdn_plan_set_compute)
+    size_t smemf = 0;              // ... with its own tile geometry: half the bytes per
+    int Rf = 0, ldmf = 0;          //     sample lets a larger R fit
+    int compute = 0;               // OSZ_COMPUTE_F64 / OSZ_COMPUTE_F32
     // double-buffered kernel
     bool dec2 = false;
     int ldm2 = 0, QB = 0;
@@ -397,13 +405,27 @@ template <int R>
 static int launch_dec(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
                       int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out, double *y,
                       int64_t ldy, cudaStream_t st) {
-    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)p->smem));
     dim3 grid((unsigned)((n_out + 32 * R - 1) / (32 * R)), (unsigned)rows);
-    upfirdn_dec_kernel<R><<<grid, UFD_NT, p->smem, st>>>(x, ldx, x_first, x_len, out_first, n_out,
-                                                         p->K, p->down, p->Q, p->ldm, p->half,
-                                                         p->d_gphase, y, ldy);
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec_kernel<R, double>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    upfirdn_dec_kernel<R, double><<<grid, UFD_NT, p->smem, st>>>(
+        x, ldx, x_first, x_len, out_first, n_out, p->K, p->down, p->Q, p->ldm, p->half,
+        p->d_gphase, y, ldy);
     OSZ_LAUNCHED("upfirdn_dec_kernel");
+    return OSZ_OK;
+}
+
+template <int R>
+static int launch_dec_f32(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
+                          int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
+                          double *y, int64_t ldy, cudaStream_t st) {
+    dim3 grid((unsigned)((n_out + 32 * R - 1) / (32 * R)), (unsigned)rows);
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec_kernel<R, float>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemf));
+    upfirdn_dec_kernel<R, float><<<grid, UFD_NT, p->smemf, st>>>(
+        x, ldx, x_first, x_len, out_first, n_out, p->K, p->down, p->Q, p->ldmf, p->half,
+        p->d_gphasef, y, ldy);
+    OSZ_LAUNCHED("upfirdn_dec_kernel<float>");
     return OSZ_OK;
 }
 
@@ -449,13 +471,13 @@ static int launch_dec2(const osz_upfirdn_plan *p, const double *x, int64_t ldx, 
     return OSZ_OK;
 }
 
-static size_t dec_smem(int R, int M, int Q, int *ldm_out) {
+static size_t dec_smem(int R, int M, int Q, int *ldm_out, size_t elem = 8) {
     const int TO = 32 * R;
     int ldm = (TO + Q + R) + (TO + Q + R) / R + 1;
     if ((ldm & 1) == 0) ++ldm;
     *ldm_out = ldm;
-    size_t tile = ((size_t)M * ldm + (size_t)M * Q) * 8;
-    size_t red = (size_t)UFD_NW * 32 * (R + 1) * 8;
+    size_t tile = ((size_t)M * ldm + (size_t)M * Q) * elem;
+    size_t red = (size_t)UFD_NW * 32 * (R + 1) * elem;
     return tile > red ? tile : red;
 }
 
@@ -531,10 +553,44 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
     return OSZ_OK;
 }
 
+int osz_upfirdn_plan_set_compute(osz_upfirdn_plan *p, int compute) {
+    if (!p || (compute != OSZ_COMPUTE_F64 && compute != OSZ_COMPUTE_F32))
+        return fail(OSZ_ERR_ARG, "osz_upfirdn_plan_set_compute: bad arguments");
+    if (compute == OSZ_COMPUTE_F64 || !p->R) {   // float32 exists for the decimating kernel
+        p->compute = OSZ_COMPUTE_F64;
+        return OSZ_OK;
+    }
+    if (!p->d_gphasef) {
+        const size_t n = (size_t)p->down * p->Q;
+        std::vector<double> gp(n);
+        std::vector<float> gf(n);
+        bool ok = cudaMemcpy(gp.data(), p->d_gphase, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+        for (size_t i = 0; i < n; ++i) gf[i] = (float)gp[i];
+        ok = ok && cudaMalloc(&p->d_gphasef, n * 4) == cudaSuccess &&
+             cudaMemcpy(p->d_gphasef, gf.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) return fail(OSZ_ERR_CUDA, "osz_upfirdn_plan_set_compute: device upload failed");
+        for (int R : {16, 8, 4}) {
+            int ldm = 0;
+            const size_t sm = dec_smem(R, p->down, p->Q, &ldm, 4);
+            if (sm <= 100 * 1024) {
+                p->Rf = R;
+                p->ldmf = ldm;
+                p->smemf = sm;
+                break;
+            }
+        }
+    }
+    if (!p->Rf) return OSZ_OK;                   // (cannot happen when the float64 tile fits)
+    p->compute = OSZ_COMPUTE_F32;
+    return OSZ_OK;
+}
+int osz_upfirdn_plan_compute(const osz_upfirdn_plan *p) { return p ? p->compute : 0; }
+
 int osz_upfirdn_plan_destroy(osz_upfirdn_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_h);
     cudaFree(p->d_gphase);
+    cudaFree(p->d_gphasef);
     cudaFree(p->d_gphase2);
     if (p->tap_slot >= 0) ufd_slot_free(p->tap_slot, p->tap_len);
     delete p;
@@ -555,6 +611,16 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
         const char *e = getenv("OSZ_UFD_DEC2");
         return e ? atoi(e) : 0;
     }();
+    if (p->compute == OSZ_COMPUTE_F32 && p->d_gphasef) {
+        switch (p->Rf) {
+            case 16:
+                return launch_dec_f32<16>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+            case 8:
+                return launch_dec_f32<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+            default:
+                return launch_dec_f32<4>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+        }
+    }
     if (p->dec2 && use_dec2)
         return launch_dec2<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
     switch (p->R) {

@@ -94,6 +94,9 @@ def main(which):
             nout = n // M - 64
             report("downsample M=%d taps=%d" % (M, len(h)),
                    timeit(lambda: plan.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
+            p32 = dv.UpfirdnPlan(h, 1, M, "float32")
+            report("downsample M=%d taps=%d float32 compute" % (M, len(h)),
+                   timeit(lambda: p32.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
             del x
         # the FIR(671) * anti-alias(561) cascade of config 5 as ONE decimating filter
         h = np.convolve(oracle.resample_filter(1, 25, 30000), Kaiser(500, 600, 30000).coeffs)
@@ -102,6 +105,9 @@ def main(which):
         nout = n // 25 - 128
         report("fused FIR+downsample M=25 taps=%d" % len(h),
                timeit(lambda: plan.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
+        p32 = dv.UpfirdnPlan(h, 1, 25, "float32")
+        report("fused FIR+downsample M=25 taps=%d float32 compute" % len(h),
+               timeit(lambda: p32.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
         del x
     if not which or "welch" in which:
         for nfft in (1024, 4096, 8192) + ((2400, 10000, 60000) if "generic" in which else ()):
