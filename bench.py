@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-narrow", action="store_true", help="skip the float32 / int16 e2e extras")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float32-compute extra pass")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-named", action="store_true",
                     help="skip the stand-alone FIR / Welch kernel timings")
@@ -557,6 +558,27 @@ def run_ours(args):
                     "alg_bytes_per_launch": 16 * rows * chunk if dom in ("sos", "fir") else None,
                     "peak_source": peak_src,
                     "share_of_step": kernels[dom]["ms_total"] / (secs * 1e3)}
+    # The same HBM-resident pipeline with the opt-in float32 arithmetic (float64 samples
+    # in, float64 results out; the IIR stays float64).  Extra information: the contract's
+    # `value` above is the reference's float64.
+    f32_mode = None
+    if not args.no_f32:
+        import openseize_b200
+
+        openseize_b200.set_compute("float32")
+        try:
+            marks_f = Marks(W, K, barrier)
+            src_f = device_source(pool, rows, chunk, nchunks, marks_f)
+            cnt_f, _, est_f = run_psd(build_pipeline(src_f, chunk))
+            torch.cuda.synchronize()
+        finally:
+            openseize_b200.set_compute("float64")
+        secs_f = max_over_ranks(marks_f.seconds())
+        f32_mode = {"value": world * K * rows * chunk / secs_f, "unit": "channel-samples/s",
+                    "ms_per_step": 1e3 * secs_f / K,
+                    "max_rel_diff_vs_float64": float(np.max(np.abs(est_f - est) / np.max(est, axis=-1,
+                                                                                      keepdims=True)))}
+        del src_f
     del pool, src
     torch.cuda.empty_cache()
     named = named_kernels(rows, chunk, hbm_peak) if rank == 0 and not args.no_named else None
@@ -628,6 +650,8 @@ def run_ours(args):
             line["per_rank"] = per_rank
         if roofline:
             line["roofline"] = roofline
+        if f32_mode:
+            line["float32_compute"] = f32_mode
         if named:
             line["named_kernels"] = named
         if e2e:

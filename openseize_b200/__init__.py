@@ -19,9 +19,11 @@ __version__ = "0.1.0"
 
 
 def set_compute(kind):
-    """Arithmetic of the FFT-based FIR path: "float64" (default, the reference's) or
-    "float32" (opt-in: float64 samples in and out, transforms in float32; results
-    within ~1e-6 of the output peak).  Also settable with OSZ_COMPUTE=float32."""
+    """Arithmetic of the FFT-based FIR, the decimating polyphase filter and the
+    Welch accumulation: "float64" (default, the reference's) or "float32" (opt-in:
+    float64 samples in and out, the kernels' arithmetic in float32; results within
+    ~1e-6 of the output peak, BASELINE's float32 tolerance is 1e-5).  IIR filters
+    always run in float64.  Also settable with OSZ_COMPUTE=float32."""
     from openseize_b200.core import device
 
     device.set_compute(kind)

@@ -409,8 +409,8 @@ COMPUTE = os.environ.get("OSZ_COMPUTE", "float64")
 
 
 def set_compute(kind):
-    """Select the arithmetic of the FFT-based FIR path and of the Welch
-    accumulation: "float64" | "float32"."""
+    """Select the arithmetic of the FFT-based FIR path, the decimating polyphase
+    filter and the Welch accumulation: "float64" | "float32"."""
     global COMPUTE
     if kind not in ("float64", "float32"):
         raise ValueError("compute must be 'float64' or 'float32'")

@@ -57,6 +57,12 @@ def bench_md():
                                v["value"] / (d["config"]["rows_per_gpu"] * d["config"]["chunk"])
                                * v["h2d_bytes_per_step"] / 1e9 / d["n_gpus"])
                               for k, v in nar.items())]
+            f32 = d.get("float32_compute")
+            if f32:
+                lines += ["* the same pipeline with the opt-in float32 arithmetic (extra): **%.2f G "
+                          "channel-samples/s**, %.3f ms per step, PSD within %.1e of the float64 "
+                          "result (per channel, of its largest bin)" %
+                          (f32["value"] / 1e9, f32["ms_per_step"], f32["max_rel_diff_vs_float64"])]
             if d.get("host_enqueue"):
                 lines += ["* host enqueue pace inside the timed region: %s" %
                           json.dumps(d["host_enqueue"])]
