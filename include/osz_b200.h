@@ -216,8 +216,9 @@ int osz_spec_plan_path(const osz_spec_plan *plan); /* 1 = shared-memory pow2, 2 
  * reference's; OSZ_COMPUTE_F32 is the opt-in float32 mode (float64 samples in,
  * float64 sums out; samples are centred in float64, then window product and
  * FFT run in float32 -- within north_star's float32 tolerance, 1e-5 of the
- * largest bin).  It exists for osz_welch_accum_f64 at nfft = 512 .. 4096;
- * other plans / entry points keep float64 (osz_spec_plan_compute tells).
+ * largest bin).  It exists for osz_welch_accum_f64, osz_periodogram_f64 and
+ * osz_stft_f64 at nfft = 512 .. 4096; other plans keep float64
+ * (osz_spec_plan_compute tells).
  * window_host: the same coefficients given to osz_spec_plan_create. */
 int osz_spec_plan_set_compute(osz_spec_plan *plan, int compute, const double *window_host);
 int osz_spec_plan_compute(const osz_spec_plan *plan);

@@ -649,6 +649,105 @@ spec_segments_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, in
     }
 }
 
+// float32-compute variant of spec_segments_kernel (opt-in, the plan's compute
+// mode; nfft 512 .. 4096): float64 samples in, float64 / complex128 out, the
+// window product, the transform and the untangling in float32.  As in
+// welch_pp_c32_kernel the samples are centred in float64 on the pair's first
+// sample before they are narrowed and the detrend sums run in float64.
+template <int LOG2N, int DETREND, int MODE>
+__global__ void __launch_bounds__(oszf::FftCfg<LOG2N>::NT, 3)
+spec_segments_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t rows, int64_t nseg,
+                         int64_t stride, const float *__restrict__ win,
+                         const float2 *__restrict__ tw, double norm, double *__restrict__ out) {
+    using C = oszf::FftCfg<LOG2N>;
+    constexpr int N = C::N, NT = C::NT, NF = N / 2 + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ double red[4 * 32];
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t sa = (int64_t)blockIdx.x * 2;
+    const bool has_b = sa + 1 < nseg;
+    const oszf::FftTw ftw = oszf::fft_load_tw<LOG2N>(tw, tid);
+    const double *xa = x + row * ldx + sa * stride;
+
+    float2 v[16];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr double tbar = 0.5 * (N - 1);
+    const double c = DETREND != OSZ_DETREND_NONE ? ldg(xa) : 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int i = tid + r * NT;
+        const double da = ldg(xa + i) - c;
+        const double db = has_b ? ldg(xa + stride + i) - c : 0.0;
+        v[r] = make_float2((float)da, (float)db);
+        if (DETREND != OSZ_DETREND_NONE) {
+            s[0] += da;
+            s[1] += db;
+            if (DETREND == OSZ_DETREND_LINEAR) {
+                const double tc = (double)i - tbar;
+                s[2] = fma(tc, da, s[2]);
+                s[3] = fma(tc, db, s[3]);
+            }
+        }
+    }
+    if (DETREND == OSZ_DETREND_NONE) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float w = ldg(win + tid + r * NT);
+            v[r].x *= w;
+            v[r].y *= w;
+        }
+    } else {
+        block_sum<4, NT>(s, red, tid);
+        const float ma = (float)(s[0] / N), mb = (float)(s[1] / N);
+        float ka = 0.0f, kb = 0.0f;
+        if (DETREND == OSZ_DETREND_LINEAR) {
+            constexpr double stt = (double)N * ((double)N * N - 1.0) / 12.0;   // sum (t - tbar)^2
+            ka = (float)(s[2] / stt);
+            kb = (float)(s[3] / stt);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float tc = (float)(tid + r * NT) - (float)tbar;
+            const float w = ldg(win + tid + r * NT);
+            v[r].x = (v[r].x - fmaf(ka, tc, ma)) * w;
+            v[r].y = (v[r].y - fmaf(kb, tc, mb)) * w;
+        }
+    }
+    oszf::fft_r2r<LOG2N>(v, sm, ftw, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[oszf::fft_phys(tid + r * NT)] = v[r];
+    __syncthreads();
+
+    const float amp = (float)sqrt(norm);
+    // bins k = tid + m*NT, m = 0..7 (k < N/2), plus k = N/2 on thread 0
+#pragma unroll
+    for (int m = 0; m <= 8; ++m) {
+        if (m == 8 && tid != 0) break;
+        const int k = tid + m * NT;
+        const float2 zk = v[m];
+        const float2 zn = sm[oszf::fft_phys((N - k) & (N - 1))];
+        // X_a = (Z[k] + conj Z[N-k]) / 2 ; X_b = (Z[k] - conj Z[N-k]) / (2i)
+        const float2 fa = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 fb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        if (MODE == SPEC_STFT) {
+            double2 *o = reinterpret_cast<double2 *>(out);
+            o[(sa * rows + row) * NF + k] = make_double2((double)(fa.x * amp), (double)(fa.y * amp));
+            if (has_b)
+                o[((sa + 1) * rows + row) * NF + k] =
+                    make_double2((double)(fb.x * amp), (double)(fb.y * amp));
+        } else {
+            const double f = (k == 0 || k == N / 2) ? norm : 2.0 * norm;
+            out[(sa * rows + row) * NF + k] = f * (double)(fa.x * fa.x + fa.y * fa.y);
+            if (has_b)
+                out[((sa + 1) * rows + row) * NF + k] = f * (double)(fb.x * fb.x + fb.y * fb.y);
+        }
+    }
+}
+
 // One zero-padded segment per row (periodogram / modified_dft with nfft > n,
 // reference numerical.py:688-699): out[r][i] = (x[r][i] - trend_r(i)) * win[i]
 // for i < n, 0 for n <= i < nfft.  One CTA per row; the transform itself then
@@ -817,6 +916,19 @@ static int launch_segments(const osz_spec_plan *p, const double *x, int64_t ldx,
     return OSZ_OK;
 }
 
+template <int LOG2N, int DETREND, int MODE>
+static int launch_segments_c32(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+                               int64_t nseg, double *out, cudaStream_t st) {
+    using C = oszf::FftCfg<LOG2N>;
+    OSZ_CUDA(cudaFuncSetAttribute(spec_segments_c32_kernel<LOG2N, DETREND, MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    dim3 grid((unsigned)((nseg + 1) / 2), (unsigned)rows);
+    spec_segments_c32_kernel<LOG2N, DETREND, MODE><<<grid, C::NT, C::SMEM_BYTES, st>>>(
+        x, ldx, rows, nseg, p->stride, p->d_winf, p->d_twf, p->norm, out);
+    OSZ_LAUNCHED("spec_segments_c32_kernel");
+    return OSZ_OK;
+}
+
 template <int LOG2N, int DETREND>
 static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int64_t ldx,
                          int64_t rows, int64_t nseg, double *out, int64_t ldp, cudaStream_t st) {
@@ -831,6 +943,13 @@ static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int6
             if (pp) return launch_welch_pp<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
         }
         return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+    }
+    if constexpr (LOG2N >= 9 && LOG2N <= 12) {
+        if (p->compute == OSZ_COMPUTE_F32 && p->d_winf && p->d_twf) {
+            if (mode == SPEC_PGRAM)
+                return launch_segments_c32<LOG2N, DETREND, SPEC_PGRAM>(p, x, ldx, rows, nseg, out, st);
+            return launch_segments_c32<LOG2N, DETREND, SPEC_STFT>(p, x, ldx, rows, nseg, out, st);
+        }
     }
     if (mode == SPEC_PGRAM)
         return launch_segments<LOG2N, DETREND, SPEC_PGRAM>(p, x, ldx, rows, nseg, out, st);

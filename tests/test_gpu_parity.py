@@ -518,3 +518,47 @@ def test_decimator_float32_compute(dv):
     assert d32.shape == ref_plain.shape and f32.shape == ref_fused.shape
     assert 1e-10 < relerr(d32, ref_plain) < 1e-5 and relerr(f32, ref_fused) < 1e-5
     assert relerr(d64, ref_plain) < 1e-12
+
+
+@pytest.mark.parametrize("nfft", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("detrend", ["constant", "linear", None])
+def test_segments_float32_compute(dv, nfft, detrend):
+    """Opt-in float32 arithmetic of the per-segment kernels (STFT / periodogram):
+    float64 samples in, complex128 / float64 out, within 1e-5 of the peak."""
+    rng = np.random.default_rng(nfft + 5)
+    rows, stride, nseg = 3, nfft // 2, 7
+    x = rng.standard_normal((rows, (nseg - 1) * stride + nfft + 2)) + (300.0 if detrend else 0.5)
+    w = sps.get_window("hann", nfft)
+    norm = 1.0 / (1000.0 * np.sum(w ** 2))
+    plan = dv.SpecPlan(nfft, stride, w, detrend, norm, "float32")
+    assert plan.compute == "float32"
+    xd = _dev(dv, x)[:, 1:]                                  # rows start at an odd element
+    X = plan.segments(xd, nseg, True).cpu().numpy()
+    X = X[..., 0] + 1j * X[..., 1]
+    P = plan.segments(xd, nseg, False).cpu().numpy()
+    for s in range(nseg):
+        seg = x[:, 1 + s * stride:1 + s * stride + nfft]
+        if detrend:
+            seg = sps.detrend(seg, axis=-1, type=detrend)
+        R = np.fft.rfft(seg * w, axis=-1) * np.sqrt(norm)
+        p = np.abs(R) ** 2
+        p[:, 1:-1] *= 2
+        assert 1e-10 < relerr(X[s], R) < 1e-5, (nfft, detrend, s)
+        assert relerr(P[s], p) < 1e-5
+
+
+def test_stft_float32_compute(dv):
+    import openseize_b200
+    from openseize_b200.spectra.estimators import stft
+
+    rng = np.random.default_rng(78)
+    fs = 2048.0
+    x = rng.standard_normal((2, 50000)) + 40.0
+    of, ot, oX = oracle.stft(x, fs, -1, fs / 1024)
+    openseize_b200.set_compute("float32")
+    try:
+        f, t, X = stft(producer(x, 20000, -1), fs, resolution=fs / 1024)
+    finally:
+        openseize_b200.set_compute("float64")
+    assert np.array_equal(f, of) and np.array_equal(t, ot) and X.shape == oX.shape
+    assert X.dtype == np.complex128 and 1e-10 < relerr(X, oX) < 1e-5

@@ -130,6 +130,8 @@ def main(which):
                 ns = plan.nseg_available(n)
                 report("stft nfft=4096 rows=32", timeit(lambda: plan.segments(xs, ns, True)),
                        32 * ns * plan.stride, 24)
+                report("stft nfft=4096 rows=32 float32 compute",
+                       timeit(lambda: p32.segments(xs, ns, True)), 32 * ns * plan.stride, 24)
             del x
 
 
