@@ -335,6 +335,7 @@ def run_reference(args):
         rates.append(rate)
     total = time.perf_counter() - t0
     value = float(np.median(rates))
+    one, _, one_sample, _ = cpu_pipeline_rate(1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "channel-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -342,7 +343,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": value, "unit": "channel-samples/s", "cores": cores,
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "sample": sample,
+                         "single_core": {"value": one, "unit": "channel-samples/s",
+                                         "sample": one_sample}},
         "e2e": {"value": value, "unit": "channel-samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -445,8 +448,12 @@ def run_ours(args):
         # before CUDA is initialised: the worker pool forks
         cores = host_cores()
         rate, wall, sample, _ = cpu_pipeline_rate(cores)
+        one, _, one_sample, _ = cpu_pipeline_rate(1)
         cpu_line = {"value": rate, "unit": "channel-samples/s", "cores": cores,
-                    "kind": "port", "sample": sample, "seconds": wall}
+                    "kind": "port", "sample": sample, "seconds": wall,
+                    # the reference as shipped is single-process, single-thread
+                    "single_core": {"value": one, "unit": "channel-samples/s",
+                                    "sample": one_sample}}
     import torch
 
     if world > 1:

@@ -70,8 +70,11 @@ def bench_md():
                 lines += ["* per rank: own ms/step %s; sum of kernel times per step %s" %
                           (d["per_rank"]["ms_per_step"], d["per_rank"]["kernel_ms_per_step"])]
             if "cpu_baseline" in d:
-                lines += ["* cpu_baseline (oracle port, %d cores): %.1f M channel-samples/s" %
-                          (d["cpu_baseline"]["cores"], d["cpu_baseline"]["value"] / 1e6)]
+                one = d["cpu_baseline"].get("single_core")
+                lines += ["* cpu_baseline (oracle port, %d cores): %.1f M channel-samples/s%s" %
+                          (d["cpu_baseline"]["cores"], d["cpu_baseline"]["value"] / 1e6,
+                           "; one core (the reference as shipped is single-threaded): %.2f M" %
+                           (one["value"] / 1e6) if one else "")]
             r = d.get("roofline")
             if r:
                 lines += ["* roofline (dominant kernel `%s`, %.0f %% of the step): %.0f GB/s "
