@@ -309,7 +309,7 @@ welch_pp_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
             }
-            double *rd = red + (it & 1) * 16 * 0;   // (single buffer: see the barrier below)
+            double *rd = red;                       // (single buffer: see the barrier below)
             if ((tid & 31) == 0) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) rd[i * 8 + (tid >> 5)] = s[i];
