@@ -674,13 +674,16 @@ def take_cols(x, idx):
         # np.take's error for a mask that is True beyond the end of the data
         raise IndexError("index {} is out of bounds for axis with size {}".format(
             int(idx[-1]), x.shape[1]))
-    idx_dev = t.from_numpy(idx).to(DEVICE)
+    # pinned staging + asynchronous copy on the compute stream: a pageable `.to()` would
+    # block the host until the copy is done and serialise the chunk pipeline
+    pin = t.empty(int(idx.size), dtype=t.int64, pin_memory=True)
+    pin.numpy()[:] = idx
+    idx_dev = pin.to(DEVICE, non_blocking=True)
     xp, ldx = _rows_ptr(x)
     yp, ldy = _rows_ptr(out)
     rc = _launch("take_cols", 16 * rows * int(idx.size), _abi.load().osz_take_cols_f64, xp, ldx,
                  rows, _vp(idx_dev.data_ptr()), int(idx.size), yp, ldy, _cur_stream())
     _abi.check(rc, "take_cols")
-    idx_dev.record_stream(t.cuda.current_stream())
     return out
 
 
