@@ -94,7 +94,7 @@ class Layout:
         return self.lead + (int(n),) + self.trail
 
 
-_calib_cache = {}
+_calib_cache = None      # _Cache(64), made below once the class exists
 _copy_pool = None
 
 
@@ -126,14 +126,10 @@ def _calibration(chunk):
     per value (they are the same for every chunk of a reader)."""
     t = torch()
     key = (chunk.chan_off.tobytes(), chunk.slopes.tobytes(), chunk.offsets.tobytes())
-    hit = _calib_cache.get(key)
-    if hit is None:
-        if len(_calib_cache) > 64:
-            _calib_cache.clear()
-        hit = (t.from_numpy(chunk.chan_off.copy()).to("cuda"), from_host(chunk.slopes),
-               from_host(chunk.offsets))
-        _calib_cache[key] = hit
-    return hit
+    # keyed by device like the plans, least recently used entry evicted (tensors still
+    # referenced by queued kernels are kept alive by torch's stream-ordered allocator)
+    return _calib_cache.get(key, lambda: (t.from_numpy(chunk.chan_off.copy()).to("cuda"),
+                                          from_host(chunk.slopes), from_host(chunk.offsets)))
 
 
 def _upload_edf(chunk, layout, alloc=None):
@@ -381,23 +377,30 @@ class _Plan:
 
 
 class _Cache:
+    """LRU keyed by (current device, ...); producers may be iterated from several
+    threads, so look-ups are serialised."""
+
     def __init__(self, size=32):
-        self.size, self.items = size, OrderedDict()
+        import threading
+
+        self.size, self.items, self.lock = size, OrderedDict(), threading.Lock()
 
     def get(self, key, make):
         dev = torch().cuda.current_device()
         key = (dev,) + key
-        if key in self.items:
-            self.items.move_to_end(key)
-            return self.items[key]
-        val = make()
-        self.items[key] = val
-        if len(self.items) > self.size:
-            self.items.popitem(last=False)
-        return val
+        with self.lock:
+            if key in self.items:
+                self.items.move_to_end(key)
+                return self.items[key]
+            val = make()
+            self.items[key] = val
+            if len(self.items) > self.size:
+                self.items.popitem(last=False)
+            return val
 
 
 _plans = _Cache()
+_calib_cache = _Cache(64)
 
 
 # Arithmetic of the FIR overlap-save transforms, the decimating polyphase filter

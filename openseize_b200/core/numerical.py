@@ -312,12 +312,15 @@ def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None, _free
     ring = _TimeRing(rows)
     ring.push_zeros(ntaps - 1)                      # the reference's zero overlap (:221-223)
     pos = 0                                         # full-convolution index of the next output
+    seen, flushed = 0, False
     for chunk in device_chunks(pro, axis, regrid=False, alloc=ring):
         n = chunk.shape[1]
         ring.push(chunk)
-        final = pos + n >= nsamp
+        seen += n
+        final = seen >= nsamp
         if final:
             ring.push_zeros(ntaps - 1)              # flush the tail (:285-298)
+            flushed = True
         n_out = n + (ntaps - 1 if final else 0)
         y = plan.run(ring.window(), n_out, out=_new_rows(_out, rows, n_out))
         ring.drop(n_out)                            # keep the last ntaps-1 samples as halo
@@ -326,6 +329,20 @@ def _oaconvolve_device(pro, window, axis, mode, nfft_factor=32, _out=None, _free
         pos += n_out
         if hi > lo:
             yield y if (lo == 0 and hi == n_out) else y[:, lo:hi]
+        if final:
+            break
+    if not flushed and seen > 0:
+        # The source ran out before its declared length (a generator with a quirky
+        # shape, a masked stream cut short): the reference flushes when the iterator
+        # ends (:285-298), so the tail belongs to the samples that did arrive.
+        last_kept = seen + ntaps - 1 - right
+        ring.push_zeros(ntaps - 1)
+        n_out = ntaps - 1
+        y = plan.run(ring.window(), n_out, out=_new_rows(_out, rows, n_out))
+        lo = max(left - pos, 0)
+        hi = min(pos + n_out, last_kept) - pos
+        if hi > lo:
+            yield y[:, lo:hi]
 
 
 def _oaconvolve_layout(pro, window, axis, mode, nfft_factor=32):
@@ -353,6 +370,63 @@ def _sos_groups(sos):
     return [dv.SosPlan.cached(sos[i:i + _MAX_SEC]) for i in range(0, sos.shape[0], _MAX_SEC)]
 
 
+def _cascade_transition(sos):
+    """One-step zero-input transition of a DF2T biquad cascade (state order:
+    z0, z1 of section 0, then section 1, ...): column j is the state after one
+    zero input sample from unit state j; section s+1's input is section s's
+    output (recurrence of reference numerical.py:334 / scipy's sosfilt)."""
+    sos = np.atleast_2d(np.asarray(sos, dtype=np.longdouble))
+    nsec = sos.shape[0]
+    T = np.zeros((2 * nsec, 2 * nsec), dtype=np.longdouble)
+    for j in range(2 * nsec):
+        xin = np.longdouble(0)
+        for s in range(nsec):
+            b0, b1, b2, a0, a1, a2 = sos[s]
+            b0, b1, b2, a1, a2 = b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0
+            z0 = np.longdouble(j == 2 * s)
+            z1 = np.longdouble(j == 2 * s + 1)
+            y = b0 * xin + z0
+            T[2 * s, j] = b1 * xin - a1 * y + z1
+            T[2 * s + 1, j] = b2 * xin - a2 * y
+            xin = y
+    return T
+
+
+def _settle_from_transition(T, tol=1e-18):
+    """Smallest n (plus a margin) with ||T^n||_inf < tol, found on the ladder
+    T^(2^k) in long double and refined bit by bit -- exact in the pole
+    multiplicities (m coinciding poles decay like n^(m-1) r^n, which a bound
+    from the largest pole radius alone misses).  None when the norm never gets
+    there (a pole on or outside the unit circle)."""
+    T = np.asarray(T, dtype=np.longdouble)
+    if T.size == 0:
+        return 0
+
+    def norm(A):
+        return float(np.max(np.sum(np.abs(A), axis=1)))
+
+    ladder = [T]
+    with np.errstate(over="ignore", invalid="ignore"):
+        while True:
+            v = norm(ladder[-1])
+            if not np.isfinite(v) or v > 1e300:
+                return None
+            if v < tol:
+                break
+            if len(ladder) > 40:
+                return None
+            ladder.append(ladder[-1] @ ladder[-1])
+        k = len(ladder) - 1
+        if k == 0:
+            return 2 * T.shape[0]
+        acc, steps = ladder[k - 1], 1 << (k - 1)
+        for j in range(k - 2, -1, -1):
+            cand = acc @ ladder[j]
+            if norm(cand) >= tol:
+                acc, steps = cand, steps + (1 << j)
+    return steps + steps // 16 + 64
+
+
 class _Cascade:
     """A biquad cascade of any length as groups of <= 16 sections."""
 
@@ -362,18 +436,10 @@ class _Cascade:
         self.nsec = self.sos.shape[0]
         self.settle = self._settle_samples()
 
-    def _settle_samples(self, tol=1e-24):
-        """Samples after which the cascade has forgotten its initial state to
-        within ``tol`` (relative): every state transient decays like
-        ``rmax**n`` (times a polynomial in n for repeated poles, covered by the
-        squared tolerance).  None if a pole sits on or outside the unit circle."""
-        a = self.sos[:, 3:] / self.sos[:, 3:4]
-        rmax = max(float(np.max(np.abs(np.roots(sec)))) if np.any(sec[1:]) else 0.0 for sec in a)
-        if rmax >= 1.0:
-            return None
-        if rmax == 0.0:
-            return 2 * self.nsec
-        return int(np.ceil(np.log(tol) / np.log(rmax))) + 64 * self.nsec
+    def _settle_samples(self):
+        """Samples after which the cascade has forgotten its initial state (to
+        1e-18 of it); None if a pole sits on or outside the unit circle."""
+        return _settle_from_transition(_cascade_transition(self.sos))
 
     def split_state(self, state):
         """(rows, nsec, 2) -> contiguous per-group states."""
@@ -510,14 +576,16 @@ class _TfFilter:
         b, a = (np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in coeffs)
         self.plan = dv.TfPlan.cached(b, a)
         self.nstate = self.plan.nstate
-        poles = np.roots(a) if len(a) > 1 else np.zeros(0)
-        rmax = float(np.max(np.abs(poles))) if len(poles) else 0.0
-        if rmax >= 1.0:
-            self.settle = None
-        elif rmax == 0.0:
-            self.settle = 2 * self.nstate
-        else:
-            self.settle = int(np.ceil(np.log(1e-24) / np.log(rmax))) + 64 * self.nstate
+        # DF2T zero-input transition (scipy lfilter's state): z_i' = z_(i+1) - a_(i+1) z_0
+        k = self.nstate
+        an = np.zeros(k + 1, dtype=np.longdouble)
+        an[:len(a)] = np.asarray(a, dtype=np.longdouble) / np.longdouble(a[0])
+        T = np.zeros((k, k), dtype=np.longdouble)
+        for i in range(k):
+            T[i, 0] = -an[i + 1]
+            if i + 1 < k:
+                T[i, i + 1] = 1
+        self.settle = _settle_from_transition(T)
 
     def zero_state(self, rows):
         return dv.zeros((rows, self.nstate))
@@ -631,6 +699,10 @@ class _Resampler:
     def compute(self, window, w_first, o_lo, o_hi, out):
         return self.plan.run(window, w_first, o_lo, o_hi - o_lo, out=out)
 
+    def truncate(self, nsamp):
+        """The source ended after ``nsamp`` samples (short of its declared shape)."""
+        self.nsamp_in = nsamp
+
 
 class _FusedFirDecimator(_Resampler):
     """``downsample(FIR(x))`` as ONE decimating filter.
@@ -662,6 +734,10 @@ class _FusedFirDecimator(_Resampler):
         # outputs j_lo .. j_hi see an untruncated intermediate signal
         self.j_lo = dv.ceil_div(self.k2 - 1 - self.half2, M)
         self.j_hi = (self.ny - 1 - self.half2) // M
+
+    def truncate(self, nsamp):
+        self.nsamp_in = self.ny = nsamp
+        self.j_hi = (self.ny - 1 - self.half2) // self.M
 
     def _fir_span(self, window, w_first, u0, u1):
         """FIR 'same' output samples [u0, u1) from the input window."""
@@ -733,6 +809,11 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs
     rows = _layout_of(pro, axis).rows
 
     src = producer(pro, csize, axis)               # same mutation as numerical.py:590
+    # scipy.signal.resample_poly divides up and down by their gcd before it scales
+    # the taps by `up` (the chunk grid above and the tap design keep the caller's
+    # L and M, as the reference's do): resample by 2/4 applies h, not 2 * h[::2]
+    g = int(np.gcd(int(L), int(M)))
+    L, M = int(L) // g, int(M) // g
     fir_taps = _fusable_fir(src, L, M, len(h), axis)
     stage = (_FusedFirDecimator(src, fir_taps, h, M, axis) if fir_taps is not None
              else _Resampler(src, h, L, M, axis))
@@ -778,7 +859,16 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs
             out = _new_rows(_out, rows, o_hi - o_lo)
             yield stage.compute(ring.window(), w_first, o_lo, o_hi, out)
             emitted += 1
+            done = o_hi
             trim(o_hi)
+    if 0 < seen < n_in:
+        # the source ran out before its declared length: what arrived is the whole
+        # recording (the reference's chunk loop ends with its iterators)
+        stage.truncate(seen)
+        total_out = dv.ceil_div(seen * L, M)
+        if total_out > done:
+            out = _new_rows(_out, rows, total_out - done)
+            yield stage.compute(ring.window(), w_first, done, total_out, out)
 
 
 def _polyphase_layout(pro, L, M, fs, fir, axis, **kwargs):

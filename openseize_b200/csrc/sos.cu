@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -365,17 +367,16 @@ struct osz_sos_plan {
     SosParams prm;
     int T = 32;                     // samples per thread of the kernel this plan uses
     int64_t settle = -1;            // samples after which the start state is forgotten (-1: never)
-    // Time-split launches read the initial state from a copy (the last span writes
-    // the carried state while span 0 may not have read it yet).  The copy lives in
-    // this plan-owned scratch, so a plan must not run on two streams at once.
-    mutable double *d_scratch = nullptr;
-    mutable int64_t scratch_count = 0;
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
-    // exact time split: per-span states (pass 1 finals | pass 2 entering) and Phi
-    mutable double *d_span = nullptr;
-    mutable int64_t span_count = 0;
-    mutable double *d_phi = nullptr;
-    mutable int64_t phi_len = -1;   // span length d_phi was built for
+    // Plans are cached process-wide by their coefficients, so two producers with the
+    // same filter may run one plan on two streams at once: a launch owns no mutable
+    // plan state.  The per-call scratch (state copy of a time-split launch, per-span
+    // states of the exact split) comes from the stream-ordered allocator
+    // (cudaMallocAsync / cudaFreeAsync on the launching stream: no device
+    // synchronisation, no sharing between streams); Phi = T^span_len is immutable once
+    // built and kept per span length under a mutex.
+    mutable std::mutex mu;
+    mutable std::map<int64_t, double *> phi;   // span length -> device (2 nsec)^2 matrix
     std::vector<long double> Tmat;  // (2 nsec)^2 one-step zero-input transition, row major
 };
 
@@ -388,6 +389,56 @@ M2 mul(const M2 &x, const M2 &y) {
             x.c * y.b + x.d * y.d};
 }
 }  // namespace
+
+// Samples after which the cascade has forgotten its start state: the smallest n
+// with ||T^n||_inf < 1e-18 (T = one-step zero-input transition of the whole
+// cascade), found on the ladder T^(2^k) in long double and refined bit by bit.
+// Exact in the pole multiplicities -- transients of m coinciding poles decay like
+// n^(m-1) r^n, which a bound from the largest pole radius alone misses.  -1 when
+// the norm never gets there (a pole on or outside the unit circle).
+static int64_t settle_samples(const std::vector<long double> &T, int n) {
+    const long double tol = 1e-18L;
+    typedef std::vector<long double> Mat;
+    auto mul = [n](const Mat &A, const Mat &B) {
+        Mat C((size_t)n * n, 0.0L);
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) {
+                const long double a = A[(size_t)i * n + k];
+                if (a == 0.0L) continue;
+                for (int j = 0; j < n; ++j) C[(size_t)i * n + j] += a * B[(size_t)k * n + j];
+            }
+        return C;
+    };
+    auto norm = [n](const Mat &A) {
+        long double best = 0.0L;
+        for (int i = 0; i < n; ++i) {
+            long double row = 0.0L;
+            for (int j = 0; j < n; ++j) row += fabsl(A[(size_t)i * n + j]);
+            if (!(row <= best)) best = row;      // also catches NaN
+        }
+        return best;
+    };
+    std::vector<Mat> ladder(1, T);               // ladder[k] = T^(2^k)
+    while (true) {
+        const long double v = norm(ladder.back());
+        if (!(v == v) || v > 1e300L) return -1;
+        if (v < tol) break;
+        if (ladder.size() > 40) return -1;
+        ladder.push_back(mul(ladder.back(), ladder.back()));
+    }
+    const int k = (int)ladder.size() - 1;
+    if (k == 0) return 2 * n;
+    Mat acc = ladder[k - 1];
+    int64_t steps = (int64_t)1 << (k - 1);
+    for (int j = k - 2; j >= 0; --j) {
+        Mat cand = mul(acc, ladder[j]);
+        if (norm(cand) >= tol) {
+            acc.swap(cand);
+            steps += (int64_t)1 << j;
+        }
+    }
+    return steps + steps / 16 + 64;
+}
 
 extern "C" {
 
@@ -500,9 +551,8 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
             }
         }
     }
-    if (rmax < 1.0)
-        p->settle = rmax <= 0.0 ? 2 * nsec
-                                : (int64_t)ceil(log(1e-24) / log(rmax)) + 64 * (int64_t)nsec;
+    (void)rmax;
+    p->settle = settle_samples(p->Tmat, 2 * nsec);
     if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
             cudaSuccess) {
@@ -516,10 +566,59 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
 int osz_sos_plan_destroy(osz_sos_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_lanepow);
-    cudaFree(p->d_scratch);
-    cudaFree(p->d_span);
-    cudaFree(p->d_phi);
+    for (auto &kv : p->phi) cudaFree(kv.second);
     delete p;
+    return OSZ_OK;
+}
+
+// Phi = T^span_len (long double repeated squaring on the host), uploaded once per
+// span length; immutable afterwards, so concurrent launches may share it.
+static int sos_phi(const osz_sos_plan *p, int64_t span_len, const double **out) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto it = p->phi.find(span_len);
+    if (it != p->phi.end()) {
+        *out = it->second;
+        return OSZ_OK;
+    }
+    const int ns2 = 2 * p->prm.nsec;
+    const size_t nn = (size_t)ns2 * ns2;
+    std::vector<long double> acc(nn, 0.0L), base(p->Tmat), tmp(nn);
+    for (int i = 0; i < ns2; ++i) acc[(size_t)i * ns2 + i] = 1.0L;
+    auto matmul = [&](const std::vector<long double> &A, const std::vector<long double> &B,
+                      std::vector<long double> &C) {
+        for (int i = 0; i < ns2; ++i)
+            for (int j = 0; j < ns2; ++j) {
+                long double sum = 0.0L;
+                for (int k = 0; k < ns2; ++k) sum += A[(size_t)i * ns2 + k] * B[(size_t)k * ns2 + j];
+                C[(size_t)i * ns2 + j] = sum;
+            }
+    };
+    for (int64_t e = span_len; e; e >>= 1) {
+        if (e & 1) {
+            matmul(base, acc, tmp);
+            acc.swap(tmp);
+        }
+        matmul(base, base, tmp);
+        base.swap(tmp);
+    }
+    std::vector<double> phi(nn);
+    for (size_t i = 0; i < nn; ++i) phi[i] = (double)acc[i];
+    double *d = nullptr;
+    OSZ_CUDA(cudaMalloc(&d, nn * 8));
+    // pageable source, default stream: complete on return (first use of a span length only)
+    cudaError_t err = cudaMemcpy(d, phi.data(), nn * 8, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        cudaFree(d);
+        return fail(OSZ_ERR_CUDA, std::string("osz_sos_exec_f64: Phi upload: ") +
+                                      cudaGetErrorString(err));
+    }
+    if (p->phi.size() >= 1024) {    // a handful per workload; a pathological stream of
+        cudaDeviceSynchronize();    // distinct lengths drains the device before it evicts
+        for (auto &kv : p->phi) cudaFree(kv.second);
+        p->phi.clear();
+    }
+    p->phi[span_len] = d;
+    *out = d;
     return OSZ_OK;
 }
 
@@ -610,64 +709,33 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     }
     const int64_t span_len = (n + nspan - 1) / nspan;
     const double *state_in = state;
+    // per-call scratch from the stream-ordered allocator: [state copy | span finals | span entering]
+    double *scratch = nullptr;
+    const int64_t n_copy = nspan > 1 ? rows * ns2 : 0;
+    const int64_t n_span = exact ? rows * nspan * ns2 : 0;
+    if (n_copy + 2 * n_span > 0)
+        OSZ_CUDA(cudaMallocAsync(&scratch, (size_t)(n_copy + 2 * n_span) * 8, st));
+    struct Release {                 // freed in stream order after the kernels below
+        double *ptr;
+        cudaStream_t st;
+        ~Release() {
+            if (ptr) cudaFreeAsync(ptr, st);
+        }
+    } release{scratch, st};
     if (nspan > 1) {
         // the last span writes the carried state while span 0 may still read it
-        const int64_t count = rows * ns2;
-        if (p->scratch_count < count) {
-            if (p->d_scratch) OSZ_CUDA(cudaFree(p->d_scratch));
-            p->d_scratch = nullptr;
-            p->scratch_count = 0;
-            OSZ_CUDA(cudaMalloc(&p->d_scratch, (size_t)count * 8));
-            p->scratch_count = count;
-        }
-        sos_copy_state_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(state, p->d_scratch,
-                                                                             count);
+        sos_copy_state_kernel<<<(unsigned)((n_copy + 255) / 256), 256, 0, st>>>(state, scratch,
+                                                                               n_copy);
         OSZ_LAUNCHED("sos_copy_state_kernel");
-        state_in = p->d_scratch;
+        state_in = scratch;
     }
     double *span_f = nullptr, *span_e = nullptr;
+    const double *d_phi = nullptr;
     if (exact) {
-        const int64_t count = rows * nspan * ns2;
-        if (p->span_count < 2 * count) {
-            if (p->d_span) OSZ_CUDA(cudaFree(p->d_span));
-            p->d_span = nullptr;
-            p->span_count = 0;
-            OSZ_CUDA(cudaMalloc(&p->d_span, (size_t)(2 * count) * 8));
-            p->span_count = 2 * count;
-        }
-        span_f = p->d_span;
-        span_e = p->d_span + count;
-        if (p->phi_len != span_len) {
-            // Phi = T^span_len by repeated squaring in long double
-            const size_t nn = (size_t)ns2 * ns2;
-            std::vector<long double> acc(nn, 0.0L), base(p->Tmat), tmp(nn);
-            for (int i = 0; i < ns2; ++i) acc[(size_t)i * ns2 + i] = 1.0L;
-            auto matmul = [&](const std::vector<long double> &A, const std::vector<long double> &B,
-                              std::vector<long double> &C) {
-                for (int i = 0; i < ns2; ++i)
-                    for (int j = 0; j < ns2; ++j) {
-                        long double sum = 0.0L;
-                        for (int k = 0; k < ns2; ++k)
-                            sum += A[(size_t)i * ns2 + k] * B[(size_t)k * ns2 + j];
-                        C[(size_t)i * ns2 + j] = sum;
-                    }
-            };
-            for (int64_t e = span_len; e; e >>= 1) {
-                if (e & 1) {
-                    matmul(base, acc, tmp);
-                    acc.swap(tmp);
-                }
-                matmul(base, base, tmp);
-                base.swap(tmp);
-            }
-            std::vector<double> phi(nn);
-            for (size_t i = 0; i < nn; ++i) phi[i] = (double)acc[i];
-            if (!p->d_phi) OSZ_CUDA(cudaMalloc(&p->d_phi, (size_t)4 * SOS_MAXSEC * SOS_MAXSEC * 8));
-            // (stream-ordered with the kernels below; pageable source: synchronous on return)
-            OSZ_CUDA(cudaMemcpyAsync(p->d_phi, phi.data(), nn * 8, cudaMemcpyHostToDevice, st));
-            OSZ_CUDA(cudaStreamSynchronize(st));
-            p->phi_len = span_len;
-        }
+        span_f = scratch + n_copy;
+        span_e = span_f + n_span;
+        const int rc = sos_phi(p, span_len, &d_phi);
+        if (rc != OSZ_OK) return rc;
     }
     const dim3 grid((unsigned)rows, (unsigned)nspan);
 #define OSZ_SOS_LAUNCH(W, TT, YY, SIN, SOUT)                                                    \
@@ -682,7 +750,7 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (exact) {
         if (p->T == 16) OSZ_SOS_LAUNCH(false, 16, nullptr, nullptr, span_f);
         else OSZ_SOS_LAUNCH(false, 32, nullptr, nullptr, span_f);
-        sos_combine_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>(p->d_phi, span_f, span_e,
+        sos_combine_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>(d_phi, span_f, span_e,
                                                                        rows, (int)nspan, ns2);
         OSZ_LAUNCHED("sos_combine_kernel");
         if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, span_e, nullptr);

@@ -182,6 +182,15 @@ def iir_oracle_sweep():
     assert nm._Cascade(lp).settle < 40000
     got = np.concatenate(list(nm.sosfiltfilt(producer(x, 40000, -1), lp, -1)), -1)
     close(got, np.concatenate(oracle.sosfiltfilt(x, lp, 40000, -1), -1), tol=1e-12)
+    # a cascade of eight IDENTICAL sections: transients of coinciding poles decay like
+    # n^7 r^n -- the settle length has to account for the multiplicity
+    one = sps.butter(1, [40, 60], btype="bandpass", fs=5000, output="sos")
+    rep = np.repeat(one, 8, axis=0)
+    s1, s8 = nm._Cascade(one).settle, nm._Cascade(rep).settle
+    assert s1 < s8 < 20000
+    xr = rng.standard_normal((2, 90001)) + 2.0
+    got = np.concatenate(list(nm.sosfiltfilt(producer(xr, 30000, -1), rep, -1)), -1)
+    close(got, np.concatenate(oracle.sosfiltfilt(xr, rep, 30000, -1), -1), tol=1e-12)
     # more than 16 sections: split cascade
     sos = sps.butter(20, [5, 400], btype="bandpass", fs=5000, output="sos")
     assert sos.shape[0] == 20
@@ -235,6 +244,15 @@ def resample_oracle_sweep():
     ref = sps.resample_poly(xt, 1, 4, axis=0, window=oracle.resample_filter(1, 4, fs))
     close(got, ref)
     assert resample(x, 3, 3, fs, 1000) is x          # identity returns the input itself
+    # non-coprime factors straight into nm.polyphase_resample (the public resample()
+    # reduces them first, resampling.py; scipy's resample_poly reduces them itself)
+    from openseize_b200.filtering.fir import Kaiser as _K
+
+    for L, M in ((2, 4), (4, 6), (6, 4)):
+        got = list(nm.polyphase_resample(producer(x, 10000, -1), L, M, fs, _K, -1))
+        ref = oracle.polyphase_resample(x, L, M, fs, 10000, -1)
+        assert [a.shape[-1] for a in got] == [a.shape[-1] for a in ref]
+        close(np.concatenate(got, -1), np.concatenate(ref, -1))
 
 
 # -------------------------------------------------------------- spectra ----
@@ -371,6 +389,60 @@ def pipeline_chain():
     close(p, rp)
     # and the intermediate producer is still iterable on the host
     close(kais(notch(producer(x, cs, -1), cs, axis=-1), cs, axis=-1).to_array(), r2)
+
+
+def c5_real_parameters(rows=2, nchunks=6, tail=123_457, cs=1_000_000):
+    """BASELINE.json config 5 -- the configuration bench.py measures -- with its
+    REAL parameters: Notch(60 Hz, width 6) at 30 kHz forward-backward (the
+    settle-shortened look-ahead is active: settle ~ 88 k < chunksize 1e6) ->
+    Kaiser(500, 600) at 30 kHz (671 taps, 'same') -> downsample M = 25 (561-tap
+    anti-alias; fused: 1231 taps) -> psd at 1200 Hz with nfft 4096; chunksize
+    1e6, a ragged last chunk.  Every stage's output against the oracle at
+    1e-9 of its peak, Welch count and frequencies exact, with the stage fusion
+    on and off.  Reference: core/numerical.py:449-520,158-298,523-632,852-947."""
+    import os
+
+    fs, M, nfft = 30000, 25, 4096
+    n = nchunks * cs + tail
+    x = signal(5, rows, n, fs)
+    notch = Notch(fstop=60, width=6, fs=fs)
+    kais = Kaiser(fpass=500, fstop=600, fs=fs)
+    assert len(kais.coeffs) == 671
+    r1 = np.concatenate(oracle.filtfilt(x, notch.coeffs, cs, -1), -1)
+    r2 = np.concatenate(oracle.oaconvolve(r1, kais.coeffs, cs, -1, "same"), -1)
+    r3_blocks = oracle.polyphase_resample(r2, 1, M, fs, cs, -1)
+    r3 = np.concatenate(r3_blocks, -1)
+    fs2 = fs // M
+    rc, rf, rp = oracle.welch_psd(r3, fs2, -1, fs2 / nfft)
+    assert rc == (r3.shape[-1] - nfft) // (nfft // 2) + 1
+    errs = {}
+    for fuse in ("1", "0"):
+        os.environ["OSZ_FUSE"] = fuse
+        try:
+            def chain():
+                p1 = notch(producer(x, cs, -1), cs, axis=-1, dephase=True)
+                p2 = kais(p1, cs, axis=-1, mode="same")
+                return downsample(p2, M, fs, cs, axis=-1)
+
+            cnt, f, p = psd(chain(), fs2, axis=-1, resolution=fs2 / nfft)
+            d = chain()
+            got = [np.array(b) for b in d]
+        finally:
+            os.environ.pop("OSZ_FUSE", None)
+        assert cnt == rc and np.array_equal(f, rf), (fuse, cnt, rc)
+        assert d.shape == r3.shape
+        assert [b.shape[-1] for b in got] == [b.shape[-1] for b in r3_blocks]
+        errs["decimated_fuse" + fuse] = close(np.concatenate(got, -1), r3)
+        # per-bin error relative to each channel's largest bin (SURVEY 8d parity metric)
+        e = float(np.max(np.abs(p - rp) / np.max(rp, axis=-1, keepdims=True)))
+        assert e <= TOL, (fuse, e)
+        errs["psd_fuse" + fuse] = e
+    # the full-rate intermediate stages on their own (host-visible producers)
+    y1 = notch(producer(x, cs, -1), cs, axis=-1, dephase=True).to_array()
+    errs["notch"] = close(y1, r1)
+    y2 = kais(notch(producer(x, cs, -1), cs, axis=-1, dephase=True), cs, axis=-1).to_array()
+    errs["fir"] = close(y2, r2)
+    return errs
 
 
 def hilbert_golden():

@@ -410,6 +410,14 @@ def test_fused_fir_decimate():
     pc.fused_fir_decimate()
 
 
+def test_c5_real_parameters():
+    """The bench's own configuration at its real parameters (30 kHz notch with the
+    shortened look-ahead active, 671-tap FIR, fused 1231-tap M=25 decimator, nfft
+    4096 on the 1200 Hz stream, chunksize 1e6, 6 chunks + ragged tail)."""
+    errs = pc.c5_real_parameters()
+    assert max(errs.values()) <= 1e-9, errs
+
+
 def test_full_size_properties(dv):
     """BASELINE-sized chunk (64 rows x 1e6): size-independent properties --
     impulse response reproduces the taps, linearity, filter-then-PSD of a sine

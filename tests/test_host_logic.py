@@ -96,6 +96,31 @@ def test_laziness_and_errors(fake_gpu):
     assert y.shape == x.shape
 
 
+def test_short_source_still_flushes(fake_gpu):
+    """A generating-function producer that yields fewer samples than its declared
+    shape: the reference flushes the FIR tail / the last resampler chunk when the
+    iterator ENDS (numerical.py:285-298, :618-632), not when the declared length
+    is reached -- the samples that arrived are the recording."""
+    import oracle
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 9000))
+
+    def source():
+        yield from (x[:, i:i + 1000] for i in range(0, 9000, 1000))
+
+    filt = Kaiser(500, 600, 5000)
+    for mode in ("same", "full"):
+        pro = producer(source, 1000, -1, shape=(2, 12000))     # declares 12000, yields 9000
+        got = np.concatenate(list(nm.oaconvolve(pro, filt.coeffs, -1, mode)), -1)
+        ref = np.stack([np.convolve(r, filt.coeffs, mode) for r in x])
+        assert got.shape == ref.shape and np.max(np.abs(got - ref)) < 1e-12
+    pro = producer(source, 1000, -1, shape=(2, 12000))
+    got = np.concatenate(list(nm.polyphase_resample(pro, 1, 4, 5000, Kaiser, -1)), -1)
+    ref = np.concatenate(oracle.polyphase_resample(x, 1, 4, 5000, 1000, -1), -1)
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) < 1e-12
+
+
 def test_producer_mutation_contract(fake_gpu):
     """producer(Producer, cs, axis) mutates and returns the same object
     (reference core/producer.py:114-117); psd forces chunksize=int(fs)."""
