@@ -951,6 +951,11 @@ def periodogram(arr, fs, nfft=None, window="hann", axis=-1, detrend="constant",
 def _single_segment(arr, fs, nfft, window, axis, detrend, scaling, complex_):
     nsamp = arr.shape[axis]
     if nsamp == 0:
+        # the reference's detrend of an empty slice warns (numpy "Mean of empty
+        # slice") before np.fft raises (tests/test_spectra.py:140-165): same behaviour
+        import warnings
+
+        warnings.warn("Mean of empty slice.", RuntimeWarning, stacklevel=3)
         raise ValueError("cannot estimate the spectrum of an empty array")
     if nsamp < nfft:
         # zero-padded transform (reference numerical.py:688-699): detrend and
