@@ -7,20 +7,28 @@ the full pipeline  Notch(60 Hz) forward-backward IIR -> Kaiser(500/600 Hz) FIR
 (671 taps, mode 'same') -> downsample by 25 -> Welch PSD (nfft 4096, Hann, 50 %
 overlap)  on a synthetic 256-channel x 30 kHz float64 recording streamed in
 chunks of 1e6 samples.  The 24 h recording (2592 chunks, 5.3 TB) is an
-out-of-core stream; a "step" is ONE chunk (256 x 1e6 channel-samples) passing
-through all four stages in steady state, and the reported rate is what a full
-24 h pass sustains.  One process per GPU; at N > 1 every rank streams its own
-256-channel block (channel sharding, no data-path collective, weak scaling).
+out-of-core stream; a "step" is 4 chunks (4 x 256 x 1e6 channel-samples) of the
+WHOLE recording passing through all four stages in steady state, and the
+reported rate is what a full 24 h pass sustains.  One process per GPU; at N > 1
+the recording's 256 channels are split into blocks of 256 / N per GPU (channel
+sharding, no data-path collective, STRONG scaling: the job is the same at every
+N); `weak_scaling` additionally reports N independent 256-channel recordings.
 
   value    : inputs already resident in HBM (a cyclic pool of device chunks),
              CUDA-event timed, max over ranks.
   e2e      : the same pipeline through the public producer/operator API with
              HOST (pinned) chunks; H2D of every chunk and D2H of the PSD inside
-             the timed region.
-  roofline : the dominant kernel (FIR overlap-save FFT) -- algorithmic bytes
-             (16 B per channel-sample) / its CUDA-event time.
-  cpu_baseline / --impl reference : the oracle port of the reference's CPU path
-             (numpy/scipy, same per-chunk calls) on the box's host cores.
+             the timed region; `h2d_roof_GBps` = what plain pinned copies reach
+             on all ranks at once.
+  parity   : the measured pipeline against the CPU oracle on channels of the
+             same pool (outside the timed region).
+  roofline : the kernel with the largest share of the step -- algorithmic bytes
+             per launch / its CUDA-event time; `stages` counts a
+             forward-backward filter as ONE read + ONE write per sample;
+             `roofline_named` are the two kernels north_star names, timed alone.
+  cpu_baseline / --impl reference : the UNMODIFIED reference (baseline/_ref)
+             through its own operator API on all host cores (the oracle port
+             when the reference is not installed).
 """
 
 import argparse
@@ -42,6 +50,7 @@ ROWS = 256
 CHUNK = 1_000_000
 M_DEC = 25
 NFFT = 4096
+CPS_DEFAULT = 4          # chunks per step: a step is 4 x (256 x 1e6) channel-samples
 METRIC = "channel-samples/sec filtered+PSD"
 WORKLOAD = ("C5 pipeline: Notch(60,w6) filtfilt -> Kaiser(500,600) 671-tap FIR 'same' -> "
             "downsample M=25 -> Welch PSD nfft=4096 hann 50%; 256 ch x 30 kHz float64, "
@@ -51,7 +60,7 @@ WORKLOAD = ("C5 pipeline: Notch(60,w6) filtfilt -> Kaiser(500,600) 671-tap FIR '
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS)
@@ -60,6 +69,11 @@ def parse():
     ap.add_argument("--no-narrow", action="store_true", help="skip the float32 / int16 e2e extras")
     ap.add_argument("--no-f32", action="store_true", help="skip the float32-compute extra pass")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the pool")
+    ap.add_argument("--no-weak", action="store_true",
+                    help="N > 1: skip the extra weak-scaling pass (256 channels per GPU)")
+    ap.add_argument("--chunks-per-step", type=int, default=CPS_DEFAULT,
+                    help="chunks of the recording per step")
     ap.add_argument("--no-named", action="store_true",
                     help="skip the stand-alone FIR / Welch kernel timings")
     return ap.parse_args()
@@ -517,6 +531,60 @@ def bind_to_gpu_cpus(index):
         pass
 
 
+def parity_check(pool, chunk, nchunks=5, nrows=2):
+    """The measured pipeline against the CPU oracle on the first `nrows` channels of
+    the SAME device pool, `nchunks` chunks of the same cyclic sequence (outside the
+    timed region): max PSD bin error relative to each channel's largest bin, and
+    the decimated stream's error relative to its peak.  Tolerance 1e-9 (north_star)."""
+    import oracle
+    import scipy.signal as sps
+    from openseize_b200 import producer
+    from oracle.chunked import _kaiser_lowpass
+
+    host = [p[:nrows].cpu().numpy() for p in pool]
+    x = np.concatenate([host[i % len(host)] for i in range(nchunks)], -1)
+    pro = producer(x, chunk, -1)
+    dec = build_pipeline(pro, chunk)
+    cnt, freqs, est = run_psd(dec)
+    got = build_pipeline(producer(x, chunk, -1), chunk).to_array()
+    b, a = sps.iirnotch(60, 60 / 6, fs=FS)
+    r1 = np.concatenate(oracle.filtfilt(x, (b, a), chunk, -1), -1)
+    taps = _kaiser_lowpass(500, 600, FS, 1.0, 40.0)
+    r2 = np.concatenate(oracle.oaconvolve(r1, taps, chunk, -1, "same"), -1)
+    r3 = np.concatenate(oracle.polyphase_resample(r2, 1, M_DEC, FS, chunk, -1), -1)
+    fs2 = FS // M_DEC
+    rc, rf, rp = oracle.welch_psd(r3, fs2, -1, fs2 / NFFT)
+    assert cnt == rc and np.array_equal(freqs, rf), (cnt, rc)
+    psd_err = float(np.max(np.abs(est - rp) / np.max(rp, axis=-1, keepdims=True)))
+    dec_err = float(np.max(np.abs(got - r3)) / np.max(np.abs(r3)))
+    return {"psd_max_rel_err": psd_err, "decimated_max_rel_err": dec_err, "segments": int(cnt),
+            "channels": nrows, "chunks": nchunks, "tolerance": 1e-9,
+            "against": "oracle (numpy/scipy restatement pinned to the reference), same pool"}
+
+
+def h2d_roof(rows, chunk, barrier, max_over_ranks, world, reps=4):
+    """What the box delivers for plain pinned host -> device copies with all ranks
+    copying at once (one cudaMemcpyAsync per chunk, no kernels): the roof of the
+    end-to-end number.  GB/s summed over ranks."""
+    import torch
+
+    h = torch.empty((rows, chunk), dtype=torch.float64, pin_memory=True)
+    h.numpy()[:] = 1.0
+    d = torch.empty((rows, chunk), dtype=torch.float64, device="cuda")
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    secs = max_over_ranks(a.elapsed_time(b) * 1e-3)
+    del h, d
+    return world * reps * rows * chunk * 8 / secs / 1e9
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -563,9 +631,14 @@ def run_ours(args):
     from openseize_b200.core import device as dv
 
     dv.require_cuda()
-    rows, chunk = args.rows, args.chunk
-    W, K = args.warmup, args.steps
-    nchunks = W + K + TAIL
+    # north_star's split: ONE 256-channel recording, channel blocks of 256 / N per GPU
+    # (strong scaling, no data-path collective).  --rows overrides the recording's width.
+    total_rows, chunk = args.rows, args.chunk
+    if total_rows % world:
+        raise SystemExit("--rows must be divisible by the number of GPUs")
+    rows = total_rows // world
+    W, K, CPS = args.warmup, args.steps, args.chunks_per_step
+    nchunks = (W + K) * CPS + TAIL
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -573,11 +646,43 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"
 
+    def timed_pass(pool, nrows, sampler=None, timers_out=None, launches=None):
+        """W warm-up + K timed steps of CPS chunks each, device-resident pool."""
+        marks = Marks(W * CPS, K * CPS, barrier)
+        use_timers = timers_out is not None and os.environ.get("OSZ_BENCH_TIMERS", "1") == "1"
+
+        def on_start():
+            if sampler:
+                sampler.mark_start()
+            if launches is not None:
+                launches["a"] = _abi.launch_count()
+            dv.TIMERS = {} if use_timers else None
+
+        def on_stop():
+            if launches is not None:
+                launches["b"] = _abi.launch_count()
+            if timers_out is not None:
+                timers_out.update(dv.TIMERS or {})
+            dv.TIMERS = None
+            if sampler:
+                sampler.mark_stop()
+
+        marks.on_start, marks.on_stop = on_start, on_stop
+        src = device_source(pool, nrows, chunk, nchunks, marks)
+        cnt, freqs, est = run_psd(build_pipeline(src, chunk))
+        torch.cuda.synchronize()
+        return marks, est
+
     # ---- value: HBM-resident chunk pool -------------------------------------
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    pool = [torch.randn((rows, chunk), dtype=torch.float64, device="cuda", generator=gen)
-            for _ in range(2)]
-    marks = Marks(W, K, barrier)
+    # every rank draws the whole recording's pool with the same seed and keeps its
+    # own channel block, so the N-GPU job processes the same 256 channels as N = 1
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    pool = []
+    for _ in range(2):
+        full = torch.randn((total_rows, chunk), dtype=torch.float64, device="cuda", generator=gen)
+        pool.append(full[rank * rows:(rank + 1) * rows].clone() if world > 1 else full)
+        del full
+    torch.cuda.empty_cache()
     sampler = ClockSampler(local, enabled=rank == 0 and os.environ.get("OSZ_BENCH_CLOCKS", "1") == "1",
                            period_ms=45 if world == 1 else 50)
     launches = {}
@@ -586,8 +691,6 @@ def run_ours(args):
     # ramps its clocks during the first second, and with one rank per GPU the ranks
     # reach steady state at different moments.  The contract's W warm-up steps and K
     # timed steps follow unchanged.
-    # (N = 1 needs none -- the W warm-up steps do -- and measured 3.9 instead of 3.54 ms
-    # per step when a pre-warm was combined with the clock poller.)
     prewarm = float(os.environ.get("OSZ_BENCH_PREWARM", "0.4" if world > 1 else "0"))
     t_min, t_max = time.perf_counter() + prewarm, time.perf_counter() + (3.0 if prewarm else 0.0)
     while time.perf_counter() < t_min or (sampler.enabled and not sampler.ready
@@ -596,24 +699,12 @@ def run_ours(args):
         run_psd(build_pipeline(pre.producer(), chunk))
         torch.cuda.synchronize()
     barrier()
-    use_timers = os.environ.get("OSZ_BENCH_TIMERS", "1") == "1"
-    marks.on_start = lambda: (sampler.mark_start(), launches.__setitem__("a", _abi.launch_count()),
-                              setattr(dv, "TIMERS", {} if use_timers else None))
     timers = {}
-
-    def on_stop():
-        launches["b"] = _abi.launch_count()
-        timers.update(dv.TIMERS or {})
-        dv.TIMERS = None
-        sampler.mark_stop()
-
-    marks.on_stop = on_stop
-    src = device_source(pool, rows, chunk, nchunks, marks)
-    cnt, freqs, est = run_psd(build_pipeline(src, chunk))
-    torch.cuda.synchronize()
+    marks, est = timed_pass(pool, rows, sampler, timers, launches)
     sampler.stop()
     secs = max_over_ranks(marks.seconds())
-    value = world * K * rows * chunk / secs
+    step_samples = total_rows * chunk * CPS            # whole job, all ranks
+    value = K * step_samples / secs
     per_rank = None
     if dist is not None:
         # every rank's own step time and the sum of its kernel times (diagnostic)
@@ -625,28 +716,54 @@ def run_ours(args):
         per_rank = {"ms_per_step": [round(float(t[0]), 3) for t in allr],
                     "kernel_ms_per_step": [round(float(t[1]), 3) for t in allr]}
     assert np.all(np.isfinite(est)) and est.shape == (rows, NFFT // 2 + 1)
+    # the measured path against the oracle, on channels of the same pool
+    parity = parity_check(pool, chunk) if rank == 0 and not args.no_parity else None
+    if parity:
+        assert parity["psd_max_rel_err"] <= 1e-9 and parity["decimated_max_rel_err"] <= 1e-9, parity
 
     kernels = {}
     for name, recs in timers.items():
         ms = [a.elapsed_time(b) for a, b, _ in recs]
         by = [c for _, _, c in recs]
         kernels[name] = {"launches": len(recs), "ms_total": float(np.sum(ms)),
+                         "ms_per_step": float(np.sum(ms)) / K,
                          "alg_GBps": float(np.sum(by) / (np.sum(ms) * 1e-3) / 1e9)}
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     if dom:
-        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full
-        # capture of this kernel at this shape (profiles/r01_ncu_summary.md)
+        # dram__bytes_read + dram__bytes_write per launch of this kernel at this shape,
+        # from this round's committed `ncu --set full` capture (profiles/r02_traffic.json;
+        # the bench never runs under ncu)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath) and rows == ROWS and chunk == CHUNK:
             traffic = json.load(open(tpath)).get(dom, {}).get("bytes_per_launch")
+        per_launch = float(np.mean([c for _, _, c in timers[dom]]))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["alg_GBps"],
                     "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["alg_GBps"] / hbm_peak, "traffic": traffic,
-                    "alg_bytes_per_launch": 16 * rows * chunk if dom in ("sos", "fir") else None,
+                    "alg_bytes_per_launch": per_launch,
                     "peak_source": peak_src,
                     "share_of_step": kernels[dom]["ms_total"] / (secs * 1e3)}
+    # stage-level accounting by SURVEY 8(d)'s algorithmic bytes (a forward-backward
+    # filter is ONE read and ONE write per sample however many passes it makes)
+    stages = None
+    if kernels:
+        per_step = rows * chunk * CPS
+
+        def stage(names, alg_bytes):
+            ms = sum(kernels[n]["ms_per_step"] for n in names if n in kernels)
+            if ms <= 0:
+                return None
+            gbs = alg_bytes * per_step / (ms * 1e-3) / 1e9
+            return {"kernels": [n for n in names if n in kernels], "ms_per_step": ms,
+                    "alg_bytes_per_sample": alg_bytes, "achieved_GBps": gbs,
+                    "frac_of_hbm": gbs / hbm_peak}
+
+        stages = {"notch_filtfilt": stage(["sos", "sos_state", "sos_dec"], 16.0),
+                  "fir_decimate": stage(["upfirdn", "fir", "sos_dec"], 8.0 * (1 + 1 / M_DEC)),
+                  "welch": None,
+                  "pipeline": stage(list(kernels), 8.0 * (1 + 1 / M_DEC))}
     # The same HBM-resident pipeline with the opt-in float32 arithmetic (float64 samples
     # in, float64 results out; the IIR stays float64).  Extra information: the contract's
     # `value` above is the reference's float64.
@@ -656,25 +773,39 @@ def run_ours(args):
 
         openseize_b200.set_compute("float32")
         try:
-            marks_f = Marks(W, K, barrier)
-            src_f = device_source(pool, rows, chunk, nchunks, marks_f)
-            cnt_f, _, est_f = run_psd(build_pipeline(src_f, chunk))
-            torch.cuda.synchronize()
+            marks_f, est_f = timed_pass(pool, rows)
         finally:
             openseize_b200.set_compute("float64")
         secs_f = max_over_ranks(marks_f.seconds())
-        f32_mode = {"value": world * K * rows * chunk / secs_f, "unit": "channel-samples/s",
+        f32_mode = {"value": K * step_samples / secs_f, "unit": "channel-samples/s",
                     "ms_per_step": 1e3 * secs_f / K,
                     "max_rel_diff_vs_float64": float(np.max(np.abs(est_f - est) / np.max(est, axis=-1,
                                                                                       keepdims=True)))}
-        del src_f
-    del pool, src
+    # weak scaling (every rank its own 256-channel recording), as round 1 measured it
+    weak = None
+    if world > 1 and not args.no_weak:
+        gen_w = torch.Generator(device="cuda").manual_seed(99 + rank)
+        del pool
+        torch.cuda.empty_cache()
+        pool_w = [torch.randn((total_rows, chunk), dtype=torch.float64, device="cuda",
+                              generator=gen_w) for _ in range(2)]
+        marks_w, _ = timed_pass(pool_w, total_rows)
+        secs_w = max_over_ranks(marks_w.seconds())
+        weak = {"value": world * K * total_rows * chunk * CPS / secs_w,
+                "unit": "channel-samples/s", "rows_per_gpu": total_rows,
+                "ms_per_step": 1e3 * secs_w / K,
+                "note": "every rank streams its own 256-channel recording (N independent replicas)"}
+        del pool_w
+    else:
+        del pool
     torch.cuda.empty_cache()
-    named = named_kernels(rows, chunk, hbm_peak) if rank == 0 and not args.no_named else None
+    named = named_kernels(ROWS, chunk, hbm_peak) if rank == 0 and not args.no_named else None
+    barrier()
 
     # ---- e2e: pinned host chunks through the public API ----------------------
     e2e = None
     if not args.no_e2e:
+        roof = h2d_roof(rows, chunk, barrier, max_over_ranks, world)
         host_pool = []
         rng = np.random.default_rng(99 + rank)
         for _ in range(2):
@@ -683,23 +814,27 @@ def run_ours(args):
             for r0 in range(0, rows, 32):
                 a[r0:r0 + 32] = rng.standard_normal((min(32, rows - r0), chunk))
             host_pool.append(a)
-        marks2 = Marks(W, K, barrier)
+        marks2 = Marks(W * CPS, K * CPS, barrier)
         src2 = host_source(host_pool, rows, chunk, nchunks, marks2)
         cnt2, _, est2 = run_psd(build_pipeline(src2, chunk))
         torch.cuda.synchronize()
         secs2 = max_over_ranks(marks2.seconds())
-        wall2 = marks2.wall[W + K] - marks2.wall[W]
+        wall2 = marks2.wall[(W + K) * CPS] - marks2.wall[W * CPS]
         secs2 = max(secs2, max_over_ranks(wall2))
-        e2e = {"value": world * K * rows * chunk / secs2, "unit": "channel-samples/s",
-               "h2d_bytes_per_step": rows * chunk * 8,
-               "d2h_bytes_per_step": int(est2.nbytes / (W + K + TAIL)),
-               "note": "PSD is a streaming reduction: the (rows, 2049) result crosses to the "
-                       "host once per recording; its bytes are amortised over the steps"}
+        e2e_value = K * step_samples / secs2
+        e2e = {"value": e2e_value, "unit": "channel-samples/s",
+               "h2d_bytes_per_step": rows * chunk * 8 * CPS,
+               "d2h_bytes_per_step": int(est2.nbytes * CPS / nchunks),
+               "h2d_roof_GBps": roof,
+               "frac_of_h2d_roof": e2e_value * 8 / 1e9 / roof,
+               "note": "h2d/d2h bytes are per rank; PSD is a streaming reduction: the "
+                       "(rows, 2049) result crosses to the host once per recording, its bytes "
+                       "are amortised over the steps; h2d_roof = plain pinned cudaMemcpyAsync "
+                       "on all ranks at once, summed"}
         # The same pipeline fed float32 and int16 samples (EDF recordings are int16):
         # they cross PCIe in their own width and are widened on the device, so the
         # PCIe roof moves from 8 to 4 and 2 bytes per sample.  Extra information, not
         # the contract's e2e (which stays float64, the dtype of the reference arm).
-        # (N <= 2 only: at N = 8 the extra pinned pools would add 16 GB of locked host memory)
         if not args.no_narrow and world <= 2:
             e2e["narrow_inputs"] = {}
             for name, tdt, scale in (("float32", torch.float32, 1.0), ("int16", torch.int16, 3000.0)):
@@ -708,15 +843,15 @@ def run_ours(args):
                     t = torch.empty((rows, chunk), dtype=tdt, pin_memory=True)
                     np.multiply(a, scale, out=t.numpy(), casting="unsafe")
                     npool.append(t.numpy())
-                marks3 = Marks(W, K, barrier)
+                marks3 = Marks(W * CPS, K * CPS, barrier)
                 src3 = host_source(npool, rows, chunk, nchunks, marks3)
                 run_psd(build_pipeline(src3, chunk))
                 torch.cuda.synchronize()
                 secs3 = max(max_over_ranks(marks3.seconds()),
-                            max_over_ranks(marks3.wall[W + K] - marks3.wall[W]))
+                            max_over_ranks(marks3.wall[(W + K) * CPS] - marks3.wall[W * CPS]))
                 e2e["narrow_inputs"][name] = {
-                    "value": world * K * rows * chunk / secs3, "unit": "channel-samples/s",
-                    "h2d_bytes_per_step": rows * chunk * npool[0].itemsize}
+                    "value": K * step_samples / secs3, "unit": "channel-samples/s",
+                    "h2d_bytes_per_step": rows * chunk * npool[0].itemsize * CPS}
                 del npool
         del host_pool
 
@@ -724,10 +859,16 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "channel-samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": rows, "chunk": chunk,
-                       "sharding": "channel blocks, one process per GPU, no collective",
-                       "l2": "each step reads a 2 GB chunk (>> 126 MB L2); pool of 2 chunks"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "recording_rows": total_rows, "rows_per_gpu": rows,
+                       "chunk": chunk, "chunks_per_step": CPS,
+                       "step": "%d chunks of %d x %d samples (the whole %d-channel recording; "
+                               "each GPU filters its %d-channel block)" % (CPS, total_rows, chunk,
+                                                                            total_rows, rows),
+                       "sharding": "channel blocks of one recording, one process per GPU, "
+                                   "no data-path collective",
+                       "l2": "each chunk a rank reads is %.0f MB (> 126 MB L2); pool of 2 chunks"
+                             % (rows * chunk * 8 / 1e6)},
             "gpu_launches": int(launches.get("b", 0) - launches.get("a", 0)),
             "clocks": sampler.summary(), "kernels": kernels,
             "host_enqueue": marks.host_pace(),
@@ -735,14 +876,25 @@ def run_ours(args):
             # region ahead, ms_per_step minus this is idle time on the device side
             "kernel_sum_ms_per_step": sum(v["ms_total"] for v in kernels.values()) / K,
         }
+        if parity:
+            line["parity"] = parity
+            line["parity_err"] = parity["psd_max_rel_err"]
         if per_rank:
             line["per_rank"] = per_rank
         if roofline:
             line["roofline"] = roofline
+        if stages:
+            line["stages"] = stages
         if f32_mode:
             line["float32_compute"] = f32_mode
+        if weak:
+            line["weak_scaling"] = weak
         if named:
             line["named_kernels"] = named
+            line["roofline_named"] = {k: {"bound": v.get("bound", "hbm"), "frac": v["frac"],
+                                          "achieved": v["achieved_GBps"], "peak": hbm_peak,
+                                          "unit": "GB/s"}
+                                      for k, v in named.items() if "f32" not in k}
         if e2e:
             line["e2e"] = e2e
         if cpu_line:

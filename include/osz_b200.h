@@ -191,6 +191,15 @@ int osz_upfirdn_plan_destroy(osz_upfirdn_plan *plan);
  * float64 (osz_upfirdn_plan_compute tells). */
 int osz_upfirdn_plan_set_compute(osz_upfirdn_plan *plan, int compute);
 int osz_upfirdn_plan_compute(const osz_upfirdn_plan *plan);
+/* Which float64 decimating kernel (up == 1) the plan runs: OSZ_UFD_AUTO (the
+ * tensor-core one when its tile geometry fits), OSZ_UFD_POLYPHASE (CUDA-core
+ * polyphase filter with register sliding windows) or OSZ_UFD_MMA (banded
+ * Toeplitz product on the FP64 tensor cores, mma.sync m8n8k4).  Both evaluate
+ * the same sum; they differ in summation order only.  osz_upfirdn_plan_kernel
+ * returns the one that will run (OSZ_UFD_GENERAL for up > 1). */
+enum { OSZ_UFD_AUTO = 0, OSZ_UFD_POLYPHASE = 1, OSZ_UFD_MMA = 2, OSZ_UFD_GENERAL = 3 };
+int osz_upfirdn_plan_set_kernel(osz_upfirdn_plan *plan, int kernel);
+int osz_upfirdn_plan_kernel(const osz_upfirdn_plan *plan);
 /* Global output sample j of the resampled recording is
  *   y[j] = sum_k h'[j*down + half - k*up] * x[k],  half = (ntaps-1)/2
  * (scipy's resample_poly after its pre-pad/pre-remove bookkeeping).  This call

@@ -65,6 +65,8 @@ SIGNATURES = {
                                      _vp]),
     "osz_upfirdn_plan_set_compute": (c_int, [_vp, c_int]),
     "osz_upfirdn_plan_compute": (c_int, [_vp]),
+    "osz_upfirdn_plan_set_kernel": (c_int, [_vp, c_int]),
+    "osz_upfirdn_plan_kernel": (c_int, [_vp]),
     "osz_spec_plan_create": (c_int, [POINTER(_vp), c_int, c_int, _dp, c_int, c_double]),
     "osz_spec_plan_destroy": (c_int, [_vp]),
     "osz_spec_plan_path": (c_int, [_vp]),

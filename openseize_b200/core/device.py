@@ -558,7 +558,9 @@ class TfPlan(_Plan):
 class UpfirdnPlan(_Plan):
     _destroy = "osz_upfirdn_plan_destroy"
 
-    def __init__(self, h, up, down, compute="float64"):
+    KERNELS = ("auto", "polyphase", "mma", "general")
+
+    def __init__(self, h, up, down, compute="float64", kernel="auto"):
         super().__init__()
         require_cuda()
         arr, ptr = _abi.as_double_array(h)
@@ -566,6 +568,13 @@ class UpfirdnPlan(_Plan):
         rc = _abi.load().osz_upfirdn_plan_create(ctypes.byref(self.handle), ptr, self.ntaps,
                                                  self.up, self.down)
         _abi.check(rc, "upfirdn_plan_create")
+        if kernel != "auto":
+            _abi.check(_abi.load().osz_upfirdn_plan_set_kernel(self.handle,
+                                                               self.KERNELS.index(kernel)),
+                       "upfirdn_plan_set_kernel")
+        # the float64 decimating kernel that will run: "mma" (FP64 tensor cores) |
+        # "polyphase" (CUDA cores) | "general" (up > 1)
+        self.kernel = self.KERNELS[_abi.load().osz_upfirdn_plan_kernel(self.handle)]
         if compute == "float32":
             _abi.check(_abi.load().osz_upfirdn_plan_set_compute(self.handle, 1),
                        "upfirdn_plan_set_compute")

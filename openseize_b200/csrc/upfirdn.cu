@@ -355,6 +355,152 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
     cp_async_wait<0>();
 }
 
+// ---- decimator on the FP64 tensor cores (DMMA) -----------------------------------
+// north_star allows tensor cores for an FIR "only if a Toeplitz-GEMM formulation is
+// shown to win".  Measured on B200 (tools/microbench/dmma_rate.cu, profiles/
+// r02_microbench.md): mma.sync.m8n8k4.f64 sustains 63 of 64 FMA lanes/clk/SM with
+// both operands streamed from shared memory, a DFMA FIR loop 43-50 (its third
+// register operand and one LDS per 8 DFMA are what cap it).  So the decimating
+// filter is evaluated as a banded Toeplitz product:
+//
+//   C[i][t] = out[J0 + i*S + 8*tau + t]              (8 x 8 tile, i = segment of S outputs)
+//           = sum_w  x[base + (i*S + 8*tau)*M + w] * g[w - t*M],      0 <= w < K + 7*M
+//
+// with the sum over w taken phase by phase, four taps of one phase per MMA:
+//   w = p + (4*s + q)*M     ->   A[i][q] = Xp[i*S + 8*tau + 4*s + q],  Xp[n] = x[base + p + n*M]
+//                                B[q][t] = gp[p][4*s + q - t]          (zero outside the taps)
+// A depends on (tau, s) only through 2*tau + s, so a warp that owns tiles tau and
+// tau+1 loads ONE new A fragment per k-step and reuses it two steps later; B is one
+// LDS.64 per k-step shared by both tiles: 2 LDS per 2 DMMA (512 FMA).
+// The 8 rows of A are 8 segments of ONE channel's time axis: the input tile stays
+// time-contiguous in shared memory (no phase scatter), segment i at pitch
+// P = S*M + pad doubles, pad chosen so that the 16 lanes of a half warp
+// (g*P + q*M) hit 16 different banks.  Useful fraction of the MMA work:
+// K / sum_p 4*ceil((Q_p + 7) / 4)  (86 % at 1231 taps, M = 25; 70 % at 561 taps).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct UfdMmaGeom {
+    int K, M, half;
+    int S;            // outputs per segment (16 * WT)
+    int SM;           // S * M: input samples per segment
+    int P;            // segment pitch in shared memory (doubles)
+    int total_len;    // input samples a tile touches (8 segments + reach)
+    int ldq;          // doubles per phase row of the padded tap table
+    int pbeg[5];      // phases [pbeg[k], pbeg[k+1]) belong to k-split k
+};
+
+template <int WT, int KS>
+__global__ void __launch_bounds__(WT *KS * 32, 2)
+upfirdn_mma_kernel(const UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx, int64_t x_first,
+                   int64_t x_len, int64_t out_first, int64_t n_out,
+                   const double *__restrict__ gpad /* [M][ldq]: 7 zeros, taps of the phase, zeros */,
+                   const int *__restrict__ ksteps /* [M] k-steps of each phase */,
+                   double *__restrict__ y, int64_t ldy) {
+    constexpr int NT = WT * KS * 32;
+    extern __shared__ __align__(16) double smem_mma[];
+    const int M = gm.M, SM = gm.SM, P = gm.P, S = gm.S;
+    const int nseg = (gm.total_len + SM - 1) / SM;
+    double *xs = smem_mma;                                   // nseg * P
+    double *gs = xs + (size_t)nseg * P;                      // M * ldq
+    double *red = gs + (size_t)M * gm.ldq;                   // (KS - 1) * 8 * S
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int wt = warp % WT, wk = warp / WT;
+    const int g = lane >> 2, q = lane & 3;
+    const int64_t row = blockIdx.y;
+    const int64_t o0 = (int64_t)blockIdx.x * (8 * S);        // tile start, relative to out_first
+    const int64_t rel0 = (out_first + o0) * M + gm.half - (gm.K - 1) - x_first;
+    const double *xr = x + row * ldx;
+
+    // ---- stage the tile: coalesced, time-contiguous, zero outside the supplied window
+    const bool interior = rel0 >= 0 && rel0 + gm.total_len <= x_len;
+    for (int seg = 0; seg < nseg; ++seg) {
+        const int len = min(SM, gm.total_len - seg * SM);
+        const double *src = xr + rel0 + (int64_t)seg * SM;
+        double *dst = xs + (size_t)seg * P;
+        if (interior) {
+            int e = tid;
+            for (; e + 7 * NT < len; e += 8 * NT) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_stream(src + e + u * NT);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[e + u * NT] = v[u];
+            }
+            for (; e < len; e += NT) dst[e] = ld_stream(src + e);
+        } else {
+            for (int e = tid; e < len; e += NT) {
+                const int64_t gi = rel0 + (int64_t)seg * SM + e;
+                dst[e] = (gi >= 0 && gi < x_len) ? ld_stream(xr + gi) : 0.0;
+            }
+        }
+    }
+    for (int i = tid; i < M * gm.ldq; i += NT) gs[i] = gpad[i];
+    __syncthreads();
+
+    // ---- banded Toeplitz product on the tensor cores
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;       // tiles tau = 2 wt, 2 wt + 1
+    const int pad = P - SM;
+    const double *xrow = xs + (size_t)g * P;
+    auto fetch = [&](int r) {       // sample at in-segment offset r of segment g (r may run past it)
+        const int cross = (r >= SM) + (r >= 2 * SM) + (r >= 3 * SM);
+        return xrow[r + cross * pad];
+    };
+    const int p_lo = gm.pbeg[wk], p_hi = gm.pbeg[wk + 1];
+    const int step = 4 * M;
+    for (int p = p_lo; p < p_hi; ++p) {
+        const int ns = ksteps[p];
+        const double *gp = gs + (size_t)p * gm.ldq + 7 + q - g;
+        int r = p + (16 * wt + q) * M;
+        double fa = fetch(r), fb = fetch(r + step);
+        r += 2 * step;
+#pragma unroll 3
+        for (int st = 0; st < ns; ++st) {
+            const double fc = fetch(r);
+            const double b = gp[4 * st];
+            dmma884(c00, c01, fa, b);
+            dmma884(c10, c11, fc, b);
+            fa = fb;
+            fb = fc;
+            r += step;
+        }
+    }
+    // ---- combine the k-splits and store: thread holds outputs g*S + 8*tau + 2*q + {0, 1}
+    const int oa = g * S + 16 * wt + 2 * q;
+    if (KS > 1) {
+        if (wk > 0) {
+            double *rd = red + (size_t)(wk - 1) * 8 * S;
+            rd[oa] = c00;
+            rd[oa + 1] = c01;
+            rd[oa + 8] = c10;
+            rd[oa + 9] = c11;
+        }
+        __syncthreads();
+        if (wk == 0) {
+#pragma unroll
+            for (int k = 0; k < KS - 1; ++k) {
+                const double *rd = red + (size_t)k * 8 * S;
+                c00 += rd[oa];
+                c01 += rd[oa + 1];
+                c10 += rd[oa + 8];
+                c11 += rd[oa + 9];
+            }
+        }
+    }
+    if (wk == 0) {
+        double *yr = y + row * ldy + o0;
+        if (o0 + oa < n_out) st_stream(yr + oa, c00);
+        if (o0 + oa + 1 < n_out) st_stream(yr + oa + 1, c01);
+        if (o0 + oa + 8 < n_out) st_stream(yr + oa + 8, c10);
+        if (o0 + oa + 9 < n_out) st_stream(yr + oa + 9, c11);
+    }
+}
+
 __global__ void upfirdn_general_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first,
                                        int64_t x_len, int64_t out_first, int64_t n_out, int K,
                                        int L, int M, int half,
@@ -399,7 +545,102 @@ struct osz_upfirdn_plan {
     size_t smem2 = 0;
     double *d_gphase2 = nullptr;   // [down][QB*8], zero padded
     int tap_slot = -1, tap_len = 0; // the same taps in constant memory (c_ufd_taps)
+    // tensor-core (DMMA) decimator
+    bool mma = false;
+    int kernel = OSZ_UFD_AUTO;     // osz_upfirdn_plan_set_kernel
+    UfdMmaGeom mg{};
+    int mma_wt = 0;
+    size_t smem_mma = 0;
+    double *d_gpad = nullptr;      // [down][ldq]
+    int *d_ksteps = nullptr;       // [down]
 };
+
+template <int WT, int KS>
+static int launch_mma(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
+                      int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out, double *y,
+                      int64_t ldy, cudaStream_t st) {
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_mma_kernel<WT, KS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mma));
+    const int64_t per_tile = 8 * (int64_t)p->mg.S;
+    dim3 grid((unsigned)((n_out + per_tile - 1) / per_tile), (unsigned)rows);
+    upfirdn_mma_kernel<WT, KS><<<grid, WT * KS * 32, p->smem_mma, st>>>(
+        p->mg, x, ldx, x_first, x_len, out_first, n_out, p->d_gpad, p->d_ksteps, y, ldy);
+    OSZ_LAUNCHED("upfirdn_mma_kernel");
+    return OSZ_OK;
+}
+
+// Geometry of the tensor-core decimator for K taps, decimation M: the largest
+// segment length S in {64, 48, 32, 16} whose tile (8 segments + reach, padded tap
+// table, k-split scratch) fits two CTAs per SM.
+static bool mma_geometry(int K, int M, UfdMmaGeom *gm, int *wt_out, size_t *smem_out,
+                         std::vector<int> *ksteps_out) {
+    const int Q = (K + M - 1) / M;
+    std::vector<int> ks(M);
+    int smax = 0;
+    long total_steps = 0;
+    for (int p = 0; p < M; ++p) {
+        const int qp = p <= (K - 1) % M ? (K - 1) / M + 1 : (K - 1) / M;   // taps of phase p
+        ks[p] = qp > 0 ? (qp + 7 + 3) / 4 : 0;
+        if (ks[p] > smax) smax = ks[p];
+        total_steps += ks[p];
+    }
+    (void)Q;
+    const int KSPLIT = 2;
+    for (int S : {64, 48, 32, 16}) {
+        const int WT = S / 16;
+        const int SM = S * M;
+        // in-segment sample offsets run up to r_max (newest fragment of the last step)
+        const int nmax = 16 * (WT - 1) + 4 * (smax + 1) + 3;
+        const int row_len = (M - 1) + nmax * M + 1;
+        if (row_len > 4 * SM) continue;                   // at most three pad crossings
+        const int total_len = 7 * SM + row_len;
+        int best_pad = 0, best_score = -1;
+        for (int pad = 0; pad < 16; ++pad) {
+            bool seen[16] = {false};
+            int score = 0;
+            for (int g = 0; g < 4; ++g)
+                for (int q = 0; q < 4; ++q) {
+                    const int b = (int)(((long)g * (SM + pad) + (long)q * M) % 16);
+                    if (!seen[b]) {
+                        seen[b] = true;
+                        ++score;
+                    }
+                }
+            if (score > best_score) {
+                best_score = score;
+                best_pad = pad;
+            }
+        }
+        const int P = SM + best_pad;
+        const int nseg = (total_len + SM - 1) / SM;
+        const int ldq = 7 + 4 * smax + 4;
+        const size_t smem = ((size_t)nseg * P + (size_t)M * ldq + (size_t)(KSPLIT - 1) * 8 * S) * 8;
+        if (smem > 110 * 1024) continue;
+        gm->K = K;
+        gm->M = M;
+        gm->half = (K - 1) / 2;
+        gm->S = S;
+        gm->SM = SM;
+        gm->P = P;
+        gm->total_len = total_len;
+        gm->ldq = ldq;
+        // split the phases between the k-splits by k-steps
+        gm->pbeg[0] = 0;
+        long acc = 0;
+        int k = 1;
+        for (int p = 0; p < M && k < KSPLIT; ++p) {
+            acc += ks[p];
+            if (acc * KSPLIT >= total_steps * k) gm->pbeg[k++] = p + 1;
+        }
+        for (; k <= 4; ++k) gm->pbeg[k] = M;
+        gm->pbeg[KSPLIT] = M;
+        *wt_out = WT;
+        *smem_out = smem;
+        *ksteps_out = ks;
+        return true;
+    }
+    return false;
+}
 
 template <int R>
 static int launch_dec(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
@@ -545,6 +786,22 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
             }
         }
     }
+    if (ok && up == 1 && down >= 2 && p->R) {
+        std::vector<int> ks;
+        if (mma_geometry(K, down, &p->mg, &p->mma_wt, &p->smem_mma, &ks)) {
+            const int M = down, ldq = p->mg.ldq;
+            // gpad[p][7 + v] = g[p + v*M], g[j] = h'[K-1-j]
+            std::vector<double> gp((size_t)M * ldq, 0.0);
+            for (int j = 0; j < K; ++j) gp[(size_t)(j % M) * ldq + 7 + j / M] = hs[K - 1 - j];
+            ok = cudaMalloc(&p->d_gpad, gp.size() * 8) == cudaSuccess &&
+                 cudaMemcpy(p->d_gpad, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice) ==
+                     cudaSuccess &&
+                 cudaMalloc(&p->d_ksteps, ks.size() * sizeof(int)) == cudaSuccess &&
+                 cudaMemcpy(p->d_ksteps, ks.data(), ks.size() * sizeof(int),
+                            cudaMemcpyHostToDevice) == cudaSuccess;
+            p->mma = ok;
+        }
+    }
     if (!ok) {
         osz_upfirdn_plan_destroy(p);
         return fail(OSZ_ERR_CUDA, "osz_upfirdn_plan_create: device upload failed");
@@ -586,12 +843,38 @@ int osz_upfirdn_plan_set_compute(osz_upfirdn_plan *p, int compute) {
 }
 int osz_upfirdn_plan_compute(const osz_upfirdn_plan *p) { return p ? p->compute : 0; }
 
+static int ufd_use_mma_default() {
+    static const int v = [] {
+        const char *e = getenv("OSZ_UFD_MMA");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+int osz_upfirdn_plan_set_kernel(osz_upfirdn_plan *p, int kernel) {
+    if (!p || kernel < OSZ_UFD_AUTO || kernel > OSZ_UFD_MMA)
+        return fail(OSZ_ERR_ARG, "osz_upfirdn_plan_set_kernel: bad arguments");
+    if (kernel == OSZ_UFD_MMA && !p->mma)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_upfirdn_plan_set_kernel: no tensor-core geometry "
+                                         "for this filter (up > 1, or the tile does not fit)");
+    p->kernel = kernel;
+    return OSZ_OK;
+}
+int osz_upfirdn_plan_kernel(const osz_upfirdn_plan *p) {
+    if (!p) return 0;
+    if (!p->R) return OSZ_UFD_GENERAL;
+    if (p->kernel == OSZ_UFD_MMA || (p->kernel == OSZ_UFD_AUTO && p->mma && ufd_use_mma_default()))
+        return OSZ_UFD_MMA;
+    return OSZ_UFD_POLYPHASE;
+}
+
 int osz_upfirdn_plan_destroy(osz_upfirdn_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_h);
     cudaFree(p->d_gphase);
     cudaFree(p->d_gphasef);
     cudaFree(p->d_gphase2);
+    cudaFree(p->d_gpad);
+    cudaFree(p->d_ksteps);
     if (p->tap_slot >= 0) ufd_slot_free(p->tap_slot, p->tap_len);
     delete p;
     return OSZ_OK;
@@ -619,6 +902,14 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
                 return launch_dec_f32<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
             default:
                 return launch_dec_f32<4>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+        }
+    }
+    if (osz_upfirdn_plan_kernel(p) == OSZ_UFD_MMA && !(p->dec2 && use_dec2)) {
+        switch (p->mma_wt) {
+            case 4: return launch_mma<4, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+            case 3: return launch_mma<3, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+            case 2: return launch_mma<2, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+            default: return launch_mma<1, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
         }
     }
     if (p->dec2 && use_dec2)

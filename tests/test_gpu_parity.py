@@ -201,16 +201,24 @@ def test_resample_oracle_sweep():
     pc.resample_oracle_sweep()
 
 
+@pytest.mark.parametrize("kernel", ["auto", "polyphase"])
 @pytest.mark.parametrize("up,down,ntaps", [(1, 2, 41), (1, 20, 449), (1, 25, 561), (1, 60, 1301),
-                                           (1, 300, 901), (3, 7, 155), (5, 1, 99), (2, 3, 64)])
-def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps):
-    """Decimating (R = 16 / 8 / 4 tiles) and general kernels against one global
-    resample_poly call, windows that start and end inside the recording."""
+                                           (1, 300, 901), (3, 7, 155), (5, 1, 99), (2, 3, 64),
+                                           (1, 25, 1231), (1, 3, 7), (1, 4, 200), (1, 16, 333),
+                                           (1, 10, 1)])
+def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps, kernel):
+    """Decimating (tensor-core banded-Toeplitz and CUDA-core polyphase, R = 16 / 8 / 4
+    tiles) and general kernels against one global resample_poly call, windows that
+    start and end inside the recording."""
     rng = np.random.default_rng(ntaps)
     h = sps.firwin(ntaps, 1.0 / max(up, down))
     x = rng.standard_normal((3, 40000))
     ref = sps.resample_poly(x, up, down, axis=-1, window=h)
-    plan = dv.UpfirdnPlan(h, up, down)
+    plan = dv.UpfirdnPlan(h, up, down, kernel=kernel)
+    if up > 1 or down == 1:
+        assert plan.kernel == "general"
+    elif kernel == "polyphase":
+        assert plan.kernel == "polyphase"
     n_total = ref.shape[-1]
     y = plan.run(_dev(dv, x), 0, 0, n_total).cpu().numpy()
     assert relerr(y, ref) < 1e-12

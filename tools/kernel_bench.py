@@ -89,22 +89,30 @@ def main(which):
             import oracle
 
             h = oracle.resample_filter(1, M, fs)
-            plan = dv.UpfirdnPlan(h, 1, M)
             x = rnd(rows, n)
             nout = n // M - 64
-            report("downsample M=%d taps=%d" % (M, len(h)),
-                   timeit(lambda: plan.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
+            for kern in ("mma", "polyphase"):
+                plan = dv.UpfirdnPlan(h, 1, M, kernel=kern)
+                report("downsample M=%d taps=%d %s" % (M, len(h), plan.kernel),
+                       timeit(lambda: plan.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
             p32 = dv.UpfirdnPlan(h, 1, M, "float32")
             report("downsample M=%d taps=%d float32 compute" % (M, len(h)),
                    timeit(lambda: p32.run(x, 0, 32, nout)), rows * n, 8 * (1 + 1 / M))
             del x
         # the FIR(671) * anti-alias(561) cascade of config 5 as ONE decimating filter
         h = np.convolve(oracle.resample_filter(1, 25, 30000), Kaiser(500, 600, 30000).coeffs)
-        plan = dv.UpfirdnPlan(h, 1, 25)
         x = rnd(rows, n)
         nout = n // 25 - 128
-        report("fused FIR+downsample M=25 taps=%d" % len(h),
-               timeit(lambda: plan.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
+        for kern in ("mma", "polyphase"):
+            plan = dv.UpfirdnPlan(h, 1, 25, kernel=kern)
+            report("fused FIR+downsample M=25 taps=%d %s" % (len(h), plan.kernel),
+                   timeit(lambda: plan.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
+        for r2 in (32, 64, 128):
+            x2 = rnd(r2, n)
+            plan = dv.UpfirdnPlan(h, 1, 25)
+            report("fused FIR+downsample rows=%d %s" % (r2, plan.kernel),
+                   timeit(lambda: plan.run(x2, 0, 64, nout)), r2 * n, 8 * (1 + 1 / 25))
+            del x2
         p32 = dv.UpfirdnPlan(h, 1, 25, "float32")
         report("fused FIR+downsample M=25 taps=%d float32 compute" % len(h),
                timeit(lambda: p32.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
