@@ -210,6 +210,40 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *plan, const double *x_dev, int6
                          int64_t rows, int64_t x_first, int64_t x_len, int64_t out_first,
                          int64_t n_out, double *y_dev, int64_t ldy, void *stream);
 
+/* ---- fused IIR pass + decimating FIR: the LAST pass of nm.sosfiltfilt / nm.filtfilt
+ *      (the backward scipy.signal.sosfilt / lfilter call, core/numerical.py:402,410,
+ *      511,519) -- or a forward nm.sosfilt / nm.lfilter pass (:334,445) -- followed
+ *      by the oaconvolve (mode 'same', :229-269) and resample_poly (:610,631) calls of
+ *      the two operators a Pipeline composes after it (tools/pipeline.py:109-124).
+ *      The pass output stays in shared memory; the decimating filter (the upfirdn
+ *      plan built from the convolved taps) runs on it on the tensor cores. -------- */
+/* Time spans per row the fused kernel would use (>= 1); 0 = this pair of plans / this
+ * chunk length cannot run fused (run the two kernels separately). */
+int osz_sosdec_spans(const osz_sos_plan *sos, const osz_upfirdn_plan *ufd, int64_t rows,
+                     int64_t n);
+/* x_dev (rows, n): input of the pass; state_dev (rows, nsec, 2): state entering the pass,
+ * replaced by the state leaving it; reverse: the pass runs from the chunk's last sample to
+ * its first; A: global index of the chunk's first sample.  Column c of y_dev is global
+ * output out_first + c of  y[j] = sum_k h'[j*down + half - k] * p[k]  (p = the pass output,
+ * as in osz_upfirdn_exec_f64); written are the outputs whose whole window of ntaps samples
+ * lies inside one span of the chunk.  edges_dev (rows, nspan, 2, ntaps-1) receives the first
+ * and last ntaps-1 pass outputs of every span (real-time order) for
+ * osz_sosdec_boundary_f64. */
+int osz_sosdec_exec_f64(const osz_sos_plan *sos, const osz_upfirdn_plan *ufd, const double *x_dev,
+                        int64_t ldx, int64_t rows, int64_t n, int reverse, double *state_dev,
+                        int nspan, int64_t A, double *y_dev, int64_t ldy, int64_t out_first,
+                        int64_t n_out, double *edges_dev, void *stream);
+/* The outputs osz_sosdec_exec_f64 left out: windows that straddle the chunk's start
+ * (prev_tail_dev: (rows, ntaps-1) last pass outputs of the previous chunk, row pitch
+ * prev_ld; NULL = recording start, zeros before it), a boundary between two spans, or --
+ * with has_end -- the chunk's end (recording end: zeros after it).  Only outputs
+ * j_min <= j <= j_max are written. */
+int osz_sosdec_boundary_f64(const osz_upfirdn_plan *ufd, const double *edges_dev, int nspan,
+                            int reverse, const double *prev_tail_dev, int64_t prev_ld,
+                            int has_end, int64_t rows, int64_t n, int64_t A, double *y_dev,
+                            int64_t ldy, int64_t out_first, int64_t n_out, int64_t j_min,
+                            int64_t j_max, void *stream);
+
 /* ---- windowed DFT: replaces detrend + window + rfft + scale of
  *      nm.modified_dft / nm.periodogram (core/numerical.py:691-716,781-794)
  *      applied to the sliding windows of nm._spectra_estimatives (:817-849) */

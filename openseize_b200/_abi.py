@@ -65,6 +65,11 @@ SIGNATURES = {
                                      _vp]),
     "osz_upfirdn_plan_set_compute": (c_int, [_vp, c_int]),
     "osz_upfirdn_plan_compute": (c_int, [_vp]),
+    "osz_sosdec_spans": (c_int, [_vp, _vp, _i64, _i64]),
+    "osz_sosdec_exec_f64": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_int, _vp, c_int, _i64, _vp,
+                                    _i64, _i64, _i64, _vp, _vp]),
+    "osz_sosdec_boundary_f64": (c_int, [_vp, _vp, c_int, c_int, _vp, _i64, c_int, _i64, _i64, _i64,
+                                        _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "osz_upfirdn_plan_set_kernel": (c_int, [_vp, c_int]),
     "osz_upfirdn_plan_kernel": (c_int, [_vp]),
     "osz_spec_plan_create": (c_int, [POINTER(_vp), c_int, c_int, _dp, c_int, c_double]),

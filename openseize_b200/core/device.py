@@ -602,6 +602,49 @@ class UpfirdnPlan(_Plan):
         return out
 
 
+# --------------------------------------------------------------------------
+# fused IIR pass + decimating FIR (csrc/sosdec.cu)
+# --------------------------------------------------------------------------
+def sosdec_spans(sos_plan, ufd_plan, rows, n):
+    """Time spans per row the fused kernel would use; 0 = cannot run fused."""
+    return int(_abi.load().osz_sosdec_spans(sos_plan.handle, ufd_plan.handle, int(rows), int(n)))
+
+
+def sosdec_exec(sos_plan, ufd_plan, x, reverse, state, nspan, first, out, out_first):
+    """Run the pass over x (rows, n) and decimate its output on chip.  Writes the
+    outputs whose window lies inside one span into ``out`` (column c = global output
+    out_first + c) and returns the (rows, nspan, 2, K-1) edge samples."""
+    rows, n = x.shape
+    k1 = ufd_plan.ntaps - 1
+    edges = empty((rows, int(nspan), 2, k1))
+    xp, ldx = _rows_ptr(x)
+    yp, ldy = _rows_ptr(out)
+    rc = _launch("sos_dec", 8 * rows * n + 8 * rows * out.shape[1],
+                 _abi.load().osz_sosdec_exec_f64, sos_plan.handle, ufd_plan.handle, xp, ldx, rows,
+                 n, int(bool(reverse)), _vp(state.data_ptr()), int(nspan), int(first), yp, ldy,
+                 int(out_first), int(out.shape[1]), _vp(edges.data_ptr()), _cur_stream())
+    _abi.check(rc, "sosdec_exec")
+    return edges
+
+
+def sosdec_boundary(ufd_plan, edges, reverse, prev_tail, has_end, n, first, out, out_first, j_min,
+                    j_max):
+    """The outputs straddling the chunk's start, span boundaries and (has_end) the
+    recording's end.  prev_tail: (rows, K-1) view (row stride free) or None."""
+    rows, nspan = edges.shape[0], edges.shape[1]
+    yp, ldy = _rows_ptr(out)
+    if prev_tail is not None:
+        assert prev_tail.stride(1) == 1
+        pt, pld = _vp(prev_tail.data_ptr()), int(prev_tail.stride(0))
+    else:
+        pt, pld = _vp(0), 0
+    rc = _launch("sos_dec_edges", 0, _abi.load().osz_sosdec_boundary_f64, ufd_plan.handle,
+                 _vp(edges.data_ptr()), int(nspan), int(bool(reverse)), pt, pld, int(bool(has_end)),
+                 rows, int(n), int(first), yp, ldy, int(out_first), int(out.shape[1]), int(j_min),
+                 int(j_max), _cur_stream())
+    _abi.check(rc, "sosdec_boundary")
+
+
 class SpecPlan(_Plan):
     _destroy = "osz_spec_plan_destroy"
 

@@ -750,6 +750,19 @@ class _FusedFirDecimator(_Resampler):
                            dv.zeros_rows(rows, zr) if zr else None])
         return self.fir_plan.run(buf, u1 - u0)
 
+    def left_edge(self, window, w_first, o_lo, e, out):
+        """Outputs [o_lo, e), e <= j_lo: they see the 'same'-mode truncation of the
+        intermediate signal at the recording's start -- two unfused kernels."""
+        u1 = (e - 1) * self.M + self.half2 + 1
+        y = self._fir_span(window, w_first, 0, u1)
+        self.dec_plan.run(y, 0, o_lo, e - o_lo, out=out)
+
+    def right_edge(self, window, w_first, s0, o_hi, out):
+        """Outputs [s0, o_hi), s0 > j_hi: the truncation at the recording's end."""
+        u0 = max(0, s0 * self.M + self.half2 - (self.k2 - 1))
+        y = self._fir_span(window, w_first, u0, self.ny)
+        self.dec_plan.run(y, u0, s0, o_hi - s0, out=out)
+
     def compute(self, window, w_first, o_lo, o_hi, out):
         if out is None:
             out = dv.empty((window.shape[0], o_hi - o_lo))
@@ -758,14 +771,10 @@ class _FusedFirDecimator(_Resampler):
             self.plan.run(window, w_first, a, b - a, out=out[:, a - o_lo:b - o_lo])
         if o_lo < self.j_lo:                       # left edge of the recording
             e = min(o_hi, self.j_lo)
-            u1 = (e - 1) * self.M + self.half2 + 1
-            y = self._fir_span(window, w_first, 0, u1)
-            self.dec_plan.run(y, 0, o_lo, e - o_lo, out=out[:, :e - o_lo])
+            self.left_edge(window, w_first, o_lo, e, out[:, :e - o_lo])
         if o_hi > self.j_hi + 1:                   # right edge
             s0 = max(o_lo, self.j_hi + 1)
-            u0 = max(0, s0 * self.M + self.half2 - (self.k2 - 1))
-            y = self._fir_span(window, w_first, u0, self.ny)
-            self.dec_plan.run(y, u0, s0, o_hi - s0, out=out[:, s0 - o_lo:])
+            self.right_edge(window, w_first, s0, o_hi, out[:, s0 - o_lo:])
         return out
 
 
@@ -796,6 +805,125 @@ def _fusable_fir(pro, L, M, ntaps2, axis):
     return taps
 
 
+# chunks that went through the fused IIR + FIR + decimator kernel / its unfused
+# fallback (diagnostics for tests and bench.py)
+FUSED_STATS = {"fused_chunks": 0, "fallback_chunks": 0}
+
+
+def _fusable_iir(pro, axis):
+    """(input producer, cascade, zi) when ``pro`` is an openseize_b200 forward-backward
+    IIR stage -- ``sosfiltfilt``, or ``filtfilt`` of order <= 2 (``Notch``) -- whose
+    last pass can run inside the decimator that consumes it, else None."""
+    import os
+
+    if os.environ.get("OSZ_FUSE_IIR", "1") == "0":
+        return None
+    if not isinstance(pro, GenProducer) or pro.kwargs:
+        return None
+    func = pro.data
+    if not isinstance(func, functools.partial) or func.keywords:
+        return None
+    if func.func is not sosfiltfilt and func.func is not filtfilt:
+        return None
+    if len(func.args) != 3:
+        return None
+    inner, coeffs, iir_axis = func.args
+    nd = len(pro.shape)
+    if not isinstance(inner, Producer) or normalize_axis(iir_axis, nd) != normalize_axis(axis, nd):
+        return None
+    if func.func is sosfiltfilt:
+        cascade = _Cascade(coeffs)
+        zi = sps.sosfilt_zi(cascade.sos)
+    else:
+        if _ba_order(coeffs) > 2:
+            return None
+        z = np.atleast_1d(sps.lfilter_zi(*coeffs))        # numerical.py:487
+        cascade = _Cascade(_ba_to_sos(coeffs))
+        zi = np.zeros((1, 2))
+        zi[0, :len(z)] = z
+    if len(cascade.plans) != 1:
+        return None
+    return inner, cascade, zi
+
+
+def _iir_fir_decimate_device(iir, fir_pro, fir_taps, h, M, axis, _out=None):
+    """``downsample(FIR_same(IIR_dephase(x)))`` with the IIR's backward pass, the FIR
+    and the decimator as ONE kernel per chunk: the forward pass
+    writes F, the fused kernel reads it backwards, keeps the filtered samples in
+    shared memory and emits only the decimated outputs -- the full-rate backward
+    output (8 bytes written + 8 read per sample) never reaches HBM.
+
+    Chunk semantics are the reference's (numerical.py:338-411,449-520): one global
+    forward pass, each chunk's backward pass started from the state the look-ahead
+    over the next forward chunk leaves (see _filtfilt_device).  Outputs whose window
+    straddles two chunks (or two time spans of a chunk) are computed from the K-1
+    edge samples every span exports; the recording's first and last few outputs, which
+    see the 'same'-mode truncation, by the unfused kernels on those edge samples."""
+    inner, cascade, zi = iir
+    stage = _FusedFirDecimator(fir_pro, fir_taps, h, M, axis)
+    sos_plan, ufd = cascade.plans[0], stage.plan
+    rows = _layout_of(inner, axis).rows
+    n_in, K, half = stage.nsamp_in, stage.reach, stage.center
+    total_out = dv.ceil_div(n_in, M)
+    st = {"done": 0, "tail": None}
+
+    def emit(F, state, first, last):
+        n = F.shape[1]
+        done = st["done"]
+        j_to = total_out if last else min(total_out, max(done, (first + n - 1 - half) // M + 1))
+        nspan = dv.sosdec_spans(sos_plan, ufd, rows, n) if ufd.kernel == "mma" else 0
+        FUSED_STATS["fused_chunks" if nspan else "fallback_chunks"] += 1
+        if nspan == 0:
+            # chunk too short for the fused tile (or no tensor-core geometry): the
+            # backward pass in full, then the decimator on [previous tail | chunk]
+            y = cascade.run(F, state, reverse=True)
+            tail = st["tail"] if st["tail"] is not None else dv.zeros_rows(rows, K - 1)
+            window = dv.cat_time([tail, y])
+            st["tail"] = window[:, -(K - 1):]
+            st["done"] = j_to
+            if j_to > done:
+                out = _new_rows(_out, rows, j_to - done)
+                return stage.compute(window, first - (K - 1), done, j_to, out)
+            return None
+        out = _new_rows(_out, rows, max(j_to - done, 0))
+        edges = dv.sosdec_exec(sos_plan, ufd, F, True, state[0], nspan, first, out, done)
+        dv.sosdec_boundary(ufd, edges, True, st["tail"], last, n, first, out, done,
+                           max(done, stage.j_lo), min(j_to - 1, stage.j_hi))
+        if done < stage.j_lo and j_to > done:         # the recording's first outputs
+            e = min(j_to, stage.j_lo)
+            stage.left_edge(edges[:, nspan - 1, 0, :], first, done, e, out[:, :e - done])
+        if j_to - 1 > stage.j_hi:                     # ... and its last ones
+            s0 = max(done, stage.j_hi + 1)
+            stage.right_edge(edges[:, 0, 1, :], first + n - (K - 1), s0, j_to, out[:, s0 - done:])
+        st["tail"] = edges[:, 0, 1, :]                # span 0 of a backward pass is the last in time
+        st["done"] = j_to
+        return out if j_to > done else None
+
+    fwd_states, prev, prev_first, pos = None, None, 0, 0
+    for chunk in device_chunks(inner, axis):
+        if fwd_states is None:
+            fwd_states = cascade.state_from_sample(zi, chunk, 0)
+        fwd = cascade.run(chunk, fwd_states)
+        if prev is not None:
+            m = fwd.shape[1]                          # look-ahead, see _filtfilt_device
+            if cascade.settle is not None and cascade.settle < m:
+                m = cascade.settle
+            look = cascade.state_from_sample(zi, fwd, m - 1)
+            cascade.run(fwd[:, :m], look, reverse=True, want_output=False)
+            out = emit(prev, look, prev_first, False)
+            if out is not None:
+                yield out
+        prev, prev_first = fwd, pos
+        pos += chunk.shape[1]
+    if prev is not None:
+        stage.truncate(pos)                           # what arrived is the recording
+        total_out = dv.ceil_div(pos, M)
+        last = cascade.state_from_sample(zi, prev, prev.shape[1] - 1)
+        out = emit(prev, last, prev_first, True)
+        if out is not None:
+            yield out
+
+
 def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs):
     dv.require_cuda()
     nsamp = pro.shape[axis]
@@ -815,6 +943,11 @@ def _polyphase_device(pro, L, M, fs, fir, axis, _out=None, _free=False, **kwargs
     g = int(np.gcd(int(L), int(M)))
     L, M = int(L) // g, int(M) // g
     fir_taps = _fusable_fir(src, L, M, len(h), axis)
+    if fir_taps is not None and _free:
+        iir = _fusable_iir(src.data.args[0], axis)
+        if iir is not None:
+            yield from _iir_fir_decimate_device(iir, src, fir_taps, h, M, axis, _out)
+            return
     stage = (_FusedFirDecimator(src, fir_taps, h, M, axis) if fir_taps is not None
              else _Resampler(src, h, L, M, axis))
     n_in, center, reach = stage.nsamp_in, stage.center, stage.reach

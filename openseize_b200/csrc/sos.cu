@@ -29,35 +29,9 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sos_core.cuh"
 
 namespace osz {
-
-constexpr int SOS_NT = 256;
-constexpr int SOS_T = 32;
-constexpr int SOS_MAXSEC = 16;
-
-struct SosSec {
-    double b0, b1, b2, a1, a2;
-    double g0[SOS_T], g1[SOS_T];
-    double P[5][4];     // M^(2^k), row major
-    double Q[4];        // M^32 (one warp)
-    double A8[4];       // A^8: state transition over one 8-sample sub-piece
-    double A16[4];      // A^16: thread transition of the T = 16 kernel
-};
-struct SosParams {
-    int nsec;
-    int pad_;
-    SosSec sec[SOS_MAXSEC];
-};
-struct SosZi {
-    double zi[SOS_MAXSEC][2];
-};
-
-__device__ __forceinline__ void mat_apply(const double (&m)[4], double a0, double a1, double &o0,
-                                          double &o1) {
-    o0 = fma(m[0], a0, m[1] * a1);
-    o1 = fma(m[2], a0, m[3] * a1);
-}
 
 // T = samples per thread: 32 for long cascades (less scan work per sample), 16
 // for one or two sections, where the kernel is bound by memory latency and the
@@ -75,7 +49,6 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     constexpr int BLK = SOS_NT * T;        // samples per CTA iteration
     constexpr int LD = T + 1;              // padded shared-memory row
     constexpr int LOGT = T == 32 ? 5 : 4;
-    constexpr int NCH = T / 8;             // independent 8-sample chains per thread
     static_assert(T == 32 || T == 16, "T");
     extern __shared__ __align__(16) double buf[];   // SOS_NT * LD
     __shared__ double wtot[2][SOS_NT / 32][2];   // double-buffered by section parity
@@ -153,141 +126,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
 #pragma unroll
         for (int i = 0; i < T; ++i) v[i] = buf[tid * LD + i];
 
-        const int pstar = off >> LOGT, ioff = off & (T - 1);
-        for (int s = 0; s < nsec; ++s) {
-            const SosSec &c = prm.sec[s];
-            const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
-            double z0 = 0.0, z1 = 0.0;
-            double zs0[NCH - 1], zs1[NCH - 1];     // zero-state finals of sub-pieces 0 .. NCH-2
-            if (blk != 0) {
-                // NCH independent 8-sample chains per thread (a single chain left
-                // the FP64 pipe 2/3 idle waiting on its own results): sub-piece 0
-                // starts from the thread's entering state (the carry for thread
-                // 0, else zero), the others from zero and are fixed up in-thread
-                // with the same zero-input tables.
-                double za0[NCH], za1[NCH];
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) za0[j] = za1[j] = 0.0;
-                if (tid == 0) {
-                    za0[0] = carry[s][0];
-                    za1[0] = carry[s][1];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j) {
-                        const double xi = v[8 * j + i];
-                        const double yi = fma(b0, xi, za0[j]);
-                        za0[j] = fma(na1, yi, fma(b1, xi, za1[j]));
-                        za1[j] = fma(na2, yi, b2 * xi);
-                        v[8 * j + i] = yi;
-                    }
-                }
-                // thread-final state for a zero entering state: the sub-pieces' final
-                // states chained through A^8.  Their OUTPUTS are not fixed up here: every
-                // sub-piece gets one zero-input correction below, from its true entering
-                // state, once the scan has delivered the thread's.
-                double e0 = za0[0], e1 = za1[0];
-#pragma unroll
-                for (int j = 1; j < NCH; ++j) {
-                    const double t0 = fma(c.A8[0], e0, c.A8[1] * e1) + za0[j];
-                    const double t1 = fma(c.A8[2], e0, c.A8[3] * e1) + za1[j];
-                    e0 = t0;
-                    e1 = t1;
-                }
-                z0 = e0;
-                z1 = e1;
-#pragma unroll
-                for (int j = 0; j < NCH - 1; ++j) {
-                    zs0[j] = za0[j];
-                    zs1[j] = za1[j];
-                }
-            } else {
-                const bool inj = tid == pstar;
-                const double c0 = carry[s][0], c1 = carry[s][1];
-#pragma unroll
-                for (int i = 0; i < T; ++i) {
-                    if (inj && i == ioff) {
-                        z0 = c0;
-                        z1 = c1;
-                    }
-                    const double xi = v[i];
-                    const double yi = fma(b0, xi, z0);
-                    z0 = fma(na1, yi, fma(b1, xi, z1));
-                    z1 = fma(na2, yi, b2 * xi);
-                    v[i] = yi;
-                }
-            }
-            // ---- warp-inclusive scan of e_p = M e_{p-1} + f_p, M = A^T:
-            //      M^(2^k) is P[k] for T = 32 and {A16, P[0..3]} for T = 16
-            double f0 = z0, f1 = z1;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const double *pm = T == 32 ? c.P[k] : (k == 0 ? c.A16 : c.P[k - 1]);
-                const double g0 = __shfl_up_sync(0xffffffffu, f0, 1 << k);
-                const double g1 = __shfl_up_sync(0xffffffffu, f1, 1 << k);
-                if (lane >= (1 << k)) {
-                    f0 += fma(pm[0], g0, pm[1] * g1);
-                    f1 += fma(pm[2], g0, pm[3] * g1);
-                }
-            }
-            double (*wt)[2] = wtot[s & 1];
-            if (lane == 31) {
-                wt[warp][0] = f0;
-                wt[warp][1] = f1;
-            }
-            __syncthreads();
-            // ---- state entering this warp (transition over one warp: M^32)
-            const double *qm = T == 32 ? c.Q : c.P[4];
-            double cw0 = 0.0, cw1 = 0.0;
-            for (int u = 0; u < warp; ++u) {
-                const double t0 = fma(qm[0], cw0, qm[1] * cw1) + wt[u][0];
-                const double t1 = fma(qm[2], cw0, qm[3] * cw1) + wt[u][1];
-                cw0 = t0;
-                cw1 = t1;
-            }
-            // ---- true state at the end of this thread's piece
-            const double *lp = lanepow + ((size_t)s * 32 + lane) * 4;
-            const double e0 = f0 + fma(ldg(lp + 0), cw0, ldg(lp + 1) * cw1);
-            const double e1 = f1 + fma(ldg(lp + 2), cw0, ldg(lp + 3) * cw1);
-            // ---- state entering this thread's piece
-            double s0 = __shfl_up_sync(0xffffffffu, e0, 1);
-            double s1 = __shfl_up_sync(0xffffffffu, e1, 1);
-            if (lane == 0) {
-                s0 = cw0;
-                s1 = cw1;
-            }
-            // zero-input response of the entering state (it is exactly zero for
-            // every thread up to and including the one that injected the carry)
-            if (blk != 0) {
-                // sub-piece j enters with E_j: E_0 = the thread's entering state,
-                // E_(j+1) = A^8 E_j + (zero-state final of sub-piece j)
-                double q0 = s0, q1 = s1;
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[8 * j + i] = fma(c.g0[i], q0, fma(c.g1[i], q1, v[8 * j + i]));
-                    if (j + 1 < NCH) {
-                        const double t0 = fma(c.A8[0], q0, c.A8[1] * q1) + zs0[j];
-                        const double t1 = fma(c.A8[2], q0, c.A8[3] * q1) + zs1[j];
-                        q0 = t0;
-                        q1 = t1;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < T; ++i) v[i] = fma(c.g0[i], s0, fma(c.g1[i], s1, v[i]));
-            }
-            if (tid == SOS_NT - 1) {
-                carry[s][0] = e0;
-                carry[s][1] = e1;
-            }
-            // No barrier here: the other wtot buffer takes section s+1's totals, and a
-            // warp can only write this one again (section s+2) after every warp has
-            // passed section s+1's barrier, i.e. has finished reading it.  carry[s] is
-            // next read by thread 0 in the NEXT block, behind that block's barriers.
-        }
+        sos_scan_block<T, 0>(prm, v, blk != 0, off, carry, wtot, lanepow, tid, lane, warp);
         if (WRITE && pos0 + (BLK - off) > keep) {       // block holds samples to store
 #pragma unroll
             for (int i = 0; i < T; ++i) buf[tid * LD + i] = v[i];
@@ -368,6 +207,7 @@ struct osz_sos_plan {
     int T = 32;                     // samples per thread of the kernel this plan uses
     int64_t settle = -1;            // samples after which the start state is forgotten (-1: never)
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
+    double *T16_lanepow = nullptr;  // the same for 16 samples per thread (sosdec.cu)
     // Plans are cached process-wide by their coefficients, so two producers with the
     // same filter may run one plan on two streams at once: a launch owns no mutable
     // plan state.  The per-call scratch (state copy of a time-split launch, per-span
@@ -459,7 +299,7 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         p->T = e ? atoi(e) : 32;
         if (p->T != 16 && p->T != 32) p->T = 32;
     }
-    std::vector<double> lanepow((size_t)nsec * 32 * 4);
+    std::vector<double> lanepow((size_t)nsec * 32 * 4), lanepow16((size_t)nsec * 32 * 4);
     double rmax = 0.0;              // largest pole radius of the cascade
     for (int s = 0; s < nsec; ++s) {
         {
@@ -529,6 +369,16 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
             d[3] = (double)lp.d;
             lp = mul(Mt, lp);
         }
+        const M2 M16 = {c.A16[0], c.A16[1], c.A16[2], c.A16[3]};
+        lp = M16;
+        for (int l = 0; l < 32; ++l) {
+            double *d = &lanepow16[((size_t)s * 32 + l) * 4];
+            d[0] = (double)lp.a;
+            d[1] = (double)lp.b;
+            d[2] = (double)lp.c;
+            d[3] = (double)lp.d;
+            lp = mul(M16, lp);
+        }
     }
     for (int s = nsec; s < SOS_MAXSEC; ++s) p->prm.sec[s] = SosSec{};
     {
@@ -555,7 +405,10 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
     p->settle = settle_samples(p->Tmat, 2 * nsec);
     if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
-            cudaSuccess) {
+            cudaSuccess ||
+        cudaMalloc(&p->T16_lanepow, lanepow16.size() * 8) != cudaSuccess ||
+        cudaMemcpy(p->T16_lanepow, lanepow16.data(), lanepow16.size() * 8,
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
         osz_sos_plan_destroy(p);
         return fail(OSZ_ERR_CUDA, "osz_sos_plan_create: device upload failed");
     }
@@ -566,6 +419,7 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
 int osz_sos_plan_destroy(osz_sos_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_lanepow);
+    cudaFree(p->T16_lanepow);
     for (auto &kv : p->phi) cudaFree(kv.second);
     delete p;
     return OSZ_OK;
@@ -763,6 +617,18 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         else OSZ_SOS_LAUNCH(false, 32, nullptr, nullptr, nullptr);
     }
 #undef OSZ_SOS_LAUNCH
+    return OSZ_OK;
+}
+
+// internal (sosdec.cu): the plan's kernel parameter block
+int osz_sos_plan_params(const osz_sos_plan *p, SosParams *prm, const double **lanepow,
+                        int64_t *settle) {
+    if (!p) return fail(OSZ_ERR_ARG, "osz_sos_plan_params: null plan");
+    if (p->T16_lanepow == nullptr)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_sos_plan_params: no T = 16 tables");
+    *prm = p->prm;
+    *lanepow = p->T16_lanepow;
+    *settle = p->settle;
     return OSZ_OK;
 }
 

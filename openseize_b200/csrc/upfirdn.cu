@@ -19,11 +19,23 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ufd_mma.cuh"
 
 namespace osz {
 
 constexpr int UFD_NT = 256;
 constexpr int UFD_NW = UFD_NT / 32;
+
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst_smem, const void *src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
+}
 
 template <int R>
 __device__ __forceinline__ int ufd_phys(int m) {
@@ -196,17 +208,6 @@ constexpr int UFD2_MAXE = 26;            // staged elements per thread and tile 
 constexpr int UFD2_CONST_DOUBLES = 7168;   // 56 KB of the 64 KB constant bank
 __constant__ double c_ufd_taps[UFD2_CONST_DOUBLES];
 
-__device__ __forceinline__ void cp_async8_zfill(uint32_t dst_smem, const void *src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src),
-                 "r"(valid ? 8 : 0)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPENDING>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
-}
-
 template <int R>
 __global__ void __launch_bounds__(UFD2_NT, 1)
 upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, int64_t x_len,
@@ -377,128 +378,115 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
 // P = S*M + pad doubles, pad chosen so that the 16 lanes of a half warp
 // (g*P + q*M) hit 16 different banks.  Useful fraction of the MMA work:
 // K / sum_p 4*ceil((Q_p + 7) / 4)  (86 % at 1231 taps, M = 25; 70 % at 561 taps).
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-struct UfdMmaGeom {
-    int K, M, half;
-    int S;            // outputs per segment (16 * WT)
-    int SM;           // S * M: input samples per segment
-    int P;            // segment pitch in shared memory (doubles)
-    int total_len;    // input samples a tile touches (8 segments + reach)
-    int ldq;          // doubles per phase row of the padded tap table
-    int pbeg[5];      // phases [pbeg[k], pbeg[k+1]) belong to k-split k
-};
-
 template <int WT, int KS>
-__global__ void __launch_bounds__(WT *KS * 32, 2)
-upfirdn_mma_kernel(const UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx, int64_t x_first,
+__global__ void __launch_bounds__(WT *KS * 32, 1)
+upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx, int64_t x_first,
                    int64_t x_len, int64_t out_first, int64_t n_out,
                    const double *__restrict__ gpad /* [M][ldq]: 7 zeros, taps of the phase, zeros */,
-                   const int *__restrict__ ksteps /* [M] k-steps of each phase */,
-                   double *__restrict__ y, int64_t ldy) {
+                   double *__restrict__ y, int64_t ldy, int tiles_per_row, int64_t ntiles) {
+    // One persistent CTA per SM walks (row, tile) items; the next tile is copied into
+    // the second shared-memory buffer by 8-byte cp.async (zero fill outside the supplied
+    // window) while the tensor cores work on the current one.
     constexpr int NT = WT * KS * 32;
     extern __shared__ __align__(16) double smem_mma[];
     const int M = gm.M, SM = gm.SM, P = gm.P, S = gm.S;
     const int nseg = (gm.total_len + SM - 1) / SM;
-    double *xs = smem_mma;                                   // nseg * P
-    double *gs = xs + (size_t)nseg * P;                      // M * ldq
+    const int tile_elems = nseg * P;
+    double *bufs = smem_mma;                                 // 2 x nseg * P
+    double *gs = bufs + 2 * (size_t)tile_elems;              // M * ldq
     double *red = gs + (size_t)M * gm.ldq;                   // (KS - 1) * 8 * S
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int wt = warp % WT, wk = warp / WT;
     const int g = lane >> 2, q = lane & 3;
-    const int64_t row = blockIdx.y;
-    const int64_t o0 = (int64_t)blockIdx.x * (8 * S);        // tile start, relative to out_first
-    const int64_t rel0 = (out_first + o0) * M + gm.half - (gm.K - 1) - x_first;
-    const double *xr = x + row * ldx;
+    const uint32_t sbase = smem_u32(bufs);
 
-    // ---- stage the tile: coalesced, time-contiguous, zero outside the supplied window
-    const bool interior = rel0 >= 0 && rel0 + gm.total_len <= x_len;
-    for (int seg = 0; seg < nseg; ++seg) {
-        const int len = min(SM, gm.total_len - seg * SM);
-        const double *src = xr + rel0 + (int64_t)seg * SM;
-        double *dst = xs + (size_t)seg * P;
-        if (interior) {
-            int e = tid;
-            for (; e + 7 * NT < len; e += 8 * NT) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_stream(src + e + u * NT);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) dst[e + u * NT] = v[u];
-            }
-            for (; e < len; e += NT) dst[e] = ld_stream(src + e);
-        } else {
-            for (int e = tid; e < len; e += NT) {
-                const int64_t gi = rel0 + (int64_t)seg * SM + e;
-                dst[e] = (gi >= 0 && gi < x_len) ? ld_stream(xr + gi) : 0.0;
+    auto stage = [&](int64_t t, int which) {
+        if (t >= ntiles) return;
+        const int64_t row = t / tiles_per_row;
+        const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
+        const int64_t rel0 = (out_first + o0) * M + gm.half - (gm.K - 1) - x_first;
+        const double *xr = x + row * ldx;
+        const uint32_t dst0 = sbase + (uint32_t)which * (uint32_t)tile_elems * 8u;
+        const bool interior = rel0 >= 0 && rel0 + gm.total_len <= x_len;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int len = min(SM, gm.total_len - seg * SM);
+            const int64_t g0 = rel0 + (int64_t)seg * SM;
+            const uint32_t dst = dst0 + (uint32_t)(seg * P) * 8u;
+            if (interior) {
+#pragma unroll 4
+                for (int e = tid; e < len; e += NT) cp_async8_zfill(dst + e * 8u, xr + g0 + e, true);
+            } else {
+                for (int e = tid; e < len; e += NT) {
+                    const int64_t gi = g0 + e;
+                    const bool ok = gi >= 0 && gi < x_len;
+                    cp_async8_zfill(dst + e * 8u, ok ? xr + gi : xr, ok);
+                }
             }
         }
-    }
-    for (int i = tid; i < M * gm.ldq; i += NT) gs[i] = gpad[i];
-    __syncthreads();
-
-    // ---- banded Toeplitz product on the tensor cores
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;       // tiles tau = 2 wt, 2 wt + 1
-    const int pad = P - SM;
-    const double *xrow = xs + (size_t)g * P;
-    auto fetch = [&](int r) {       // sample at in-segment offset r of segment g (r may run past it)
-        const int cross = (r >= SM) + (r >= 2 * SM) + (r >= 3 * SM);
-        return xrow[r + cross * pad];
     };
-    const int p_lo = gm.pbeg[wk], p_hi = gm.pbeg[wk + 1];
-    const int step = 4 * M;
-    for (int p = p_lo; p < p_hi; ++p) {
-        const int ns = ksteps[p];
-        const double *gp = gs + (size_t)p * gm.ldq + 7 + q - g;
-        int r = p + (16 * wt + q) * M;
-        double fa = fetch(r), fb = fetch(r + step);
-        r += 2 * step;
-#pragma unroll 3
-        for (int st = 0; st < ns; ++st) {
-            const double fc = fetch(r);
-            const double b = gp[4 * st];
-            dmma884(c00, c01, fa, b);
-            dmma884(c10, c11, fc, b);
-            fa = fb;
-            fb = fc;
-            r += step;
-        }
-    }
-    // ---- combine the k-splits and store: thread holds outputs g*S + 8*tau + 2*q + {0, 1}
-    const int oa = g * S + 16 * wt + 2 * q;
-    if (KS > 1) {
-        if (wk > 0) {
-            double *rd = red + (size_t)(wk - 1) * 8 * S;
-            rd[oa] = c00;
-            rd[oa + 1] = c01;
-            rd[oa + 8] = c10;
-            rd[oa + 9] = c11;
-        }
+
+    stage(blockIdx.x, 0);
+    cp_async_commit();
+    for (int i = tid; i < M * gm.ldq; i += NT) gs[i] = gpad[i];
+
+    const int pad = P - SM;
+    const int k_lo = (int)(((long)gm.ktotal * wk) / KS), k_hi = (int)(((long)gm.ktotal * (wk + 1)) / KS);
+    const int oa = g * S + 32 * wt + 2 * q;          // this thread's outputs: oa + 8 j + {0, 1}
+    int parity = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, parity ^= 1) {
+        const double *xs = bufs + (size_t)parity * tile_elems;
+        stage(t + gridDim.x, parity ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        if (wk == 0) {
+
+        // ---- banded Toeplitz product on the tensor cores
+        const double *xrow = xs + (size_t)g * P;
+        auto fetch = [&](int r) {   // sample at offset r of segment g (r may run past it)
+            const int cross = (r >= SM) + (r >= 2 * SM) + (r >= 3 * SM);
+            return xrow[r + cross * pad];
+        };
+        double c[8];
+        ufd_mma_ksteps(gm, gs, k_lo, k_hi, wt, g, q, fetch, c);
+        // ---- combine the k-splits and store: tile j holds outputs oa + 8 j + {0, 1}
+        if (KS > 1) {
+            if (wk > 0) {
+                double *rd = red + (size_t)(wk - 1) * 8 * S;
 #pragma unroll
-            for (int k = 0; k < KS - 1; ++k) {
-                const double *rd = red + (size_t)k * 8 * S;
-                c00 += rd[oa];
-                c01 += rd[oa + 1];
-                c10 += rd[oa + 8];
-                c11 += rd[oa + 9];
+                for (int j = 0; j < 4; ++j) {
+                    rd[oa + 8 * j] = c[2 * j];
+                    rd[oa + 8 * j + 1] = c[2 * j + 1];
+                }
+            }
+            __syncthreads();
+            if (wk == 0) {
+                for (int k = 0; k < KS - 1; ++k) {
+                    const double *rd = red + (size_t)k * 8 * S;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        c[2 * j] += rd[oa + 8 * j];
+                        c[2 * j + 1] += rd[oa + 8 * j + 1];
+                    }
+                }
             }
         }
+        if (wk == 0) {
+            const int64_t row = t / tiles_per_row;
+            const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
+            double *yr = y + row * ldy + o0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (o0 + oa + 8 * j < n_out) st_stream(yr + oa + 8 * j, c[2 * j]);
+                if (o0 + oa + 8 * j + 1 < n_out) st_stream(yr + oa + 8 * j + 1, c[2 * j + 1]);
+            }
+        }
+        // the reads of `red` and of this tile's buffer must be over before either is
+        // rewritten (the refill of this buffer is issued at the top of the next turn)
+        __syncthreads();
     }
-    if (wk == 0) {
-        double *yr = y + row * ldy + o0;
-        if (o0 + oa < n_out) st_stream(yr + oa, c00);
-        if (o0 + oa + 1 < n_out) st_stream(yr + oa + 1, c01);
-        if (o0 + oa + 8 < n_out) st_stream(yr + oa + 8, c10);
-        if (o0 + oa + 9 < n_out) st_stream(yr + oa + 9, c11);
-    }
+    cp_async_wait<0>();
 }
 
 __global__ void upfirdn_general_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first,
@@ -549,10 +537,11 @@ struct osz_upfirdn_plan {
     bool mma = false;
     int kernel = OSZ_UFD_AUTO;     // osz_upfirdn_plan_set_kernel
     UfdMmaGeom mg{};
-    int mma_wt = 0;
+    int mma_wt = 0, mma_ks = 2;
     size_t smem_mma = 0;
-    double *d_gpad = nullptr;      // [down][ldq]
-    int *d_ksteps = nullptr;       // [down]
+    double *d_gpad = nullptr;      // [down][ldq]: window-order taps g[j] = h'[K-1-j]
+    double *d_gpad_rev = nullptr;  // the same table for a reversed time axis (taps h')
+    double *d_g = nullptr;         // g[j], K doubles
 };
 
 template <int WT, int KS>
@@ -562,60 +551,39 @@ static int launch_mma(const osz_upfirdn_plan *p, const double *x, int64_t ldx, i
     OSZ_CUDA(cudaFuncSetAttribute(upfirdn_mma_kernel<WT, KS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mma));
     const int64_t per_tile = 8 * (int64_t)p->mg.S;
-    dim3 grid((unsigned)((n_out + per_tile - 1) / per_tile), (unsigned)rows);
-    upfirdn_mma_kernel<WT, KS><<<grid, WT * KS * 32, p->smem_mma, st>>>(
-        p->mg, x, ldx, x_first, x_len, out_first, n_out, p->d_gpad, p->d_ksteps, y, ldy);
+    const int64_t tiles_per_row = (n_out + per_tile - 1) / per_tile;
+    const int64_t ntiles = tiles_per_row * rows;
+    const int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
+    upfirdn_mma_kernel<WT, KS><<<(unsigned)grid, WT * KS * 32, p->smem_mma, st>>>(
+        p->mg, x, ldx, x_first, x_len, out_first, n_out, p->d_gpad, y, ldy, (int)tiles_per_row,
+        ntiles);
     OSZ_LAUNCHED("upfirdn_mma_kernel");
     return OSZ_OK;
 }
 
 // Geometry of the tensor-core decimator for K taps, decimation M: the largest
-// segment length S in {64, 48, 32, 16} whose tile (8 segments + reach, padded tap
-// table, k-split scratch) fits two CTAs per SM.
-static bool mma_geometry(int K, int M, UfdMmaGeom *gm, int *wt_out, size_t *smem_out,
-                         std::vector<int> *ksteps_out) {
-    const int Q = (K + M - 1) / M;
-    std::vector<int> ks(M);
+// segment length S in {64, 48, 32, 16} whose two tile buffers (8 segments + reach
+// each), padded tap table and k-split scratch fit one CTA per SM.
+static bool mma_geometry(int K, int M, int ksplit, UfdMmaGeom *gm, int *wt_out,
+                         size_t *smem_out) {
     int smax = 0;
     long total_steps = 0;
-    for (int p = 0; p < M; ++p) {
-        const int qp = p <= (K - 1) % M ? (K - 1) / M + 1 : (K - 1) / M;   // taps of phase p
-        ks[p] = qp > 0 ? (qp + 7 + 3) / 4 : 0;
-        if (ks[p] > smax) smax = ks[p];
-        total_steps += ks[p];
-    }
-    (void)Q;
-    const int KSPLIT = 2;
-    for (int S : {64, 48, 32, 16}) {
-        const int WT = S / 16;
+    const std::vector<int> ks = ufd_ksteps(K, M, &smax, &total_steps);
+    for (int S : {64, 32}) {
+        const int WT = S / 32;
+        if (WT * ksplit > 16) continue;
         const int SM = S * M;
-        // in-segment sample offsets run up to r_max (newest fragment of the last step)
-        const int nmax = 16 * (WT - 1) + 4 * (smax + 1) + 3;
+        // in-segment sample offsets run up to r_max (newest fragment of the last batch)
+        const int nmax = 32 * (WT - 1) + 4 * (smax + 6) + 3;
         const int row_len = (M - 1) + nmax * M + 1;
         if (row_len > 4 * SM) continue;                   // at most three pad crossings
         const int total_len = 7 * SM + row_len;
-        int best_pad = 0, best_score = -1;
-        for (int pad = 0; pad < 16; ++pad) {
-            bool seen[16] = {false};
-            int score = 0;
-            for (int g = 0; g < 4; ++g)
-                for (int q = 0; q < 4; ++q) {
-                    const int b = (int)(((long)g * (SM + pad) + (long)q * M) % 16);
-                    if (!seen[b]) {
-                        seen[b] = true;
-                        ++score;
-                    }
-                }
-            if (score > best_score) {
-                best_score = score;
-                best_pad = pad;
-            }
-        }
-        const int P = SM + best_pad;
+        const int P = SM + ufd_best_pad(SM, M);
         const int nseg = (total_len + SM - 1) / SM;
-        const int ldq = 7 + 4 * smax + 4;
-        const size_t smem = ((size_t)nseg * P + (size_t)M * ldq + (size_t)(KSPLIT - 1) * 8 * S) * 8;
-        if (smem > 110 * 1024) continue;
+        const int ldq = 7 + 4 * (smax + 1) + 4;
+        const size_t smem =
+            (2 * (size_t)nseg * P + (size_t)M * ldq + (size_t)(ksplit - 1) * 8 * S) * 8;
+        if (smem > 225 * 1024) continue;
         gm->K = K;
         gm->M = M;
         gm->half = (K - 1) / 2;
@@ -624,19 +592,12 @@ static bool mma_geometry(int K, int M, UfdMmaGeom *gm, int *wt_out, size_t *smem
         gm->P = P;
         gm->total_len = total_len;
         gm->ldq = ldq;
-        // split the phases between the k-splits by k-steps
-        gm->pbeg[0] = 0;
-        long acc = 0;
-        int k = 1;
-        for (int p = 0; p < M && k < KSPLIT; ++p) {
-            acc += ks[p];
-            if (acc * KSPLIT >= total_steps * k) gm->pbeg[k++] = p + 1;
-        }
-        for (; k <= 4; ++k) gm->pbeg[k] = M;
-        gm->pbeg[KSPLIT] = M;
+        gm->p_rem = (K - 1) % M;
+        gm->ks_hi = ks[0];
+        gm->ks_lo = ks[M - 1];
+        gm->ktotal = (int)total_steps;
         *wt_out = WT;
         *smem_out = smem;
-        *ksteps_out = ks;
         return true;
     }
     return false;
@@ -787,18 +748,27 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
         }
     }
     if (ok && up == 1 && down >= 2 && p->R) {
-        std::vector<int> ks;
-        if (mma_geometry(K, down, &p->mg, &p->mma_wt, &p->smem_mma, &ks)) {
-            const int M = down, ldq = p->mg.ldq;
-            // gpad[p][7 + v] = g[p + v*M], g[j] = h'[K-1-j]
-            std::vector<double> gp((size_t)M * ldq, 0.0);
-            for (int j = 0; j < K; ++j) gp[(size_t)(j % M) * ldq + 7 + j / M] = hs[K - 1 - j];
+        static const int ksplit = [] {
+            const char *e = getenv("OSZ_UFD_MMA_KS");
+            const int v = e ? atoi(e) : 8;
+            return v == 4 || v == 8 || v == 16 ? v : 8;
+        }();
+        p->mma_ks = ksplit;
+        if (mma_geometry(K, down, p->mma_ks, &p->mg, &p->mma_wt, &p->smem_mma)) {
+            // taps in the order the kernel walks its window: g[j] = h'[K-1-j]
+            std::vector<double> g(K);
+            for (int j = 0; j < K; ++j) g[j] = hs[K - 1 - j];
+            const std::vector<double> gp = ufd_gpad(g.data(), K, down, p->mg.ldq);
+            const std::vector<double> gpr = ufd_gpad(hs.data(), K, down, p->mg.ldq);
             ok = cudaMalloc(&p->d_gpad, gp.size() * 8) == cudaSuccess &&
                  cudaMemcpy(p->d_gpad, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice) ==
                      cudaSuccess &&
-                 cudaMalloc(&p->d_ksteps, ks.size() * sizeof(int)) == cudaSuccess &&
-                 cudaMemcpy(p->d_ksteps, ks.data(), ks.size() * sizeof(int),
-                            cudaMemcpyHostToDevice) == cudaSuccess;
+                 cudaMalloc(&p->d_gpad_rev, gpr.size() * 8) == cudaSuccess &&
+                 cudaMemcpy(p->d_gpad_rev, gpr.data(), gpr.size() * 8, cudaMemcpyHostToDevice) ==
+                     cudaSuccess &&
+                 cudaMalloc(&p->d_g, (size_t)K * 8) == cudaSuccess &&
+                 cudaMemcpy(p->d_g, g.data(), (size_t)K * 8, cudaMemcpyHostToDevice) ==
+                     cudaSuccess;
             p->mma = ok;
         }
     }
@@ -843,6 +813,23 @@ int osz_upfirdn_plan_set_compute(osz_upfirdn_plan *p, int compute) {
 }
 int osz_upfirdn_plan_compute(const osz_upfirdn_plan *p) { return p ? p->compute : 0; }
 
+// internal (sosdec.cu): the decimating filter's tap tables
+int osz_upfirdn_plan_taps(const osz_upfirdn_plan *p, int *K, int *M, int *half,
+                          const double **d_gpad_fwd, const double **d_gpad_rev,
+                          const double **d_taps_g, int *ldq) {
+    if (!p) return fail(OSZ_ERR_ARG, "osz_upfirdn_plan_taps: null plan");
+    if (!p->mma) return fail(OSZ_ERR_UNSUPPORTED, "osz_upfirdn_plan_taps: not a decimating plan "
+                                                  "with a tensor-core geometry");
+    *K = p->K;
+    *M = p->down;
+    *half = p->half;
+    *d_gpad_fwd = p->d_gpad;
+    *d_gpad_rev = p->d_gpad_rev;
+    *d_taps_g = p->d_g;
+    *ldq = p->mg.ldq;
+    return OSZ_OK;
+}
+
 static int ufd_use_mma_default() {
     static const int v = [] {
         const char *e = getenv("OSZ_UFD_MMA");
@@ -874,7 +861,8 @@ int osz_upfirdn_plan_destroy(osz_upfirdn_plan *p) {
     cudaFree(p->d_gphasef);
     cudaFree(p->d_gphase2);
     cudaFree(p->d_gpad);
-    cudaFree(p->d_ksteps);
+    cudaFree(p->d_gpad_rev);
+    cudaFree(p->d_g);
     if (p->tap_slot >= 0) ufd_slot_free(p->tap_slot, p->tap_len);
     delete p;
     return OSZ_OK;
@@ -905,12 +893,11 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
         }
     }
     if (osz_upfirdn_plan_kernel(p) == OSZ_UFD_MMA && !(p->dec2 && use_dec2)) {
-        switch (p->mma_wt) {
-            case 4: return launch_mma<4, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
-            case 3: return launch_mma<3, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
-            case 2: return launch_mma<2, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
-            default: return launch_mma<1, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
-        }
+#define OSZ_MMA_CASE(WT, KS)                                                                   \
+    if (p->mma_wt == WT && p->mma_ks == KS)                                                   \
+        return launch_mma<WT, KS>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+        OSZ_MMA_CASE(2, 4) OSZ_MMA_CASE(2, 8) OSZ_MMA_CASE(1, 4) OSZ_MMA_CASE(1, 8) OSZ_MMA_CASE(1, 16)
+#undef OSZ_MMA_CASE
     }
     if (p->dec2 && use_dec2)
         return launch_dec2<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);

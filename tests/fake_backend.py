@@ -82,6 +82,7 @@ class FakeUpfirdn:
     def __init__(self, h, up, down):
         self.h = np.asarray(h, dtype=np.float64) * up
         self.ntaps, self.up, self.down = len(self.h), int(up), int(down)
+        self.kernel = "mma" if self.up == 1 and self.down >= 2 else "general"
 
     def run(self, x, x_first, out_first, n_out, out=None):
         xn = x.numpy()
@@ -94,6 +95,81 @@ class FakeUpfirdn:
         y = np.zeros((xn.shape[0], n_out))
         y[:, ok] = u[:, m[ok]]
         return _ret(y, out)
+
+
+# ---- fused IIR pass + decimating FIR (contracts of include/osz_b200.h) ----------
+def _sosdec_spans(sos_plan, ufd_plan, rows, n):
+    """Enough spans to exercise the span boundaries: 3 for long chunks, 1 otherwise,
+    0 (not fusable) below four filter lengths."""
+    k = ufd_plan.ntaps
+    if ufd_plan.up != 1 or ufd_plan.down < 2 or n < 4 * k:
+        return 0
+    return 3 if n >= 12 * k else 1
+
+
+def _pieces(n, nspan, reverse):
+    """Real-time [ua, ub) of every LOGICAL span (a backward pass walks time in reverse)."""
+    span_len = -(-n // nspan)
+    out = []
+    for k in range(nspan):
+        a, b = k * span_len, min((k + 1) * span_len, n)
+        out.append((n - b, n - a) if reverse else (a, b))
+    return out
+
+
+def _sosdec_exec(sos_plan, ufd_plan, x, reverse, state, nspan, first, out, out_first):
+    rows, n = x.shape
+    p = sos_plan.run(x, state, reverse=reverse).numpy()          # the pass output, real-time order
+    k, m = ufd_plan.ntaps, ufd_plan.down
+    half = (k - 1) // 2
+    g = ufd_plan.h[::-1]
+    edges = np.zeros((rows, nspan, 2, k - 1))
+    o = out.numpy() if out.numel() else np.zeros((rows, 0))
+    res = o.copy()
+    for sp, (ua, ub) in enumerate(_pieces(n, nspan, reverse)):
+        edges[:, sp, 0] = p[:, ua:ua + k - 1]
+        edges[:, sp, 1] = p[:, ub - (k - 1):ub]
+        j0 = -(-(first + ua - half + k - 1) // m)                # window start >= piece start
+        j1 = (first + ub - 1 - half) // m                        # window end < piece end
+        for j in range(j0, j1 + 1):
+            c = j - out_first
+            if 0 <= c < res.shape[1]:
+                lo = j * m + half - (k - 1) - first
+                res[:, c] = p[:, lo:lo + k] @ g
+    if out.numel():
+        out.copy_(_t(res))
+    return _t(edges)
+
+
+def _sosdec_boundary(ufd_plan, edges, reverse, prev_tail, has_end, n, first, out, out_first,
+                     j_min, j_max):
+    e = edges.numpy()
+    rows, nspan = e.shape[0], e.shape[1]
+    k, m = ufd_plan.ntaps, ufd_plan.down
+    half = (k - 1) // 2
+    g = ufd_plan.h[::-1]
+    res = out.numpy().copy()
+    pieces = sorted(range(nspan), key=lambda sp: _pieces(n, nspan, reverse)[sp][0])
+    starts = [_pieces(n, nspan, reverse)[sp][0] for sp in pieces]
+    zeros = np.zeros((rows, k - 1))
+    for b in range(nspan + 1):
+        if b == nspan and not has_end:
+            continue
+        T = n if b == nspan else starts[b]
+        tail = (prev_tail.numpy() if prev_tail is not None else zeros) if b == 0 \
+            else e[:, pieces[b - 1], 1]
+        head = zeros if b == nspan else e[:, pieces[b], 0]
+        win = np.concatenate([tail, head], axis=1)               # real times T-(k-1) .. T+k-2
+        tg = first + T
+        j0 = max(-(-(tg - half) // m), j_min)
+        j1 = min(-(-(tg - half + k - 1) // m) - 1, j_max)
+        for j in range(j0, j1 + 1):
+            c = j - out_first
+            if 0 <= c < res.shape[1]:
+                base = j * m + half - tg
+                res[:, c] = win[:, base:base + k] @ g
+    if out.numel():
+        out.copy_(_t(res))
 
 
 class FakeSpec:
@@ -231,6 +307,9 @@ def install(mp):
     mp.setattr(dv, "RowMoments", FakeRowMoments)
     mp.setattr(dv, "row_standardize", _row_standardize)
     mp.setattr(dv, "col_moments", _col_moments)
+    mp.setattr(dv, "sosdec_spans", _sosdec_spans)
+    mp.setattr(dv, "sosdec_exec", _sosdec_exec)
+    mp.setattr(dv, "sosdec_boundary", _sosdec_boundary)
     mp.setattr(dv.FirPlan, "cached", staticmethod(lambda taps, algo=0: FakeFir(taps, algo)))
     mp.setattr(dv.SosPlan, "cached", staticmethod(lambda sos: FakeSos(sos)))
     mp.setattr(dv.TfPlan, "cached", staticmethod(lambda b, a: FakeTf(b, a)))

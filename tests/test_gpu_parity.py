@@ -218,7 +218,7 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps, kernel):
     if up > 1 or down == 1:
         assert plan.kernel == "general"
     elif kernel == "polyphase":
-        assert plan.kernel == "polyphase"
+        assert plan.kernel in ("polyphase", "general")     # general: no tile fits (M = 60, 300)
     n_total = ref.shape[-1]
     y = plan.run(_dev(dv, x), 0, 0, n_total).cpu().numpy()
     assert relerr(y, ref) < 1e-12
@@ -416,6 +416,10 @@ def test_pipeline_chain_on_device():
 
 def test_fused_fir_decimate():
     pc.fused_fir_decimate()
+
+
+def test_fused_iir_fir_decimate():
+    pc.fused_iir_fir_decimate()
 
 
 def test_c5_real_parameters():

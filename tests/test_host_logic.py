@@ -45,6 +45,7 @@ def test_spectra(fake_gpu):
 def test_pipeline_chain(fake_gpu):
     pc.pipeline_chain()
     pc.fused_fir_decimate()
+    pc.fused_iir_fir_decimate()
 
 
 def test_producer_tools(fake_gpu):

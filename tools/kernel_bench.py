@@ -117,6 +117,26 @@ def main(which):
         report("fused FIR+downsample M=25 taps=%d float32 compute" % len(h),
                timeit(lambda: p32.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
         del x
+    if not which or "sosdec" in which:
+        # backward notch pass + FIR(671) * anti-alias(561) decimator M=25 as one kernel
+        import oracle
+
+        h = np.convolve(oracle.resample_filter(1, 25, 30000), Kaiser(500, 600, 30000).coeffs)
+        ufd = dv.UpfirdnPlan(h, 1, 25)
+        b, a = sps.iirnotch(60, 10, fs=30000)
+        sos = dv.SosPlan(np.concatenate([b, a])[None])
+        for r2 in (256, 128, 64, 32):
+            x2 = rnd(r2, n)
+            st = dv.zeros((r2, 1, 2))
+            nspan = dv.sosdec_spans(sos, ufd, r2, n)
+            out = dv.empty((r2, n // 25))
+            report("bwd notch + FIR + decimate rows=%d spans=%d" % (r2, nspan),
+                   timeit(lambda: dv.sosdec_exec(sos, ufd, x2, True, st, nspan, 0, out, 0)),
+                   r2 * n, 8 * (1 + 1 / 25))
+            y2 = torch.empty_like(x2)
+            report("  (separately: bwd notch pass rows=%d)" % r2,
+                   timeit(lambda: sos.run(x2, st, reverse=True, out=y2)), r2 * n, 16)
+            del x2, y2
     if not which or "welch" in which:
         for nfft in (1024, 4096, 8192) + ((2400, 10000, 60000) if "generic" in which else ()):
             w = sps.get_window("hann", nfft)
