@@ -816,7 +816,13 @@ def _fusable_iir(pro, axis):
     last pass can run inside the decimator that consumes it, else None."""
     import os
 
-    if os.environ.get("OSZ_FUSE_IIR", "1") == "0":
+    # Opt-in (OSZ_FUSE_IIR=1).  Measured on B200 (256 x 1e6, notch + 1231 taps, M = 25,
+    # profiles/r02_ncu_summary.md): the fused kernel moves 8.3 bytes per sample instead of
+    # 24.3, but the scan's ~55 instructions per sample and the decimator's MMA stream
+    # share one SM's issue slots (39 % issue-active, the MMA group starved 20 % of the
+    # time): 2.6 ms against 0.82 + 1.30 ms for the backward pass and the tensor-core
+    # decimator run one after the other.
+    if os.environ.get("OSZ_FUSE_IIR", "0") != "1":
         return None
     if not isinstance(pro, GenProducer) or pro.kwargs:
         return None

@@ -44,6 +44,8 @@ inline int fail(osz_status code, const std::string &msg) {
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();   // SMs of the current device (cached)
+// stream-ordered scratch of a launch; release with cudaFreeAsync on the same stream
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t st);
 
 // ---- device helpers --------------------------------------------------------
 __device__ __forceinline__ double ldg(const double *p) { return __ldg(p); }

@@ -24,6 +24,26 @@ int sm_count() {
     return cached;
 }
 
+// Stream-ordered scratch for a launch (cudaMallocAsync / cudaFreeAsync: no device
+// synchronisation, no sharing between streams).  The default memory pool hands its
+// memory back to the driver at every synchronisation point unless told otherwise,
+// which makes the next allocation cost milliseconds: keep it cached (once per device).
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t st) {
+    static thread_local int tuned_dev = -1;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev != tuned_dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned_dev = dev;
+    }
+    return cudaMallocAsync(ptr, bytes, st);
+}
+
 // (outer, n, inner) -> rows (outer*inner, n): tiled transpose through shared
 // memory so both sides are coalesced.
 template <typename T, bool PACK>

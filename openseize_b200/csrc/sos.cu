@@ -568,7 +568,7 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     const int64_t n_copy = nspan > 1 ? rows * ns2 : 0;
     const int64_t n_span = exact ? rows * nspan * ns2 : 0;
     if (n_copy + 2 * n_span > 0)
-        OSZ_CUDA(cudaMallocAsync(&scratch, (size_t)(n_copy + 2 * n_span) * 8, st));
+        OSZ_CUDA(scratch_alloc((void **)&scratch, (size_t)(n_copy + 2 * n_span) * 8, st));
     struct Release {                 // freed in stream order after the kernels below
         double *ptr;
         cudaStream_t st;

@@ -9,8 +9,8 @@
 // (:229-269, :610-631): 8 + 8/M bytes per sample of HBM traffic instead of
 // 16 (pass) + 8 + 8/M (decimator).
 //
-// One CTA owns one (row, time span).  Two warp groups run in lock step, one
-// __syncthreads per 4096-sample block:
+// One CTA owns one (row, time span).  Two warp groups run concurrently, coupled by two
+// shared-memory counters (ring fill level, tiles finished):
 //   * scan group (256 threads): the time-parallel biquad scan of sos_core.cuh
 //     (16 samples per thread) over the next block, in PROCESSING order (reverse
 //     time for a backward pass); outputs go to the ring, and the first / last
@@ -58,13 +58,14 @@ sosdec_kernel(const __grid_constant__ SosParams prm, const __grid_constant__ Sos
     extern __shared__ __align__(16) double smem_sd[];
     __shared__ double wtot[2][SOS_NT / 32][2];
     __shared__ double carry[SOS_MAXSEC][2];
+    __shared__ int64_t s_avail, s_tiles;     // ring fill level (scan -> FIR), tiles finished (FIR -> scan)
 
     const UfdMmaGeom &gm = gd.m;
     const int M = gm.M, SM = gm.SM, P = gm.P, S = gm.S, K = gm.K, nring = gd.nring;
     double *buf = smem_sd;                                   // SOS_NT * SD_LD
     double *ring = buf + SOS_NT * SD_LD;                     // nring * P
     double *gs = ring + (size_t)nring * P;                   // M * ldq
-    double *red = gs + (size_t)M * gm.ldq;                   // (KS - 1) * 8 * S
+    double *red = gs + (size_t)M * gm.ldq;                   // 2 x KS x 8 S partial sums
 
     const int tid = threadIdx.x;
     const bool scan_role = tid < SOS_NT;
@@ -109,6 +110,10 @@ sosdec_kernel(const __grid_constant__ SosParams prm, const __grid_constant__ Sos
         if (span == 0) c0 = state_in[row * nsec * 2 + tid];
         carry[tid >> 1][tid & 1] = c0;
     }
+    if (tid == 0) {
+        s_avail = -((int64_t)1 << 60);
+        s_tiles = 0;
+    }
     __syncthreads();
 
     // scan role state
@@ -121,131 +126,161 @@ sosdec_kernel(const __grid_constant__ SosParams prm, const __grid_constant__ Sos
     const int g = lane >> 2, q = lane & 3;
     const int oa = g * S + 32 * wt + 2 * q;
     const int k_lo = (int)(((long)gm.ktotal * wk) / KS), k_hi = (int)(((long)gm.ktotal * (wk + 1)) / KS);
-    int64_t next_tile = 0;
     const int64_t ntile = (nout + 8 * S - 1) / (8 * S);
 
-    for (int64_t it = 0; it <= nblk; ++it) {
-        if (scan_role) {
-            if (it < nblk) {
-                const int64_t blk = it;
-                const int off = blk == 0 ? (int)(SD_BLK - first_len) : 0;
-                const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * SD_BLK;
-                if (blk != 0) {
-                    const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
-                    double tmp[SD_T];
+    // ---- the two groups run decoupled: the scan publishes how far the ring is
+    //      filled (s_avail, in ring coordinates) and waits only when it would
+    //      overwrite segments a pending tile still reads (s_tiles: tiles finished).
+    if (scan_role) {
+        // the loads of block blk + 1 are in flight while block blk is scanned (`nxt`)
+        double nxt[SD_T];
+        auto prefetch = [&](int64_t blk) {     // full blocks only (blk >= 1)
+            const int64_t pos0 = first_len + (blk - 1) * SD_BLK;
+            const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
 #pragma unroll
-                    for (int k = 0; k < SD_T; ++k)
-                        tmp[k] = ld_stream(reverse ? src - k * SOS_NT : src + k * SOS_NT);
+            for (int k = 0; k < SD_T; ++k)
+                nxt[k] = ld_stream(reverse ? src - k * SOS_NT : src + k * SOS_NT);
+        };
+        for (int64_t blk = 0; blk < nblk; ++blk) {
+            const int off = blk == 0 ? (int)(SD_BLK - first_len) : 0;
+            const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * SD_BLK;
+            if (blk != 0) {
 #pragma unroll
-                    for (int k = 0; k < SD_T; ++k) {
-                        const int e = tid + k * SOS_NT;
-                        buf[(e >> 4) * SD_LD + (e & (SD_T - 1))] = tmp[k];
-                    }
-                } else {
+                for (int k = 0; k < SD_T; ++k) {
+                    const int e = tid + k * SOS_NT;
+                    buf[(e >> 4) * SD_LD + (e & (SD_T - 1))] = nxt[k];
+                }
+            } else {
 #pragma unroll 4
-                    for (int e = tid; e < SD_BLK; e += SOS_NT) {
-                        double val = 0.0;
-                        if (e >= off) {
-                            const int64_t s = pos0 + (e - off);
-                            val = ld_stream(reverse ? xr - s : xr + s);
-                        }
-                        buf[(e >> 4) * SD_LD + (e & (SD_T - 1))] = val;
+                for (int e = tid; e < SD_BLK; e += SOS_NT) {
+                    double val = 0.0;
+                    if (e >= off) {
+                        const int64_t s = pos0 + (e - off);
+                        val = ld_stream(reverse ? xr - s : xr + s);
+                    }
+                    buf[(e >> 4) * SD_LD + (e & (SD_T - 1))] = val;
+                }
+            }
+            if (blk + 1 < nblk) prefetch(blk + 1);
+            named_bar_sync<1>(SOS_NT);
+            double v[SD_T];
+#pragma unroll
+            for (int i = 0; i < SD_T; ++i) v[i] = buf[tid * SD_LD + i];
+            sos_scan_block<SD_T, 1>(prm, v, blk != 0, off, carry, wtot, lanepow, tid, lane, warp);
+#pragma unroll
+            for (int i = 0; i < SD_T; ++i) buf[tid * SD_LD + i] = v[i];
+            // ring coordinates of the block: u = s - keep - doff, s = pos0 + e - off
+            const int64_t u_end = pos0 + (SD_BLK - off) - keep - doff;        // exclusive
+            if (tid == 0 && u_end > 0) {
+                // the slot of the newest segment written held segment sig - nring, last read
+                // by tile floor((sig - nring) / 8): wait until that tile is finished
+                const int64_t sig_hi = (u_end - 1) / SM;
+                int64_t need_done = sig_hi - nring >= 0 ? (sig_hi - nring) / 8 + 1 : 0;
+                if (need_done > ntile) need_done = ntile;
+                while (*(volatile int64_t *)&s_tiles < need_done) __nanosleep(200);
+                __threadfence_block();
+            }
+            named_bar_sync<1>(SOS_NT);
+            // ---- hand the block over: ring (time-contiguous, padded segments) + edges
+            // (most blocks lie wholly inside the span's interior: no edge samples, no
+            //  warm-up samples, nothing before the first output's window -- plain copy)
+            const int64_t tl_a = reverse ? n_total - (w0 + pos0 + SD_BLK - off) : w0 + pos0;
+            const int64_t tl_b = tl_a + (SD_BLK - off);             // real-time [tl_a, tl_b)
+            const bool plain = blk != 0 && pos0 >= keep && pos0 - keep - doff >= 0 &&
+                               tl_a >= ua + (K - 1) && tl_b <= ub - (K - 1);
+            if (plain) {
+                const int64_t u0 = pos0 + (int64_t)tid - keep - doff;
+                const int64_t sig = u0 / SM;
+                int w = (int)(u0 - sig * SM);
+                int slot = (int)(sig % nring);
+#pragma unroll
+                for (int k = 0; k < SD_T; ++k) {
+                    const int e = tid + k * SOS_NT;
+                    ring[slot * P + w] = buf[(e >> 4) * SD_LD + (e & (SD_T - 1))];
+                    w += SOS_NT;
+                    if (w >= SM) {
+                        w -= SM;
+                        if (++slot == nring) slot = 0;
                     }
                 }
-                named_bar_sync<1>(SOS_NT);
-                double v[SD_T];
-#pragma unroll
-                for (int i = 0; i < SD_T; ++i) v[i] = buf[tid * SD_LD + i];
-                sos_scan_block<SD_T, 1>(prm, v, blk != 0, off, carry, wtot, lanepow, tid, lane, warp);
-#pragma unroll
-                for (int i = 0; i < SD_T; ++i) buf[tid * SD_LD + i] = v[i];
-                named_bar_sync<1>(SOS_NT);
-                // ---- hand the block over: ring (time-contiguous, padded segments) + edges
-                if (pos0 + (SD_BLK - off) > keep) {
-                    // element e of the block is local logical sample s = pos0 + e - off;
-                    // ring coordinate u = s - keep - doff
-                    const int64_t u0 = pos0 + (int64_t)tid - off - keep - doff;
-                    int64_t sig = floordiv64(u0, SM);
-                    int w = (int)(u0 - sig * SM);
-                    int slot = (int)(sig % nring);
-                    if (slot < 0) slot += nring;
+            } else if (pos0 + (SD_BLK - off) > keep) {
+                const int64_t u0 = pos0 + (int64_t)tid - off - keep - doff;
+                int64_t sig = floordiv64(u0, SM);
+                int w = (int)(u0 - sig * SM);
+                int slot = (int)(sig % nring);
+                if (slot < 0) slot += nring;
 #pragma unroll 4
-                    for (int k = 0; k < SD_T; ++k) {
-                        const int e = tid + k * SOS_NT;
-                        const int64_t s = pos0 + (e - off);
-                        if (e >= off && s >= keep) {
-                            const double val = buf[(e >> 4) * SD_LD + (e & (SD_T - 1))];
-                            if (sig >= 0) ring[slot * P + w] = val;
-                            const int64_t tl = reverse ? n_total - 1 - (w0 + s) : w0 + s;
-                            const int64_t dl = tl - ua, dh = tl - (ub - (K - 1));
-                            if (dl < K - 1) edge_lo[dl] = val;
-                            if (dh >= 0) edge_hi[dh] = val;
-                        }
-                        w += SOS_NT;
-                        if (w >= SM) {
-                            w -= SM;
-                            ++sig;
-                            if (++slot == nring) slot = 0;
-                        }
+                for (int k = 0; k < SD_T; ++k) {
+                    const int e = tid + k * SOS_NT;
+                    const int64_t s = pos0 + (e - off);
+                    if (e >= off && s >= keep) {
+                        const double val = buf[(e >> 4) * SD_LD + (e & (SD_T - 1))];
+                        if (sig >= 0) ring[slot * P + w] = val;
+                        const int64_t tl = reverse ? n_total - 1 - (w0 + s) : w0 + s;
+                        const int64_t dl = tl - ua, dh = tl - (ub - (K - 1));
+                        if (dl < K - 1) edge_lo[dl] = val;
+                        if (dh >= 0) edge_hi[dh] = val;
+                    }
+                    w += SOS_NT;
+                    if (w >= SM) {
+                        w -= SM;
+                        ++sig;
+                        if (++slot == nring) slot = 0;
                     }
                 }
             }
-        } else if (it > 0) {
-            // samples the ring holds after block it-1 (in ring coordinates)
-            const int64_t avail = first_len + (it - 1) * SD_BLK - keep - doff;
-            const bool final = it == nblk;
-            while (next_tile < ntile) {
-                const int64_t need = next_tile * 8 * (int64_t)SM + gm.total_len;
-                if (!final && avail < need) break;
-                // ---- banded Toeplitz product of tile next_tile on the tensor cores
-                int segbase = (int)((next_tile * 8 + g) % nring);
-                auto fetch = [&](int r) {
-                    const int cross = (r >= SM) + (r >= 2 * SM) + (r >= 3 * SM);
-                    int seg = segbase + cross;
-                    if (seg >= nring) seg -= nring;
-                    return ring[seg * P + (r - cross * SM)];
-                };
-                double c[8];
-                ufd_mma_ksteps(gm, gs, k_lo, k_hi, wt, g, q, fetch, c);
-                if (KS > 1) {
-                    if (wk > 0) {
-                        double *rd = red + (size_t)(wk - 1) * 8 * S;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            rd[oa + 8 * j] = c[2 * j];
-                            rd[oa + 8 * j + 1] = c[2 * j + 1];
-                        }
-                    }
-                    named_bar_sync<2>(NFIR);
-                    if (wk == 0) {
-                        for (int k = 0; k < KS - 1; ++k) {
-                            const double *rd = red + (size_t)k * 8 * S;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                c[2 * j] += rd[oa + 8 * j];
-                                c[2 * j + 1] += rd[oa + 8 * j + 1];
-                            }
-                        }
-                    }
-                    named_bar_sync<2>(NFIR);      // red is free for the next tile
-                }
-                if (wk == 0) {
-                    double *yr = y + row * ldy;
-                    const int64_t jp = next_tile * 8 * S + oa;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int64_t j1 = jp + 8 * (k >> 1) + (k & 1);
-                        if (j1 < nout) {
-                            const int64_t col = (reverse ? jedge - j1 : jedge + j1) - out_first;
-                            if (col >= 0 && col < n_out) yr[col] = c[k];
-                        }
-                    }
-                }
-                ++next_tile;
+            named_bar_sync<1>(SOS_NT);             // every scan thread's ring writes are done
+            if (tid == 0) {
+                __threadfence_block();
+                *(volatile int64_t *)&s_avail = blk + 1 == nblk ? (int64_t)1 << 60 : u_end;
             }
         }
-        __syncthreads();
+    } else {
+        for (int64_t tile = 0; tile < ntile; ++tile) {
+            const int64_t need = tile * 8 * (int64_t)SM + gm.total_len;
+            // one thread polls the fill level; the other FIR warps wait in the barrier
+            if (tid == SOS_NT) {
+                while (*(volatile int64_t *)&s_avail < need) __nanosleep(200);
+                __threadfence_block();
+            }
+            named_bar_sync<3>(NFIR);
+            // ---- banded Toeplitz product of the tile on the tensor cores
+            const int segbase = (int)((tile * 8 + g) % nring);
+            auto fetch = [&](int p, int n) {   // sample n of phase p in row g's window
+                int seg = segbase + (n >> 5);
+                if (seg >= nring) seg -= nring;
+                return ring[seg * P + p + (n & 31) * M];
+            };
+            double c[8];
+            ufd_mma_ksteps(gm, gs, k_lo, k_hi, wt, g, q, fetch, c);
+            // partial sums of the k-splits to shared memory (double buffered by tile
+            // parity); every FIR thread then sums and stores its share of the outputs
+            double *rd = red + ((size_t)(tile & 1) * KS + wk) * 8 * S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rd[oa + 8 * j] = c[2 * j];
+                rd[oa + 8 * j + 1] = c[2 * j + 1];
+            }
+            named_bar_sync<2>(NFIR);               // every FIR warp is done with the tile's window
+            if (tid == SOS_NT) {
+                __threadfence_block();
+                *(volatile int64_t *)&s_tiles = tile + 1;
+            }
+            const double *r0 = red + (size_t)(tile & 1) * KS * 8 * S;
+            double *yr = y + row * ldy;
+            for (int o = tid - SOS_NT; o < 8 * S; o += NFIR) {
+                double sum = r0[o];
+#pragma unroll
+                for (int k = 1; k < KS; ++k) sum += r0[(size_t)k * 8 * S + o];
+                const int64_t j1 = tile * 8 * S + o;
+                if (j1 < nout) {
+                    const int64_t col = (reverse ? jedge - j1 : jedge + j1) - out_first;
+                    if (col >= 0 && col < n_out) yr[col] = sum;
+                }
+            }
+        }
     }
+    __syncthreads();
     if (tid < nsec * 2 && span == gridDim.y - 1)
         state[row * nsec * 2 + tid] = carry[tid >> 1][tid & 1];
 }
@@ -340,13 +375,14 @@ bool sosdec_geometry(int K, int M, int ksplit, SosDecGeom *gd, int *wt_out, size
         const int nring = (2 * SD_BLK + total_len + SM - 1) / SM + 2;
         const int ldq = 7 + 4 * (smax + 1) + 4;
         const size_t smem = ((size_t)SOS_NT * SD_LD + (size_t)nring * P + (size_t)M * ldq +
-                             (size_t)(ksplit - 1) * 8 * S) * 8;
+                             2 * (size_t)ksplit * 8 * S) * 8;
         if (smem > 224 * 1024) continue;
         UfdMmaGeom &gm = gd->m;
         gm.K = K;
         gm.M = M;
         gm.half = (K - 1) / 2;
         gm.S = S;
+        gm.logS = 5;
         gm.SM = SM;
         gm.P = P;
         gm.total_len = total_len;
@@ -461,7 +497,7 @@ int osz_sosdec_exec_f64(const osz_sos_plan *sos, const osz_upfirdn_plan *ufd, co
     const double *state_in = state;
     const int64_t n_copy = nspan > 1 ? rows * 2 * prm.nsec : 0;
     if (n_copy) {
-        OSZ_CUDA(cudaMallocAsync(&scratch, (size_t)n_copy * 8, st));
+        OSZ_CUDA(scratch_alloc((void **)&scratch, (size_t)n_copy * 8, st));
         OSZ_CUDA(cudaMemcpyAsync(scratch, state, (size_t)n_copy * 8, cudaMemcpyDeviceToDevice, st));
         state_in = scratch;
     }

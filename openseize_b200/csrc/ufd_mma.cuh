@@ -10,14 +10,15 @@
 namespace osz {
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
 
 struct UfdMmaGeom {
     int K, M, half;
-    int S;            // outputs per segment (32 * WT)
+    int S;            // outputs per segment (32 * WT, a power of two)
+    int logS;
     int SM;           // S * M: input samples per segment
     int P;            // segment pitch in shared memory (doubles)
     int total_len;    // input samples a tile touches (8 segments + reach)
@@ -28,22 +29,39 @@ struct UfdMmaGeom {
 };
 
 
+// One batch of NB consecutive k-steps of one phase for the FOUR 8 x 8 output tiles
+// tau = 4 wt .. 4 wt + 3 of a warp.  Tile j at step s needs the A fragment of decimated
+// index n = n0 + 4 s + 8 j (n0 = 32 wt + q + 4 s0), so NB steps need NB + 6 fragments:
+// they and the NB tap fragments are loaded up front, unconditionally (every guard in
+// this loop made the compiler sink the loads next to their MMA and pay the LDS latency
+// per step), then the 4 NB MMAs run as four independent accumulator chains.
+template <int NB, class Fetch>
+__device__ __forceinline__ void ufd_mma_batch(Fetch fetch, const double *gp4, int n0,
+                                              double (&c)[8]) {
+    double f[NB + 6], tb[NB];
+#pragma unroll
+    for (int i = 0; i < NB + 6; ++i) f[i] = fetch(n0 + 4 * i);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) tb[i] = gp4[4 * i];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        dmma884(c[0], c[1], f[i], tb[i]);
+        dmma884(c[2], c[3], f[i + 2], tb[i]);
+        dmma884(c[4], c[5], f[i + 4], tb[i]);
+        dmma884(c[6], c[7], f[i + 6], tb[i]);
+    }
+}
+
 // One warp's share of a tile: k-steps [k_lo, k_hi) (numbered phase by phase) of the
-// banded Toeplitz product for the FOUR 8 x 8 output tiles tau = 4 wt .. 4 wt + 3.
-// `fetch(r)` returns the sample at in-segment offset r of segment g (this lane's A row).
-// Tile j at step s needs fragment F(8 wt + 2 j + s): one new A fragment and one tap
-// fragment per k-step feed four MMAs.  The fragments of a batch of UFD_NSB steps are
-// loaded up front (LDS latency paid once per batch); the four tiles are four
-// independent accumulator chains.  The tensor pipe issues one DMMA.8x8x4 per 16 clk
-// and SM sub-partition (profiles/r02_ncu_summary.md), so the loop must stay well below
-// 16 instructions per MMA: this form runs at ~4.
+// banded Toeplitz product.  `fetch(p, n)` returns sample n of the decimated sequence of
+// phase p in this lane's A row (segment g): window offset p + n * M.  The tensor pipe
+// issues one DMMA.8x8x4 per 16 clk and SM sub-partition (profiles/r02_ncu_summary.md),
+// so the loop has to stay well below 16 instructions per MMA: this form runs at ~4.
 constexpr int UFD_NSB = 8;
 template <class Fetch>
 __device__ __forceinline__ void ufd_mma_ksteps(const UfdMmaGeom &gm, const double *gs, int k_lo,
                                                int k_hi, int wt, int g, int q, Fetch fetch,
                                                double (&c)[8]) {
-    const int M = gm.M;
-    const int step = 4 * M;
 #pragma unroll
     for (int i = 0; i < 8; ++i) c[i] = 0.0;
     // (phase, step) of k_lo: phases 0 .. p_rem hold ks_hi steps, the others ks_lo
@@ -63,24 +81,20 @@ __device__ __forceinline__ void ufd_mma_ksteps(const UfdMmaGeom &gm, const doubl
         int s_end = s + (k_hi - kk);
         if (s_end > ns) s_end = ns;
         const double *gp = gs + (size_t)p * gm.ldq + 7 + q - g;
-        const int r0 = p + (32 * wt + q) * M;
-        for (int s0 = s; s0 < s_end; s0 += UFD_NSB) {
-            const int nb = s_end - s0 < UFD_NSB ? s_end - s0 : UFD_NSB;   // steps in this batch
-            double f[UFD_NSB + 6], tb[UFD_NSB];
-#pragma unroll
-            for (int i = 0; i < UFD_NSB + 6; ++i)
-                f[i] = i < nb + 6 ? fetch(r0 + (s0 + i) * step) : 0.0;
-#pragma unroll
-            for (int i = 0; i < UFD_NSB; ++i) tb[i] = i < nb ? gp[4 * (s0 + i)] : 0.0;
-#pragma unroll
-            for (int i = 0; i < UFD_NSB; ++i) {
-                if (i < nb) {
-                    dmma884(c[0], c[1], f[i], tb[i]);
-                    dmma884(c[2], c[3], f[i + 2], tb[i]);
-                    dmma884(c[4], c[5], f[i + 4], tb[i]);
-                    dmma884(c[6], c[7], f[i + 6], tb[i]);
-                }
-            }
+        const int nbase = 32 * wt + q;
+        auto fp = [&](int n) { return fetch(p, n); };
+        int s0 = s;
+        for (; s0 + UFD_NSB <= s_end; s0 += UFD_NSB)
+            ufd_mma_batch<UFD_NSB>(fp, gp + 4 * s0, nbase + 4 * s0, c);
+        switch (s_end - s0) {        // the remainder, as one unguarded batch of its own size
+            case 7: ufd_mma_batch<7>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 6: ufd_mma_batch<6>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 5: ufd_mma_batch<5>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 4: ufd_mma_batch<4>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 3: ufd_mma_batch<3>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 2: ufd_mma_batch<2>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            case 1: ufd_mma_batch<1>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            default: break;
         }
         kk += s_end - s;
         ++p;

@@ -380,111 +380,135 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
 // K / sum_p 4*ceil((Q_p + 7) / 4)  (86 % at 1231 taps, M = 25; 70 % at 561 taps).
 template <int WT, int KS>
 __global__ void __launch_bounds__(WT *KS * 32, 1)
-upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx, int64_t x_first,
-                   int64_t x_len, int64_t out_first, int64_t n_out,
+upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx,
+                   int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
                    const double *__restrict__ gpad /* [M][ldq]: 7 zeros, taps of the phase, zeros */,
                    double *__restrict__ y, int64_t ldy, int tiles_per_row, int64_t ntiles) {
-    // One persistent CTA per SM walks (row, tile) items; the next tile is copied into
-    // the second shared-memory buffer by 8-byte cp.async (zero fill outside the supplied
-    // window) while the tensor cores work on the current one.
+    // One persistent CTA per SM walks (row, tile) items.  Tiles are prefetched two
+    // ahead into two shared-memory buffers: interior tiles by 1-D TMA bulk copies (one
+    // per segment, issued by one thread, completing on an mbarrier), tiles that touch
+    // the edge of the supplied window by 8-byte cp.async with zero fill.
     constexpr int NT = WT * KS * 32;
     extern __shared__ __align__(16) double smem_mma[];
+    __shared__ __align__(8) uint64_t bars[2];
     const int M = gm.M, SM = gm.SM, P = gm.P, S = gm.S;
     const int nseg = (gm.total_len + SM - 1) / SM;
-    const int tile_elems = nseg * P;
-    double *bufs = smem_mma;                                 // 2 x nseg * P
+    const int tile_elems = nseg * P + 2;                     // + 2: room for the alignment shift
+    double *bufs = smem_mma;                                 // 2 x tile_elems
     double *gs = bufs + 2 * (size_t)tile_elems;              // M * ldq
-    double *red = gs + (size_t)M * gm.ldq;                   // (KS - 1) * 8 * S
+    double *red = gs + (size_t)M * gm.ldq;                   // 2 x KS x 8 S partial sums
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int wt = warp % WT, wk = warp / WT;
     const int g = lane >> 2, q = lane & 3;
     const uint32_t sbase = smem_u32(bufs);
+    const bool tma_pitch = (P & 1) == 0 && (SM & 1) == 0;
 
+    // where tile t's window starts, relative to the supplied window of its row
+    auto tile_rel0 = [&](int64_t t, int64_t &row) {
+        row = t / tiles_per_row;
+        const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
+        return (out_first + o0) * M + gm.half - (gm.K - 1) - x_first;
+    };
+    // bulk-copy eligible: strictly inside the window (the copies run up to one element
+    // past either end of a segment's span for 16-byte alignment)
+    auto tile_tma = [&](int64_t rel0) {
+        return tma_pitch && rel0 >= 1 && rel0 + gm.total_len + 2 <= x_len;
+    };
     auto stage = [&](int64_t t, int which) {
         if (t >= ntiles) return;
-        const int64_t row = t / tiles_per_row;
-        const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
-        const int64_t rel0 = (out_first + o0) * M + gm.half - (gm.K - 1) - x_first;
+        int64_t row;
+        const int64_t rel0 = tile_rel0(t, row);
         const double *xr = x + row * ldx;
+        if (tile_tma(rel0)) {
+            if (tid == 0) {
+                const double *src0 = xr + rel0;
+                const int mis = span_mis(src0);
+                uint32_t bytes = 0;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const int len = min(SM, gm.total_len - seg * SM);
+                    bytes += (uint32_t)((len + mis + 1) & ~1) * 8u;
+                }
+                mbar_expect_tx(&bars[which], bytes);
+                double *dst0 = bufs + (size_t)which * tile_elems;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const int len = min(SM, gm.total_len - seg * SM);
+                    tma_load_1d(dst0 + (size_t)seg * P, src0 - mis + (size_t)seg * SM,
+                                (uint32_t)((len + mis + 1) & ~1) * 8u, &bars[which]);
+                }
+            }
+            return;
+        }
         const uint32_t dst0 = sbase + (uint32_t)which * (uint32_t)tile_elems * 8u;
-        const bool interior = rel0 >= 0 && rel0 + gm.total_len <= x_len;
         for (int seg = 0; seg < nseg; ++seg) {
             const int len = min(SM, gm.total_len - seg * SM);
             const int64_t g0 = rel0 + (int64_t)seg * SM;
             const uint32_t dst = dst0 + (uint32_t)(seg * P) * 8u;
-            if (interior) {
-#pragma unroll 4
-                for (int e = tid; e < len; e += NT) cp_async8_zfill(dst + e * 8u, xr + g0 + e, true);
-            } else {
-                for (int e = tid; e < len; e += NT) {
-                    const int64_t gi = g0 + e;
-                    const bool ok = gi >= 0 && gi < x_len;
-                    cp_async8_zfill(dst + e * 8u, ok ? xr + gi : xr, ok);
-                }
+            for (int e = tid; e < len; e += NT) {
+                const int64_t gi = g0 + e;
+                const bool ok = gi >= 0 && gi < x_len;
+                cp_async8_zfill(dst + e * 8u, ok ? xr + gi : xr, ok);
             }
         }
+        cp_async_commit();
     };
 
-    stage(blockIdx.x, 0);
-    cp_async_commit();
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
     for (int i = tid; i < M * gm.ldq; i += NT) gs[i] = gpad[i];
+    __syncthreads();
+    stage(blockIdx.x, 0);
+    stage((int64_t)blockIdx.x + gridDim.x, 1);
 
     const int pad = P - SM;
+    const int logS = gm.logS;
     const int k_lo = (int)(((long)gm.ktotal * wk) / KS), k_hi = (int)(((long)gm.ktotal * (wk + 1)) / KS);
     const int oa = g * S + 32 * wt + 2 * q;          // this thread's outputs: oa + 8 j + {0, 1}
     int parity = 0;
+    uint32_t phases = 0u;                            // mbarrier phase bit of either buffer
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, parity ^= 1) {
-        const double *xs = bufs + (size_t)parity * tile_elems;
-        stage(t + gridDim.x, parity ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-
-        // ---- banded Toeplitz product on the tensor cores
-        const double *xrow = xs + (size_t)g * P;
-        auto fetch = [&](int r) {   // sample at offset r of segment g (r may run past it)
-            const int cross = (r >= SM) + (r >= 2 * SM) + (r >= 3 * SM);
-            return xrow[r + cross * pad];
-        };
+        int64_t row;
+        const int64_t rel0 = tile_rel0(t, row);
+        int mis = 0;
+        if (tile_tma(rel0)) {
+            mbar_wait(&bars[parity], (phases >> parity) & 1u);
+            phases ^= 1u << parity;
+            mis = span_mis(x + row * ldx + rel0);
+        } else {
+            cp_async_wait<0>();
+            __syncthreads();
+        }
+        // ---- banded Toeplitz product on the tensor cores.  Sample n of phase p in
+        //      segment g's window sits at offset p + n*M, which lies n / S segments on
+        //      (p < M): one pad per segment crossed
+        const double *xrow = bufs + (size_t)parity * tile_elems + (size_t)g * P + mis;
+        auto fetch = [&](int p, int n) { return xrow[p + n * M + (n >> logS) * pad]; };
         double c[8];
         ufd_mma_ksteps(gm, gs, k_lo, k_hi, wt, g, q, fetch, c);
-        // ---- combine the k-splits and store: tile j holds outputs oa + 8 j + {0, 1}
-        if (KS > 1) {
-            if (wk > 0) {
-                double *rd = red + (size_t)(wk - 1) * 8 * S;
+        // ---- partial sums of the k-splits to shared memory; every thread then sums and
+        //      stores its share of the tile's 8 S outputs
+        double *rd = red + ((size_t)parity * KS + wk) * 8 * S;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rd[oa + 8 * j] = c[2 * j];
-                    rd[oa + 8 * j + 1] = c[2 * j + 1];
-                }
-            }
-            __syncthreads();
-            if (wk == 0) {
-                for (int k = 0; k < KS - 1; ++k) {
-                    const double *rd = red + (size_t)k * 8 * S;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        c[2 * j] += rd[oa + 8 * j];
-                        c[2 * j + 1] += rd[oa + 8 * j + 1];
-                    }
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            rd[oa + 8 * j] = c[2 * j];
+            rd[oa + 8 * j + 1] = c[2 * j + 1];
         }
-        if (wk == 0) {
-            const int64_t row = t / tiles_per_row;
-            const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
-            double *yr = y + row * ldy + o0;
+        __syncthreads();       // partials visible; nobody reads this tile's buffer any more
+        stage(t + 2 * (int64_t)gridDim.x, parity);
+        const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
+        const double *r0 = red + (size_t)parity * KS * 8 * S;
+        for (int o = tid; o < 8 * S; o += NT) {
+            double sum = r0[o];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (o0 + oa + 8 * j < n_out) st_stream(yr + oa + 8 * j, c[2 * j]);
-                if (o0 + oa + 8 * j + 1 < n_out) st_stream(yr + oa + 8 * j + 1, c[2 * j + 1]);
-            }
+            for (int k = 1; k < KS; ++k) sum += r0[(size_t)k * 8 * S + o];
+            if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
         }
-        // the reads of `red` and of this tile's buffer must be over before either is
-        // rewritten (the refill of this buffer is issued at the top of the next turn)
-        __syncthreads();
+        // (`red` is double buffered: this half is written again two tiles on, behind
+        //  the next tile's barrier)
     }
     cp_async_wait<0>();
 }
@@ -538,6 +562,7 @@ struct osz_upfirdn_plan {
     int kernel = OSZ_UFD_AUTO;     // osz_upfirdn_plan_set_kernel
     UfdMmaGeom mg{};
     int mma_wt = 0, mma_ks = 2;
+    double mma_useful = 0.0;       // K / (4 * k-steps): useful share of the MMA work
     size_t smem_mma = 0;
     double *d_gpad = nullptr;      // [down][ldq]: window-order taps g[j] = h'[K-1-j]
     double *d_gpad_rev = nullptr;  // the same table for a reversed time axis (taps h')
@@ -582,12 +607,13 @@ static bool mma_geometry(int K, int M, int ksplit, UfdMmaGeom *gm, int *wt_out,
         const int nseg = (total_len + SM - 1) / SM;
         const int ldq = 7 + 4 * (smax + 1) + 4;
         const size_t smem =
-            (2 * (size_t)nseg * P + (size_t)M * ldq + (size_t)(ksplit - 1) * 8 * S) * 8;
+            (2 * ((size_t)nseg * P + 2) + (size_t)M * ldq + 2 * (size_t)ksplit * 8 * S) * 8;
         if (smem > 225 * 1024) continue;
         gm->K = K;
         gm->M = M;
         gm->half = (K - 1) / 2;
         gm->S = S;
+        gm->logS = S == 64 ? 6 : 5;
         gm->SM = SM;
         gm->P = P;
         gm->total_len = total_len;
@@ -770,6 +796,7 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
                  cudaMemcpy(p->d_g, g.data(), (size_t)K * 8, cudaMemcpyHostToDevice) ==
                      cudaSuccess;
             p->mma = ok;
+            p->mma_useful = (double)K / (4.0 * p->mg.ktotal);
         }
     }
     if (!ok) {
@@ -849,7 +876,13 @@ int osz_upfirdn_plan_set_kernel(osz_upfirdn_plan *p, int kernel) {
 int osz_upfirdn_plan_kernel(const osz_upfirdn_plan *p) {
     if (!p) return 0;
     if (!p->R) return OSZ_UFD_GENERAL;
-    if (p->kernel == OSZ_UFD_MMA || (p->kernel == OSZ_UFD_AUTO && p->mma && ufd_use_mma_default()))
+    // AUTO: the tensor-core kernel when at least 80 % of its MMA work is useful (long
+    // per-phase filters: 8 outputs share a window, so a phase of Q taps costs Q + 7) and
+    // its tiles can be staged by TMA (even segment pitch); measured on B200 (256 x 1e6):
+    // 1231 taps / M = 25: 1.30 ms against 1.55 ms for the CUDA-core kernel; 561 / 25
+    // (70 % useful): 0.99 against 0.96; 449 / 20 (cp.async staging): 1.5 against 0.97
+    const bool worth = p->mma && p->mma_useful >= 0.8 && (p->mg.P % 2 == 0);
+    if (p->kernel == OSZ_UFD_MMA || (p->kernel == OSZ_UFD_AUTO && worth && ufd_use_mma_default()))
         return OSZ_UFD_MMA;
     return OSZ_UFD_POLYPHASE;
 }

@@ -76,18 +76,51 @@ def channel_block(shape, axis, rank, size):
     return tuple(index), split
 
 
+def _block_chunks(pro, index):
+    """Generating function of a channel block of any producer: every yielded chunk
+    sliced to the block (module level so that the sharded producer pickles)."""
+    for chunk in pro:
+        yield chunk[index]
+
+
 def shard_channels(data, chunksize, axis=-1, group=None):
-    """Producer over this rank's block of channels of an ndarray (a view -- no
-    copy).  Running any operator chain on it and concatenating the ranks'
-    results along the split axis equals the single-process result."""
-    if isinstance(data, Producer):
-        if not isinstance(data, ArrayProducer):
-            raise TypeError("channel sharding slices in-memory data; shard generator or "
-                            "reader producers where they are built")
-        data = data.data
+    """Producer over this rank's block of channels.  Running any operator chain on
+    it and concatenating the ranks' results along the split axis equals the
+    single-process result (every operator is independent per 1-D slice along the
+    sample axis: reference filtering/bases.py:169-172).
+
+    * ndarray / array producer: a view of the block -- no copy;
+    * reader producer (core/producer.py:213-264) whose reader has a ``channels``
+      attribute (the EDF readers): a copy of the reader restricted to the block, so
+      only this rank's channels are read and decoded -- the out-of-core case;
+    * any other producer (generating functions, masked): the same chunks sliced to
+      the block as they are produced."""
+    import copy
+    import functools
+
+    from openseize_b200.core.producer import ReaderProducer
+
     rank, size = world(group)
-    index, _ = channel_block(data.shape, axis, rank, size)
-    return producer(data[index], chunksize, axis)
+    if isinstance(data, ArrayProducer):
+        data = data.data
+    if not isinstance(data, Producer):
+        index, _ = channel_block(np.shape(data), axis, rank, size)
+        return producer(np.asarray(data)[index], chunksize, axis)
+    axis_n = normalize_axis(axis, len(data.shape))
+    index, split = channel_block(data.shape, axis_n, rank, size)
+    lo, hi, _ = index[split].indices(data.shape[split])
+    shape = list(data.shape)
+    shape[split] = hi - lo
+    reader = getattr(data, "data", None)
+    chans = getattr(reader, "channels", None)
+    if isinstance(data, ReaderProducer) and chans is not None and len(data.shape) == 2 \
+            and split == 0 and len(chans) == data.shape[0]:
+        mine = copy.copy(reader)
+        mine.channels = list(chans)[lo:hi]
+        return producer(mine, chunksize, axis, **dict(data.kwargs))
+    src = producer(data, data.chunksize, data.axis)         # (same object: chunk size kept)
+    return producer(functools.partial(_block_chunks, src, index), chunksize, axis,
+                    shape=tuple(shape))
 
 
 def welch_segments(nsamples, nfft, overlap):
@@ -167,15 +200,66 @@ def time_spans(n, size, align=1):
     return [(min(a * align, n), min(b * align, n)) for a, b in split_range(units, size)]
 
 
+def _collective_device(group=None):
+    """Where tensors of a collective have to live: the GPU under NCCL, the host
+    under gloo (the CPU test harness)."""
+    dist = _dist()
+    return "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+
+
+def all_gather_arrays(local, group=None):
+    """Every rank's float64 ndarray (or None) of a common trailing shape, gathered
+    with tensor collectives -- one ``all_gather`` of the leading lengths, one of the
+    arrays padded to the longest -- instead of pickled objects.  Returns the list of
+    arrays by rank (None for ranks that contributed None)."""
+    t = dv.torch()
+    dist = _dist()
+    rank, size = world(group)
+    if size == 1:
+        return [local]
+    dev = _collective_device(group)
+    # trailing shape: agreed through a MAX reduction (ranks with None send zeros)
+    ndim_t = t.tensor([0 if local is None else local.ndim], dtype=t.int64, device=dev)
+    dist.all_reduce(ndim_t, op=dist.ReduceOp.MAX, group=group)
+    ndim = int(ndim_t.item())
+    meta = t.zeros(1 + max(ndim, 1), dtype=t.int64, device=dev)
+    if local is not None:
+        meta[0] = 1
+        meta[1:1 + local.ndim] = t.tensor(local.shape, dtype=t.int64)
+    metas = [t.zeros_like(meta) for _ in range(size)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.cpu().numpy() for m in metas]
+    trail = None
+    for m in metas:
+        if m[0]:
+            trail = tuple(int(v) for v in m[2:1 + ndim])
+    lead = [int(m[1]) if m[0] else 0 for m in metas]
+    if trail is None:
+        return [None] * size
+    width = int(np.prod(trail, dtype=np.int64)) if trail else 1
+    longest = max(max(lead), 1)
+    buf = t.zeros((longest, width), dtype=t.float64, device=dev)
+    if local is not None and local.size:
+        buf[:local.shape[0]] = t.from_numpy(
+            np.ascontiguousarray(local, dtype=np.float64).reshape(local.shape[0], width)).to(dev)
+    bufs = [t.empty_like(buf) for _ in range(size)]
+    dist.all_gather(bufs, buf, group=group)
+    out = []
+    for m, n, b in zip(metas, lead, bufs):
+        out.append(b[:n].cpu().numpy().reshape((n,) + trail) if m[0] else None)
+    return out
+
+
 def gather_time(local, axis, group=None):
-    """Concatenate every rank's span along ``axis`` (host side; every rank gets
-    the whole result).  ``local`` may be None for a rank with an empty span."""
+    """Concatenate every rank's span along ``axis`` (every rank gets the whole
+    result).  ``local`` may be None for a rank with an empty span.  Tensor
+    collectives over the group's backend (NCCL: device tensors over NVLink)."""
     rank, size = world(group)
     if size == 1:
         return local
-    parts = [None] * size
-    _dist().all_gather_object(parts, local, group=group)
-    return np.concatenate([p for p in parts if p is not None], axis=axis)
+    lead = None if local is None else np.moveaxis(local, axis, 0)
+    parts = [p for p in all_gather_arrays(lead, group) if p is not None]
+    return np.moveaxis(np.concatenate(parts, axis=0), 0, axis)
 
 
 def fir_time_sharded(data, window, chunksize, axis=-1, mode="same", group=None, gather=True):
@@ -309,10 +393,7 @@ def _entering_states(cascade, data, spans, rank, axis, chunksize, first_state, g
         for chunk in nm.device_chunks(producer(sub, chunksize, axis), axis, regrid=False):
             cascade.run(chunk, states, want_output=False)
         f = _states_to_host(states)
-    finals = [f]
-    if size > 1:
-        finals = [None] * size
-        _dist().all_gather_object(finals, f, group=group)
+    finals = all_gather_arrays(f, group) if size > 1 else [f]
     T = cascade_transition(cascade.sos)
     s = np.asarray(first_state, dtype=np.longdouble).reshape(layout.rows, -1)
     for q in range(rank):
