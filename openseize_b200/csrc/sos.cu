@@ -37,8 +37,10 @@ namespace osz {
 // for one or two sections, where the kernel is bound by memory latency and the
 // smaller footprint (32 registers of samples, 35 KB of shared memory) lets four
 // CTAs share an SM instead of two.
-template <bool WRITE, int T>
-__global__ void __launch_bounds__(SOS_NT, (T == 32 ? 2 : 4))
+// PF: the loads of block blk + 1 are issued into registers before block blk is scanned
+// (T = 16 only: 32 more registers, two CTAs per SM), so a CTA always has loads in flight.
+template <bool WRITE, int T, bool PF = false>
+__global__ void __launch_bounds__(SOS_NT, (T == 32 || PF ? 2 : 4))
 sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
                 int64_t n_total, int reverse, const double *__restrict__ state_in,
                 double *__restrict__ state, double *__restrict__ y, int64_t ldy,
@@ -92,13 +94,27 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     const int64_t nblk = (n + BLK - 1) / BLK;
     const int64_t first_len = n - (nblk - 1) * BLK;
 
+    double nxt[PF ? T : 1];
+    auto prefetch = [&](int64_t blk) {          // a full block (blk >= 1)
+        const int64_t p0 = first_len + (blk - 1) * BLK;
+        const double *src = reverse ? xr - p0 - tid : xr + p0 + tid;
+#pragma unroll
+        for (int it = 0; it < (PF ? T : 1); ++it)
+            nxt[it] = ld_stream(reverse ? src - it * SOS_NT : src + it * SOS_NT);
+    };
     for (int64_t blk = 0; blk < nblk; ++blk) {
         // The first block is the short one and sits at the END of the BLK
         // slots, behind `off` virtual zero samples that keep a zero state.
         const int off = blk == 0 ? (int)(BLK - first_len) : 0;
         const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * BLK;
         __syncthreads();   // carry[] visible / buf free
-        if (blk != 0) {
+        if (blk != 0 && PF) {
+#pragma unroll
+            for (int it = 0; it < (PF ? T : 1); ++it) {
+                const int e = tid + it * SOS_NT;
+                buf[(e >> LOGT) * LD + (e & (T - 1))] = nxt[it];
+            }
+        } else if (blk != 0) {
             // full block: T independent coalesced loads in flight per thread
             const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
             double tmp[T];
@@ -121,6 +137,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 buf[(e >> LOGT) * LD + (e & (T - 1))] = val;
             }
         }
+        if (PF && blk + 1 < nblk) prefetch(blk + 1);
         __syncthreads();
         double v[T];
 #pragma unroll
@@ -205,6 +222,7 @@ using namespace osz;
 struct osz_sos_plan {
     SosParams prm;
     int T = 32;                     // samples per thread of the kernel this plan uses
+    bool prefetch = false;          // T = 16: register prefetch of the next block
     int64_t settle = -1;            // samples after which the start state is forgotten (-1: never)
     double *d_lanepow = nullptr;    // [sec][32][4]: A^(T*(lane+1))
     double *T16_lanepow = nullptr;  // the same for 16 samples per thread (sosdec.cu)
@@ -298,6 +316,8 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
         const char *e = getenv("OSZ_SOS_T");
         p->T = e ? atoi(e) : 32;
         if (p->T != 16 && p->T != 32) p->T = 32;
+        const char *pf = getenv("OSZ_SOS_PF");
+        p->prefetch = pf ? atoi(pf) != 0 : false;
     }
     std::vector<double> lanepow((size_t)nsec * 32 * 4), lanepow16((size_t)nsec * 32 * 4);
     double rmax = 0.0;              // largest pole radius of the cascade
@@ -594,11 +614,19 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     const dim3 grid((unsigned)rows, (unsigned)nspan);
 #define OSZ_SOS_LAUNCH(W, TT, YY, SIN, SOUT)                                                    \
     do {                                                                                        \
-        OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                                   \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-        sos_scan_kernel<W, TT><<<grid, SOS_NT, smem, st>>>(p->prm, x, ldx, n, reverse, state_in, \
-                                                           state, YY, ldy, p->d_lanepow,        \
-                                                           span_len, p->settle, SIN, SOUT);     \
+        if (TT == 16 && p->prefetch) {                                                          \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 16, true>,                         \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            sos_scan_kernel<W, 16, true><<<grid, SOS_NT, smem, st>>>(                           \
+                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+                p->settle, SIN, SOUT);                                                          \
+        } else {                                                                                \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                               \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            sos_scan_kernel<W, TT><<<grid, SOS_NT, smem, st>>>(                                 \
+                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+                p->settle, SIN, SOUT);                                                          \
+        }                                                                                       \
         OSZ_LAUNCHED("sos_scan_kernel");                                                        \
     } while (0)
     if (exact) {

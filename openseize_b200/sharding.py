@@ -152,19 +152,15 @@ def psd_time_sharded(data, fs, axis=-1, resolution=0.5, window="hann", overlap=0
     single-process one up to the order of the floating-point sum."""
     t = dv.require_cuda()
     dist = _dist()
-    if isinstance(data, ArrayProducer):
-        data = data.data
-    if not isinstance(data, np.ndarray):
-        raise TypeError("time sharding slices in-memory data")
-    axis = normalize_axis(axis, data.ndim)
+    data = _Source(data, axis)
+    axis = data.axis
     rank, size = world(group)
     nfft = int(fs / resolution)
     nsamples = data.shape[axis]
     start, stop = time_span(nsamples, nfft, overlap, rank, size)
     layout = dv.Layout(data.shape, axis)
     if stop > start:
-        mine = slice_along_axis(data, start, stop, axis=axis)
-        cnt, psd_sum = nm.welch_sum(producer(mine, int(fs), axis), fs, nfft, window, overlap,
+        cnt, psd_sum = nm.welch_sum(data.window(start, stop, int(fs)), fs, nfft, window, overlap,
                                     axis, detrend, scaling)
     else:
         cnt, psd_sum = 0, dv.zeros((layout.rows, nfft // 2 + 1))
@@ -185,12 +181,61 @@ def psd_time_sharded(data, fs, axis=-1, resolution=0.5, window="hann", overlap=0
 # ---------------------------------------------------------------------------
 # time sharding of the filters (few-channel recordings)
 # ---------------------------------------------------------------------------
-def _in_memory(data):
-    if isinstance(data, ArrayProducer):
-        data = data.data
-    if not isinstance(data, np.ndarray):
-        raise TypeError("time sharding slices in-memory data")
-    return data
+def _window_chunks(pro, a, b, axis):
+    """Generating function of samples [a, b) of any producer: chunks outside the window
+    are skipped as they are produced (a generating function cannot seek)."""
+    pos = 0
+    for chunk in pro:
+        n = chunk.shape[axis]
+        lo, hi = max(a - pos, 0), min(b - pos, n)
+        if hi > lo:
+            yield slice_along_axis(chunk, lo, hi, axis=axis)
+        pos += n
+        if pos >= b:
+            return
+
+
+class _Source:
+    """A recording that can hand out time windows: an ndarray or array producer (views),
+    a reader producer (``read(start, stop)`` of the window only -- the out-of-core
+    case), or any other producer (its chunks, cut to the window as they come)."""
+
+    def __init__(self, data, axis):
+        from openseize_b200.core.producer import ReaderProducer
+
+        if isinstance(data, ArrayProducer):
+            data = data.data
+        self.data = data
+        self.kind = ("array" if not isinstance(data, Producer)
+                     else "reader" if isinstance(data, ReaderProducer) else "producer")
+        if self.kind == "array":
+            self.data = np.asarray(data)
+        self.shape = tuple(self.data.shape)
+        self.ndim = len(self.shape)
+        self.axis = normalize_axis(axis, self.ndim)
+
+    def window(self, a, b, chunksize):
+        """Producer of samples [a, b) along the sample axis."""
+        import functools
+
+        a, b = int(a), int(b)
+        if self.kind == "array":
+            return producer(slice_along_axis(self.data, a, b, axis=self.axis), chunksize, self.axis)
+        if self.kind == "reader":
+            pro = self.data
+            return producer(pro.data, chunksize, self.axis, start=pro.start + a,
+                            stop=pro.start + b, **dict(pro.kwargs))
+        shape = list(self.shape)
+        shape[self.axis] = b - a
+        src = producer(self.data, self.data.chunksize, self.data.axis)
+        return producer(functools.partial(_window_chunks, src, a, b, self.axis), chunksize,
+                        self.axis, shape=tuple(shape))
+
+    def array(self, a, b):
+        """Samples [a, b) as an ndarray (small windows: first sample, halos)."""
+        if self.kind == "array":
+            return slice_along_axis(self.data, int(a), int(b), axis=self.axis)
+        return self.window(a, b, max(int(b) - int(a), 1)).to_array()
 
 
 def time_spans(n, size, align=1):
@@ -268,8 +313,8 @@ def fir_time_sharded(data, window, chunksize, axis=-1, mode="same", group=None, 
     outside the recording, as numpy's convolution modes imply) and keeps outputs
     [o0, o1); the halo comes from the host array.  Returns the whole result
     (``gather``) or ``((o0, o1), this rank's span)``."""
-    data = _in_memory(data)
-    axis = normalize_axis(axis, data.ndim)
+    data = _Source(data, axis)
+    axis = data.axis
     window = np.asarray(window, dtype=np.float64)
     k, n = len(window), data.shape[axis]
     if n < k:
@@ -286,8 +331,7 @@ def fir_time_sharded(data, window, chunksize, axis=-1, mode="same", group=None, 
         if in_hi - in_lo < k:                         # a sliver: widen the halo to K samples
             in_lo = max(in_hi - k, 0)
             in_hi = min(in_lo + k, n)
-        sub = slice_along_axis(data, in_lo, in_hi, axis=axis)
-        blocks = list(nm.oaconvolve(producer(sub, chunksize, axis), window, axis, "full"))
+        blocks = list(nm.oaconvolve(data.window(in_lo, in_hi, chunksize), window, axis, "full"))
         full = np.concatenate(blocks, axis=axis)      # full[j] is full-convolution index in_lo + j
         local = slice_along_axis(full, f0 - in_lo, f1 - in_lo, axis=axis)
     if not gather:
@@ -305,8 +349,8 @@ def resample_time_sharded(data, L, M, fs, chunksize, axis=-1, group=None, gather
 
     from openseize_b200.filtering.fir import Kaiser
 
-    data = _in_memory(data)
-    axis = normalize_axis(axis, data.ndim)
+    data = _Source(data, axis)
+    axis = data.axis
     n = data.shape[axis]
     g = gcd(int(L), int(M))
     up, down = int(L) // g, int(M) // g
@@ -324,8 +368,7 @@ def resample_time_sharded(data, L, M, fs, chunksize, axis=-1, group=None, gather
         in_hi = min(max(in_hi, in_lo + 3 * down + len(h)), n)
         in_lo = max(min(in_lo, in_hi - 3 * down - len(h)), 0)
         in_lo -= in_lo % down
-        sub = slice_along_axis(data, in_lo, in_hi, axis=axis)
-        sub_pro = producer(sub, chunksize, axis)
+        sub_pro = data.window(in_lo, in_hi, chunksize)
         blocks = list(nm.polyphase_resample(sub_pro, L, M, fs, Kaiser, axis, **kwargs))
         y = np.concatenate(blocks, axis=axis)
         first = in_lo * up // down                    # global index of y's first sample
@@ -389,8 +432,7 @@ def _entering_states(cascade, data, spans, rank, axis, chunksize, first_state, g
     f = np.zeros((layout.rows, cascade.nsec, 2))
     if size > 1 and b > a and rank < size - 1:
         states = cascade.zero_state(layout.rows)
-        sub = slice_along_axis(data, a, b, axis=axis)
-        for chunk in nm.device_chunks(producer(sub, chunksize, axis), axis, regrid=False):
+        for chunk in nm.device_chunks(data.window(a, b, chunksize), axis, regrid=False):
             cascade.run(chunk, states, want_output=False)
         f = _states_to_host(states)
     finals = all_gather_arrays(f, group) if size > 1 else [f]
@@ -414,8 +456,8 @@ def iir_time_sharded(data, coeffs, chunksize, axis=-1, dephase=True, zi=None, fm
     filters keep the reference's dependence on the chunk grid."""
     import scipy.signal as sps
 
-    data = _in_memory(data)
-    axis = normalize_axis(axis, data.ndim)
+    data = _Source(data, axis)
+    axis = data.axis
     n = data.shape[axis]
     chunksize = int(chunksize)
     layout = dv.Layout(data.shape, axis)
@@ -434,7 +476,7 @@ def iir_time_sharded(data, coeffs, chunksize, axis=-1, dephase=True, zi=None, fm
 
     # state entering the recording
     if dephase:
-        x0 = np.moveaxis(slice_along_axis(data, 0, 1, axis=axis).reshape(
+        x0 = np.moveaxis(np.asarray(data.array(0, 1), dtype=np.float64).reshape(
             layout.outer, 1, layout.inner), 1, 2).reshape(layout.rows)
         first = zi_ss[None, :, :] * x0[:, None, None]            # zi * x0, numerical.py:385
     elif zi is None:
@@ -450,13 +492,11 @@ def iir_time_sharded(data, coeffs, chunksize, axis=-1, dephase=True, zi=None, fm
         states = cascade.split_state(dv.from_host(entering))
         if dephase:
             stop = min(b + chunksize, n)                          # borrow the look-ahead chunk
-            sub = slice_along_axis(data, a, stop, axis=axis)
-            gen = nm._filtfilt_device(producer(sub, chunksize, axis), cascade, zi_ss, axis,
+            gen = nm._filtfilt_device(data.window(a, stop, chunksize), cascade, zi_ss, axis,
                                       _fwd_states=states, _drop_last=stop > b)
         else:
-            sub = slice_along_axis(data, a, b, axis=axis)
             gen = (cascade.run(chunk, states)
-                   for chunk in nm.device_chunks(producer(sub, chunksize, axis), axis,
+                   for chunk in nm.device_chunks(data.window(a, b, chunksize), axis,
                                                  regrid=False))
         local = np.concatenate(list(nm._to_host(gen, layout)), axis=axis)
         assert local.shape[axis] == b - a

@@ -477,8 +477,9 @@ def c5_real_parameters(rows=2, nchunks=6, tail=123_457, cs=1_000_000):
     rc, rf, rp = oracle.welch_psd(r3, fs2, -1, fs2 / nfft)
     assert rc == (r3.shape[-1] - nfft) // (nfft // 2) + 1
     errs = {}
-    for fuse in ("1", "0"):
+    for fuse, fuse_iir in (("1", "0"), ("0", "0"), ("1", "1")):
         os.environ["OSZ_FUSE"] = fuse
+        os.environ["OSZ_FUSE_IIR"] = fuse_iir
         try:
             def chain():
                 p1 = notch(producer(x, cs, -1), cs, axis=-1, dephase=True)
@@ -490,8 +491,10 @@ def c5_real_parameters(rows=2, nchunks=6, tail=123_457, cs=1_000_000):
             got = [np.array(b) for b in d]
         finally:
             os.environ.pop("OSZ_FUSE", None)
+            os.environ.pop("OSZ_FUSE_IIR", None)
         assert cnt == rc and np.array_equal(f, rf), (fuse, cnt, rc)
         assert d.shape == r3.shape
+        fuse = fuse + fuse_iir
         errs["decimated_fuse" + fuse] = close(np.concatenate(got, -1), r3)
         # per-bin error relative to each channel's largest bin (SURVEY 8d parity metric)
         e = float(np.max(np.abs(p - rp) / np.max(rp, axis=-1, keepdims=True)))

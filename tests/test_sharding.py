@@ -166,6 +166,95 @@ def test_time_shards_simulated(fake_gpu, monkeypatch):
             assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
 
 
+class _ArrayReader:
+    """Minimal reader (shape, read(start, stop), open, close): what ReaderProducer needs;
+    `channels` restricts the rows like the EDF readers' attribute of that name."""
+
+    def __init__(self, x):
+        self.x, self.channels, self.reads = x, list(range(x.shape[0])), []
+
+    @property
+    def shape(self):
+        return (len(self.channels), self.x.shape[1])
+
+    def read(self, start, stop):
+        self.reads.append((start, stop))
+        return self.x[self.channels, start:stop]
+
+    def open(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def _gen_source(x, step):
+    for i in range(0, x.shape[-1], step):
+        yield x[..., i:i + step]
+
+
+def test_shards_of_out_of_core_sources(fake_gpu, monkeypatch):
+    """Channel and time shards of reader and generating-function producers (the
+    out-of-core recording of BASELINE config 5): a rank reads only its channel block /
+    its time span plus the filter halo, and the stitched result equals the
+    single-process one."""
+    import functools
+
+    import oracle
+    from openseize_b200 import producer
+    from openseize_b200.filtering.fir import Kaiser
+    from openseize_b200.spectra.estimators import psd
+    from oracle.chunked import _kaiser_lowpass
+
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((6, 45000)) + 0.3
+    fs = 1024
+    filt = Kaiser(100, 150, fs)
+    taps = _kaiser_lowpass(100, 150, fs, 1.0, 40.0)
+    ref_fir = np.concatenate(oracle.oaconvolve(x, taps, 6000, -1, "same"), -1)
+    rc, rf, ref_psd = oracle.welch_psd(ref_fir, fs, -1, 1.0)
+    size = 3
+    for kind in ("reader", "generator"):
+        parts, readers = [], []
+        for r in range(size):
+            monkeypatch.setattr(sharding, "world", lambda group=None, r=r: (r, size))
+            if kind == "reader":
+                rd = _ArrayReader(x)
+                src = producer(rd, 6000, -1)
+                readers.append(rd)
+            else:
+                src = producer(functools.partial(_gen_source, x, 5000), 6000, -1, shape=x.shape)
+            mine = sharding.shard_channels(src, 6000)
+            assert mine.shape == (2, 45000)
+            cnt, f, p = psd(filt(mine, 6000), fs, resolution=1.0)
+            assert cnt == rc
+            parts.append(p)
+        got = np.concatenate(parts, 0)
+        assert np.max(np.abs(got - ref_psd)) / np.max(np.abs(ref_psd)) < 1e-12
+    # time shards of a reader: every rank reads its own span (+ halo) only
+    parts, spans = [], []
+    for r in range(size):
+        monkeypatch.setattr(sharding, "world", lambda group=None, r=r: (r, size))
+        rd = _ArrayReader(x)
+        (o0, o1), loc = sharding.fir_time_sharded(producer(rd, 6000, -1), taps, 6000, mode="same",
+                                                  gather=False)
+        parts.append(loc)
+        spans.append((min(a for a, _ in rd.reads), max(b for _, b in rd.reads)))
+        assert spans[-1][1] - spans[-1][0] < x.shape[1] // size + 2 * len(taps)
+    got = np.concatenate(parts, -1)
+    assert np.max(np.abs(got - ref_fir)) / np.max(np.abs(ref_fir)) < 1e-12
+    # ... and of a generating function (chunks outside the span are skipped)
+    parts = []
+    for r in range(size):
+        monkeypatch.setattr(sharding, "world", lambda group=None, r=r: (r, size))
+        src = producer(functools.partial(_gen_source, x, 5000), 6000, -1, shape=x.shape)
+        (o0, o1), loc = sharding.resample_time_sharded(src, 1, 4, fs, 6000, gather=False)
+        parts.append(loc)
+    ref = np.concatenate(oracle.polyphase_resample(x, 1, 4, fs, 6000, -1), -1)
+    got = np.concatenate(parts, -1)
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
 def test_cascade_transition_matches_recurrence():
     import scipy.signal as sps
 

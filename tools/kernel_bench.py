@@ -79,11 +79,14 @@ def main(which):
                    timeit(lambda: plan.run(x, st, want_output=False)), r * n, 8)
         b, a = sps.iirnotch(60, 10, fs=30000)
         plan = dv.SosPlan(np.concatenate([b, a])[None])
-        x = rnd(256, n)
-        y = torch.empty_like(x)
-        st = dv.zeros((256, 1, 2))
-        report("notch biquad fwd rows=256", timeit(lambda: plan.run(x, st, out=y)), 256 * n, 16)
-        del x, y
+        for r in (256, 128, 64, 32):
+            x = rnd(r, n)
+            y = torch.empty_like(x)
+            st = dv.zeros((r, 1, 2))
+            report("notch biquad fwd rows=%d" % r, timeit(lambda: plan.run(x, st, out=y)), r * n, 16)
+            report("notch biquad bwd rows=%d" % r,
+                   timeit(lambda: plan.run(x, st, reverse=True, out=y)), r * n, 16)
+            del x, y
     if not which or "upfirdn" in which:
         for fs, M in ((5000, 20), (30000, 25)):
             import oracle
