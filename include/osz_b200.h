@@ -82,6 +82,12 @@ int osz_unpack_rows_f64(const double *src_dev, int64_t ld_src, int64_t outer, in
 /* complex128 variant (STFT output) */
 int osz_unpack_rows_c128(const double *src_dev, int64_t ld_src, int64_t outer, int64_t n,
                          int64_t inner, double *dst_dev, void *stream);
+/* z[r][t] = re[r][t] + i im[r][t]: (rows, n) real and imaginary rows -> (rows, n)
+ * complex128 (interleaved).  The analytic signal x + i H(x) of
+ * experimental/coupling/transforms.py:185-192 (protools.multiply / protools.add of two
+ * producers) assembled on the device. */
+int osz_zip_complex_f64(const double *re_dev, int64_t ldre, const double *im_dev, int64_t ldim,
+                        int64_t rows, int64_t n, double *z_dev, void *stream);
 /* widen float32 / int16 chunks to float64 on the device (the reference
  * returns float64 for every input dtype). */
 int osz_widen_f32_f64(const float *src_dev, double *dst_dev, int64_t count, void *stream);
@@ -155,6 +161,20 @@ int osz_sos_exec_f64(const osz_sos_plan *plan, const double *x_dev, int64_t ldx,
 int osz_sos_state_from_sample_f64(const osz_sos_plan *plan, const double *zi_host,
                                   const double *x_dev, int64_t ldx, int64_t rows,
                                   int64_t sample, double *state_dev, void *stream);
+
+/* State the cascade holds after filtering the n samples of x_dev (rows, n) FROM REST
+ * (reverse: last sample first), without running the recurrence: a weighted sum of the
+ * last `settle` samples processed (osz_sos_plan_settle), whose weights decay like the
+ * impulse response -- exact to ~1e-18 of the state scale.  This is the look-ahead pass of
+ * nm.sosfiltfilt / nm.filtfilt (core/numerical.py:397-399, :508-509), whose start state
+ * zi * x[last] has been forgotten after `settle` samples.  One or two sections only
+ * (osz_sos_plan_has_weights) and n >= settle; OSZ_ERR_UNSUPPORTED otherwise. */
+int osz_sos_tail_state_f64(const osz_sos_plan *plan, const double *x_dev, int64_t ldx,
+                           int64_t rows, int64_t n, int reverse, double *state_dev, void *stream);
+/* Samples after which the cascade has forgotten its start state (||T^n|| < 1e-18), -1 for
+ * a pole on or outside the unit circle. */
+int64_t osz_sos_plan_settle(const osz_sos_plan *plan);
+int osz_sos_plan_has_weights(const osz_sos_plan *plan);
 
 /* ---- transfer-function IIR of any order: replaces scipy.signal.lfilter as
  *      called by nm.lfilter / nm.filtfilt (core/numerical.py:445,508,511,519)

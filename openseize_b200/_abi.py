@@ -40,6 +40,7 @@ SIGNATURES = {
     "osz_pack_rows_f64": (c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "osz_unpack_rows_f64": (c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "osz_unpack_rows_c128": (c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "osz_zip_complex_f64": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp]),
     "osz_widen_f32_f64": (c_int, [_vp, _vp, _i64, _vp]),
     "osz_widen_i16_f64": (c_int, [_vp, _vp, _i64, _vp]),
     "osz_widen_rows_f32_f64": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
@@ -65,6 +66,9 @@ SIGNATURES = {
                                      _vp]),
     "osz_upfirdn_plan_set_compute": (c_int, [_vp, c_int]),
     "osz_upfirdn_plan_compute": (c_int, [_vp]),
+    "osz_sos_tail_state_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp]),
+    "osz_sos_plan_settle": (_i64, [_vp]),
+    "osz_sos_plan_has_weights": (c_int, [_vp]),
     "osz_sosdec_spans": (c_int, [_vp, _vp, _i64, _i64]),
     "osz_sosdec_exec_f64": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_int, _vp, c_int, _i64, _vp,
                                     _i64, _i64, _i64, _vp, _vp]),

@@ -74,6 +74,39 @@ class _Streams:
         return cls._by_device[dev]
 
 
+_named_streams = {}
+
+
+def side_stream(name):
+    """A per-device CUDA stream for a stage that may run ahead of the stream its
+    consumer launches on (e.g. the forward pass of a forward-backward filter); None
+    off-GPU (test stand-ins)."""
+    if DEVICE != "cuda":
+        return None
+    t = torch()
+    key = (t.cuda.current_device(), name)
+    if key not in _named_streams:
+        _named_streams[key] = t.cuda.Stream()
+    return _named_streams[key]
+
+
+class on_stream:
+    """``with on_stream(s):`` -- launches and allocations go to stream ``s`` (no-op for
+    None).  Never held across a ``yield``."""
+
+    def __init__(self, stream):
+        self.ctx = torch().cuda.stream(stream) if stream is not None else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 # --------------------------------------------------------------------------
 # layout of a chunk
 # --------------------------------------------------------------------------
@@ -490,6 +523,26 @@ class SosPlan(_Plan):
         _abi.check(rc, "sos_exec")
         return out
 
+    @property
+    def has_weights(self):
+        """True for cascades of one or two decaying sections: ``tail_state`` works."""
+        if not hasattr(self, "_has_weights"):
+            self._has_weights = bool(_abi.load().osz_sos_plan_has_weights(self.handle))
+            self._settle = int(_abi.load().osz_sos_plan_settle(self.handle))
+        return self._has_weights
+
+    def tail_state(self, x, reverse=False):
+        """State after filtering x (rows, n >= settle) from rest, as a weighted sum of
+        the last ``settle`` samples processed (no recurrence, fully parallel)."""
+        rows, n = x.shape
+        state = empty((rows, self.nsec, 2))
+        xp, ldx = _rows_ptr(x)
+        rc = _launch("sos_state", 8 * rows * min(n, self._settle),
+                     _abi.load().osz_sos_tail_state_f64, self.handle, xp, ldx, rows, n,
+                     int(bool(reverse)), _vp(state.data_ptr()), _cur_stream())
+        _abi.check(rc, "sos_tail_state")
+        return state
+
     def state_from_sample(self, zi, x, sample):
         """state[r, s, :] = zi[s, :] * x[r, sample]."""
         t = torch()
@@ -795,6 +848,19 @@ def col_moments(x, ignore_nan=True, want="mean"):
     rc = _launch("col_moments", 8 * rows * n, _abi.load().osz_col_moments_f64, xp, ldx, rows,
                  int(n), int(bool(ignore_nan)), *args, _cur_stream())
     _abi.check(rc, "col_moments")
+    return out
+
+
+def zip_complex(re, im):
+    """(rows, n) real and imaginary device rows -> (rows, n, 2) complex128 rows."""
+    rows, n = re.shape
+    assert im.shape == re.shape
+    out = empty((rows, n, 2))
+    rp, ldr = _rows_ptr(re)
+    ip, ldi = _rows_ptr(im)
+    rc = _launch("zip_complex", 32 * rows * n, _abi.load().osz_zip_complex_f64, rp, ldr, ip, ldi,
+                 rows, int(n), _vp(out.data_ptr()), _cur_stream())
+    _abi.check(rc, "zip_complex")
     return out
 
 

@@ -462,6 +462,23 @@ class _Cascade:
             s += p.nsec
         return out
 
+    def look_ahead(self, zi, fwd):
+        """State the backward pass of the PREVIOUS chunk starts from: the state left by
+        filtering this forward chunk backwards from zi * (its last sample) (reference
+        numerical.py:397-399, :508-509).  A stable cascade has forgotten where it
+        started after `settle` samples, so only the first `settle` samples of the chunk
+        matter (to ~1e-18): they are either re-filtered by a state-only pass, or -- for
+        one or two sections -- folded into the state by one weighted sum."""
+        m = fwd.shape[1]
+        if self.settle is not None and self.settle < m:
+            m = self.settle
+            plan = self.plans[0]
+            if len(self.plans) == 1 and getattr(plan, "has_weights", False):
+                return [plan.tail_state(fwd[:, :m], reverse=True)]
+        look = self.state_from_sample(zi, fwd, m - 1)
+        self.run(fwd[:, :m], look, reverse=True, want_output=False)
+        return look
+
     def run(self, x, states, reverse=False, want_output=True, out=None):
         y, last = x, len(self.plans) - 1
         for i, (p, st) in enumerate(zip(self.plans, states)):
@@ -514,27 +531,86 @@ def _filtfilt_device(pro, cascade, zi, axis, _out=None, _fwd_states=None, _drop_
     zi * first sample) and ``_drop_last`` marks the span's last chunk as the
     look-ahead chunk borrowed from the next span -- it is filtered forward but
     its own backward pass belongs to the next rank."""
-    fwd_states, prev = _fwd_states, None
-    for chunk in device_chunks(pro, axis):
-        if fwd_states is None:
-            fwd_states = cascade.state_from_sample(zi, chunk, 0)
-        fwd = cascade.run(chunk, fwd_states)
+    prev = None
+    forward = _ForwardPass(pro, cascade, zi, axis, _fwd_states)
+    for fwd in forward:
         if prev is not None:
             # Look-ahead pass (numerical.py:397-399): only its final state is
             # used.  A stable cascade forgets where it started after `settle`
             # samples, so filtering the first `settle` samples of the next chunk
             # backwards from zi * (that sample) leaves the same state as the
-            # reference's run from the chunk's far end, to ~1e-24 relative.
-            m = fwd.shape[1]
-            if cascade.settle is not None and cascade.settle < m:
-                m = cascade.settle
-            look = cascade.state_from_sample(zi, fwd, m - 1)
-            cascade.run(fwd[:, :m], look, reverse=True, want_output=False)
-            yield cascade.run(prev, look, reverse=True, out=_out)
+            # reference's run from the chunk's far end, to ~1e-18 relative.
+            look = cascade.look_ahead(zi, fwd)
+            y = cascade.run(prev, look, reverse=True, out=_out)
+            forward.release(prev)
+            yield y
         prev = fwd
     if prev is not None and not _drop_last:
         last = cascade.state_from_sample(zi, prev, prev.shape[1] - 1)
         yield cascade.run(prev, last, reverse=True, out=_out)
+
+
+class _ForwardPass:
+    """The global forward pass of a forward-backward filter (numerical.py:394-396,
+    :503-506), chunk by chunk, launched on its own CUDA stream: it depends only on the
+    input and on the forward pass of the chunk before, so on the device it overlaps the
+    backward pass of the previous chunk and whatever the consumer launches after it
+    (the host issues chunk k+1's forward pass right after chunk k-1's backward pass).
+    Iterating yields the forward output F of every chunk, ready for the current stream;
+    ``release(F)`` hands its buffer back once the consumer has launched its last reader.
+
+    F lives in a small pool of buffers owned by this object and allocated on the
+    CONSUMER's stream; the side stream borrows them, fenced by the event recorded at
+    ``release``.  (Blocks of the caching allocator passed between streams with
+    record_stream are not reusable until the other stream has drained -- the allocator
+    then grows with synchronous cudaMallocs; and an event recorded on the consumer's
+    stream when a block is ALLOCATED would make the forward pass wait for everything
+    queued there, which is exactly the work it is meant to overlap.)"""
+
+    def __init__(self, pro, cascade, zi, axis, fwd_states=None):
+        import os
+
+        self.pro, self.cascade, self.zi, self.axis = pro, cascade, zi, axis
+        self.states = fwd_states
+        self.side = (dv.side_stream("iir-forward")
+                     if os.environ.get("OSZ_FWD_STREAM", "1") == "1" else None)
+        self.free = []                      # (buffer, event after its last reader)
+        self.rows = _layout_of(pro, axis).rows
+
+    def _take(self, n):
+        for i, (buf, ev) in enumerate(self.free):
+            if buf.shape[1] >= n:
+                del self.free[i]
+                return buf, ev
+        return dv.empty((self.rows, n)), dv.record_event()
+
+    def release(self, fwd):
+        buf = getattr(fwd, "_osz_buf", None)
+        if buf is not None:
+            self.free.append((buf, dv.record_event()))
+
+    def __iter__(self):
+        side, cascade = self.side, self.cascade
+        chunks = iter(device_chunks(self.pro, self.axis))
+        while True:
+            with dv.on_stream(side):
+                chunk = next(chunks, None)   # upstream stages / uploads run on the side stream too
+            if chunk is None:
+                return
+            n = chunk.shape[1]
+            buf, fence = self._take(n)
+            view = buf if buf.shape[1] == n else buf[:, :n]
+            with dv.on_stream(side):
+                if side is not None and fence is not None:
+                    side.wait_event(fence)
+                if self.states is None:
+                    self.states = cascade.state_from_sample(self.zi, chunk, 0)
+                fwd = cascade.run(chunk, self.states, out=lambda r, m, view=view: view)
+                done = dv.record_event() if side is not None else None
+            if side is not None:
+                dv.torch().cuda.current_stream().wait_event(done)
+            fwd._osz_buf = buf
+            yield fwd
 
 
 def _sosfiltfilt_device(pro, sos, axis, _out=None, _free=False):
@@ -589,6 +665,15 @@ class _TfFilter:
 
     def zero_state(self, rows):
         return dv.zeros((rows, self.nstate))
+
+    def look_ahead(self, zi, fwd):
+        """See _Cascade.look_ahead (state-only pass over the first `settle` samples)."""
+        m = fwd.shape[1]
+        if self.settle is not None and self.settle < m:
+            m = self.settle
+        look = self.state_from_sample(zi, fwd, m - 1)
+        self.run(fwd[:, :m], look, reverse=True, want_output=False)
+        return look
 
     def state_from_sample(self, zi, x, sample):
         return self.plan.state_from_sample(zi, x, sample)
@@ -905,22 +990,17 @@ def _iir_fir_decimate_device(iir, fir_pro, fir_taps, h, M, axis, _out=None):
         st["done"] = j_to
         return out if j_to > done else None
 
-    fwd_states, prev, prev_first, pos = None, None, 0, 0
-    for chunk in device_chunks(inner, axis):
-        if fwd_states is None:
-            fwd_states = cascade.state_from_sample(zi, chunk, 0)
-        fwd = cascade.run(chunk, fwd_states)
+    prev, prev_first, pos = None, 0, 0
+    forward = _ForwardPass(inner, cascade, zi, axis)
+    for fwd in forward:
         if prev is not None:
-            m = fwd.shape[1]                          # look-ahead, see _filtfilt_device
-            if cascade.settle is not None and cascade.settle < m:
-                m = cascade.settle
-            look = cascade.state_from_sample(zi, fwd, m - 1)
-            cascade.run(fwd[:, :m], look, reverse=True, want_output=False)
+            look = cascade.look_ahead(zi, fwd)        # see _filtfilt_device
             out = emit(prev, look, prev_first, False)
+            forward.release(prev)
             if out is not None:
                 yield out
         prev, prev_first = fwd, pos
-        pos += chunk.shape[1]
+        pos += fwd.shape[1]
     if prev is not None:
         stage.truncate(pos)                           # what arrived is the recording
         total_out = dv.ceil_div(pos, M)

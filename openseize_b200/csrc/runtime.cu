@@ -249,6 +249,30 @@ int osz_unpack_rows_c128(const double *src, int64_t ld, int64_t outer, int64_t n
                                             reinterpret_cast<double2 *>(dst), outer, n, inner, ld,
                                             stream);
 }
+// (re, im) rows -> interleaved complex128 rows: z[r][t] = re[r][t] + i im[r][t]
+__global__ void zip_complex_kernel(const double *__restrict__ re, int64_t ldre,
+                                   const double *__restrict__ im, int64_t ldim, int64_t n,
+                                   double2 *__restrict__ z) {
+    const int64_t row = blockIdx.y;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x)
+        z[row * n + t] = make_double2(ld_stream(re + row * ldre + t), ld_stream(im + row * ldim + t));
+}
+int osz_zip_complex_f64(const double *re, int64_t ldre, const double *im, int64_t ldim,
+                        int64_t rows, int64_t n, double *z, void *stream) {
+    if (!re || !im || !z) return fail(OSZ_ERR_ARG, "osz_zip_complex_f64: null argument");
+    if (rows <= 0 || n <= 0) return OSZ_OK;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "osz_zip_complex_f64: more than 65535 rows");
+    int bx = (int)((n + 255) / 256);
+    const int cap = (sm_count() * 16 + (int)rows - 1) / (int)rows;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    zip_complex_kernel<<<dim3((unsigned)bx, (unsigned)rows), 256, 0, as_stream(stream)>>>(
+        re, ldre, im, ldim, n, reinterpret_cast<double2 *>(z));
+    OSZ_LAUNCHED("zip_complex_kernel");
+    return OSZ_OK;
+}
+
 int osz_widen_f32_f64(const float *src, double *dst, int64_t count, void *stream) {
     if (count <= 0) return OSZ_OK;
     int blocks = (int)((count + 255) / 256);

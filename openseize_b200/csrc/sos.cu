@@ -37,10 +37,12 @@ namespace osz {
 // for one or two sections, where the kernel is bound by memory latency and the
 // smaller footprint (32 registers of samples, 35 KB of shared memory) lets four
 // CTAs share an SM instead of two.
-// PF: the loads of block blk + 1 are issued into registers before block blk is scanned
-// (T = 16 only: 32 more registers, two CTAs per SM), so a CTA always has loads in flight.
+// PF: the loads of block blk + 1 are issued into registers before block blk is scanned, so
+// a CTA always has loads in flight.  T = 32 with PF takes 64 more registers (one CTA per
+// SM): the build for launches with no more CTAs than SMs (few rows), where a lone CTA per
+// SM otherwise leaves HBM idle through its scan phase.
 template <bool WRITE, int T, bool PF = false>
-__global__ void __launch_bounds__(SOS_NT, (T == 32 || PF ? 2 : 4))
+__global__ void __launch_bounds__(SOS_NT, (T == 32 ? (PF ? 1 : 2) : (PF ? 2 : 4)))
 sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
                 int64_t n_total, int reverse, const double *__restrict__ state_in,
                 double *__restrict__ state, double *__restrict__ y, int64_t ldy,
@@ -199,6 +201,67 @@ __global__ void sos_combine_kernel(const double *__restrict__ phi /* ns2 x ns2 *
     }
 }
 
+// Entering state of every time span but the first, WITHOUT running the recurrence: the
+// state a cascade holds after a run of samples is a linear functional of them,
+//   s = sum_d W[d] * x[last - d],   W[d] = T^d b   (T: one-step zero-input transition,
+//   b: the state one unit sample leaves behind),
+// and W decays like the filter's impulse response, so the `settle` samples before a
+// span fix its entering state to ~1e-18 -- the same truncation as re-filtering them
+// from rest (the warm-up split), but 2 nsec FMAs per sample, fully parallel, instead of
+// the scan.  One CTA per (span >= 1, row); W: [settle][ns2] doubles.
+template <int NS2>
+__global__ void __launch_bounds__(256)
+sos_entering_kernel(const double *__restrict__ W, int64_t settle, const double *__restrict__ x,
+                    int64_t ldx, int64_t n_total, int reverse, int64_t span_len,
+                    double *__restrict__ span_e /* [rows][nspan][NS2] */, int nspan, int span_off) {
+    const int64_t span = blockIdx.x + 1, row = blockIdx.y;
+    const int64_t a = span * span_len;               // first logical sample of the span
+    const double *xr = x + row * ldx;
+    double acc[NS2];
+#pragma unroll
+    for (int c = 0; c < NS2; ++c) acc[c] = 0.0;
+    const int64_t m = settle < a ? settle : a;
+    // sample d back from the span is logical index a - 1 - d: global a - 1 - d forward,
+    // n_total - a + d reversed
+    const double *x0 = xr + (reverse ? n_total - a : a - 1);
+    const int64_t dir = reverse ? 1 : -1;
+    constexpr int U = 8;                             // independent loads in flight per thread
+    int64_t d = threadIdx.x;
+    for (; d + (U - 1) * (int64_t)blockDim.x < m; d += U * (int64_t)blockDim.x) {
+        double v[U], w[U][NS2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t du = d + u * (int64_t)blockDim.x;
+            v[u] = ld_stream(x0 + dir * du);
+#pragma unroll
+            for (int c = 0; c < NS2; ++c) w[u][c] = ldg(W + du * NS2 + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < NS2; ++c) acc[c] = fma(w[u][c], v[u], acc[c]);
+    }
+    for (; d < m; d += blockDim.x) {
+        const double v = ld_stream(x0 + dir * d);
+#pragma unroll
+        for (int c = 0; c < NS2; ++c) acc[c] = fma(ldg(W + d * NS2 + c), v, acc[c]);
+    }
+    __shared__ double part[8][NS2];
+#pragma unroll
+    for (int c = 0; c < NS2; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS2) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w][threadIdx.x];
+        span_e[(row * nspan + span - span_off) * NS2 + threadIdx.x] = v;
+    }
+}
+
 __global__ void sos_copy_state_kernel(const double *__restrict__ src, double *__restrict__ dst,
                                       int64_t count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +299,7 @@ struct osz_sos_plan {
     mutable std::mutex mu;
     mutable std::map<int64_t, double *> phi;   // span length -> device (2 nsec)^2 matrix
     std::vector<long double> Tmat;  // (2 nsec)^2 one-step zero-input transition, row major
+    double *d_weights = nullptr;    // [settle][2 nsec]: W[d] = T^d b (sos_entering_kernel)
 };
 
 namespace {
@@ -423,12 +487,40 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
     }
     (void)rmax;
     p->settle = settle_samples(p->Tmat, 2 * nsec);
+    std::vector<double> weights;
+    if (nsec <= 2 && p->settle > 0 && p->settle <= (1 << 20)) {
+        // b: the state one unit input sample leaves behind from rest; W[d] = T^d b
+        const int ns2 = 2 * nsec;
+        std::vector<long double> w(ns2), nxt(ns2);
+        long double xin = 1.0L;
+        for (int s2 = 0; s2 < nsec; ++s2) {
+            const SosSec &c = p->prm.sec[s2];
+            const long double yv = (long double)c.b0 * xin;
+            w[2 * s2] = (long double)c.b1 * xin - (long double)c.a1 * yv;
+            w[2 * s2 + 1] = (long double)c.b2 * xin - (long double)c.a2 * yv;
+            xin = yv;
+        }
+        weights.resize((size_t)p->settle * ns2);
+        for (int64_t d = 0; d < p->settle; ++d) {
+            for (int i = 0; i < ns2; ++i) weights[(size_t)d * ns2 + i] = (double)w[i];
+            for (int i = 0; i < ns2; ++i) {
+                long double acc = 0.0L;
+                for (int j = 0; j < ns2; ++j) acc += p->Tmat[(size_t)i * ns2 + j] * w[j];
+                nxt[i] = acc;
+            }
+            w.swap(nxt);
+        }
+    }
     if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
             cudaSuccess ||
         cudaMalloc(&p->T16_lanepow, lanepow16.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->T16_lanepow, lanepow16.data(), lanepow16.size() * 8,
-                   cudaMemcpyHostToDevice) != cudaSuccess) {
+                   cudaMemcpyHostToDevice) != cudaSuccess ||
+        (!weights.empty() &&
+         (cudaMalloc(&p->d_weights, weights.size() * 8) != cudaSuccess ||
+          cudaMemcpy(p->d_weights, weights.data(), weights.size() * 8, cudaMemcpyHostToDevice) !=
+              cudaSuccess))) {
         osz_sos_plan_destroy(p);
         return fail(OSZ_ERR_CUDA, "osz_sos_plan_create: device upload failed");
     }
@@ -440,6 +532,7 @@ int osz_sos_plan_destroy(osz_sos_plan *p) {
     if (!p) return OSZ_OK;
     cudaFree(p->d_lanepow);
     cudaFree(p->T16_lanepow);
+    cudaFree(p->d_weights);
     for (auto &kv : p->phi) cudaFree(kv.second);
     delete p;
     return OSZ_OK;
@@ -514,9 +607,30 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     //            kernel composes them with Phi = T^(span length), pass 2 filters
     //            every span from its true entering state (cost ~2.1 n/k).
     // OSZ_SOS_SPLIT / OSZ_SOS_EXACT force a span count of either kind.
+    //   weights: (one or two sections) the entering state of every later span as a
+    //            weighted sum of the `settle` samples before it (sos_entering_kernel:
+    //            2 nsec FMAs per sample, no recurrence), then every span from its own
+    //            entering state: cost n/k per CTA plus a small parallel pre-pass -- what
+    //            lets 32 rows (one GPU's share of a 256-channel recording split over 8)
+    //            fill the SMs twice: 0.22 -> see profiles/r02_kernel_bench.md.
+    // OSZ_SOS_SPLIT / OSZ_SOS_EXACT / OSZ_SOS_WEIGHTS force a span count of a kind.
     int64_t nspan = 1;
-    bool exact = false;
-    if (y) {                        // a state-only pass wants the last span only
+    bool exact = false, weighted = false;
+    static const int forced_weights = [] {
+        const char *e = getenv("OSZ_SOS_WEIGHTS");
+        return e ? atoi(e) : -1;            // -1: automatic, 0: off, k: k spans
+    }();
+    if (y && p->d_weights && forced_weights != 0 && n >= 2 * p->settle) {
+        const int64_t min_span = p->settle > 8 * BLK ? p->settle : 8 * BLK;
+        int64_t k = forced_weights > 0 ? forced_weights : (2 * (int64_t)sm_count()) / rows;
+        if (k > n / min_span) k = n / min_span;
+        if (k > 64) k = 64;
+        if (k >= 2) {
+            nspan = k;
+            weighted = true;
+        }
+    }
+    if (y && !weighted) {           // a state-only pass wants the last span only
         static const int forced = [] {
             const char *e = getenv("OSZ_SOS_SPLIT");
             return e ? atoi(e) : 0;
@@ -586,7 +700,7 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     // per-call scratch from the stream-ordered allocator: [state copy | span finals | span entering]
     double *scratch = nullptr;
     const int64_t n_copy = nspan > 1 ? rows * ns2 : 0;
-    const int64_t n_span = exact ? rows * nspan * ns2 : 0;
+    const int64_t n_span = exact || weighted ? rows * nspan * ns2 : 0;
     if (n_copy + 2 * n_span > 0)
         OSZ_CUDA(scratch_alloc((void **)&scratch, (size_t)(n_copy + 2 * n_span) * 8, st));
     struct Release {                 // freed in stream order after the kernels below
@@ -611,10 +725,35 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         const int rc = sos_phi(p, span_len, &d_phi);
         if (rc != OSZ_OK) return rc;
     }
+    if (weighted) {
+        span_e = scratch + n_copy;
+        const dim3 g2((unsigned)(nspan - 1), (unsigned)rows);
+        if (ns2 == 2)
+            sos_entering_kernel<2><<<g2, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse,
+                                                       span_len, span_e, (int)nspan, 0);
+        else
+            sos_entering_kernel<4><<<g2, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse,
+                                                       span_len, span_e, (int)nspan, 0);
+        OSZ_LAUNCHED("sos_entering_kernel");
+    }
     const dim3 grid((unsigned)rows, (unsigned)nspan);
+    static const int lone_ok = [] {
+        // measured on B200 (notch, 32 rows x 4 spans = 128 CTAs): 0.242 ms with the
+        // prefetching build against 0.224 ms without -- the 255-register build loses more
+        // to its lower issue rate than the earlier loads win; opt-in
+        const char *e = getenv("OSZ_SOS_LONE");
+        return e ? atoi(e) : 0;
+    }();
+    const bool lone = lone_ok && rows * nspan <= (int64_t)sm_count();
 #define OSZ_SOS_LAUNCH(W, TT, YY, SIN, SOUT)                                                    \
     do {                                                                                        \
-        if (TT == 16 && p->prefetch) {                                                          \
+        if (TT == 32 && lone) {                                                                 \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 32, true>,                         \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            sos_scan_kernel<W, 32, true><<<grid, SOS_NT, smem, st>>>(                           \
+                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+                p->settle, SIN, SOUT);                                                          \
+        } else if (TT == 16 && p->prefetch) {                                                          \
             OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 16, true>,                         \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
             sos_scan_kernel<W, 16, true><<<grid, SOS_NT, smem, st>>>(                           \
@@ -637,6 +776,9 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         OSZ_LAUNCHED("sos_combine_kernel");
         if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, span_e, nullptr);
         else OSZ_SOS_LAUNCH(true, 32, y, span_e, nullptr);
+    } else if (weighted) {
+        if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, span_e, nullptr);
+        else OSZ_SOS_LAUNCH(true, 32, y, span_e, nullptr);
     } else if (y) {
         if (p->T == 16) OSZ_SOS_LAUNCH(true, 16, y, nullptr, nullptr);
         else OSZ_SOS_LAUNCH(true, 32, y, nullptr, nullptr);
@@ -647,6 +789,28 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
 #undef OSZ_SOS_LAUNCH
     return OSZ_OK;
 }
+
+int osz_sos_tail_state_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows,
+                           int64_t n, int reverse, double *state, void *stream) {
+    if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_tail_state_f64: null argument");
+    if (rows <= 0) return OSZ_OK;
+    if (!p->d_weights || p->settle <= 0 || n < p->settle)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_sos_tail_state_f64: needs a cascade of one or two "
+                                         "sections and at least `settle` samples");
+    const dim3 grid(1, (unsigned)rows);
+    cudaStream_t st = as_stream(stream);
+    if (p->prm.nsec == 1)
+        sos_entering_kernel<2><<<grid, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse, n,
+                                                     state, 1, 1);
+    else
+        sos_entering_kernel<4><<<grid, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse, n,
+                                                     state, 1, 1);
+    OSZ_LAUNCHED("sos_entering_kernel");
+    return OSZ_OK;
+}
+
+int64_t osz_sos_plan_settle(const osz_sos_plan *p) { return p ? p->settle : -1; }
+int osz_sos_plan_has_weights(const osz_sos_plan *p) { return p && p->d_weights ? 1 : 0; }
 
 // internal (sosdec.cu): the plan's kernel parameter block
 int osz_sos_plan_params(const osz_sos_plan *p, SosParams *prm, const double **lanepow,

@@ -42,6 +42,10 @@ __device__ __forceinline__ void named_bar_sync(int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"n"(BAR), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_sync_id(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // One block of SOS_NT * T samples through every section of the cascade.
 //   v[T]     the thread's T consecutive samples (in: section 0 input, out: cascade output)
 //   full     every slot holds a real sample and the block starts on the carried

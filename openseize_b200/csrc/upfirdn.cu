@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sos_core.cuh"
 #include "ufd_mma.cuh"
 
 namespace osz {
@@ -378,17 +379,23 @@ upfirdn_dec2_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, 
 // P = S*M + pad doubles, pad chosen so that the 16 lanes of a half warp
 // (g*P + q*M) hit 16 different banks.  Useful fraction of the MMA work:
 // K / sum_p 4*ceil((Q_p + 7) / 4)  (86 % at 1231 taps, M = 25; 70 % at 561 taps).
-template <int WT, int KS>
-__global__ void __launch_bounds__(WT *KS * 32, 1)
+template <int WT, int KS, int RB>
+__global__ void __launch_bounds__(WT *KS * 32 + 32, 1)
 upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restrict__ x, int64_t ldx,
                    int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
                    const double *__restrict__ gpad /* [M][ldq]: 7 zeros, taps of the phase, zeros */,
                    double *__restrict__ y, int64_t ldy, int tiles_per_row, int64_t ntiles) {
-    // One persistent CTA per SM walks (row, tile) items.  Tiles are prefetched two
-    // ahead into two shared-memory buffers: interior tiles by 1-D TMA bulk copies (one
-    // per segment, issued by one thread, completing on an mbarrier), tiles that touch
-    // the edge of the supplied window by 8-byte cp.async with zero fill.
-    constexpr int NT = WT * KS * 32;
+    // One persistent CTA per SM walks (row, tile) items with two shared-memory tile
+    // buffers.  WT * KS MMA warps (each: four 8 x 8 output tiles of its segment quarter,
+    // 1 / KS of the k-steps) never meet at a CTA-wide barrier: they hand their partial
+    // sums to ONE epilogue warp through named barriers and go on to the next tile, whose
+    // data is already in the other buffer.  The epilogue warp sums the KS partials,
+    // stores the tile's 8 S outputs and refills the buffer just released two tiles
+    // ahead: interior tiles by 1-D TMA bulk copies (one per segment, completing on an
+    // mbarrier), tiles that touch the edge of the supplied window by 8-byte cp.async
+    // with zero fill.
+    constexpr int NMMA = WT * KS * 32;                       // MMA threads
+    constexpr int NT = NMMA + 32;
     extern __shared__ __align__(16) double smem_mma[];
     __shared__ __align__(8) uint64_t bars[2];
     const int M = gm.M, SM = gm.SM, P = gm.P, S = gm.S;
@@ -396,12 +403,11 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
     const int tile_elems = nseg * P + 2;                     // + 2: room for the alignment shift
     double *bufs = smem_mma;                                 // 2 x tile_elems
     double *gs = bufs + 2 * (size_t)tile_elems;              // M * ldq
-    double *red = gs + (size_t)M * gm.ldq;                   // 2 x KS x 8 S partial sums
+    double *red = gs + (size_t)M * gm.ldq;                   // RB x KS x 8 S partial sums
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int wt = warp % WT, wk = warp / WT;
-    const int g = lane >> 2, q = lane & 3;
+    const bool epilogue = warp == WT * KS;
     const uint32_t sbase = smem_u32(bufs);
     const bool tma_pitch = (P & 1) == 0 && (SM & 1) == 0;
 
@@ -416,13 +422,14 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
     auto tile_tma = [&](int64_t rel0) {
         return tma_pitch && rel0 >= 1 && rel0 + gm.total_len + 2 <= x_len;
     };
+    // epilogue warp: fill buffer `which` with tile t; completes one phase of bars[which]
     auto stage = [&](int64_t t, int which) {
         if (t >= ntiles) return;
         int64_t row;
         const int64_t rel0 = tile_rel0(t, row);
         const double *xr = x + row * ldx;
         if (tile_tma(rel0)) {
-            if (tid == 0) {
+            if (lane == 0) {
                 const double *src0 = xr + rel0;
                 const int mis = span_mis(src0);
                 uint32_t bytes = 0;
@@ -445,13 +452,19 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
             const int len = min(SM, gm.total_len - seg * SM);
             const int64_t g0 = rel0 + (int64_t)seg * SM;
             const uint32_t dst = dst0 + (uint32_t)(seg * P) * 8u;
-            for (int e = tid; e < len; e += NT) {
+            for (int e = lane; e < len; e += 32) {
                 const int64_t gi = g0 + e;
                 const bool ok = gi >= 0 && gi < x_len;
                 cp_async8_zfill(dst + e * 8u, ok ? xr + gi : xr, ok);
             }
         }
         cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[which]))
+                         : "memory");
+        }
     };
 
     if (tid == 0) {
@@ -461,9 +474,38 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
     }
     for (int i = tid; i < M * gm.ldq; i += NT) gs[i] = gpad[i];
     __syncthreads();
-    stage(blockIdx.x, 0);
-    stage((int64_t)blockIdx.x + gridDim.x, 1);
 
+    // named barriers: 1 + p  "partials of a tile of parity p are in red[p]" (MMA warps
+    // arrive, the epilogue warp waits); 3 + p  "red[p] has been summed" (the epilogue
+    // warp arrives, MMA warps wait before they write red[p] again, two tiles later)
+    if (epilogue) {
+        stage(blockIdx.x, 0);
+        stage((int64_t)blockIdx.x + gridDim.x, 1);
+        asm volatile("bar.arrive 3, %0;" ::"n"(NT) : "memory");      // red starts free
+        if (RB == 2) asm volatile("bar.arrive 4, %0;" ::"n"(NT) : "memory");
+        int parity = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, parity ^= 1) {
+            if (parity == 0) named_bar_sync_id(1, NT); else named_bar_sync_id(2, NT);
+            // every MMA warp is done with buffer `parity`: sum, store, refill
+            int64_t row;
+            tile_rel0(t, row);
+            const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
+            const double *r0 = red + (size_t)(RB == 2 ? parity : 0) * KS * 8 * S;
+            for (int o = lane; o < 8 * S; o += 32) {
+                double sum = r0[o];
+#pragma unroll
+                for (int k = 1; k < KS; ++k) sum += r0[(size_t)k * 8 * S + o];
+                if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
+            }
+            if (RB == 1 || parity == 0) asm volatile("bar.arrive 3, %0;" ::"n"(NT) : "memory");
+            else asm volatile("bar.arrive 4, %0;" ::"n"(NT) : "memory");
+            stage(t + 2 * (int64_t)gridDim.x, parity);
+        }
+        return;
+    }
+
+    const int wt = warp % WT, wk = warp / WT;
+    const int g = lane >> 2, q = lane & 3;
     const int pad = P - SM;
     const int logS = gm.logS;
     const int k_lo = (int)(((long)gm.ktotal * wk) / KS), k_hi = (int)(((long)gm.ktotal * (wk + 1)) / KS);
@@ -473,15 +515,9 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, parity ^= 1) {
         int64_t row;
         const int64_t rel0 = tile_rel0(t, row);
-        int mis = 0;
-        if (tile_tma(rel0)) {
-            mbar_wait(&bars[parity], (phases >> parity) & 1u);
-            phases ^= 1u << parity;
-            mis = span_mis(x + row * ldx + rel0);
-        } else {
-            cp_async_wait<0>();
-            __syncthreads();
-        }
+        mbar_wait(&bars[parity], (phases >> parity) & 1u);
+        phases ^= 1u << parity;
+        const int mis = tile_tma(rel0) ? span_mis(x + row * ldx + rel0) : 0;
         // ---- banded Toeplitz product on the tensor cores.  Sample n of phase p in
         //      segment g's window sits at offset p + n*M, which lies n / S segments on
         //      (p < M): one pad per segment crossed
@@ -489,28 +525,19 @@ upfirdn_mma_kernel(const __grid_constant__ UfdMmaGeom gm, const double *__restri
         auto fetch = [&](int p, int n) { return xrow[p + n * M + (n >> logS) * pad]; };
         double c[8];
         ufd_mma_ksteps(gm, gs, k_lo, k_hi, wt, g, q, fetch, c);
-        // ---- partial sums of the k-splits to shared memory; every thread then sums and
-        //      stores its share of the tile's 8 S outputs
-        double *rd = red + ((size_t)parity * KS + wk) * 8 * S;
+        // ---- partial sums to red[parity] once the epilogue warp has summed its previous
+        //      contents, then on to the next tile
+        if (RB == 1 || parity == 0) named_bar_sync_id(3, NT); else named_bar_sync_id(4, NT);
+        double *rd = red + ((size_t)(RB == 2 ? parity : 0) * KS + wk) * 8 * S;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             rd[oa + 8 * j] = c[2 * j];
             rd[oa + 8 * j + 1] = c[2 * j + 1];
         }
-        __syncthreads();       // partials visible; nobody reads this tile's buffer any more
-        stage(t + 2 * (int64_t)gridDim.x, parity);
-        const int64_t o0 = (t - row * tiles_per_row) * (8 * S);
-        const double *r0 = red + (size_t)parity * KS * 8 * S;
-        for (int o = tid; o < 8 * S; o += NT) {
-            double sum = r0[o];
-#pragma unroll
-            for (int k = 1; k < KS; ++k) sum += r0[(size_t)k * 8 * S + o];
-            if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, sum);
-        }
-        // (`red` is double buffered: this half is written again two tiles on, behind
-        //  the next tile's barrier)
+        __threadfence_block();
+        if (parity == 0) asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
+        else asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory");
     }
-    cp_async_wait<0>();
 }
 
 __global__ void upfirdn_general_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first,
@@ -561,7 +588,7 @@ struct osz_upfirdn_plan {
     bool mma = false;
     int kernel = OSZ_UFD_AUTO;     // osz_upfirdn_plan_set_kernel
     UfdMmaGeom mg{};
-    int mma_wt = 0, mma_ks = 2;
+    int mma_wt = 0, mma_ks = 2, mma_rb = 1;   // tiles per warp group, k-splits, partial-sum buffers
     double mma_useful = 0.0;       // K / (4 * k-steps): useful share of the MMA work
     size_t smem_mma = 0;
     double *d_gpad = nullptr;      // [down][ldq]: window-order taps g[j] = h'[K-1-j]
@@ -569,17 +596,17 @@ struct osz_upfirdn_plan {
     double *d_g = nullptr;         // g[j], K doubles
 };
 
-template <int WT, int KS>
+template <int WT, int KS, int RB>
 static int launch_mma(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
                       int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out, double *y,
                       int64_t ldy, cudaStream_t st) {
-    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_mma_kernel<WT, KS>,
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_mma_kernel<WT, KS, RB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mma));
     const int64_t per_tile = 8 * (int64_t)p->mg.S;
     const int64_t tiles_per_row = (n_out + per_tile - 1) / per_tile;
     const int64_t ntiles = tiles_per_row * rows;
     const int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
-    upfirdn_mma_kernel<WT, KS><<<(unsigned)grid, WT * KS * 32, p->smem_mma, st>>>(
+    upfirdn_mma_kernel<WT, KS, RB><<<(unsigned)grid, WT * KS * 32 + 32, p->smem_mma, st>>>(
         p->mg, x, ldx, x_first, x_len, out_first, n_out, p->d_gpad, y, ldy, (int)tiles_per_row,
         ntiles);
     OSZ_LAUNCHED("upfirdn_mma_kernel");
@@ -589,14 +616,13 @@ static int launch_mma(const osz_upfirdn_plan *p, const double *x, int64_t ldx, i
 // Geometry of the tensor-core decimator for K taps, decimation M: the largest
 // segment length S in {64, 48, 32, 16} whose two tile buffers (8 segments + reach
 // each), padded tap table and k-split scratch fit one CTA per SM.
-static bool mma_geometry(int K, int M, int ksplit, UfdMmaGeom *gm, int *wt_out,
+static bool mma_geometry(int K, int M, int ksplit, int red_bufs, UfdMmaGeom *gm, int *wt_out,
                          size_t *smem_out) {
     int smax = 0;
     long total_steps = 0;
     const std::vector<int> ks = ufd_ksteps(K, M, &smax, &total_steps);
-    for (int S : {64, 32}) {
+    for (int S : {32}) {
         const int WT = S / 32;
-        if (WT * ksplit > 16) continue;
         const int SM = S * M;
         // in-segment sample offsets run up to r_max (newest fragment of the last batch)
         const int nmax = 32 * (WT - 1) + 4 * (smax + 6) + 3;
@@ -607,7 +633,7 @@ static bool mma_geometry(int K, int M, int ksplit, UfdMmaGeom *gm, int *wt_out,
         const int nseg = (total_len + SM - 1) / SM;
         const int ldq = 7 + 4 * (smax + 1) + 4;
         const size_t smem =
-            (2 * ((size_t)nseg * P + 2) + (size_t)M * ldq + 2 * (size_t)ksplit * 8 * S) * 8;
+            (2 * ((size_t)nseg * P + 2) + (size_t)M * ldq + (size_t)red_bufs * ksplit * 8 * S) * 8;
         if (smem > 225 * 1024) continue;
         gm->K = K;
         gm->M = M;
@@ -777,10 +803,18 @@ int osz_upfirdn_plan_create(osz_upfirdn_plan **out, const double *h, int K, int 
         static const int ksplit = [] {
             const char *e = getenv("OSZ_UFD_MMA_KS");
             const int v = e ? atoi(e) : 8;
-            return v == 4 || v == 8 || v == 16 ? v : 8;
+            return v == 8 || v == 12 || v == 16 ? v : 8;
         }();
         p->mma_ks = ksplit;
-        if (mma_geometry(K, down, p->mma_ks, &p->mg, &p->mma_wt, &p->smem_mma)) {
+        // one partial-sum buffer (default) keeps the CTA at 160 KB of shared memory, which
+        // leaves room for a CTA of the biquad scan on the same SM (its forward pass runs
+        // on another stream): OSZ_UFD_MMA_RED=2 double-buffers the partial sums
+        static const int red_bufs = [] {
+            const char *e = getenv("OSZ_UFD_MMA_RED");
+            return e && atoi(e) == 2 ? 2 : 1;
+        }();
+        p->mma_rb = red_bufs;
+        if (mma_geometry(K, down, p->mma_ks, p->mma_rb, &p->mg, &p->mma_wt, &p->smem_mma)) {
             // taps in the order the kernel walks its window: g[j] = h'[K-1-j]
             std::vector<double> g(K);
             for (int j = 0; j < K; ++j) g[j] = hs[K - 1 - j];
@@ -927,9 +961,12 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
     }
     if (osz_upfirdn_plan_kernel(p) == OSZ_UFD_MMA && !(p->dec2 && use_dec2)) {
 #define OSZ_MMA_CASE(WT, KS)                                                                   \
-    if (p->mma_wt == WT && p->mma_ks == KS)                                                   \
-        return launch_mma<WT, KS>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
-        OSZ_MMA_CASE(2, 4) OSZ_MMA_CASE(2, 8) OSZ_MMA_CASE(1, 4) OSZ_MMA_CASE(1, 8) OSZ_MMA_CASE(1, 16)
+    if (p->mma_wt == WT && p->mma_ks == KS) {                                                 \
+        if (p->mma_rb == 1)                                                                   \
+            return launch_mma<WT, KS, 1>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st); \
+        return launch_mma<WT, KS, 2>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);     \
+    }
+        OSZ_MMA_CASE(1, 8) OSZ_MMA_CASE(1, 12) OSZ_MMA_CASE(1, 16)
 #undef OSZ_MMA_CASE
     }
     if (p->dec2 && use_dec2)

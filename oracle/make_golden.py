@@ -133,13 +133,30 @@ def hilbert_golden(report):
     report.append(("hilbert", "bit-exact vs reference"))
 
 
+def analytic_golden(report):
+    """Analytic signal, amplitudes and phases (experimental/coupling/transforms.py:
+    107-192)."""
+    from openseize.experimental.coupling.transforms import Analytic
+
+    fs = 400
+    x = signal(81, 2, 9000, fs)
+    ana = Analytic(x, fs, chunksize=2500, axis=-1, width=4)
+    z = ana.signal.to_array()
+    amp = ana.amplitudes.to_array()
+    ph = ana.phases.to_array()
+    assert z.dtype == np.complex128 and z.shape == x.shape
+    np.savez_compressed(os.path.join(GOLD, "analytic.npz"), seed=81, rows=2, n=9000, fs=fs,
+                        width=4, chunksize=2500, x_sum=x.sum(), z=z, amplitudes=amp, phases=ph)
+    report.append(("analytic", "reference outputs stored"))
+
+
 def main():
     sys.path.insert(0, ROOT)
     import oracle
     producer, nm, fir, iir, resampling, estimators = _import_reference()
     os.makedirs(GOLD, exist_ok=True)
     report = []
-    only = {"protools": protools_golden, "hilbert": hilbert_golden}
+    only = {"protools": protools_golden, "hilbert": hilbert_golden, "analytic": analytic_golden}
     if sys.argv[1:] and all(a in only for a in sys.argv[1:]):   # only the named fixtures
         for a in sys.argv[1:]:
             only[a](report)
@@ -286,6 +303,7 @@ def main():
 
     protools_golden(report)
     hilbert_golden(report)
+    analytic_golden(report)
 
     for name, status in report:
         print("%-18s %s" % (name, status))

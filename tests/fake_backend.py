@@ -307,6 +307,7 @@ def install(mp):
     mp.setattr(dv, "RowMoments", FakeRowMoments)
     mp.setattr(dv, "row_standardize", _row_standardize)
     mp.setattr(dv, "col_moments", _col_moments)
+    mp.setattr(dv, "zip_complex", lambda re, im: torch.stack([re, im], dim=-1).contiguous())
     mp.setattr(dv, "sosdec_spans", _sosdec_spans)
     mp.setattr(dv, "sosdec_exec", _sosdec_exec)
     mp.setattr(dv, "sosdec_boundary", _sosdec_boundary)

@@ -521,6 +521,29 @@ def hilbert_golden():
     close(hil(producer(x, cs, -1), cs, axis=-1).to_array(), g["y"])
 
 
+def analytic_golden():
+    """Analytic signal x + i H(x) (reference experimental/coupling/transforms.py:107-192):
+    complex signal, amplitudes and phases against the real reference's outputs."""
+    from openseize_b200.experimental.coupling.transforms import Analytic
+
+    g = golden("analytic")
+    fs, cs = int(g["fs"]), int(g["chunksize"])
+    x = signal(int(g["seed"]), int(g["rows"]), int(g["n"]), fs)
+    assert x.sum() == float(g["x_sum"])
+    ana = Analytic(x, fs, chunksize=cs, axis=-1, width=float(g["width"]))
+    z = ana.signal.to_array()
+    assert z.dtype == np.complex128 and ana.signal.shape == x.shape
+    close(z, g["z"])
+    close(ana.amplitudes.to_array(), g["amplitudes"])
+    ph, rph = ana.phases.to_array(), g["phases"]
+    d = np.abs(ph - rph)
+    assert np.max(np.minimum(d, 2 * np.pi - d)) < 1e-9          # phases wrap at 2 pi
+    # sample axis first, chunk size that does not divide the recording
+    xt = np.ascontiguousarray(x.T)
+    zt = Analytic(xt, fs, chunksize=1777, axis=0, width=float(g["width"])).signal.to_array()
+    close(zt, g["z"].T)
+
+
 # ------------------------------------------------- producer tools (N3) ----
 def protools_golden():
     """Masked producers consumed by GPU operators and protools.mean / std /

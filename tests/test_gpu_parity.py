@@ -166,16 +166,21 @@ def test_sos_kernel_vs_scipy(dv, n, kind, per_thread, monkeypatch):
         assert relerr(state2.cpu().numpy(), state.cpu().numpy()) < 2e-8
 
 
-@pytest.mark.parametrize("kind", ["butter8", "notch"])
+@pytest.mark.parametrize("kind", ["butter8", "notch", "butter2"])
 @pytest.mark.parametrize("n", [131072, 300001, 1000000])
 def test_sos_exact_time_split(dv, n, kind):
-    """Few rows, long chunk: the row is cut into spans that run concurrently
-    (two passes: span finals from rest -> combine with T^len -> true entering
-    states).  The split must be invisible: same output and carried state as the
-    sequential recurrence, forward and reversed."""
+    """Few rows, long chunk: the row is cut into spans that run concurrently --
+    two passes (span finals from rest -> combine with T^len -> true entering states)
+    for long cascades, entering states as weighted sums of the `settle` samples before
+    each span for one or two sections (notch: 3 / 12 spans at 300001 / 1e6 samples).
+    The split must be invisible: same output and carried state as the sequential
+    recurrence, forward and reversed."""
     rng = np.random.default_rng(n)
     if kind == "butter8":
         sos = sps.butter(8, [1, 100], btype="bandpass", fs=5000, output="sos")
+    elif kind == "butter2":
+        sos = sps.butter(2, [40, 60], btype="bandpass", fs=5000, output="sos")
+        assert sos.shape[0] == 2
     else:
         b, a = sps.iirnotch(60, 10, fs=30000)
         sos = np.concatenate([b, a])[None]
@@ -234,6 +239,10 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps, kernel):
     o_hi = ((hi - ntaps) * up) // down - 2
     y = plan.run(_dev(dv, x[:, lo:hi]), lo, o_lo, o_hi - o_lo).cpu().numpy()
     assert relerr(y, ref[:, o_lo:o_hi]) < 1e-12
+
+
+def test_analytic_golden():
+    pc.analytic_golden()
 
 
 def test_producer_tools_golden():

@@ -48,6 +48,10 @@ def test_pipeline_chain(fake_gpu):
     pc.fused_iir_fir_decimate()
 
 
+def test_analytic(fake_gpu):
+    pc.analytic_golden()
+
+
 def test_producer_tools(fake_gpu):
     pc.protools_golden()
     pc.masked_chain()
