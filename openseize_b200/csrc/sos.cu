@@ -612,13 +612,17 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     //            2 nsec FMAs per sample, no recurrence), then every span from its own
     //            entering state: cost n/k per CTA plus a small parallel pre-pass -- what
     //            lets 32 rows (one GPU's share of a 256-channel recording split over 8)
-    //            fill the SMs twice: 0.22 -> see profiles/r02_kernel_bench.md.
+    //            fill the SMs twice -- measured slower than the warm-up split, see below.
     // OSZ_SOS_SPLIT / OSZ_SOS_EXACT / OSZ_SOS_WEIGHTS force a span count of a kind.
     int64_t nspan = 1;
     bool exact = false, weighted = false;
     static const int forced_weights = [] {
+        // Measured on B200 (notch, 1e6 samples; profiles/r02_kernel_bench.md): 32 rows
+        // 0.262 ms against 0.227 ms for the warm-up split, 64 rows 0.357 / 0.277, 128 rows
+        // 0.547 / 0.470 -- the pre-pass reads 24 bytes per sample (sample + two weights)
+        // and that costs more than re-scanning `settle` samples does.  Opt-in.
         const char *e = getenv("OSZ_SOS_WEIGHTS");
-        return e ? atoi(e) : -1;            // -1: automatic, 0: off, k: k spans
+        return e ? atoi(e) : 0;             // -1: automatic, 0: off, k: k spans
     }();
     if (y && p->d_weights && forced_weights != 0 && n >= 2 * p->settle) {
         const int64_t min_span = p->settle > 8 * BLK ? p->settle : 8 * BLK;

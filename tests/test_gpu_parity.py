@@ -198,6 +198,29 @@ def test_sos_exact_time_split(dv, n, kind):
         assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
+@pytest.mark.parametrize("kind", ["notch", "butter2"])
+def test_sos_tail_state(dv, kind):
+    """State after a run of samples from rest as ONE weighted sum of the last `settle`
+    samples (osz_sos_tail_state_f64) against the recurrence, forward and reversed."""
+    rng = np.random.default_rng(17)
+    if kind == "notch":
+        b, a = sps.iirnotch(60, 10, fs=5000)
+        sos = np.concatenate([b, a])[None]
+    else:
+        sos = sps.butter(2, [40, 60], btype="bandpass", fs=5000, output="sos")
+    plan = dv.SosPlan(sos)
+    assert plan.has_weights
+    n = 3 * plan._settle + 1234
+    x = rng.standard_normal((3, n)) + 0.5
+    for reverse in (False, True):
+        got = plan.tail_state(_dev(dv, x), reverse=reverse).cpu().numpy()
+        xr = x[:, ::-1] if reverse else x
+        _, zf = sps.sosfilt(sos, xr, axis=-1, zi=np.zeros((sos.shape[0], 3, 2)))
+        assert relerr(got, np.transpose(zf, (1, 0, 2))) < 1e-10
+    assert not dv.SosPlan(sps.butter(8, [1, 100], btype="bandpass", fs=5000,
+                                     output="sos")).has_weights
+
+
 def test_resample_golden():
     pc.resample_golden()
 
