@@ -335,6 +335,36 @@ int osz_col_moments_f64(const double *x_dev, int64_t ldx, int64_t rows, int64_t 
                         int ignore_nan, double *mean_out_dev, double *std_out_dev,
                         double *y_dev, int64_t ldy, void *stream);
 
+/* ---- float32 I/O mode (opt-in; the reference returns float64 for every input dtype,
+ *      core/numerical.py:699): float samples in and out for the operators
+ *      whose arithmetic already runs in float32 -- 8 / 4.2 / 4 bytes per sample of HBM
+ *      traffic for FIR / resampling / Welch instead of 16 / 8.4 / 8 -- and for the biquad
+ *      scan, whose recurrence, scan and carried state stay float64 (a float32 recurrence
+ *      misses north_star's 1e-5 tolerance).  Results within 1e-5 of the
+ *      output peak.  Python: openseize_b200.set_io("float32"). --------------------- */
+/* plan created with OSZ_FIR_FFT_F32 (at most 1025 taps) */
+int osz_fir_exec_f32(const osz_fir_plan *plan, const float *x_dev, int64_t ldx, int64_t rows,
+                     int64_t n_out, float *y_dev, int64_t ldy, void *stream);
+int osz_sos_exec_f32(const osz_sos_plan *plan, const float *x_dev, int64_t ldx, int64_t rows,
+                     int64_t n, int reverse, double *state_dev, float *y_dev, int64_t ldy,
+                     void *stream);
+int osz_sos_state_from_sample_f32(const osz_sos_plan *plan, const double *zi_host,
+                                  const float *x_dev, int64_t ldx, int64_t rows, int64_t sample,
+                                  double *state_dev, void *stream);
+/* decimating plan (up == 1) set to OSZ_COMPUTE_F32 */
+int osz_upfirdn_exec_f32(const osz_upfirdn_plan *plan, const float *x_dev, int64_t ldx,
+                         int64_t rows, int64_t x_first, int64_t x_len, int64_t out_first,
+                         int64_t n_out, float *y_dev, int64_t ldy, void *stream);
+/* plan set to OSZ_COMPUTE_F32 (power-of-two nfft 512 ... 4096); sums stay float64 */
+int osz_welch_accum_f32(const osz_spec_plan *plan, const float *x_dev, int64_t ldx, int64_t rows,
+                        int64_t nseg, double *psd_sum_dev, int64_t ldp, void *stream);
+/* rows between the sample types: operators without a float32 kernel of their own run in
+ * float64 between a widen (osz_widen_rows_f32_f64) and a narrow */
+int osz_narrow_rows_f64_f32(const double *src_dev, int64_t ld_src, float *dst_dev, int64_t ld_dst,
+                            int64_t rows, int64_t n, void *stream);
+int osz_widen_rows_i16_f32(const int16_t *src_dev, int64_t ld_src, float *dst_dev, int64_t ld_dst,
+                           int64_t rows, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

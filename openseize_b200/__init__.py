@@ -27,3 +27,15 @@ def set_compute(kind):
     from openseize_b200.core import device
 
     device.set_compute(kind)
+
+
+def set_io(kind):
+    """Type of the samples in device memory and of the arrays handed back: "float64"
+    (default: the reference returns float64 / complex128 for every input dtype) or
+    "float32" (opt-in float32 I/O mode: float32 chunks cross PCIe and HBM as they are,
+    results come back float32 / complex64, within 1e-5 of the output peak -- north_star's
+    float32 tolerance; implies ``set_compute("float32")``; IIR recurrences, carried
+    states and every sum stay float64).  Also settable with OSZ_IO=float32."""
+    from openseize_b200.core import device
+
+    device.set_io(kind)

@@ -66,6 +66,14 @@ SIGNATURES = {
                                      _vp]),
     "osz_upfirdn_plan_set_compute": (c_int, [_vp, c_int]),
     "osz_upfirdn_plan_compute": (c_int, [_vp]),
+    "osz_fir_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "osz_sos_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, _i64, _vp]),
+    "osz_sos_state_from_sample_f32": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "osz_upfirdn_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64,
+                                     _vp]),
+    "osz_welch_accum_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "osz_narrow_rows_f64_f32": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "osz_widen_rows_i16_f32": (c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "osz_sos_tail_state_f64": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp]),
     "osz_sos_plan_settle": (_i64, [_vp]),
     "osz_sos_plan_has_weights": (c_int, [_vp]),

@@ -52,7 +52,7 @@ def _cur_stream():
 def _rows_ptr(t):
     """(pointer, leading dimension) of a 2-D float64 device tensor whose rows
     are time-contiguous."""
-    assert t.dim() == 2 and t.dtype == torch().float64 and t.is_cuda
+    assert t.dim() == 2 and t.dtype in (torch().float64, torch().float32) and t.is_cuda
     if t.shape[1] > 1:
         assert t.stride(1) == 1, "rows must be time-contiguous"
     ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
@@ -198,6 +198,64 @@ def _upload_edf(chunk, layout, alloc=None):
 
 
 def upload(arr, layout, alloc=None):
+    """Host chunk -> device rows ``(rows, n)`` of the I/O type on the current stream
+    (float64; float32 in the float32 I/O mode, where float64 / int16 host chunks are
+    converted to float32 -- float64 on the host, int16 on the device)."""
+    if IO != "float32":
+        return _upload_f64(arr, layout, alloc)
+    t = require_cuda()
+    raw_chunk = hasattr(arr, "records") and hasattr(arr, "chan_off")
+    a = None if raw_chunk else np.asarray(arr)
+    if raw_chunk or layout.inner != 1 or a.dtype not in (np.float32, np.float64, np.int16):
+        # EDF records / sample axis not last / other dtypes: the float64 path, then narrow
+        dev64 = _upload_f64(arr, layout, None)
+        rows, n = dev64.shape
+        return to_io(dev64, alloc(rows, n) if alloc is not None else None)
+    n = a.shape[layout.axis]
+    if a.dtype == np.float64:
+        a = a.astype(np.float32)             # half the PCIe traffic
+    a2 = np.ascontiguousarray(a.reshape(layout.outer, n))
+    h2d, _ = _Streams.get()
+    cur = t.cuda.current_stream()
+    tdt = t.float32 if a2.dtype == np.float32 else t.int16
+    src = t.from_numpy(a2) if a2.flags.writeable else t.from_numpy(a2.copy())
+    if a2.dtype == np.float32:
+        dev = alloc(layout.outer, n) if alloc is not None else None
+        ev = getattr(alloc, "ready_event", None)
+        if ev is not None:
+            h2d.wait_event(ev)
+        elif alloc is not None:
+            h2d.wait_stream(cur)
+        with t.cuda.stream(h2d):
+            if dev is None:
+                dev = t.empty((layout.outer, n), dtype=t.float32, device="cuda")
+            if not src.is_pinned():
+                stage = t.empty((layout.outer, n), dtype=tdt, pin_memory=True)
+                stage.copy_(src)
+                src = stage
+            dev.copy_(src, non_blocking=True)
+            dev._osz_keepalive = src
+        cur.wait_stream(h2d)
+        dev.record_stream(cur)
+        return dev
+    with t.cuda.stream(h2d):                 # int16: widened to float32 on the device
+        raw = t.empty((layout.outer, n), dtype=tdt, device="cuda")
+        if not src.is_pinned():
+            stage = t.empty((layout.outer, n), dtype=tdt, pin_memory=True)
+            stage.copy_(src)
+            src = stage
+        raw.copy_(src, non_blocking=True)
+        raw._osz_keepalive = src
+    cur.wait_stream(h2d)
+    raw.record_stream(cur)
+    dev = alloc(layout.outer, n) if alloc is not None else empty_rows((layout.outer, n))
+    ldd = dev.stride(0) if layout.outer > 1 else n
+    _abi.check(_abi.load().osz_widen_rows_i16_f32(_vp(raw.data_ptr()), n, _vp(dev.data_ptr()), ldd,
+                                                  layout.outer, n, _cur_stream()), "widen")
+    return dev
+
+
+def _upload_f64(arr, layout, alloc=None):
     """Host chunk -> device rows ``(rows, n)`` float64 on the current stream.
     ``alloc(rows, n)`` places the rows in the consumer's staging ring.
 
@@ -310,15 +368,17 @@ class Pending:
     """A device -> pinned-host copy in flight; ``get()`` waits and returns the
     ndarray in the reference's layout (backed by the pinned block)."""
 
-    def __init__(self, host, event, shape, complex_=False):
+    def __init__(self, host, event, shape, complex_=False, cast=None):
         self._host, self._event, self._shape, self._complex = host, event, shape, complex_
+        self._cast = cast
 
     def get(self):
         self._event.synchronize()
         out = self._host.numpy()
         if self._complex:
             out = out.view(np.complex128)
-        return out.reshape(self._shape)
+        out = out.reshape(self._shape)
+        return out.astype(self._cast) if self._cast is not None else out
 
 
 class _PendingBlock:
@@ -354,6 +414,22 @@ def download(dev, layout, complex_=False):
     n = dev.shape[1]
     cur = t.cuda.current_stream()
     _, d2h = _Streams.get()
+    cast = None
+    if IO == "float32":
+        # float32 rows go to the host as they are when the sample axis is last; other
+        # layouts and complex results take the float64 path and are narrowed on the host
+        if dev.dtype == t.float32 and layout.inner == 1 and not complex_:
+            host = t.empty(tuple(dev.shape), dtype=t.float32, pin_memory=True)
+            d2h.wait_stream(cur)
+            with t.cuda.stream(d2h):
+                host.copy_(dev, non_blocking=True)
+                ev = t.cuda.Event()
+                ev.record(d2h)
+            dev.record_stream(d2h)
+            return Pending(host, ev, layout.host_shape(n))
+        cast = np.complex64 if complex_ else np.float32
+        if dev.dtype == t.float32:
+            dev = to_f64(dev)
     if layout.inner > 1:
         shape = (layout.outer, n, layout.inner) + ((2,) if complex_ else ())
         tmp = t.empty(shape, dtype=t.float64, device="cuda")
@@ -370,7 +446,7 @@ def download(dev, layout, complex_=False):
         ev = t.cuda.Event()
         ev.record(d2h)
     dev.record_stream(d2h)
-    return Pending(host, ev, layout.host_shape(n), complex_)
+    return Pending(host, ev, layout.host_shape(n), complex_, cast)
 
 
 # --------------------------------------------------------------------------
@@ -453,6 +529,64 @@ def set_compute(kind):
     COMPUTE = kind
 
 
+# Type of the SAMPLES in device memory and of the arrays handed back: "float64" (default:
+# the reference returns float64 / complex128 for every input dtype, numerical.py:699) or
+# "float32" (opt-in float32 I/O mode, SURVEY.md 8b / 8d: float32 in, float32 / complex64
+# out, half the HBM and PCIe traffic; implies the float32 arithmetic of `set_compute`;
+# IIR recurrences, their carried state and all sums stay float64).
+IO = os.environ.get("OSZ_IO", "float64")
+if IO == "float32":
+    COMPUTE = "float32"
+
+
+def set_io(kind):
+    """"float64" | "float32": see IO.  Switching to float32 also selects the float32
+    arithmetic; switching back restores float64 arithmetic."""
+    global IO
+    if kind not in ("float64", "float32"):
+        raise ValueError("io must be 'float64' or 'float32'")
+    IO = kind
+    set_compute(kind)
+
+
+def rows_dtype():
+    t = torch()
+    return t.float32 if IO == "float32" else t.float64
+
+
+def to_f64(x):
+    """float32 device rows -> float64 rows (operators without a float32 kernel)."""
+    t = torch()
+    if x.dtype == t.float64:
+        return x
+    rows, n = x.shape
+    out = t.empty((rows, n), dtype=t.float64, device=x.device)
+    ld_src = x.stride(0) if rows > 1 else max(n, 1)
+    _abi.check(_abi.load().osz_widen_rows_f32_f64(_vp(x.data_ptr()), int(ld_src),
+                                                  _vp(out.data_ptr()), n, rows, n, _cur_stream()),
+               "widen")
+    return out
+
+
+def to_io(x, out=None):
+    """float64 device rows -> rows of the I/O type (a no-op in float64 mode)."""
+    t = torch()
+    if x.dtype == rows_dtype() and out is None:
+        return x
+    rows, n = x.shape
+    if out is None:
+        out = t.empty((rows, n), dtype=rows_dtype(), device=x.device)
+    if x.dtype == out.dtype:
+        out.copy_(x)
+        return out
+    ld_src = x.stride(0) if rows > 1 else max(n, 1)
+    ld_dst = out.stride(0) if rows > 1 else max(n, 1)
+    _abi.check(_abi.load().osz_narrow_rows_f64_f32(_vp(x.data_ptr()), int(ld_src),
+                                                   _vp(out.data_ptr()), int(ld_dst), rows, n,
+                                                   _cur_stream()), "narrow")
+    return out
+
+
 class FirPlan(_Plan):
     _destroy = "osz_fir_plan_destroy"
 
@@ -477,6 +611,19 @@ class FirPlan(_Plan):
         t = torch()
         rows = xbuf.shape[0]
         assert xbuf.shape[1] >= n_out + self.ntaps - 1
+        if xbuf.dtype == t.float32:
+            if out is None:
+                out = empty_rows((rows, n_out))
+            if self.algo != _abi.FIR_FFT_F32:
+                # no float32 kernel for this tap count: float64 between a widen and a narrow
+                y64 = self.run(to_f64(xbuf[:, :n_out + self.ntaps - 1]), n_out)
+                return to_io(y64, out)
+            xp, ldx = _rows_ptr(xbuf)
+            yp, ldy = _rows_ptr(out)
+            rc = _launch("fir", 8 * rows * n_out, _abi.load().osz_fir_exec_f32, self.handle, xp,
+                         ldx, rows, n_out, yp, ldy, _cur_stream())
+            _abi.check(rc, "fir_exec_f32")
+            return out
         if out is None:
             out = empty((rows, n_out))
         xp, ldx = _rows_ptr(xbuf)
@@ -510,16 +657,20 @@ class SosPlan(_Plan):
         t = torch()
         rows, n = x.shape
         assert state.shape == (rows, self.nsec, 2) and state.is_contiguous()
+        f32 = x.dtype == t.float32
         xp, ldx = _rows_ptr(x)
         if want_output:
             if out is None:
-                out = empty((rows, n))
+                out = t.empty((rows, n), dtype=x.dtype, device=x.device)
+            assert out.dtype == x.dtype
             yp, ldy = _rows_ptr(out)
         else:
             out, yp, ldy = None, _vp(0), 0
-        rc = _launch("sos" if want_output else "sos_state", (16 if want_output else 8) * rows * n,
-                     _abi.load().osz_sos_exec_f64, self.handle, xp, ldx, rows, n,
-                     int(bool(reverse)), _vp(state.data_ptr()), yp, ldy, _cur_stream())
+        per = (4 if f32 else 8) * (2 if want_output else 1)
+        fn = _abi.load().osz_sos_exec_f32 if f32 else _abi.load().osz_sos_exec_f64
+        rc = _launch("sos" if want_output else "sos_state", per * rows * n, fn, self.handle, xp,
+                     ldx, rows, n, int(bool(reverse)), _vp(state.data_ptr()), yp, ldy,
+                     _cur_stream())
         _abi.check(rc, "sos_exec")
         return out
 
@@ -551,9 +702,10 @@ class SosPlan(_Plan):
         assert zarr.shape == (self.nsec, 2)
         state = empty((rows, self.nsec, 2))
         xp, ldx = _rows_ptr(x)
-        rc = _abi.load().osz_sos_state_from_sample_f64(self.handle, zptr, xp, ldx, rows,
-                                                       int(sample), _vp(state.data_ptr()),
-                                                       _cur_stream())
+        fn = (_abi.load().osz_sos_state_from_sample_f32 if x.dtype == t.float32
+              else _abi.load().osz_sos_state_from_sample_f64)
+        rc = fn(self.handle, zptr, xp, ldx, rows, int(sample), _vp(state.data_ptr()),
+                _cur_stream())
         _abi.check(rc, "sos_state_from_sample")
         return state
 
@@ -582,6 +734,9 @@ class TfPlan(_Plan):
         """Filter x (rows, n); ``state`` (rows, nstate) is updated in place."""
         rows, n = x.shape
         assert state.shape == (rows, self.nstate) and state.is_contiguous()
+        if x.dtype == torch().float32:           # float32 I/O: float64 between widen and narrow
+            y64 = self.run(to_f64(x), state, reverse=reverse, want_output=want_output)
+            return to_io(y64, out) if want_output else None
         xp, ldx = _rows_ptr(x)
         if want_output:
             if out is None:
@@ -600,6 +755,9 @@ class TfPlan(_Plan):
         zarr, zptr = _abi.as_double_array(zi)
         assert zarr.shape == (self.nstate,)
         state = empty((rows, self.nstate))
+        if x.dtype == torch().float32:
+            x = to_f64(x[:, int(sample):int(sample) + 1])
+            sample = 0
         xp, ldx = _rows_ptr(x)
         rc = _abi.load().osz_tf_state_from_sample_f64(self.handle, zptr, xp, ldx, rows,
                                                       int(sample), _vp(state.data_ptr()),
@@ -644,6 +802,20 @@ class UpfirdnPlan(_Plan):
         """x: (rows, m) holding global input samples x_first .. x_first+m-1.
         Returns global output samples out_first .. out_first+n_out-1."""
         rows, m = x.shape
+        if x.dtype == torch().float32:
+            if out is None:
+                out = empty_rows((rows, n_out))
+            if self.compute != "float32":
+                # (up > 1, or a tile that does not fit): float64 between widen and narrow
+                y64 = self.run(to_f64(x), x_first, out_first, n_out)
+                return to_io(y64, out)
+            xp, ldx = _rows_ptr(x)
+            yp, ldy = _rows_ptr(out)
+            rc = _launch("upfirdn", 4 * rows * (n_out * self.down // self.up + n_out),
+                         _abi.load().osz_upfirdn_exec_f32, self.handle, xp, ldx, rows,
+                         int(x_first), m, int(out_first), int(n_out), yp, ldy, _cur_stream())
+            _abi.check(rc, "upfirdn_exec_f32")
+            return out
         if out is None:
             out = empty((rows, n_out))
         xp, ldx = _rows_ptr(x)
@@ -731,10 +903,13 @@ class SpecPlan(_Plan):
         rows = x.shape[0]
         assert x.shape[1] >= (nseg - 1) * self.stride + self.nfft
         assert psd_sum.shape == (rows, self.nfreq) and psd_sum.is_contiguous()
+        f32 = x.dtype == torch().float32
+        if f32 and self.compute != "float32":
+            x, f32 = to_f64(x), False            # no float32 kernel for this nfft
         xp, ldx = _rows_ptr(x)
-        rc = _launch("welch", 8 * rows * int(nseg) * self.stride,
-                     _abi.load().osz_welch_accum_f64, self.handle, xp, ldx, rows, int(nseg),
-                     _vp(psd_sum.data_ptr()), self.nfreq, _cur_stream())
+        fn = _abi.load().osz_welch_accum_f32 if f32 else _abi.load().osz_welch_accum_f64
+        rc = _launch("welch", (4 if f32 else 8) * rows * int(nseg) * self.stride, fn, self.handle,
+                     xp, ldx, rows, int(nseg), _vp(psd_sum.data_ptr()), self.nfreq, _cur_stream())
         _abi.check(rc, "welch_accum")
 
     def segments(self, x, nseg, complex_):
@@ -744,6 +919,7 @@ class SpecPlan(_Plan):
         assert x.shape[1] >= (nseg - 1) * self.stride + self.nfft
         shape = (nseg, rows, self.nfreq) + ((2,) if complex_ else ())
         out = empty(shape)
+        x = to_f64(x)          # (float32 I/O: the per-segment kernels read float64 samples)
         xp, ldx = _rows_ptr(x)
         fn = _abi.load().osz_stft_f64 if complex_ else _abi.load().osz_periodogram_f64
         rc = fn(self.handle, xp, ldx, rows, int(nseg), _vp(out.data_ptr()), _cur_stream())
@@ -755,6 +931,7 @@ def spec_prepare(x, n, nfft, window, detrend):
     """(rows, nfft) device rows: the first n samples of x detrended and
     windowed, then zeros (periodogram / modified_dft with nfft > n)."""
     rows = x.shape[0]
+    x = to_f64(x)
     w = from_host(np.ascontiguousarray(window, dtype=np.float64))
     out = empty((rows, int(nfft)))
     xp, ldx = _rows_ptr(x)
@@ -775,6 +952,8 @@ def take_cols(x, idx):
     t = require_cuda()
     idx = np.ascontiguousarray(idx, dtype=np.int64)
     rows = x.shape[0]
+    if x.dtype == t.float32:                 # float32 I/O: float64 between widen and narrow
+        return to_io(take_cols(to_f64(x), idx))
     out = empty((rows, int(idx.size)))
     if idx.size == 0 or rows == 0:
         return out
@@ -808,6 +987,7 @@ class RowMoments:
 
     def add(self, x):
         assert x.shape[0] == self.rows
+        x = to_f64(x)
         xp, ldx = _rows_ptr(x)
         rc = _launch("row_moments", 8 * self.rows * x.shape[1], _abi.load().osz_row_moments_f64,
                      xp, ldx, self.rows, int(x.shape[1]), int(self.ignore_nan),
@@ -821,6 +1001,8 @@ class RowMoments:
 def row_standardize(x, mean_dev, std_dev, out=None):
     """(x - mean[r]) / std[r] per device row (protools.standardize, production axis)."""
     rows, n = x.shape
+    if x.dtype == torch().float32:
+        return to_io(row_standardize(to_f64(x), mean_dev, std_dev), out)
     if out is None:
         out = empty((rows, n))
     xp, ldx = _rows_ptr(x)
@@ -835,6 +1017,8 @@ def col_moments(x, ignore_nan=True, want="mean"):
     """Per-sample statistics ACROSS the rows of a device chunk: ``want`` =
     "mean" | "std" -> (1, n) rows, "standardize" -> (rows, n)."""
     rows, n = x.shape
+    if x.dtype == torch().float32:
+        return to_io(col_moments(to_f64(x), ignore_nan, want))
     xp, ldx = _rows_ptr(x)
     null = _vp(0)
     if want == "standardize":
@@ -855,6 +1039,7 @@ def zip_complex(re, im):
     """(rows, n) real and imaginary device rows -> (rows, n, 2) complex128 rows."""
     rows, n = re.shape
     assert im.shape == re.shape
+    re, im = to_f64(re), to_f64(im)
     out = empty((rows, n, 2))
     rp, ldr = _rows_ptr(re)
     ip, ldi = _rows_ptr(im)
@@ -877,18 +1062,26 @@ def cat_time(parts):
 
 
 def zeros(shape):
-    """Zero-filled float64 device tensor."""
+    """Zero-filled float64 device tensor (states, sums)."""
     t = require_cuda()
     return t.zeros(tuple(shape), dtype=t.float64, device=DEVICE)
 
 
 def empty(shape):
+    """float64 device tensor (states, sums, spectra)."""
     t = require_cuda()
     return t.empty(tuple(shape), dtype=t.float64, device=DEVICE)
 
 
+def empty_rows(shape):
+    """Sample rows: float64, or float32 in the float32 I/O mode."""
+    t = require_cuda()
+    return t.empty(tuple(shape), dtype=rows_dtype(), device=DEVICE)
+
+
 def zeros_rows(rows, n):
-    return zeros((rows, n))
+    t = require_cuda()
+    return t.zeros((rows, n), dtype=rows_dtype(), device=DEVICE)
 
 
 def record_event():

@@ -181,7 +181,7 @@ def _masked_device(pro):
 
 def _new_rows(out, rows, n):
     """Output block of a stage: in the consumer's staging ring when it asked."""
-    return out(rows, n) if out is not None else dv.empty((rows, n))
+    return out(rows, n) if out is not None else dv.empty_rows((rows, n))
 
 
 class _TimeRing:
@@ -199,7 +199,7 @@ class _TimeRing:
     def _reserve(self, n):
         live = self.pos - self.start
         if self.buf is None or self.pos + n > self.buf.shape[1]:
-            new = dv.empty((self.rows, live + 2 * n + 64))
+            new = dv.empty_rows((self.rows, live + 2 * n + 64))
             if live:
                 new[:, :live].copy_(self.buf[:, self.start:self.pos])
             self.buf, self.start, self.pos = new, 0, live
@@ -218,7 +218,7 @@ class _TimeRing:
         if self.buf is None:
             return False
         lo = self.buf.data_ptr()
-        return lo <= block.data_ptr() < lo + self.buf.numel() * 8
+        return lo <= block.data_ptr() < lo + self.buf.numel() * self.buf.element_size()
 
     def push(self, block):
         n = block.shape[1]
@@ -586,7 +586,7 @@ class _ForwardPass:
             if buf.shape[1] >= n:
                 del self.free[i]
                 return buf, ev
-        return dv.empty((self.rows, n)), dv.record_event()
+        return dv.empty_rows((self.rows, n)), dv.record_event()
 
     def release(self, fwd):
         buf = getattr(fwd, "_osz_buf", None)
@@ -854,7 +854,7 @@ class _FusedFirDecimator(_Resampler):
 
     def compute(self, window, w_first, o_lo, o_hi, out):
         if out is None:
-            out = dv.empty((window.shape[0], o_hi - o_lo))
+            out = dv.empty_rows((window.shape[0], o_hi - o_lo))
         a, b = max(o_lo, self.j_lo), min(o_hi, self.j_hi + 1)
         if b > a:
             self.plan.run(window, w_first, a, b - a, out=out[:, a - o_lo:b - o_lo])
@@ -911,7 +911,7 @@ def _fusable_iir(pro, axis):
     # share one SM's issue slots (39 % issue-active, the MMA group starved 20 % of the
     # time): 2.6 ms against 0.82 + 1.30 ms for the backward pass and the tensor-core
     # decimator run one after the other.
-    if os.environ.get("OSZ_FUSE_IIR", "0") != "1":
+    if os.environ.get("OSZ_FUSE_IIR", "0") != "1" or dv.IO != "float64":
         return None
     if not isinstance(pro, GenProducer) or pro.kwargs:
         return None
@@ -1252,6 +1252,8 @@ def _split_windows(pending, layout, complex_):
     host = block.get()                      # (nseg, rows, nfreq[, 2]) float64, pinned
     if complex_:
         host = host.view(np.complex128)[..., 0]
+    if dv.IO == "float32":
+        host = host.astype(np.complex64 if complex_ else np.float32)
     nfreq = host.shape[2]
     for k in range(nseg):
         yield host[k].reshape(layout.host_shape(nfreq))
@@ -1297,7 +1299,8 @@ def welch_mean(pro, fs, nfft, window, overlap, axis, detrend, scaling):
     if cnt == 0:
         raise ValueError("psd: the data holds no complete nfft={} segment".format(nfft))
     layout = _layout_of(pro, axis)
-    return cnt, np.array(dv.download(psd_sum, layout).get()) / cnt
+    est = np.array(dv.download(psd_sum, layout).get()) / cnt
+    return cnt, est.astype(np.float32) if dv.IO == "float32" else est
 
 
 def stft(pro, fs, nfft, window, overlap, axis, detrend, scaling, boundary, padded):

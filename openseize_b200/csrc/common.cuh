@@ -61,6 +61,15 @@ __device__ __forceinline__ void st_stream(double *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
 
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float *p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared::cta) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -135,6 +144,22 @@ __device__ __forceinline__ void tma_fetch_span(double *dst, const double *src, i
     }
     mbar_expect_tx(bar, (uint32_t)cnt * 8u);
     if (cnt > 0) tma_load_1d(dst, src - mis, (uint32_t)cnt * 8u, bar);
+}
+
+// float32 samples (the opt-in float32 I/O mode): the same span fetch with four
+// elements per 16 bytes; up to three tail elements are copied by hand.
+__device__ __forceinline__ int span_mis(const float *src) {
+    return (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+}
+__device__ __forceinline__ void tma_fetch_span(float *dst, const float *src, int64_t need,
+                                               uint64_t *bar) {
+    const int mis = span_mis(src);
+    int64_t cnt = need + mis;
+    const int tail = (int)(cnt & 3);
+    for (int i = 0; i < tail; ++i) dst[cnt - tail + i] = src[need - tail + i];
+    cnt -= tail;
+    mbar_expect_tx(bar, (uint32_t)cnt * 4u);
+    if (cnt > 0) tma_load_1d(dst, src - mis, (uint32_t)cnt * 4u, bar);
 }
 
 }  // namespace osz

@@ -365,11 +365,14 @@ struct FirPPC32 {
     static constexpr int SMEM = OFF_X + 2 * GROUP_BYTES;
 };
 
-template <int LOG2N, bool ACC, bool TOKEN>
+// TIO: the samples' type in memory -- double (float64 samples in and out, the default
+// of the float32 ARITHMETIC mode) or float (the float32 I/O mode: 8 bytes per sample of
+// HBM traffic instead of 16).
+template <int LOG2N, bool ACC, bool TOKEN, typename TIO>
 __global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, 1)
-fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
+fir_fft_pp_c32_kernel(const TIO *__restrict__ x, int64_t ldx, int64_t n_out, int ntaps,
                       const float2 *__restrict__ H, const float2 *__restrict__ tw,
-                      double *__restrict__ y, int64_t ldy, int64_t npairs, int64_t nwork,
+                      TIO *__restrict__ y, int64_t ldy, int64_t npairs, int64_t nwork,
                       int iters, int lag, int zero) {
     using C = oszf::FftCfg<LOG2N>;
     using L = FirPPC32<LOG2N>;
@@ -383,8 +386,7 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
     float2 *h_sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_H);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L::OFF_BAR) + g;
     float2 *sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_X + g * L::GROUP_BYTES);
-    double *sx = reinterpret_cast<double *>(smem_raw + L::OFF_X + g * L::GROUP_BYTES +
-                                            C::SMEM_BYTES);
+    TIO *sx = reinterpret_cast<TIO *>(smem_raw + L::OFF_X + g * L::GROUP_BYTES + C::SMEM_BYTES);
 
     for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
     for (int i = threadIdx.x; i < L::NH; i += 2 * NT) h_sm[i] = ldg(H + i);
@@ -405,7 +407,7 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
 
     auto issue = [&](int64_t w_, int64_t row_, int64_t pair_) {
         if (w_ >= nwork) return;
-        const double *src = x + row_ * ldx + pair_ * 2 * step;
+        const TIO *src = x + row_ * ldx + pair_ * 2 * step;
         const int64_t left = span - pair_ * 2 * step;
         tma_fetch_span(sx, src, left < step + N ? left : step + N, bar);
     };
@@ -425,7 +427,7 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
         }
         float2 v[16];
         if (live) {
-            const double *xa = sx + span_mis(x + row * ldx + base_a) + tid, *xb = xa + step;
+            const TIO *xa = sx + span_mis(x + row * ldx + base_a) + tid, *xb = xa + step;
             while (!mbar_try_wait(bar, it & 1)) {
             }
             if (left >= step + N) {
@@ -475,8 +477,8 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
         oszf::fft_r2r_tail<LOG2N, Sync, true>(v, sm, tid, sync);
 
         if (live) {
-            double *ya = y + row * ldy + base_a + tid - k1;
-            double *yb = ya + step;
+            TIO *ya = y + row * ldy + base_a + tid - k1;
+            TIO *yb = ya + step;
             const int64_t oa = n_out - base_a + k1, ob = oa - step;
             const int out_a = (int)(oa > N ? N : oa), out_b = (int)(ob < 0 ? 0 : (ob > N ? N : ob));
 #pragma unroll
@@ -484,11 +486,11 @@ fir_fft_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t n_out, 
                 const int i = tid + r * NT;
                 if (i >= k1) {
                     if (ACC) {
-                        if (i < out_a) ya[r * NT] += (double)v[r].y;
-                        if (i < out_b) yb[r * NT] += (double)v[r].x;
+                        if (i < out_a) ya[r * NT] += (TIO)v[r].y;
+                        if (i < out_b) yb[r * NT] += (TIO)v[r].x;
                     } else {
-                        if (i < out_a) st_stream(ya + r * NT, (double)v[r].y);
-                        if (i < out_b) st_stream(yb + r * NT, (double)v[r].x);
+                        if (i < out_a) st_stream(ya + r * NT, (TIO)v[r].y);
+                        if (i < out_b) st_stream(yb + r * NT, (TIO)v[r].x);
                     }
                 }
             }
@@ -565,9 +567,9 @@ static int launch_fir_fft_pp(const osz_fir_plan *p, const double *x, int64_t ldx
     return OSZ_OK;
 }
 
-template <int LOG2N, bool ACC>
-static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
-                                 int64_t n_out, double *y, int64_t ldy, cudaStream_t st) {
+template <int LOG2N, bool ACC, typename TIO>
+static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const TIO *x, int64_t ldx, int64_t rows,
+                                 int64_t n_out, TIO *y, int64_t ldy, cudaStream_t st) {
     using C = oszf::FftCfg<LOG2N>;
     constexpr int SMEM = FirPPC32<LOG2N>::SMEM;
     static_assert(SMEM <= 227 * 1024, "float32-compute FIR: shared memory");
@@ -575,8 +577,8 @@ static int launch_fir_fft_pp_c32(const osz_fir_plan *p, const double *x, int64_t
         const char *e = getenv("OSZ_FIR32_TOKEN");
         return e ? atoi(e) : 0;
     }();
-    auto kern = token ? fir_fft_pp_c32_kernel<LOG2N, ACC, true>
-                      : fir_fft_pp_c32_kernel<LOG2N, ACC, false>;
+    auto kern = token ? fir_fft_pp_c32_kernel<LOG2N, ACC, true, TIO>
+                      : fir_fft_pp_c32_kernel<LOG2N, ACC, false, TIO>;
     OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int64_t step = C::N - p->ntaps + 1;
     const int64_t nblocks = (n_out + step - 1) / step;
@@ -737,6 +739,19 @@ int osz_fir_exec_f64(const osz_fir_plan *p, const double *x, int64_t ldx, int64_
     return fir_exec(p, x, ldx, rows, n_out, y, ldy, st, 0);
 }
 
+// float32 I/O: float samples in and out, the float32-arithmetic overlap-save kernel
+// (plans created with OSZ_FIR_FFT_F32, 25 ... 1025 taps).
+int osz_fir_exec_f32(const osz_fir_plan *p, const float *x, int64_t ldx, int64_t rows,
+                     int64_t n_out, float *y, int64_t ldy, void *stream) {
+    if (!p || !x || !y) return fail(OSZ_ERR_ARG, "osz_fir_exec_f32: null argument");
+    if (rows <= 0 || n_out <= 0) return OSZ_OK;
+    if (p->algo != OSZ_FIR_FFT_F32 || p->log2n != 12 || !p->parts.empty())
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_fir_exec_f32: needs a float32-arithmetic FFT plan "
+                                         "(OSZ_FIR_FFT_F32, at most 1025 taps)");
+    return launch_fir_fft_pp_c32<12, false, float>(p, x, ldx, rows, n_out, y, ldy,
+                                                   as_stream(stream));
+}
+
 }  // extern "C"
 
 static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t rows,
@@ -754,8 +769,9 @@ static int fir_exec(const osz_fir_plan *p, const double *x, int64_t ldx, int64_t
         return OSZ_OK;
     }
     if (p->algo == OSZ_FIR_FFT_F32 && p->log2n == 12)
-        return accumulate ? launch_fir_fft_pp_c32<12, true>(p, x, ldx, rows, n_out, y, ldy, st)
-                          : launch_fir_fft_pp_c32<12, false>(p, x, ldx, rows, n_out, y, ldy, st);
+        return accumulate
+                   ? launch_fir_fft_pp_c32<12, true, double>(p, x, ldx, rows, n_out, y, ldy, st)
+                   : launch_fir_fft_pp_c32<12, false, double>(p, x, ldx, rows, n_out, y, ldy, st);
     if (p->log2n == 12) {
         // Two CTAs per SM at 128 registers beat three at 80 (104 B of spills):
         // 217 vs 184 G samples/s at 113 taps (profiles/r01_kernel_bench.md).

@@ -85,15 +85,15 @@ __global__ void widen_kernel(const S *__restrict__ src, double *__restrict__ dst
     for (; i < count; i += step) dst[i] = (double)src[i];
 }
 
-template <typename S>
+template <typename S, typename D = double>
 __global__ void widen_rows_kernel(const S *__restrict__ src, int64_t ld_src,
-                                  double *__restrict__ dst, int64_t ld_dst, int64_t n) {
+                                  D *__restrict__ dst, int64_t ld_dst, int64_t n) {
     const int64_t row = blockIdx.y;
     const S *s = src + row * ld_src;
-    double *d = dst + row * ld_dst;
+    D *d = dst + row * ld_dst;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += step) d[i] = (double)s[i];
+    for (; i < n; i += step) d[i] = (D)s[i];
 }
 
 // EDF ingest on the device.  `rec` holds whole data records exactly as they sit
@@ -122,15 +122,15 @@ __global__ void decode_edf_records_kernel(const int16_t *__restrict__ rec, int64
     }
 }
 
-template <typename S>
-static int launch_widen_rows(const S *src, int64_t ld_src, double *dst, int64_t ld_dst,
+template <typename S, typename D = double>
+static int launch_widen_rows(const S *src, int64_t ld_src, D *dst, int64_t ld_dst,
                              int64_t rows, int64_t n, void *stream) {
     if (rows <= 0 || n <= 0) return OSZ_OK;
     if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "widen: more than 65535 rows per call");
     int bx = (int)((n + 255) / 256);
     const int cap = (sm_count() * 16 + (int)rows - 1) / (int)rows;
     if (bx > cap) bx = cap < 1 ? 1 : cap;
-    widen_rows_kernel<S><<<dim3((unsigned)bx, (unsigned)rows), 256, 0, as_stream(stream)>>>(
+    widen_rows_kernel<S, D><<<dim3((unsigned)bx, (unsigned)rows), 256, 0, as_stream(stream)>>>(
         src, ld_src, dst, ld_dst, n);
     OSZ_LAUNCHED("widen_rows");
     return OSZ_OK;
@@ -297,6 +297,16 @@ int osz_widen_rows_f32_f64(const float *src, int64_t ld_src, double *dst, int64_
 int osz_widen_rows_i16_f64(const int16_t *src, int64_t ld_src, double *dst, int64_t ld_dst,
                            int64_t rows, int64_t n, void *stream) {
     return launch_widen_rows<int16_t>(src, ld_src, dst, ld_dst, rows, n, stream);
+}
+// float32 I/O mode: rows between the two sample types (operators without a float32
+// kernel of their own run in float64 between a widen and a narrow), int16 -> float32
+int osz_narrow_rows_f64_f32(const double *src, int64_t ld_src, float *dst, int64_t ld_dst,
+                            int64_t rows, int64_t n, void *stream) {
+    return launch_widen_rows<double, float>(src, ld_src, dst, ld_dst, rows, n, stream);
+}
+int osz_widen_rows_i16_f32(const int16_t *src, int64_t ld_src, float *dst, int64_t ld_dst,
+                           int64_t rows, int64_t n, void *stream) {
+    return launch_widen_rows<int16_t, float>(src, ld_src, dst, ld_dst, rows, n, stream);
 }
 int osz_decode_edf_records_f64(const int16_t *rec, int64_t per_record, int64_t spr,
                                const int *chan_off_dev, const double *slope_dev,

@@ -26,6 +26,7 @@
 
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -41,11 +42,13 @@ namespace osz {
 // a CTA always has loads in flight.  T = 32 with PF takes 64 more registers (one CTA per
 // SM): the build for launches with no more CTAs than SMs (few rows), where a lone CTA per
 // SM otherwise leaves HBM idle through its scan phase.
-template <bool WRITE, int T, bool PF = false>
+// TIO: the samples' type in memory (double, or float for the float32 I/O mode: the
+// recurrence, the scan and the carried state stay float64 -- SURVEY.md 8d).
+template <bool WRITE, int T, bool PF = false, typename TIO = double>
 __global__ void __launch_bounds__(SOS_NT, (T == 32 ? (PF ? 1 : 2) : (PF ? 2 : 4)))
-sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict__ x, int64_t ldx,
+sos_scan_kernel(const __grid_constant__ SosParams prm, const TIO *__restrict__ x, int64_t ldx,
                 int64_t n_total, int reverse, const double *__restrict__ state_in,
-                double *__restrict__ state, double *__restrict__ y, int64_t ldy,
+                double *__restrict__ state, TIO *__restrict__ y, int64_t ldy,
                 const double *__restrict__ lanepow /* [sec][32][4]: A^(T*(lane+1)) */,
                 int64_t span_len, int64_t settle,
                 const double *__restrict__ span_in /* exact split, pass 2: entering states */,
@@ -81,8 +84,8 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     const int64_t n = b - w0;                           // samples this CTA runs through
     const int64_t keep = a - w0;                        // local index of the first stored sample
     // logical sample s (local) <-> global index: forward w0 + s, reverse n_total-1-(w0+s)
-    const double *xr = x + row * ldx + (reverse ? n_total - 1 - w0 : w0);
-    double *yr = WRITE ? y + row * ldy + (reverse ? n_total - 1 - w0 : w0) : nullptr;
+    const TIO *xr = x + row * ldx + (reverse ? n_total - 1 - w0 : w0);
+    TIO *yr = WRITE ? y + row * ldy + (reverse ? n_total - 1 - w0 : w0) : nullptr;
 
     if (tid < nsec * 2) {
         double c0 = 0.0;
@@ -99,7 +102,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
     double nxt[PF ? T : 1];
     auto prefetch = [&](int64_t blk) {          // a full block (blk >= 1)
         const int64_t p0 = first_len + (blk - 1) * BLK;
-        const double *src = reverse ? xr - p0 - tid : xr + p0 + tid;
+        const TIO *src = reverse ? xr - p0 - tid : xr + p0 + tid;
 #pragma unroll
         for (int it = 0; it < (PF ? T : 1); ++it)
             nxt[it] = ld_stream(reverse ? src - it * SOS_NT : src + it * SOS_NT);
@@ -118,7 +121,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             }
         } else if (blk != 0) {
             // full block: T independent coalesced loads in flight per thread
-            const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
+            const TIO *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
             double tmp[T];
 #pragma unroll
             for (int it = 0; it < T; ++it)
@@ -134,7 +137,7 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
                 double val = 0.0;
                 if (e >= off) {
                     const int64_t s = pos0 + (e - off);
-                    val = ld_stream(reverse ? xr - s : xr + s);
+                    val = (double)ld_stream(reverse ? xr - s : xr + s);
                 }
                 buf[(e >> LOGT) * LD + (e & (T - 1))] = val;
             }
@@ -151,19 +154,20 @@ sos_scan_kernel(const __grid_constant__ SosParams prm, const double *__restrict_
             for (int i = 0; i < T; ++i) buf[tid * LD + i] = v[i];
             __syncthreads();
             if (blk != 0 && pos0 >= keep) {
-                double *dst = reverse ? yr - pos0 - tid : yr + pos0 + tid;
+                TIO *dst = reverse ? yr - pos0 - tid : yr + pos0 + tid;
 #pragma unroll
                 for (int it = 0; it < T; ++it) {
                     const int e = tid + it * SOS_NT;
                     st_stream(reverse ? dst - it * SOS_NT : dst + it * SOS_NT,
-                              buf[(e >> LOGT) * LD + (e & (T - 1))]);
+                              (TIO)buf[(e >> LOGT) * LD + (e & (T - 1))]);
                 }
             } else {
 #pragma unroll 4
                 for (int e = tid; e < BLK; e += SOS_NT) {
                     const int64_t s = pos0 + (e - off);
                     if (e >= off && s >= keep)
-                        st_stream(reverse ? yr - s : yr + s, buf[(e >> LOGT) * LD + (e & (T - 1))]);
+                        st_stream(reverse ? yr - s : yr + s,
+                                  (TIO)buf[(e >> LOGT) * LD + (e & (T - 1))]);
                 }
             }
         }
@@ -268,14 +272,15 @@ __global__ void sos_copy_state_kernel(const double *__restrict__ src, double *__
     if (i < count) dst[i] = src[i];
 }
 
-__global__ void sos_state_from_sample_kernel(SosZi zi, int nsec, const double *__restrict__ x,
+template <typename TIO>
+__global__ void sos_state_from_sample_kernel(SosZi zi, int nsec, const TIO *__restrict__ x,
                                              int64_t ldx, int64_t rows, int64_t sample,
                                              double *__restrict__ state) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * nsec * 2) return;
     const int64_t row = i / (nsec * 2);
     const int sj = (int)(i % (nsec * 2));
-    state[i] = zi.zi[sj >> 1][sj & 1] * x[row * ldx + sample];
+    state[i] = zi.zi[sj >> 1][sj & 1] * (double)x[row * ldx + sample];
 }
 
 }  // namespace osz
@@ -589,9 +594,12 @@ static int sos_phi(const osz_sos_plan *p, int64_t span_len, const double **out) 
     return OSZ_OK;
 }
 
-int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t n,
-                     int reverse, double *state, double *y, int64_t ldy, void *stream) {
-    if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_exec_f64: null argument");
+}  // extern "C"
+
+template <typename TIO>
+static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t rows, int64_t n,
+                      int reverse, double *state, TIO *y, int64_t ldy, void *stream) {
+    if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_exec: null argument");
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
     const int smem = SOS_NT * (p->T + 1) * 8;
@@ -624,7 +632,8 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
         const char *e = getenv("OSZ_SOS_WEIGHTS");
         return e ? atoi(e) : 0;             // -1: automatic, 0: off, k: k spans
     }();
-    if (y && p->d_weights && forced_weights != 0 && n >= 2 * p->settle) {
+    if (std::is_same<TIO, double>::value && y && p->d_weights && forced_weights != 0 &&
+        n >= 2 * p->settle) {
         const int64_t min_span = p->settle > 8 * BLK ? p->settle : 8 * BLK;
         int64_t k = forced_weights > 0 ? forced_weights : (2 * (int64_t)sm_count()) / rows;
         if (k > n / min_span) k = n / min_span;
@@ -732,11 +741,12 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     if (weighted) {
         span_e = scratch + n_copy;
         const dim3 g2((unsigned)(nspan - 1), (unsigned)rows);
+        const double *xd = reinterpret_cast<const double *>(x);      // (TIO is double here)
         if (ns2 == 2)
-            sos_entering_kernel<2><<<g2, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse,
+            sos_entering_kernel<2><<<g2, 256, 0, st>>>(p->d_weights, p->settle, xd, ldx, n, reverse,
                                                        span_len, span_e, (int)nspan, 0);
         else
-            sos_entering_kernel<4><<<g2, 256, 0, st>>>(p->d_weights, p->settle, x, ldx, n, reverse,
+            sos_entering_kernel<4><<<g2, 256, 0, st>>>(p->d_weights, p->settle, xd, ldx, n, reverse,
                                                        span_len, span_e, (int)nspan, 0);
         OSZ_LAUNCHED("sos_entering_kernel");
     }
@@ -752,22 +762,22 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
 #define OSZ_SOS_LAUNCH(W, TT, YY, SIN, SOUT)                                                    \
     do {                                                                                        \
         if (TT == 32 && lone) {                                                                 \
-            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 32, true>,                         \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 32, true, TIO>,                         \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-            sos_scan_kernel<W, 32, true><<<grid, SOS_NT, smem, st>>>(                           \
-                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+            sos_scan_kernel<W, 32, true, TIO><<<grid, SOS_NT, smem, st>>>(                           \
+                p->prm, x, ldx, n, reverse, state_in, state, (TIO *)(YY), ldy, p->d_lanepow, span_len,   \
                 p->settle, SIN, SOUT);                                                          \
         } else if (TT == 16 && p->prefetch) {                                                          \
-            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 16, true>,                         \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, 16, true, TIO>,                         \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-            sos_scan_kernel<W, 16, true><<<grid, SOS_NT, smem, st>>>(                           \
-                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+            sos_scan_kernel<W, 16, true, TIO><<<grid, SOS_NT, smem, st>>>(                           \
+                p->prm, x, ldx, n, reverse, state_in, state, (TIO *)(YY), ldy, p->d_lanepow, span_len,   \
                 p->settle, SIN, SOUT);                                                          \
         } else {                                                                                \
-            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT>,                               \
+            OSZ_CUDA(cudaFuncSetAttribute(sos_scan_kernel<W, TT, false, TIO>,                               \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-            sos_scan_kernel<W, TT><<<grid, SOS_NT, smem, st>>>(                                 \
-                p->prm, x, ldx, n, reverse, state_in, state, YY, ldy, p->d_lanepow, span_len,   \
+            sos_scan_kernel<W, TT, false, TIO><<<grid, SOS_NT, smem, st>>>(                                 \
+                p->prm, x, ldx, n, reverse, state_in, state, (TIO *)(YY), ldy, p->d_lanepow, span_len,   \
                 p->settle, SIN, SOUT);                                                          \
         }                                                                                       \
         OSZ_LAUNCHED("sos_scan_kernel");                                                        \
@@ -792,6 +802,18 @@ int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_
     }
 #undef OSZ_SOS_LAUNCH
     return OSZ_OK;
+}
+
+extern "C" {
+
+int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t n,
+                     int reverse, double *state, double *y, int64_t ldy, void *stream) {
+    return sos_exec_t<double>(p, x, ldx, rows, n, reverse, state, y, ldy, stream);
+}
+// float32 I/O: float samples in and out; recurrence, scan and carried state in float64
+int osz_sos_exec_f32(const osz_sos_plan *p, const float *x, int64_t ldx, int64_t rows, int64_t n,
+                     int reverse, double *state, float *y, int64_t ldy, void *stream) {
+    return sos_exec_t<float>(p, x, ldx, rows, n, reverse, state, y, ldy, stream);
 }
 
 int osz_sos_tail_state_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows,
@@ -828,11 +850,14 @@ int osz_sos_plan_params(const osz_sos_plan *p, SosParams *prm, const double **la
     return OSZ_OK;
 }
 
-int osz_sos_state_from_sample_f64(const osz_sos_plan *p, const double *zi, const double *x,
-                                  int64_t ldx, int64_t rows, int64_t sample, double *state,
-                                  void *stream) {
+}  // extern "C"
+
+template <typename TIO>
+static int sos_state_from_sample_t(const osz_sos_plan *p, const double *zi, const TIO *x,
+                                   int64_t ldx, int64_t rows, int64_t sample, double *state,
+                                   void *stream) {
     if (!p || !zi || !x || !state)
-        return fail(OSZ_ERR_ARG, "osz_sos_state_from_sample_f64: null argument");
+        return fail(OSZ_ERR_ARG, "osz_sos_state_from_sample: null argument");
     if (rows <= 0) return OSZ_OK;
     SosZi z{};
     for (int s = 0; s < p->prm.nsec; ++s) {
@@ -840,10 +865,24 @@ int osz_sos_state_from_sample_f64(const osz_sos_plan *p, const double *zi, const
         z.zi[s][1] = zi[2 * s + 1];
     }
     const int64_t total = rows * p->prm.nsec * 2;
-    sos_state_from_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-        z, p->prm.nsec, x, ldx, rows, sample, state);
+    sos_state_from_sample_kernel<TIO><<<(unsigned)((total + 255) / 256), 256, 0,
+                                        as_stream(stream)>>>(z, p->prm.nsec, x, ldx, rows, sample,
+                                                             state);
     OSZ_LAUNCHED("sos_state_from_sample_kernel");
     return OSZ_OK;
+}
+
+extern "C" {
+
+int osz_sos_state_from_sample_f64(const osz_sos_plan *p, const double *zi, const double *x,
+                                  int64_t ldx, int64_t rows, int64_t sample, double *state,
+                                  void *stream) {
+    return sos_state_from_sample_t<double>(p, zi, x, ldx, rows, sample, state, stream);
+}
+int osz_sos_state_from_sample_f32(const osz_sos_plan *p, const double *zi, const float *x,
+                                  int64_t ldx, int64_t rows, int64_t sample, double *state,
+                                  void *stream) {
+    return sos_state_from_sample_t<float>(p, zi, x, ldx, rows, sample, state, stream);
 }
 
 }  // extern "C"

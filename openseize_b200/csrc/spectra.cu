@@ -402,9 +402,11 @@ struct WelchPPC32 {
     static constexpr int CTAS_PER_SM = 4096 / C::N < FIT ? 4096 / C::N : FIT;
 };
 
-template <int LOG2N, int DETREND, bool TOKEN>
+// TIO: the samples' type in memory -- double, or float for the float32 I/O mode (4 bytes
+// per sample of HBM traffic instead of 8; sums and the centring stay float64).
+template <int LOG2N, int DETREND, bool TOKEN, typename TIO>
 __global__ void __launch_bounds__(2 * oszf::FftCfg<LOG2N>::NT, WelchPPC32<LOG2N>::CTAS_PER_SM)
-welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
+welch_pp_c32_kernel(const TIO *__restrict__ x, int64_t ldx, int64_t nseg, int64_t stride,
                     const float *__restrict__ win, const float2 *__restrict__ tw, double norm,
                     double *__restrict__ psd_sum, int64_t ldp, int64_t npairs, int64_t nwork,
                     int64_t per_group, int lag, int zero) {
@@ -422,8 +424,7 @@ welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int
     double *red = reinterpret_cast<double *>(smem_raw + L::OFF_RED) + g * 32;
     float *win_sm = reinterpret_cast<float *>(smem_raw + L::OFF_WIN);
     float2 *sm = reinterpret_cast<float2 *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES);
-    double *sx = reinterpret_cast<double *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES +
-                                            C::SMEM_BYTES);
+    TIO *sx = reinterpret_cast<TIO *>(smem_raw + L::OFF_G + g * L::GROUP_BYTES + C::SMEM_BYTES);
 
     for (int i = threadIdx.x; i < C::TW_TOTAL; i += 2 * NT) tw_sm[i] = ldg(tw + i);
     for (int i = threadIdx.x; i < N; i += 2 * NT) win_sm[i] = ldg(win + i);
@@ -478,18 +479,18 @@ welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int
         double s[4] = {0.0, 0.0, 0.0, 0.0};
         constexpr double tbar = 0.5 * (N - 1);
         if (live) {
-            const double *x0 = sx + span_mis(x + row * ldx + 2 * pair * stride);
-            const double *xa = x0 + tid;
-            const double *xb = xa + stride;
+            const TIO *x0 = sx + span_mis(x + row * ldx + 2 * pair * stride);
+            const TIO *xa = x0 + tid;
+            const TIO *xb = xa + stride;
             while (!mbar_try_wait(bar, (uint32_t)(it & 1))) {
             }
-            const double c = DETREND != OSZ_DETREND_NONE ? x0[0] : 0.0;
+            const double c = DETREND != OSZ_DETREND_NONE ? (double)x0[0] : 0.0;
             const bool has_b = 2 * pair + 1 < nseg;
             if (has_b && stride == N / 2) {
                 // 50 % overlap: the second segment's first half is the first one's second
                 double d[24];
 #pragma unroll
-                for (int r = 0; r < 24; ++r) d[r] = xa[r * NT] - c;
+                for (int r = 0; r < 24; ++r) d[r] = (double)xa[r * NT] - c;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) v[r] = make_float2((float)d[r], (float)d[r + 8]);
                 if (DETREND != OSZ_DETREND_NONE) {
@@ -507,8 +508,8 @@ welch_pp_c32_kernel(const double *__restrict__ x, int64_t ldx, int64_t nseg, int
             } else {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    const double da = xa[r * NT] - c;
-                    const double db = has_b ? xb[r * NT] - c : 0.0;
+                    const double da = (double)xa[r * NT] - c;
+                    const double db = has_b ? (double)xb[r * NT] - c : 0.0;
                     v[r] = make_float2((float)da, (float)db);
                     if (DETREND != OSZ_DETREND_NONE) {
                         s[0] += da;
@@ -873,8 +874,8 @@ static int launch_welch_pp(const osz_spec_plan *p, const double *x, int64_t ldx,
     return OSZ_OK;
 }
 
-template <int LOG2N, int DETREND>
-static int launch_welch_pp_c32(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
+template <int LOG2N, int DETREND, typename TIO>
+static int launch_welch_pp_c32(const osz_spec_plan *p, const TIO *x, int64_t ldx, int64_t rows,
                                int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
     using C = oszf::FftCfg<LOG2N>;
     using L = WelchPPC32<LOG2N>;
@@ -884,8 +885,8 @@ static int launch_welch_pp_c32(const osz_spec_plan *p, const double *x, int64_t 
         const char *e = getenv("OSZ_WELCH32_TOKEN");
         return e ? atoi(e) : 0;
     }();
-    auto kern = token ? welch_pp_c32_kernel<LOG2N, DETREND, true>
-                      : welch_pp_c32_kernel<LOG2N, DETREND, false>;
+    auto kern = token ? welch_pp_c32_kernel<LOG2N, DETREND, true, TIO>
+                      : welch_pp_c32_kernel<LOG2N, DETREND, false, TIO>;
     OSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     const int64_t npairs = (nseg + 1) / 2;
     const int64_t nwork = npairs * rows;
@@ -939,7 +940,8 @@ static int dispatch_mode(const osz_spec_plan *p, int mode, const double *x, int6
         }();
         if constexpr (LOG2N >= 9 && LOG2N <= 12) {
             if (p->compute == OSZ_COMPUTE_F32 && p->d_winf && p->d_twf)
-                return launch_welch_pp_c32<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
+                return launch_welch_pp_c32<LOG2N, DETREND, double>(p, x, ldx, rows, nseg, out, ldp,
+                                                                   st);
             if (pp) return launch_welch_pp<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
         }
         return launch_welch<LOG2N, DETREND>(p, x, ldx, rows, nseg, out, ldp, st);
@@ -996,6 +998,24 @@ static int spec_exec(const osz_spec_plan *p, int mode, const double *x, int64_t 
         case 13: return dispatch_detrend<13>(p, mode, x, ldx, rows, nseg, out, ldp, st);
     }
     return fail(OSZ_ERR_UNSUPPORTED, "spectra: unsupported nfft");
+}
+
+// float32 I/O: float samples in, float64 sums out; plans whose Welch accumulation runs in
+// float32 arithmetic (osz_spec_plan_set_compute, power-of-two nfft 512 ... 4096).
+template <int LOG2N>
+static int welch_f32_detrend(const osz_spec_plan *p, const float *x, int64_t ldx, int64_t rows,
+                             int64_t nseg, double *psd, int64_t ldp, cudaStream_t st) {
+    switch (p->detrend) {
+        case OSZ_DETREND_NONE:
+            return launch_welch_pp_c32<LOG2N, OSZ_DETREND_NONE, float>(p, x, ldx, rows, nseg, psd,
+                                                                       ldp, st);
+        case OSZ_DETREND_CONSTANT:
+            return launch_welch_pp_c32<LOG2N, OSZ_DETREND_CONSTANT, float>(p, x, ldx, rows, nseg,
+                                                                           psd, ldp, st);
+        default:
+            return launch_welch_pp_c32<LOG2N, OSZ_DETREND_LINEAR, float>(p, x, ldx, rows, nseg, psd,
+                                                                         ldp, st);
+    }
 }
 
 extern "C" {
@@ -1083,6 +1103,22 @@ int osz_spec_plan_compute(const osz_spec_plan *p) { return p ? p->compute : 0; }
 int osz_welch_accum_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                         int64_t nseg, double *psd_sum, int64_t ldp, void *stream) {
     return spec_exec(p, SPEC_ACCUM, x, ldx, rows, nseg, psd_sum, ldp, stream);
+}
+int osz_welch_accum_f32(const osz_spec_plan *p, const float *x, int64_t ldx, int64_t rows,
+                        int64_t nseg, double *psd_sum, int64_t ldp, void *stream) {
+    if (!p || !x || !psd_sum) return fail(OSZ_ERR_ARG, "osz_welch_accum_f32: null argument");
+    if (rows <= 0 || nseg <= 0) return OSZ_OK;
+    if (p->path != 1 || p->compute != OSZ_COMPUTE_F32 || !p->d_winf || !p->d_twf)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_welch_accum_f32: needs a plan set to float32 "
+                                         "arithmetic (power-of-two nfft 512 ... 4096)");
+    cudaStream_t st = as_stream(stream);
+    switch (p->log2n) {
+        case 9: return welch_f32_detrend<9>(p, x, ldx, rows, nseg, psd_sum, ldp, st);
+        case 10: return welch_f32_detrend<10>(p, x, ldx, rows, nseg, psd_sum, ldp, st);
+        case 11: return welch_f32_detrend<11>(p, x, ldx, rows, nseg, psd_sum, ldp, st);
+        case 12: return welch_f32_detrend<12>(p, x, ldx, rows, nseg, psd_sum, ldp, st);
+    }
+    return fail(OSZ_ERR_UNSUPPORTED, "osz_welch_accum_f32: unsupported nfft");
 }
 int osz_periodogram_f64(const osz_spec_plan *p, const double *x, int64_t ldx, int64_t rows,
                         int64_t nseg, double *out, void *stream) {

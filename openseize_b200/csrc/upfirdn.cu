@@ -47,13 +47,14 @@ __device__ __forceinline__ int ufd_phys(int m) {
 // opt-in float32 arithmetic (float64 samples in and out: they are narrowed when the
 // tile is staged, taps, windows and partial sums are float32, the result is widened
 // when it is stored; half the shared memory, twice the FMA rate).
-template <int R, typename T>
+// TIO: the samples' type in memory -- double, or float for the float32 I/O mode.
+template <int R, typename T, typename TIO = double>
 __global__ void __launch_bounds__(UFD_NT, 2)
-upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, int64_t x_len,
+upfirdn_dec_kernel(const TIO *__restrict__ x, int64_t ldx, int64_t x_first, int64_t x_len,
                    int64_t out_first, int64_t n_out, int K, int M, int Q /* taps per phase */,
                    int ldm /* smem row length, odd */, int half,
                    const T *__restrict__ gphase /* [M][Q] reversed taps by phase */,
-                   double *__restrict__ y, int64_t ldy) {
+                   TIO *__restrict__ y, int64_t ldy) {
     constexpr int TO = 32 * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
@@ -65,7 +66,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
     const int64_t o0 = (int64_t)blockIdx.x * TO;              // tile-relative to out_first
     // global index of the first input sample of this tile
     const int64_t in0 = (out_first + o0) * M + half - (K - 1);
-    const double *xr = x + row * ldx;
+    const TIO *xr = x + row * ldx;
 
     // stage [TO + Q] decimated samples of every phase, phase-major, skewed;
     // eight independent loads in flight per thread.  Tiles that lie wholly
@@ -78,9 +79,9 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
         int p = tid % M, m = tid / M;
         const int64_t rel0 = in0 - x_first;
         const bool interior = rel0 >= 0 && rel0 + n_in <= x_len;
-        const double *src = xr + rel0 + tid;
+        const TIO *src = xr + rel0 + tid;
         for (int e0 = tid; e0 < n_in; e0 += U * UFD_NT, src += U * UFD_NT) {
-            double val[U];
+            TIO val[U];
             if (interior && e0 + (U - 1) * UFD_NT < n_in) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) val[u] = ld_stream(src + u * UFD_NT);
@@ -99,7 +100,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
                 for (int u = 0; u < U; ++u) {
                     const int e = e0 + u * UFD_NT;
                     const int64_t g = rel0 + e;
-                    val[u] = (e < n_in && g >= 0 && g < x_len) ? ld_stream(xr + g) : 0.0;
+                    val[u] = (e < n_in && g >= 0 && g < x_len) ? ld_stream(xr + g) : (TIO)0;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -182,7 +183,7 @@ upfirdn_dec_kernel(const double *__restrict__ x, int64_t ldx, int64_t x_first, i
         T sum = (T)0;
 #pragma unroll
         for (int w8 = 0; w8 < UFD_NW; ++w8) sum += red[w8 * LDR + idx];
-        if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, (double)sum);
+        if (o0 + o < n_out) st_stream(y + row * ldy + o0 + o, (TIO)sum);
     }
 }
 
@@ -669,14 +670,14 @@ static int launch_dec(const osz_upfirdn_plan *p, const double *x, int64_t ldx, i
     return OSZ_OK;
 }
 
-template <int R>
-static int launch_dec_f32(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
+template <int R, typename TIO>
+static int launch_dec_f32(const osz_upfirdn_plan *p, const TIO *x, int64_t ldx, int64_t rows,
                           int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
-                          double *y, int64_t ldy, cudaStream_t st) {
+                          TIO *y, int64_t ldy, cudaStream_t st) {
     dim3 grid((unsigned)((n_out + 32 * R - 1) / (32 * R)), (unsigned)rows);
-    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec_kernel<R, float>,
+    OSZ_CUDA(cudaFuncSetAttribute(upfirdn_dec_kernel<R, float, TIO>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemf));
-    upfirdn_dec_kernel<R, float><<<grid, UFD_NT, p->smemf, st>>>(
+    upfirdn_dec_kernel<R, float, TIO><<<grid, UFD_NT, p->smemf, st>>>(
         x, ldx, x_first, x_len, out_first, n_out, p->K, p->down, p->Q, p->ldmf, p->half,
         p->d_gphasef, y, ldy);
     OSZ_LAUNCHED("upfirdn_dec_kernel<float>");
@@ -935,6 +936,28 @@ int osz_upfirdn_plan_destroy(osz_upfirdn_plan *p) {
     return OSZ_OK;
 }
 
+// float32 I/O: float samples in and out, the float32-arithmetic decimating kernel (plans
+// with up == 1 set to OSZ_COMPUTE_F32).
+int osz_upfirdn_exec_f32(const osz_upfirdn_plan *p, const float *x, int64_t ldx, int64_t rows,
+                         int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
+                         float *y, int64_t ldy, void *stream) {
+    if (!p || !x || !y) return fail(OSZ_ERR_ARG, "osz_upfirdn_exec_f32: null argument");
+    if (rows <= 0 || n_out <= 0) return OSZ_OK;
+    if (rows > 65535) return fail(OSZ_ERR_UNSUPPORTED, "upfirdn: more than 65535 rows per call");
+    if (p->compute != OSZ_COMPUTE_F32 || !p->d_gphasef || !p->Rf)
+        return fail(OSZ_ERR_UNSUPPORTED, "osz_upfirdn_exec_f32: needs a decimating plan set to "
+                                         "float32 arithmetic");
+    cudaStream_t st = as_stream(stream);
+    switch (p->Rf) {
+        case 16:
+            return launch_dec_f32<16, float>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+        case 8:
+            return launch_dec_f32<8, float>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+        default:
+            return launch_dec_f32<4, float>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+    }
+}
+
 int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx, int64_t rows,
                          int64_t x_first, int64_t x_len, int64_t out_first, int64_t n_out,
                          double *y, int64_t ldy, void *stream) {
@@ -952,11 +975,11 @@ int osz_upfirdn_exec_f64(const osz_upfirdn_plan *p, const double *x, int64_t ldx
     if (p->compute == OSZ_COMPUTE_F32 && p->d_gphasef) {
         switch (p->Rf) {
             case 16:
-                return launch_dec_f32<16>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+                return launch_dec_f32<16, double>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
             case 8:
-                return launch_dec_f32<8>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+                return launch_dec_f32<8, double>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
             default:
-                return launch_dec_f32<4>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
+                return launch_dec_f32<4, double>(p, x, ldx, rows, x_first, x_len, out_first, n_out, y, ldy, st);
         }
     }
     if (osz_upfirdn_plan_kernel(p) == OSZ_UFD_MMA && !(p->dec2 && use_dec2)) {

@@ -107,6 +107,69 @@ def narrow_input_dtypes():
         close(p, rp)
 
 
+def float32_io():
+    """Opt-in float32 I/O mode (north_star: 1e-5 of the signal peak in float32;
+    reference dtype rule: SURVEY.md 8b, core/numerical.py:699): float32 chunks in,
+    float32 / complex64 results out for FIR, IIR, resampling, Welch and STFT, against the
+    float64 oracle.  The IIR recurrence stays float64 inside."""
+    import openseize_b200
+
+    rng = np.random.default_rng(41)
+    fs, cs = 5000, 30000
+    x64 = rng.standard_normal((3, 150000)) + 2.0
+    x = x64.astype(np.float32)
+    ref_in = x.astype(np.float64)
+    kais = Kaiser(fpass=500, fstop=600, fs=fs)
+    notch = Notch(fstop=60, width=6, fs=fs)
+    butter = Butter(fpass=[1, 100], fstop=[0.5, 200], fs=fs, gpass=1, gstop=40)
+    openseize_b200.set_io("float32")
+    try:
+        y = kais(producer(x, cs, -1), cs, axis=-1, mode="same").to_array()
+        z = notch(producer(x, cs, -1), cs, axis=-1, dephase=True).to_array()
+        zb = butter(producer(x, cs, -1), cs, axis=-1, dephase=True).to_array()
+        d = downsample(producer(x, cs, -1), 4, fs, cs, axis=-1).to_array()
+        cnt, f, p = psd(producer(x, cs, -1), fs, axis=-1, resolution=fs / 1024)
+        fq, tq, X = stft(producer(x[:, :60000], cs, -1), fs, axis=-1, resolution=fs / 1024)
+        # the chain on the device, float64 host input (narrowed on the host)
+        chain = downsample(kais(notch(producer(x64, cs, -1), cs, axis=-1), cs, axis=-1), 4, fs, cs,
+                           axis=-1)
+        cnt2, _, p2 = psd(chain, fs / 4, axis=-1, resolution=fs / 4 / 256)
+        # sample axis first
+        yt = kais(producer(np.ascontiguousarray(x[:2].T), cs, 0), cs, axis=0).to_array()
+    finally:
+        openseize_b200.set_io("float64")
+    for arr in (y, z, zb, d, p, yt, p2):
+        assert arr.dtype == np.float32, arr.dtype
+    assert X.dtype == np.complex64
+
+    def within(got, ref, tol=1e-5):
+        err = relerr(got.astype(ref.dtype), ref)
+        assert 1e-12 < err <= tol, err          # float32 really was used, and it is close
+        return err
+
+    within(y, np.concatenate(oracle.oaconvolve(ref_in, kais.coeffs, cs, -1, "same"), -1))
+    within(yt, np.concatenate(oracle.oaconvolve(ref_in[:2], kais.coeffs, cs, -1, "same"), -1).T)
+    within(z, np.concatenate(oracle.filtfilt(ref_in, notch.coeffs, cs, -1), -1))
+    within(zb, np.concatenate(oracle.sosfiltfilt(ref_in, butter.coeffs, cs, -1), -1))
+    within(d, np.concatenate(oracle.polyphase_resample(ref_in, 1, 4, fs, cs, -1), -1))
+    rc, rf, rp = oracle.welch_psd(ref_in, fs, -1, fs / 1024)
+    assert cnt == rc and np.array_equal(f, rf)
+    assert np.max(np.abs(p - rp) / np.max(rp, axis=-1, keepdims=True)) <= 1e-5
+    of, ot, oX = oracle.stft(ref_in[:, :60000], fs, -1, fs / 1024)
+    assert np.array_equal(fq, of) and np.array_equal(tq, ot)
+    within(X, oX)
+    r1 = np.concatenate(oracle.filtfilt(x64.astype(np.float32).astype(np.float64), notch.coeffs,
+                                        cs, -1), -1)
+    r2 = np.concatenate(oracle.oaconvolve(r1, kais.coeffs, cs, -1, "same"), -1)
+    r3 = np.concatenate(oracle.polyphase_resample(r2, 1, 4, fs, cs, -1), -1)
+    rc2, _, rp2 = oracle.welch_psd(r3, fs / 4, -1, fs / 4 / 256)
+    assert cnt2 == rc2
+    assert np.max(np.abs(p2 - rp2) / np.max(rp2, axis=-1, keepdims=True)) <= 1e-5
+    # and the default mode is untouched afterwards
+    y64 = kais(producer(x64, cs, -1), cs, axis=-1, mode="same").to_array()
+    assert y64.dtype == np.float64
+
+
 # ------------------------------------------------------------------ IIR ----
 def iir_golden():
     g = golden("iir_butter8")

@@ -264,6 +264,10 @@ def test_upfirdn_kernels_vs_scipy(dv, up, down, ntaps, kernel):
     assert relerr(y, ref[:, o_lo:o_hi]) < 1e-12
 
 
+def test_float32_io_mode():
+    pc.float32_io()
+
+
 def test_analytic_golden():
     pc.analytic_golden()
 

@@ -120,6 +120,39 @@ def main(which):
         report("fused FIR+downsample M=25 taps=%d float32 compute" % len(h),
                timeit(lambda: p32.run(x, 0, 64, nout)), rows * n, 8 * (1 + 1 / 25))
         del x
+    if "f32io" in which:
+        # float32 I/O mode: float samples in and out (8 / 4.2 / 4 bytes per sample)
+        dv.set_io("float32")
+        try:
+            import oracle
+
+            xf = torch.randn((rows, n + 700), dtype=torch.float32, device="cuda", generator=g)
+            for fs, label in ((5000, "113"), (30000, "671")):
+                taps = Kaiser(500, 600, fs).coeffs
+                plan = dv.FirPlan.cached(taps)
+                yf = torch.empty((rows, n), dtype=torch.float32, device="cuda")
+                report("fir %s taps float32 I/O" % label,
+                       timeit(lambda: plan.run(xf, n, out=yf)), rows * n, 8)
+            for fs, M in ((5000, 20), (30000, 25)):
+                h = oracle.resample_filter(1, M, fs)
+                plan = dv.UpfirdnPlan.cached(h, 1, M)
+                nout = n // M - 64
+                report("downsample M=%d taps=%d float32 I/O" % (M, len(h)),
+                       timeit(lambda: plan.run(xf, 0, 32, nout)), rows * n, 4 * (1 + 1 / M))
+            w = sps.get_window("hann", 4096)
+            plan = dv.SpecPlan.cached(4096, 2048, w, "constant", 1.0 / (30000 * np.sum(w ** 2)))
+            nseg = plan.nseg_available(n)
+            acc = dv.zeros((rows, 2049))
+            report("welch nfft=4096 float32 I/O", timeit(lambda: plan.welch_accum(xf, nseg, acc)),
+                   rows * nseg * plan.stride, 4)
+            b, a = sps.iirnotch(60, 10, fs=30000)
+            plan = dv.SosPlan(np.concatenate([b, a])[None])
+            st = dv.zeros((rows, 1, 2))
+            yf = torch.empty((rows, n), dtype=torch.float32, device="cuda")
+            report("notch biquad fwd float32 I/O", timeit(lambda: plan.run(xf[:, :n], st, out=yf)),
+                   rows * n, 8)
+        finally:
+            dv.set_io("float64")
     if not which or "sosdec" in which:
         # backward notch pass + FIR(671) * anti-alias(561) decimator M=25 as one kernel
         import oracle
