@@ -54,7 +54,7 @@ CPS_DEFAULT = 4          # chunks per step: a step is 4 x (256 x 1e6) channel-sa
 METRIC = "channel-samples/sec filtered+PSD"
 WORKLOAD = ("C5 pipeline: Notch(60,w6) filtfilt -> Kaiser(500,600) 671-tap FIR 'same' -> "
             "downsample M=25 -> Welch PSD nfft=4096 hann 50%; 256 ch x 30 kHz float64, "
-            "chunksize 1e6, step = 1 chunk of the 24 h stream (2592 chunks)")
+            "chunksize 1e6, step = 4 chunks of the 24 h stream (2592 chunks)")
 
 
 def parse():

@@ -60,6 +60,80 @@ def main():
         ok &= err < 1e-9 and cnt == rc
         print("time-sharded psd  world=%d  max err / peak = %.2e  segments %d/%d" % (size, err, cnt, rc))
         print("SHARD_CHECK", "OK" if ok else "FAILED")
+    # ---- BASELINE config 1 (4 channels x 18 M samples, Kaiser 113 taps, then Welch nfft
+    #      4096): few channels, so the TIME axis is sharded.  Wall time of the sharded
+    #      operators per rank count (host chunks in, gathered result out) and, separately,
+    #      the one collective on the path: the all-reduce of the Welch partial sums.
+    import json
+    import time
+
+    n1 = 18_000_000
+    x1 = np.random.default_rng(3).standard_normal((4, n1))
+
+    def wall(fn, reps=2):
+        best = 1e9
+        for _ in range(reps):
+            if size > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            if size > 1:
+                dist.barrier()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    t_fir = wall(lambda: sharding.fir_time_sharded(x1, taps, 1_000_000, mode="same", gather=False))
+    t_psd = wall(lambda: sharding.psd_time_sharded(x1, fs, resolution=fs / 4096))
+    msg = torch.zeros(4 * 2049 + 1, dtype=torch.float64, device="cuda")
+    t_ar = None
+    if size > 1:
+        for _ in range(3):
+            dist.all_reduce(msg)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            dist.all_reduce(msg)
+        b.record()
+        torch.cuda.synchronize()
+        t_ar = a.elapsed_time(b) / 20
+    # the same FIR shard from a READER source: every rank reads only its span + halo
+    class _Reader:
+        def __init__(self, arr):
+            self.arr, self.read_samples = arr, 0
+            self.shape = arr.shape
+
+        def read(self, start, stop):
+            self.read_samples += stop - start
+            return self.arr[:, start:stop]
+
+        def open(self):
+            pass
+
+        def close(self):
+            pass
+
+    from openseize_b200 import producer
+
+    rd = _Reader(x1[:, :6_000_000])
+    (o0, o1), loc = sharding.fir_time_sharded(producer(rd, 1_000_000, -1), taps, 1_000_000,
+                                              mode="same", gather=False)
+    refl = cat_ref = None
+    if rank == 0:
+        refl = np.concatenate(oracle.oaconvolve(x1[:, :6_000_000], taps, 1_000_000, -1, "same"), -1)
+    full = sharding.gather_time(loc, -1)
+    if rank == 0:
+        err = np.max(np.abs(full - refl)) / np.max(np.abs(refl))
+        print("time-sharded fir from a reader source world=%d  max err / peak = %.2e, rank 0 read "
+              "%d of %d samples" % (size, err, rd.read_samples, 6_000_000))
+        print("SHARD_BENCH", json.dumps({
+            "world": size, "config": "C1: 4 ch x 18e6 float64 host array, Kaiser 113 taps 'same', "
+                                     "psd nfft 4096",
+            "fir_time_sharded_s": t_fir, "fir_channel_samples_per_s": 4 * n1 / t_fir,
+            "psd_time_sharded_s": t_psd, "psd_channel_samples_per_s": 4 * n1 / t_psd,
+            "welch_allreduce_ms": t_ar, "allreduce_bytes": int(msg.numel() * 8)}))
     if size > 1:
         dist.barrier()
         dist.destroy_process_group()
