@@ -199,10 +199,15 @@ class _TimeRing:
     def _reserve(self, n):
         live = self.pos - self.start
         if self.buf is None or self.pos + n > self.buf.shape[1]:
-            new = dv.empty_rows((self.rows, live + 2 * n + 64))
+            # the write position and the row pitch stay multiples of 16 samples (as long
+            # as the blocks are): upstream kernels that move tiles with the TMA need
+            # 16-byte aligned rows (csrc/sos_tile.cuh)
+            lead = -live % 16
+            width = lead + live + 2 * n + 64
+            new = dv.empty_rows((self.rows, width + (-width % 16)))
             if live:
-                new[:, :live].copy_(self.buf[:, self.start:self.pos])
-            self.buf, self.start, self.pos = new, 0, live
+                new[:, lead:lead + live].copy_(self.buf[:, self.start:self.pos])
+            self.buf, self.start, self.pos = new, lead, lead + live
             self.ready_event = dv.record_event()
 
     def __call__(self, rows, n):

@@ -15,7 +15,7 @@ LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libosz_b200.so")
 SOURCES = ["runtime.cu", "fir.cu", "sos.cu", "tf.cu", "upfirdn.cu", "sosdec.cu", "spectra.cu",
            "spectra_generic.cu", "spectra_mixed.cu", "protools.cu"]
-HEADERS = ["common.cuh", "sos_core.cuh", "ufd_mma.cuh", "fft_core.cuh", "fft_core_body.inc", os.path.join("..", "..", "include", "osz_b200.h")]
+HEADERS = ["common.cuh", "sos_core.cuh", "sos_tile.cuh", "ufd_mma.cuh", "fft_core.cuh", "fft_core_body.inc", os.path.join("..", "..", "include", "osz_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

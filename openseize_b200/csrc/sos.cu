@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "sos_core.cuh"
+#include "sos_tile.cuh"
 
 namespace osz {
 
@@ -305,6 +306,7 @@ struct osz_sos_plan {
     mutable std::map<int64_t, double *> phi;   // span length -> device (2 nsec)^2 matrix
     std::vector<long double> Tmat;  // (2 nsec)^2 one-step zero-input transition, row major
     double *d_weights = nullptr;    // [settle][2 nsec]: W[d] = T^d b (sos_entering_kernel)
+    SosTileTab *d_tiletab = nullptr;   // one section: tables of the tiled look-back scan (sos_tile.cuh)
 };
 
 namespace {
@@ -516,6 +518,37 @@ int osz_sos_plan_create(osz_sos_plan **out, const double *sos, int nsec) {
             w.swap(nxt);
         }
     }
+    if (nsec == 1) {
+        // tiled look-back scan: A^(16 p) per thread and Phi^j, Phi = A^TILE, per look-back lane
+        std::vector<SosTileTab> tab(1);
+        const SosSec &c = p->prm.sec[0];
+        const M2 A = {-(long double)c.a1, 1.0L, -(long double)c.a2, 0.0L};
+        M2 A16 = {1.0L, 0.0L, 0.0L, 1.0L};
+        for (int i = 0; i < TILE_T; ++i) A16 = mul(A, A16);
+        M2 pw = {1.0L, 0.0L, 0.0L, 1.0L};
+        for (int t = 0; t < SOS_NT; ++t) {
+            tab[0].thr[t][0] = (double)pw.a;
+            tab[0].thr[t][1] = (double)pw.b;
+            tab[0].thr[t][2] = (double)pw.c;
+            tab[0].thr[t][3] = (double)pw.d;
+            pw = mul(A16, pw);
+        }
+        const M2 Phi = pw;                  // A^(16 * 256)
+        pw = {1.0L, 0.0L, 0.0L, 1.0L};
+        for (int j = 0; j <= 32; ++j) {
+            tab[0].phi[j][0] = (double)pw.a;
+            tab[0].phi[j][1] = (double)pw.b;
+            tab[0].phi[j][2] = (double)pw.c;
+            tab[0].phi[j][3] = (double)pw.d;
+            pw = mul(Phi, pw);
+        }
+        if (cudaMalloc(&p->d_tiletab, sizeof(SosTileTab)) != cudaSuccess ||
+            cudaMemcpy(p->d_tiletab, tab.data(), sizeof(SosTileTab), cudaMemcpyHostToDevice) !=
+                cudaSuccess) {
+            osz_sos_plan_destroy(p);
+            return fail(OSZ_ERR_CUDA, "osz_sos_plan_create: device upload failed");
+        }
+    }
     if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
         cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
             cudaSuccess ||
@@ -538,6 +571,7 @@ int osz_sos_plan_destroy(osz_sos_plan *p) {
     cudaFree(p->d_lanepow);
     cudaFree(p->T16_lanepow);
     cudaFree(p->d_weights);
+    cudaFree(p->d_tiletab);
     for (auto &kv : p->phi) cudaFree(kv.second);
     delete p;
     return OSZ_OK;
@@ -596,6 +630,54 @@ static int sos_phi(const osz_sos_plan *p, int64_t span_len, const double **out) 
 
 }  // extern "C"
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*osz_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                       const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static osz_tmap_encode_fn tmap_encoder() {
+    static osz_tmap_encode_fn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) !=
+                cudaSuccess || q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<osz_tmap_encode_fn>(ptr);
+    }();
+    return fn;
+}
+
+// Rows of float64 samples as [rows][lines][16] with 256-line boxes and the 128-byte swizzle
+// (sos_tile_tma_kernel).  `base` must be 16-byte aligned and `ld` even.
+static bool tile_tensor_map(CUtensorMap *map, const double *base, int64_t ld, int64_t rows,
+                            int64_t lines) {
+    osz_tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)TILE_T, (cuuint64_t)lines, (cuuint64_t)rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)TILE_T * 8, (cuuint64_t)ld * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)TILE_T, (cuuint32_t)SOS_NT, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides,
+               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename TIO>
+static bool tile_tma_ok(const TIO *, int64_t, const TIO *, int64_t, int64_t, int64_t, int) {
+    return false;
+}
+template <>
+bool tile_tma_ok<double>(const double *x, int64_t ldx, const double *y, int64_t ldy, int64_t n,
+                         int64_t ntile, int reverse) {
+    if (ntile < 2) return false;
+    const int64_t first_len = n - (ntile - 1) * TILE;
+    const int64_t shift = reverse ? 0 : first_len;
+    auto ok = [&](const double *p, int64_t ld) {
+        return (reinterpret_cast<uintptr_t>(p + shift) & 15) == 0 && (ld & 1) == 0 && ld >= n;
+    };
+    return ok(x, ldx) && (!y || ok(y, ldy));
+}
+
 template <typename TIO>
 static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t rows, int64_t n,
                       int reverse, double *state, TIO *y, int64_t ldy, void *stream) {
@@ -605,6 +687,114 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
     const int smem = SOS_NT * (p->T + 1) * 8;
     const int64_t BLK = (int64_t)SOS_NT * p->T;
     const int ns2 = 2 * p->prm.nsec;
+    // One section: tiles of 4096 samples with a decoupled look-back (sos_tile.cuh): every
+    // sample read once, any number of rows fills the GPU.  OSZ_SOS_TILE=0 turns it off.
+    // (read per call: the tests switch it within one process)
+    const char *tile_env = getenv("OSZ_SOS_TILE");
+    const int tile_mode = tile_env ? atoi(tile_env) : -1;
+    if (p->d_tiletab && tile_mode != 0) {
+        const int64_t ntile = (n + TILE - 1) / TILE;
+        if (rows * ntile < ((int64_t)1 << 31) && rows < ((int64_t)1 << 24)) {
+            const int64_t total = rows * ntile;
+            const char *tma_env = getenv("OSZ_SOS_TILE_TMA");
+            if ((!tma_env || atoi(tma_env) != 0) && tile_tma_ok<TIO>(x, ldx, y, ldy, n, ntile, reverse)) {
+                // float64, 16-byte aligned tiles: boxes moved by the TMA
+                const int64_t first_len = n - (ntile - 1) * TILE;
+                const int64_t shift = reverse ? 0 : first_len;
+                const int64_t lines = (ntile - 1) * SOS_NT;
+                alignas(64) CUtensorMap mx, my;
+                const double *xd = reinterpret_cast<const double *>(x);
+                double *yd = reinterpret_cast<double *>(y);
+                bool ok = tile_tensor_map(&mx, xd + shift, ldx, rows, lines);
+                if (ok && y) ok = tile_tensor_map(&my, yd + shift, ldy, rows, lines);
+                if (ok) {
+                    if (!y) my = mx;
+                    char *scr = nullptr;
+                    const size_t bytes = 16 + (size_t)total * 32;
+                    OSZ_CUDA(scratch_alloc((void **)&scr, bytes, st));
+                    OSZ_CUDA(cudaMemsetAsync(scr, 0xFF, bytes, st));   // nothing published, rank -1
+                    unsigned *ticket = reinterpret_cast<unsigned *>(scr);
+                    double2 *agg = reinterpret_cast<double2 *>(scr + 16);
+                    double2 *incl = agg + total;
+                    const int tsmem = 2 * TILE_BYTES + 1024;
+                    int64_t ctas = total;
+                    cudaError_t lerr = cudaSuccess;
+#define OSZ_TMA_LAUNCH(W)                                                                        \
+    do {                                                                                         \
+        static const int per_sm = [] {   /* the CTAs wait on each other: co-resident grid */      \
+            int v = 0;                                                                           \
+            if (cudaFuncSetAttribute(sos_tile_tma_kernel<W>,                                     \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                     2 * TILE_BYTES + 1024) != cudaSuccess ||                    \
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, sos_tile_tma_kernel<W>, SOS_NT, \
+                                                              2 * TILE_BYTES + 1024) != cudaSuccess) \
+                v = 0;                                                                           \
+            return v;                                                                            \
+        }();                                                                                     \
+        if (per_sm < 1) lerr = cudaErrorLaunchOutOfResources;                                    \
+        if (lerr == cudaSuccess) {                                                               \
+            if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
+            sos_tile_tma_kernel<W><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                       \
+                p->prm, mx, my, p->d_tiletab, xd, ldx, (int)rows, n, reverse, state, state, yd,  \
+                ldy, p->T16_lanepow, ticket, agg, incl, (int)ntile);                             \
+            lerr = cudaGetLastError();                                                           \
+        }                                                                                        \
+    } while (0)
+                    if (y) OSZ_TMA_LAUNCH(true);
+                    else OSZ_TMA_LAUNCH(false);
+#undef OSZ_TMA_LAUNCH
+                    cudaFreeAsync(scr, st);
+                    if (lerr != cudaSuccess)
+                        return fail(OSZ_ERR_CUDA, std::string("sos_tile_tma_kernel launch: ") +
+                                                      cudaGetErrorString(lerr));
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    return OSZ_OK;
+                }
+            }
+        }
+        // Unaligned rows / float32 samples: plain loads and stores through a transposing
+        // buffer.  Measured on B200 (notch, 1e6 samples): ahead of one CTA per row below
+        // ~48 rows (32 rows 0.176 against 0.218 ms), behind it above (256 rows 1.09 / 0.81).
+        if (rows * ntile < ((int64_t)1 << 31) && rows < ((int64_t)1 << 24) &&
+            (tile_mode > 0 || rows * 3 <= sm_count())) {
+            const int64_t total = rows * ntile;
+            const size_t flag_bytes = (((size_t)total + 4) * 4 + 15) & ~(size_t)15;
+            char *scr = nullptr;
+            OSZ_CUDA(scratch_alloc((void **)&scr, flag_bytes + (size_t)total * 32, st));
+            OSZ_CUDA(cudaMemsetAsync(scr, 0, flag_bytes, st));
+            unsigned *ticket = reinterpret_cast<unsigned *>(scr);
+            unsigned *flag = ticket + 4;
+            double2 *agg = reinterpret_cast<double2 *>(scr + flag_bytes);
+            double2 *incl = agg + total;
+            const int tsmem = SOS_NT * (TILE_T + 1) * (int)sizeof(TIO);
+            int64_t ctas = total;
+#define OSZ_TILE_LAUNCH(W, YY, LDY)                                                             \
+    do {                                                                                        \
+        static const int per_sm = [] {   /* the CTAs wait on each other: co-resident grid */     \
+            int v = 0;                                                                          \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, sos_tile_kernel<W, TIO>,      \
+                                                              SOS_NT, tsmem) != cudaSuccess)    \
+                v = 0;                                                                          \
+            return v;                                                                           \
+        }();                                                                                    \
+        if (per_sm < 1) return fail(OSZ_ERR_CUDA, "sos_tile_kernel: no CTA fits an SM");        \
+        if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();           \
+        sos_tile_kernel<W, TIO><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                         \
+            p->prm, p->d_tiletab, x, ldx, (int)rows, n, reverse, state, state, YY, LDY,         \
+            p->T16_lanepow, ticket, flag, agg, incl, (int)ntile);                               \
+    } while (0)
+            if (y) OSZ_TILE_LAUNCH(true, y, ldy);
+            else OSZ_TILE_LAUNCH(false, (TIO *)nullptr, 0);
+#undef OSZ_TILE_LAUNCH
+            const cudaError_t lerr = cudaGetLastError();
+            cudaFreeAsync(scr, st);
+            if (lerr != cudaSuccess)
+                return fail(OSZ_ERR_CUDA, std::string("sos_tile_kernel launch: ") +
+                                              cudaGetErrorString(lerr));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return OSZ_OK;
+        }
+    }
     // Spans per row.  Splitting pays only while one CTA per row leaves SMs idle
     // (rows <= SM count).  Two ways to cut a row:
     //   warm-up: every later span re-filters the `settle` samples before it from

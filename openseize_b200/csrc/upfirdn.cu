@@ -27,17 +27,6 @@ namespace osz {
 constexpr int UFD_NT = 256;
 constexpr int UFD_NW = UFD_NT / 32;
 
-__device__ __forceinline__ void cp_async8_zfill(uint32_t dst_smem, const void *src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src),
-                 "r"(valid ? 8 : 0)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPENDING>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
-}
-
 template <int R>
 __device__ __forceinline__ int ufd_phys(int m) {
     return m + m / R;

@@ -198,6 +198,43 @@ def test_sos_exact_time_split(dv, n, kind):
         assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
+@pytest.mark.parametrize("tile", ["1", "0"])
+@pytest.mark.parametrize("rows,n", [(1, 4096 * 70 + 5), (2, 4096 * 3), (32, 1_000_000), (300, 41_000),
+                                    (7, 4097), (3, 2_000_003)])
+def test_sos_tile_lookback(dv, rows, n, tile, monkeypatch):
+    """One section: the tiled scan with a decoupled look-back (every 4096-sample tile
+    scanned from rest, entering state composed from its predecessors' aggregates) against
+    the sequential recurrence -- output, carried state, state-only pass, forward and
+    reversed, float64 and float32 samples -- and the same cases on the one-CTA-per-row
+    kernel it replaces (OSZ_SOS_TILE=0)."""
+    monkeypatch.setenv("OSZ_SOS_TILE", tile)
+    rng = np.random.default_rng(rows * 7 + n)
+    b, a = sps.iirnotch(60, 10, fs=30000)
+    sos = np.concatenate([b, a])[None]
+    plan = dv.SosPlan(sos)
+    x = rng.standard_normal((rows, n)) + 1.0
+    zi = rng.standard_normal((rows, 1, 2))
+    for reverse in (False, True):
+        state = _dev(dv, zi)
+        y = plan.run(_dev(dv, x), state, reverse=reverse).cpu().numpy()
+        xr = x[:, ::-1] if reverse else x
+        ry, rz = sps.sosfilt(sos, xr, axis=-1, zi=np.transpose(zi, (1, 0, 2)))
+        ry = ry[:, ::-1] if reverse else ry
+        assert relerr(y, ry) < 1e-10, (n, reverse)
+        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
+        state2 = _dev(dv, zi)
+        assert plan.run(_dev(dv, x), state2, reverse=reverse, want_output=False) is None
+        assert relerr(state2.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
+    import torch
+    x32 = torch.from_numpy(x.astype(np.float32)).cuda()
+    state = _dev(dv, zi)
+    y32 = plan.run(x32, state).cpu().numpy()
+    assert y32.dtype == np.float32
+    ry, _ = sps.sosfilt(sos, x.astype(np.float32).astype(np.float64), axis=-1,
+                        zi=np.transpose(zi, (1, 0, 2)))
+    assert np.max(np.abs(y32 - ry)) / np.max(np.abs(ry)) < 1e-6
+
+
 @pytest.mark.parametrize("kind", ["notch", "butter2"])
 def test_sos_tail_state(dv, kind):
     """State after a run of samples from rest as ONE weighted sum of the last `settle`

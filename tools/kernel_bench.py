@@ -87,6 +87,26 @@ def main(which):
             report("notch biquad bwd rows=%d" % r,
                    timeit(lambda: plan.run(x, st, reverse=True, out=y)), r * n, 16)
             del x, y
+    if "sostile" in which:
+        # one section: tiled look-back scan (default) against one CTA per row / time splits
+        b, a = sps.iirnotch(60, 10, fs=30000)
+        plan = dv.SosPlan(np.concatenate([b, a])[None])
+        for r in (256, 128, 64, 32, 16, 8):
+            x = rnd(r, n)
+            y = torch.empty_like(x)
+            st = dv.zeros((r, 1, 2))
+            for mode in ("1", "1n", "0"):
+                os.environ["OSZ_SOS_TILE"] = mode[0]
+                os.environ["OSZ_SOS_TILE_TMA"] = "0" if mode == "1n" else "1"
+                tag = {"1": "tma ", "1n": "tile", "0": "row "}[mode]
+                report("notch %s fwd rows=%d" % (tag, r), timeit(lambda: plan.run(x, st, out=y)), r * n, 16)
+                report("notch %s bwd rows=%d" % (tag, r),
+                       timeit(lambda: plan.run(x, st, reverse=True, out=y)), r * n, 16)
+                xs = x[:, :66_000]
+                report("notch %s state-only 66k rows=%d" % (tag, r),
+                       timeit(lambda: plan.run(xs, st, want_output=False)), r * 66_000, 8)
+            del x, y
+        os.environ.pop("OSZ_SOS_TILE", None)
     if not which or "upfirdn" in which:
         for fs, M in ((5000, 20), (30000, 25)):
             import oracle
