@@ -694,6 +694,10 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
     const int tile_mode = tile_env ? atoi(tile_env) : -1;
     if (p->d_tiletab && tile_mode != 0) {
         const int64_t ntile = (n + TILE - 1) / TILE;
+        SosParams1 prm1;
+        prm1.nsec = 1;
+        prm1.pad_ = 0;
+        prm1.sec[0] = p->prm.sec[0];
         if (rows * ntile < ((int64_t)1 << 31) && rows < ((int64_t)1 << 24)) {
             const int64_t total = rows * ntile;
             const char *tma_env = getenv("OSZ_SOS_TILE_TMA");
@@ -735,7 +739,7 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         if (lerr == cudaSuccess) {                                                               \
             if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
             sos_tile_tma_kernel<W><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                       \
-                p->prm, mx, my, p->d_tiletab, xd, ldx, (int)rows, n, reverse, state, state, yd,  \
+                prm1, mx, my, p->d_tiletab, xd, ldx, (int)rows, n, reverse, state, state, yd,  \
                 ldy, p->T16_lanepow, ticket, agg, incl, (int)ntile);                             \
             lerr = cudaGetLastError();                                                           \
         }                                                                                        \
@@ -780,7 +784,7 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         if (per_sm < 1) return fail(OSZ_ERR_CUDA, "sos_tile_kernel: no CTA fits an SM");        \
         if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();           \
         sos_tile_kernel<W, TIO><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                         \
-            p->prm, p->d_tiletab, x, ldx, (int)rows, n, reverse, state, state, YY, LDY,         \
+            prm1, p->d_tiletab, x, ldx, (int)rows, n, reverse, state, state, YY, LDY,         \
             p->T16_lanepow, ticket, flag, agg, incl, (int)ntile);                               \
     } while (0)
             if (y) OSZ_TILE_LAUNCH(true, y, ldy);

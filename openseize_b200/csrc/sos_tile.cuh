@@ -35,6 +35,14 @@ namespace osz {
 constexpr int TILE_T = 16;
 constexpr int TILE = SOS_NT * TILE_T;       // 4096 samples
 
+// Kernel parameter block of the one-section kernels: the head of SosParams (nsec, one
+// section) -- 0.8 KB per launch instead of the 13 KB of the full 16-section block.
+struct SosParams1 {
+    int nsec;
+    int pad_;
+    SosSec sec[1];
+};
+
 struct SosTileTab {
     double thr[SOS_NT][4];      // A^(16 p): thread p's entering state per unit tile-entering state
     double phi[33][4];          // Phi^j, j = 0 .. 32
@@ -54,7 +62,7 @@ constexpr unsigned TILE_NONE = 0, TILE_AGG = 1, TILE_INCL = 2;
 
 template <bool WRITE, typename TIO>
 __global__ void __launch_bounds__(SOS_NT, 4)
-sos_tile_kernel(const __grid_constant__ SosParams prm, const SosTileTab *__restrict__ tab,
+sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__restrict__ tab,
                 const TIO *__restrict__ x, int64_t ldx, int rows, int64_t n_total, int reverse,
                 const double *state_in, double *state,   // may be the same array
                 TIO *__restrict__ y, int64_t ldy,
@@ -70,7 +78,9 @@ sos_tile_kernel(const __grid_constant__ SosParams prm, const SosTileTab *__restr
     __shared__ unsigned s_rank;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SosSec &c = prm.sec[0];
+    // (sos_scan_block only touches sec[0 .. nsec-1] of the block it is handed)
+    const SosParams &prm = reinterpret_cast<const SosParams &>(prm1);
+    const SosSec &c = prm1.sec[0];
     const unsigned total = (unsigned)rows * (unsigned)ntile;
     const int64_t first_len = n_total - (int64_t)(ntile - 1) * TILE;
 
@@ -383,7 +393,7 @@ constexpr int TILE_BYTES = TILE * 8;               // 32 KB
 
 template <bool WRITE>
 __global__ void __launch_bounds__(SOS_NT, 3)
-sos_tile_tma_kernel(const __grid_constant__ SosParams prm, const __grid_constant__ CUtensorMap mx,
+sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_constant__ CUtensorMap mx,
                     const __grid_constant__ CUtensorMap my, const SosTileTab *__restrict__ tab,
                     const double *__restrict__ x, int64_t ldx, int rows, int64_t n_total,
                     int reverse, const double *state_in, double *state, double *__restrict__ y,
@@ -398,7 +408,9 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams prm, const __grid_constant
     __shared__ unsigned s_rank;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SosSec &c = prm.sec[0];
+    // (sos_scan_block only touches sec[0 .. nsec-1] of the block it is handed)
+    const SosParams &prm = reinterpret_cast<const SosParams &>(prm1);
+    const SosSec &c = prm1.sec[0];
     const unsigned total = (unsigned)rows * (unsigned)ntile;
     const int64_t first_len = n_total - (int64_t)(ntile - 1) * TILE;
     // two 1024-byte aligned stages

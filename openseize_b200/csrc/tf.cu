@@ -7,12 +7,22 @@
 //     y      = b0 x + z[0]
 //     z[i]   = b[i+1] x - a[i+1] y + z[i+1]        (i < S-1, S = K-1 states)
 //     z[S-1] = b[S] x - a[S] y
-// evaluated here in exactly that order, one thread per row walking its row in
-// time (the critical path is two dependent FMAs per sample, so a row costs
-// ~20 cycles per sample whatever the order; rows run concurrently).  This is
-// the coverage path for the reference's `fmt='ba'` designs above second order
-// -- openseize's own designs use SOS except Notch (order 2) -- not a
-// bandwidth-bound kernel.
+// Three kernels (osz_tf_exec_f64 picks): tf_split_kernel -- the row cut into spans that
+// run concurrently after a warm-up of one settle length, the recurrence itself sequential
+// (see there); tf_scan_kernel, orders 3 .. 8 -- a time-parallel scan over the filter's
+// companion matrix: the zero-input step is z' = A z with A[i][0] = -a[i+1],
+// A[i][i+1] = 1, so -- exactly as for one biquad in sos.cu, with S x S matrices in place
+// of 2 x 2 -- every thread runs the recurrence over its 16 samples from rest, the true
+// state at every thread boundary is the scan of e_p = M e_(p-1) + f_p, M = A^16
+// (Kogge-Stone in the warp with M^(2^k), warps chained with M^32), and each thread adds
+// the zero-input response g_i . s of its entering state to its outputs.  One CTA of 256
+// threads per row; the recurrence itself is evaluated in scipy's order.
+// Orders above 8 (and OSZ_TF_SCAN=0) take tf_seq_kernel: one thread per row walking its
+// row in time (two dependent FMAs per sample: ~20 cycles per sample whatever the order).
+#include <math.h>
+#include <stdlib.h>
+
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -75,6 +85,286 @@ tf_seq_kernel(const __grid_constant__ TfParams prm, const double *__restrict__ x
     for (int i = 0; i < S; ++i) st[i] = z[i];
 }
 
+// ---- time-parallel scan, S = 3 .. 8 states ---------------------------------------------
+constexpr int TFS_NT = 256;        // threads per CTA (one CTA per row)
+constexpr int TFS_T = 16;          // samples per thread
+constexpr int TFS_BLK = TFS_NT * TFS_T;
+
+template <int S>
+struct TfScanParams {
+    double b[S + 1], a[S + 1];
+    double g[TFS_T][S];            // row 0 of A^i: output i of the zero-input response
+    double P[5][S * S];            // M^(2^k), M = A^16, row major
+};
+
+template <int S, bool WRITE>
+__global__ void __launch_bounds__(TFS_NT, 2)
+tf_scan_kernel(const __grid_constant__ TfScanParams<S> prm, const double *__restrict__ x,
+               int64_t ldx, int64_t n, int reverse, double *__restrict__ state,
+               double *__restrict__ y, int64_t ldy,
+               const double *__restrict__ lanepow /* [32][S*S]: M^(lane+1) */,
+               const double *__restrict__ warpmat /* [S*S]: M^32 */) {
+    constexpr int T = TFS_T, LD = T + 1;
+    extern __shared__ __align__(16) double tfs_buf[];     // TFS_NT * LD
+    __shared__ double wtot[TFS_NT / 32][S];
+    __shared__ double carry[S];
+    __shared__ double qm[S * S];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row = blockIdx.x;
+    double *st = state + row * S;
+    const double *xr = x + row * ldx + (reverse ? n - 1 : 0);
+    double *yr = WRITE ? y + row * ldy + (reverse ? n - 1 : 0) : nullptr;
+    if (tid < S) carry[tid] = st[tid];
+    if (tid < S * S) qm[tid] = warpmat[tid];
+
+    const int64_t nblk = (n + TFS_BLK - 1) / TFS_BLK;
+    const int64_t first_len = n - (nblk - 1) * TFS_BLK;
+    for (int64_t blk = 0; blk < nblk; ++blk) {
+        // the first block is the short one, right-aligned behind `off` virtual zeros (a
+        // zero state stays zero through them); the carried state enters at slot `off`
+        const int off = blk == 0 ? (int)(TFS_BLK - first_len) : 0;
+        const int64_t pos0 = blk == 0 ? 0 : first_len + (blk - 1) * TFS_BLK;
+        __syncthreads();                       // carry[] visible, tfs_buf free
+        if (blk != 0) {
+            const double *src = reverse ? xr - pos0 - tid : xr + pos0 + tid;
+            double tmp[T];
+#pragma unroll
+            for (int it = 0; it < T; ++it)
+                tmp[it] = ld_stream(reverse ? src - it * TFS_NT : src + it * TFS_NT);
+#pragma unroll
+            for (int it = 0; it < T; ++it) {
+                const int e = tid + it * TFS_NT;
+                tfs_buf[(e >> 4) * LD + (e & (T - 1))] = tmp[it];
+            }
+        } else {
+#pragma unroll 8
+            for (int e = tid; e < TFS_BLK; e += TFS_NT) {
+                double val = 0.0;
+                if (e >= off) {
+                    const int64_t sidx = e - off;
+                    val = ld_stream(reverse ? xr - sidx : xr + sidx);
+                }
+                tfs_buf[(e >> 4) * LD + (e & (T - 1))] = val;
+            }
+        }
+        __syncthreads();
+        double v[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) v[i] = tfs_buf[tid * LD + i];
+
+        // ---- thread-level recurrence from rest (the injecting thread picks the carry up)
+        double z[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) z[j] = 0.0;
+        const bool inj = tid == (off >> 4);
+        const int ioff = off & (T - 1);
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            if (inj && i == ioff) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) z[j] = carry[j];
+            }
+            const double xi = v[i];
+            const double yi = fma(prm.b[0], xi, z[0]);
+#pragma unroll
+            for (int j = 0; j < S - 1; ++j)
+                z[j] = fma(-prm.a[j + 1], yi, fma(prm.b[j + 1], xi, z[j + 1]));
+            z[S - 1] = fma(-prm.a[S], yi, prm.b[S] * xi);
+            v[i] = yi;
+        }
+        // ---- warp-inclusive scan of e_p = M e_(p-1) + f_p
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double gsh[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) gsh[j] = __shfl_up_sync(0xffffffffu, z[j], 1 << k);
+            if (lane >= (1 << k)) {
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    double acc = z[i];
+#pragma unroll
+                    for (int j = 0; j < S; ++j) acc = fma(prm.P[k][i * S + j], gsh[j], acc);
+                    z[i] = acc;
+                }
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) wtot[warp][j] = z[j];
+        }
+        __syncthreads();
+        // ---- state entering this warp: lane i < S carries component i through the
+        //      totals of the warps before (one row of M^32 per lane)
+        double cwi = 0.0;
+        const int li = lane < S ? lane : 0;
+        for (int u = 0; u < warp; ++u) {
+            double acc = wtot[u][li];
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                acc = fma(qm[li * S + j], __shfl_sync(0xffffffffu, cwi, j), acc);
+            cwi = acc;
+        }
+        double cw[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) cw[j] = __shfl_sync(0xffffffffu, cwi, j);
+        // ---- true state at the end of this thread's piece, then the state entering it
+        const double *lpw = lanepow + (size_t)lane * S * S;
+        double sin_[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            double acc = z[i];
+#pragma unroll
+            for (int j = 0; j < S; ++j) acc = fma(ldg(lpw + i * S + j), cw[j], acc);
+            z[i] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const double up = __shfl_up_sync(0xffffffffu, z[j], 1);
+            sin_[j] = lane == 0 ? cw[j] : up;
+        }
+        // zero-input response of the entering state (exactly zero up to the injecting thread)
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            double acc = v[i];
+#pragma unroll
+            for (int j = 0; j < S; ++j) acc = fma(prm.g[i][j], sin_[j], acc);
+            v[i] = acc;
+        }
+        if (tid == TFS_NT - 1) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) carry[j] = z[j];
+        }
+        if (WRITE) {
+#pragma unroll
+            for (int i = 0; i < T; ++i) tfs_buf[tid * LD + i] = v[i];
+            __syncthreads();
+            if (blk != 0) {
+                double *dst = reverse ? yr - pos0 - tid : yr + pos0 + tid;
+#pragma unroll
+                for (int it = 0; it < T; ++it) {
+                    const int e = tid + it * TFS_NT;
+                    st_stream(reverse ? dst - it * TFS_NT : dst + it * TFS_NT,
+                              tfs_buf[(e >> 4) * LD + (e & (T - 1))]);
+                }
+            } else {
+#pragma unroll 4
+                for (int e = tid; e < TFS_BLK; e += TFS_NT) {
+                    const int64_t sidx = e - off;
+                    if (e >= off)
+                        st_stream(reverse ? yr - sidx : yr + sidx,
+                                  tfs_buf[(e >> 4) * LD + (e & (T - 1))]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < S) st[tid] = carry[tid];
+}
+
+// ---- time-split sequential recurrence ----------------------------------------------------
+// A stable filter forgets its start state after `settle` samples (||A^n|| < 1e-18), so a row
+// is cut into spans that run CONCURRENTLY, one thread per span: each thread first re-filters
+// the `settle` samples before its span from rest, storing nothing, then filters its span --
+// the recurrence itself in scipy's order, sample after sample, so the rounding is the
+// sequential kernel's (the scan above re-associates the state through powers of the
+// companion matrix, which costs digits on ill-conditioned high-order (b, a) designs).
+// A CTA is 128 consecutive spans of one row; samples travel through shared memory in
+// batches of 16 per span so that global loads and stores stay coalesced by 128-byte lines.
+constexpr int TFP_NT = 128;
+constexpr int TFP_B = 32;                   // samples per span per batch (a 256-byte run)
+constexpr int TFP_LPI = TFP_NT / TFP_B;     // span lines one loader pass covers
+
+template <int S, bool WRITE>
+__global__ void __launch_bounds__(TFP_NT)
+tf_split_kernel(const __grid_constant__ TfParams prm, const double *__restrict__ x, int64_t ldx,
+                int64_t n, int reverse, const double *__restrict__ state_in,
+                double *__restrict__ state, double *__restrict__ y, int64_t ldy, int64_t span_len,
+                int64_t warm, int64_t nspan, int64_t span0) {
+    __shared__ double tile[TFP_NT * (TFP_B + 1)];
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.y;
+    const int64_t sp0 = span0 + (int64_t)blockIdx.x * TFP_NT;    // first span of this CTA
+    const int64_t sp = sp0 + tid;
+    const double *xr = x + row * ldx + (reverse ? n - 1 : 0);
+    double *yr = WRITE ? y + row * ldy + (reverse ? n - 1 : 0) : nullptr;
+    double z[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) z[j] = 0.0;
+    const int64_t own = sp * span_len;                 // first sample this thread keeps
+    const int64_t nbatch = (warm + span_len) / TFP_B;
+    const int lj = tid / TFP_B, li = tid % TFP_B;      // loader role: span lj + LPI it, sample li
+    // the next batch's samples are fetched into registers while this one is filtered
+    double nxt[TFP_NT / TFP_LPI];
+    auto fetch = [&](int64_t q) {
+        const int64_t rel = q * TFP_B - warm;
+#pragma unroll
+        for (int it = 0; it < TFP_NT / TFP_LPI; ++it) {
+            const int j = lj + TFP_LPI * it;
+            const int64_t pos = (sp0 + j) * span_len + rel + li;
+            double val = 0.0;
+            if (sp0 + j < nspan && pos >= 0 && pos < n) val = ld_stream(reverse ? xr - pos : xr + pos);
+            nxt[it] = val;
+        }
+    };
+    fetch(0);
+    for (int64_t q = 0; q < nbatch; ++q) {
+        const int64_t rel = q * TFP_B - warm;          // position relative to the span start
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < TFP_NT / TFP_LPI; ++it) tile[(lj + TFP_LPI * it) * (TFP_B + 1) + li] = nxt[it];
+        __syncthreads();
+        if (q + 1 < nbatch) fetch(q + 1);
+        const int64_t pos = own + rel;
+        const bool live = sp < nspan && pos + TFP_B > 0 && pos < n;
+        double v[TFP_B];
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < TFP_B; ++i) v[i] = tile[tid * (TFP_B + 1) + i];
+            if (pos == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) z[j] = state_in[row * S + j];
+            }
+#pragma unroll
+            for (int i = 0; i < TFP_B; ++i) {
+                if (pos + i >= 0 && pos + i < n) {     // (pos is a multiple of the batch: only the tail cuts)
+                    const double xi = v[i];
+                    const double yi = fma(prm.b[0], xi, z[0]);
+#pragma unroll
+                    for (int j = 0; j < S - 1; ++j)
+                        z[j] = fma(-prm.a[j + 1], yi, fma(prm.b[j + 1], xi, z[j + 1]));
+                    z[S - 1] = fma(-prm.a[S], yi, prm.b[S] * xi);
+                    v[i] = yi;
+                    if (pos + i == n - 1) {
+#pragma unroll
+                        for (int j = 0; j < S; ++j) state[row * S + j] = z[j];
+                    }
+                }
+            }
+        }
+        if (WRITE && rel >= 0) {
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < TFP_B; ++i) tile[tid * (TFP_B + 1) + i] = v[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < TFP_NT / TFP_LPI; ++it) {
+                const int j = lj + TFP_LPI * it;
+                const int64_t p2 = (sp0 + j) * span_len + rel + li;
+                if (sp0 + j < nspan && p2 < n)
+                    st_stream(reverse ? yr - p2 : yr + p2, tile[j * (TFP_B + 1) + li]);
+            }
+        }
+    }
+}
+
+__global__ void tf_copy_state_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                     int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[i];
+}
+
 __global__ void tf_state_from_sample_kernel(TfParams zi /* zi in .b[0..S) */, const double *x,
                                             int64_t ldx, int64_t rows, int64_t sample,
                                             double *state) {
@@ -90,7 +380,82 @@ using namespace osz;
 
 struct osz_tf_plan {
     TfParams prm;
+    // tables of the scan kernel (orders 3 .. 8): [g: 16 x S | P: 5 x S x S] on the host
+    // (copied into the kernel's parameter block), lanepow / M^32 on the device
+    std::vector<double> g, P;
+    double *d_lanepow = nullptr, *d_warpmat = nullptr;
+    int64_t settle = -1;           // samples after which ||A^n||_inf < 1e-18 (-1: never)
+    double growth = 0.0;           // max_i ||A^i||_inf: how much the scan's re-association costs
 };
+
+namespace {
+typedef std::vector<long double> LMat;
+LMat lmul(const LMat &A, const LMat &B, int S) {
+    LMat C((size_t)S * S, 0.0L);
+    for (int i = 0; i < S; ++i)
+        for (int k = 0; k < S; ++k) {
+            const long double a = A[(size_t)i * S + k];
+            if (a == 0.0L) continue;
+            for (int j = 0; j < S; ++j) C[(size_t)i * S + j] += a * B[(size_t)k * S + j];
+        }
+    return C;
+}
+}  // namespace
+
+template <int S, bool WRITE>
+static int launch_tf_scan_w(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t rows,
+                            int64_t n, int reverse, double *state, double *y, int64_t ldy,
+                            cudaStream_t st) {
+    TfScanParams<S> prm;
+    for (int i = 0; i <= S; ++i) {
+        prm.b[i] = p->prm.b[i];
+        prm.a[i] = p->prm.a[i];
+    }
+    for (int i = 0; i < TFS_T; ++i)
+        for (int j = 0; j < S; ++j) prm.g[i][j] = p->g[(size_t)i * S + j];
+    for (int k = 0; k < 5; ++k)
+        for (int e = 0; e < S * S; ++e) prm.P[k][e] = p->P[(size_t)k * S * S + e];
+    const int smem = TFS_NT * (TFS_T + 1) * 8;
+    tf_scan_kernel<S, WRITE><<<(unsigned)rows, TFS_NT, smem, st>>>(
+        prm, x, ldx, n, reverse, state, y, ldy, p->d_lanepow, p->d_warpmat);
+    OSZ_LAUNCHED("tf_scan_kernel");
+    return OSZ_OK;
+}
+
+template <int S>
+static int launch_tf_split(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t rows,
+                           int64_t n, int reverse, double *state, double *y, int64_t ldy,
+                           int64_t span_len, int64_t warm, cudaStream_t st) {
+    const int64_t nspan = (n + span_len - 1) / span_len;
+    double *copy = nullptr;          // the last span writes the carried state span 0 reads
+    OSZ_CUDA(scratch_alloc((void **)&copy, (size_t)rows * S * 8, st));
+    tf_copy_state_kernel<<<(unsigned)((rows * S + 255) / 256), 256, 0, st>>>(state, copy, rows * S);
+    if (y) {
+        const dim3 grid((unsigned)((nspan + TFP_NT - 1) / TFP_NT), (unsigned)rows);
+        tf_split_kernel<S, true><<<grid, TFP_NT, 0, st>>>(p->prm, x, ldx, n, reverse, copy, state, y,
+                                                          ldy, span_len, warm, nspan, 0);
+    } else {
+        // only the state is wanted: the last span (after its warm-up) is all it takes
+        const dim3 grid(1, (unsigned)rows);
+        tf_split_kernel<S, false><<<grid, TFP_NT, 0, st>>>(p->prm, x, ldx, n, reverse, copy, state,
+                                                           nullptr, 0, span_len, warm, nspan,
+                                                           nspan - 1);
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaFreeAsync(copy, st);
+    if (err != cudaSuccess)
+        return fail(OSZ_ERR_CUDA, std::string("tf_split_kernel launch: ") + cudaGetErrorString(err));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return OSZ_OK;
+}
+
+template <int S>
+static int launch_tf_scan(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t rows,
+                          int64_t n, int reverse, double *state, double *y, int64_t ldy,
+                          cudaStream_t st) {
+    return y ? launch_tf_scan_w<S, true>(p, x, ldx, rows, n, reverse, state, y, ldy, st)
+             : launch_tf_scan_w<S, false>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+}
 
 template <int SC>
 static int launch_tf(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t n,
@@ -122,11 +487,106 @@ int osz_tf_plan_create(osz_tf_plan **out, const double *b, int nb, const double 
         p->prm.b[i] = i < nb ? b[i] / a[0] : 0.0;
         p->prm.a[i] = i < na ? a[i] / a[0] : 0.0;
     }
+    const int S = K - 1;
+    {
+        // zero-input step z' = A z: settle length (smallest n with ||A^n||_inf < 1e-18, on the
+        // ladder A^(2^k), refined bit by bit) and the transient growth max_i ||A^i||_inf
+        LMat A((size_t)S * S, 0.0L);
+        for (int i = 0; i < S; ++i) {
+            A[(size_t)i * S] = -(long double)p->prm.a[i + 1];
+            if (i + 1 < S) A[(size_t)i * S + i + 1] = 1.0L;
+        }
+        auto norm = [S](const LMat &X) {
+            long double best = 0.0L;
+            for (int i = 0; i < S; ++i) {
+                long double r = 0.0L;
+                for (int j = 0; j < S; ++j) r += fabsl(X[(size_t)i * S + j]);
+                if (!(r <= best)) best = r;
+            }
+            return best;
+        };
+        std::vector<LMat> ladder(1, A);
+        long double grow = norm(A);
+        bool stable = true;
+        while (true) {
+            const long double v = norm(ladder.back());
+            if (!(v == v) || v > 1e300L || ladder.size() > 40) {
+                stable = false;
+                break;
+            }
+            if (v > grow) grow = v;
+            if (v < 1e-18L) break;
+            ladder.push_back(lmul(ladder.back(), ladder.back(), S));
+        }
+        if (stable) {
+            const int k = (int)ladder.size() - 1;
+            int64_t steps = 1;
+            if (k > 0) {
+                LMat acc = ladder[k - 1];
+                steps = (int64_t)1 << (k - 1);
+                for (int j = k - 2; j >= 0; --j) {
+                    LMat cand = lmul(acc, ladder[j], S);
+                    if (norm(cand) >= 1e-18L) {
+                        acc.swap(cand);
+                        steps += (int64_t)1 << j;
+                    }
+                }
+            }
+            p->settle = steps + steps / 16 + 64;
+            LMat pw = A;                       // the growth peaks early: scan the first powers
+            for (int i = 1; i < 2048 && i < p->settle; ++i) {
+                const long double v = norm(pw);
+                if (v > grow) grow = v;
+                pw = lmul(A, pw, S);
+            }
+        }
+        p->growth = stable ? (double)grow : INFINITY;
+    }
+    if (S >= 3 && S <= 8) {
+        // zero-input step z' = A z (y = z[0]): A[i][0] = -a[i+1], A[i][i+1] = 1
+        LMat A((size_t)S * S, 0.0L), pw((size_t)S * S, 0.0L);
+        for (int i = 0; i < S; ++i) {
+            A[(size_t)i * S] = -(long double)p->prm.a[i + 1];
+            if (i + 1 < S) A[(size_t)i * S + i + 1] = 1.0L;
+            pw[(size_t)i * S + i] = 1.0L;
+        }
+        p->g.resize((size_t)TFS_T * S);
+        for (int i = 0; i < TFS_T; ++i) {          // pw = A^i
+            for (int j = 0; j < S; ++j) p->g[(size_t)i * S + j] = (double)pw[j];
+            pw = lmul(A, pw, S);
+        }
+        LMat M = pw;                                 // A^16
+        p->P.resize((size_t)5 * S * S);
+        LMat q = M;
+        for (int k = 0; k < 5; ++k) {
+            for (int e = 0; e < S * S; ++e) p->P[(size_t)k * S * S + e] = (double)q[e];
+            q = lmul(q, q, S);
+        }
+        std::vector<double> warpmat((size_t)S * S), lanepow((size_t)32 * S * S);
+        for (int e = 0; e < S * S; ++e) warpmat[e] = (double)q[e];     // M^32
+        LMat lp = M;
+        for (int l = 0; l < 32; ++l) {               // M^(l+1)
+            for (int e = 0; e < S * S; ++e) lanepow[(size_t)l * S * S + e] = (double)lp[e];
+            lp = lmul(M, lp, S);
+        }
+        if (cudaMalloc(&p->d_lanepow, lanepow.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p->d_lanepow, lanepow.data(), lanepow.size() * 8, cudaMemcpyHostToDevice) !=
+                cudaSuccess ||
+            cudaMalloc(&p->d_warpmat, warpmat.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p->d_warpmat, warpmat.data(), warpmat.size() * 8, cudaMemcpyHostToDevice) !=
+                cudaSuccess) {
+            osz_tf_plan_destroy(p);
+            return fail(OSZ_ERR_CUDA, "osz_tf_plan_create: device upload failed");
+        }
+    }
     *out = p;
     return OSZ_OK;
 }
 
 int osz_tf_plan_destroy(osz_tf_plan *p) {
+    if (!p) return OSZ_OK;
+    cudaFree(p->d_lanepow);
+    cudaFree(p->d_warpmat);
     delete p;
     return OSZ_OK;
 }
@@ -138,6 +598,52 @@ int osz_tf_exec_f64(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t 
     if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_tf_exec_f64: null argument");
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
+    // Which kernel (OSZ_TF_KERNEL=split|scan|seq forces one; read per call, the tests run
+    // all three in one process):
+    //   split  spans of >= 4 settle lengths run concurrently after a warm-up: the sequential
+    //          recurrence's rounding, every thread busy -- whenever the chunk holds two spans;
+    //   scan   companion-matrix scan: only where its re-association is harmless (transient
+    //          growth max ||A^i|| <= 16; measured: 4e3 eps per unit of growth);
+    //   seq    one thread per row.
+    const char *force = getenv("OSZ_TF_KERNEL");
+    const int S = p->prm.S;
+    const int64_t warm = p->settle > 0 ? (p->settle + TFP_B - 1) / TFP_B * TFP_B : 0;
+    bool split = warm > 0 && n >= 8 * warm && S >= 3 && S <= 12;
+    bool scan = !split && p->d_lanepow && p->growth <= 16.0;
+    if (force) {
+        const std::string f(force);
+        split = f == "split" && warm > 0 && S >= 3 && S <= 12;
+        scan = f == "scan" && p->d_lanepow != nullptr;
+    }
+    if (split) {
+        // enough spans to fill the GPU twice over, none shorter than 4 settle lengths
+        // enough spans to fill the GPU, none shorter than 4 settle lengths; a row's spans
+        // fill whole CTAs of 128 (k CTAs per row, rows * k close to two per SM)
+        int64_t k = (2 * (int64_t)sm_count() + rows - 1) / rows;
+        if (rows * k > 2 * (int64_t)sm_count() && k > 1) --k;
+        int64_t len = ((n + k * TFP_NT - 1) / (k * TFP_NT) + TFP_B - 1) / TFP_B * TFP_B;
+        if (len < 4 * warm) len = 4 * warm;
+        if (len < 256) len = 256;
+        switch (S) {
+#define OSZ_TF_SPLIT(SS) \
+    case SS: return launch_tf_split<SS>(p, x, ldx, rows, n, reverse, state, y, ldy, len, warm, st);
+            OSZ_TF_SPLIT(3) OSZ_TF_SPLIT(4) OSZ_TF_SPLIT(5) OSZ_TF_SPLIT(6) OSZ_TF_SPLIT(7)
+            OSZ_TF_SPLIT(8) OSZ_TF_SPLIT(9) OSZ_TF_SPLIT(10) OSZ_TF_SPLIT(11) OSZ_TF_SPLIT(12)
+#undef OSZ_TF_SPLIT
+            default: break;
+        }
+    }
+    if (scan) {
+        switch (S) {
+            case 3: return launch_tf_scan<3>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            case 4: return launch_tf_scan<4>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            case 5: return launch_tf_scan<5>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            case 6: return launch_tf_scan<6>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            case 7: return launch_tf_scan<7>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            case 8: return launch_tf_scan<8>(p, x, ldx, rows, n, reverse, state, y, ldy, st);
+            default: break;
+        }
+    }
     switch (p->prm.S) {
 #define OSZ_TF_CASE(S) \
     case S: return launch_tf<S>(p, x, ldx, rows, n, reverse, state, y, ldy, st);

@@ -198,6 +198,41 @@ def test_sos_exact_time_split(dv, n, kind):
         assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
+@pytest.mark.parametrize("kernel", ["split", "scan", "seq", "auto"])
+@pytest.mark.parametrize("design", ["butter3", "cheby5", "butter4bp", "ellip6", "butter7", "butter10"])
+def test_tf_kernels_vs_scipy(dv, design, kernel, monkeypatch):
+    """(b, a) filters above second order against scipy.signal.lfilter, on each kernel:
+    spans running concurrently after a settle-length warm-up (sequential arithmetic), the
+    scan over the companion matrix (orders 3..8; it re-associates the state through matrix
+    powers, so it is held to 1e-7 here and only chosen by itself for benign designs), and
+    one thread per row -- output, carried state, state-only pass, forward and reversed,
+    lengths around the block sizes and long enough for many spans."""
+    if kernel != "auto":
+        monkeypatch.setenv("OSZ_TF_KERNEL", kernel)
+    b, a = {"butter3": sps.butter(3, 0.2), "cheby5": sps.cheby1(5, 1, 0.25),
+            "butter4bp": sps.butter(4, [0.05, 0.3], btype="bandpass"),
+            "ellip6": sps.ellip(6, 0.5, 40, 0.3), "butter7": sps.butter(7, 0.15),
+            "butter10": sps.butter(10, 0.4)}[design]
+    k = max(len(a), len(b)) - 1
+    plan = dv.TfPlan(b, a)
+    rng = np.random.default_rng(k)
+    tol = 1e-7 if kernel == "scan" else 1e-9
+    for n in (1, 15, 16, 17, 4095, 4096, 4097, 9000, 50001, 400_003):
+        x = rng.standard_normal((3, n)) + 0.5
+        zi = rng.standard_normal((3, k)) * 0.1
+        for reverse in (False, True):
+            state = _dev(dv, zi)
+            y = plan.run(_dev(dv, x), state, reverse=reverse).cpu().numpy()
+            xr = x[:, ::-1] if reverse else x
+            ry, rz = sps.lfilter(b, a, xr, axis=-1, zi=zi)
+            ry = ry[:, ::-1] if reverse else ry
+            assert relerr(y, ry) < tol, (design, n, reverse)
+            assert relerr(state.cpu().numpy(), rz) < 100 * tol, (design, n, reverse)
+            state2 = _dev(dv, zi)
+            assert plan.run(_dev(dv, x), state2, reverse=reverse, want_output=False) is None
+            assert relerr(state2.cpu().numpy(), rz) < 100 * tol
+
+
 @pytest.mark.parametrize("tile", ["1", "0"])
 @pytest.mark.parametrize("rows,n", [(1, 4096 * 70 + 5), (2, 4096 * 3), (32, 1_000_000), (300, 41_000),
                                     (7, 4097), (3, 2_000_003)])

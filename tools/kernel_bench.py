@@ -87,6 +87,20 @@ def main(which):
             report("notch biquad bwd rows=%d" % r,
                    timeit(lambda: plan.run(x, st, reverse=True, out=y)), r * n, 16)
             del x, y
+    if "tf" in which:
+        # (b, a) of order 8 (Butterworth band-pass): companion-matrix scan against the
+        # sequential kernel
+        b, a = sps.butter(4, [0.05, 0.3], btype="bandpass")
+        plan = dv.TfPlan(b, a)
+        for r in (256, 32):
+            x = rnd(r, n)
+            y = torch.empty_like(x)
+            st = dv.zeros((r, 8))
+            for mode in ("split", "scan", "seq"):
+                os.environ["OSZ_TF_KERNEL"] = mode
+                report("(b,a) order 8 %-5s rows=%d" % (mode, r),
+                       timeit(lambda: plan.run(x, st, out=y), reps=3, warm=1), r * n, 16)
+        os.environ.pop("OSZ_TF_KERNEL", None)
     if "sostile" in which:
         # one section: tiled look-back scan (default) against one CTA per row / time splits
         b, a = sps.iirnotch(60, 10, fs=30000)
