@@ -646,8 +646,9 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"
 
-    def timed_pass(pool, nrows, sampler=None, timers_out=None, launches=None):
-        """W warm-up + K timed steps of CPS chunks each, device-resident pool."""
+    def timed_pass(pool, nrows, sampler=None, timers_out=None, launches=None, only=None):
+        """W warm-up + K timed steps of CPS chunks each, device-resident pool.  `only`:
+        names of the launches bracketed by CUDA events (None: every launch)."""
         marks = Marks(W * CPS, K * CPS, barrier)
         use_timers = timers_out is not None and os.environ.get("OSZ_BENCH_TIMERS", "1") == "1"
 
@@ -657,6 +658,7 @@ def run_ours(args):
             if launches is not None:
                 launches["a"] = _abi.launch_count()
             dv.TIMERS = {} if use_timers else None
+            dv.TIMERS_ONLY = set(only) if only else None
 
         def on_stop():
             if launches is not None:
@@ -664,6 +666,7 @@ def run_ours(args):
             if timers_out is not None:
                 timers_out.update(dv.TIMERS or {})
             dv.TIMERS = None
+            dv.TIMERS_ONLY = None
             if sampler:
                 sampler.mark_stop()
 
@@ -699,8 +702,19 @@ def run_ours(args):
         run_psd(build_pipeline(pre.producer(), chunk))
         torch.cuda.synchronize()
     barrier()
+    # Two passes of the same W + K steps.  The first brackets EVERY launch with CUDA events
+    # (per-kernel table, stage accounting, which kernel dominates); the second is the one
+    # `value` comes from and brackets only the dominant kernel's launches -- the events that
+    # roofline.achieved is computed from -- because two event records around each of the
+    # ~12 launches of a chunk cost 5 % of the step at 32 rows per GPU (1.80 -> 1.70 ms).
+    timers_all = {}
+    timed_pass(pool, rows, None, timers_all, None)
+    dom_name = (max(timers_all, key=lambda k: sum(a.elapsed_time(b) for a, b, _ in timers_all[k]))
+                if timers_all else None)
+    barrier()
     timers = {}
-    marks, est = timed_pass(pool, rows, sampler, timers, launches)
+    marks, est = timed_pass(pool, rows, sampler, timers, launches,
+                            only=[dom_name] if dom_name else None)
     sampler.stop()
     secs = max_over_ranks(marks.seconds())
     step_samples = total_rows * chunk * CPS            # whole job, all ranks
@@ -709,7 +723,7 @@ def run_ours(args):
     if dist is not None:
         # every rank's own step time and the sum of its kernel times (diagnostic)
         own = torch.tensor([1e3 * marks.own_seconds() / K,
-                            sum(a.elapsed_time(b) for recs in timers.values()
+                            sum(a.elapsed_time(b) for recs in timers_all.values()
                                 for a, b, _ in recs) / K], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(own) for _ in range(world)]
         dist.all_gather(allr, own)
@@ -722,7 +736,9 @@ def run_ours(args):
         assert parity["psd_max_rel_err"] <= 1e-9 and parity["decimated_max_rel_err"] <= 1e-9, parity
 
     kernels = {}
-    for name, recs in timers.items():
+    for name, recs in timers_all.items():
+        if name in timers:           # the dominant kernel: its events of the timed region
+            recs = timers[name]
         ms = [a.elapsed_time(b) for a, b, _ in recs]
         by = [c for _, _, c in recs]
         kernels[name] = {"launches": len(recs), "ms_total": float(np.sum(ms)),
@@ -738,7 +754,7 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath) and rows == ROWS and chunk == CHUNK:
             traffic = json.load(open(tpath)).get(dom, {}).get("bytes_per_launch")
-        per_launch = float(np.mean([c for _, _, c in timers[dom]]))
+        per_launch = float(np.mean([c for _, _, c in (timers.get(dom) or timers_all[dom])]))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["alg_GBps"],
                     "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["alg_GBps"] / hbm_peak, "traffic": traffic,
@@ -871,6 +887,9 @@ def run_ours(args):
                              % (rows * chunk * 8 / 1e6)},
             "gpu_launches": int(launches.get("b", 0) - launches.get("a", 0)),
             "clocks": sampler.summary(), "kernels": kernels,
+            "kernels_note": "per-kernel CUDA-event times: the dominant kernel (%s) over the timed "
+                            "region itself, the others from a pass of the same W + K steps run "
+                            "just before it with every launch bracketed" % dom,
             "host_enqueue": marks.host_pace(),
             # sum of our kernels' CUDA-event times per step: with the host a whole timed
             # region ahead, ms_per_step minus this is idle time on the device side

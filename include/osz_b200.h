@@ -162,6 +162,14 @@ int osz_sos_state_from_sample_f64(const osz_sos_plan *plan, const double *zi_hos
                                   const double *x_dev, int64_t ldx, int64_t rows,
                                   int64_t sample, double *state_dev, void *stream);
 
+/* The look-ahead pass of nm.sosfiltfilt / nm.filtfilt in one call (core/numerical.py:397-399,
+ * :508-509: `z = zi * chunk[last]; _, z = sosfilt(sos, flip(chunk), zi=z)`): the state left by
+ * filtering x_dev (rows, n) -- reverse: last sample first -- starting from
+ * zi_host * (the first sample processed).  state_dev (rows, nsec, 2) is written only. */
+int osz_sos_lookahead_f64(const osz_sos_plan *plan, const double *zi_host, const double *x_dev,
+                          int64_t ldx, int64_t rows, int64_t n, int reverse, double *state_dev,
+                          void *stream);
+
 /* State the cascade holds after filtering the n samples of x_dev (rows, n) FROM REST
  * (reverse: last sample first), without running the recurrence: a weighted sum of the
  * last `settle` samples processed (osz_sos_plan_settle), whose weights decay like the
@@ -351,6 +359,9 @@ int osz_sos_exec_f32(const osz_sos_plan *plan, const float *x_dev, int64_t ldx, 
 int osz_sos_state_from_sample_f32(const osz_sos_plan *plan, const double *zi_host,
                                   const float *x_dev, int64_t ldx, int64_t rows, int64_t sample,
                                   double *state_dev, void *stream);
+int osz_sos_lookahead_f32(const osz_sos_plan *plan, const double *zi_host, const float *x_dev,
+                          int64_t ldx, int64_t rows, int64_t n, int reverse, double *state_dev,
+                          void *stream);
 /* decimating plan (up == 1) set to OSZ_COMPUTE_F32 */
 int osz_upfirdn_exec_f32(const osz_upfirdn_plan *plan, const float *x_dev, int64_t ldx,
                          int64_t rows, int64_t x_first, int64_t x_len, int64_t out_first,

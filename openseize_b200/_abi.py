@@ -69,6 +69,8 @@ SIGNATURES = {
     "osz_fir_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "osz_sos_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, _i64, _vp]),
     "osz_sos_state_from_sample_f32": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "osz_sos_lookahead_f64": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, c_int, _vp, _vp]),
+    "osz_sos_lookahead_f32": (c_int, [_vp, _dp, _vp, _i64, _i64, _i64, c_int, _vp, _vp]),
     "osz_upfirdn_exec_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64,
                                      _vp]),
     "osz_welch_accum_f32": (c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),

@@ -454,10 +454,11 @@ def download(dev, layout, complex_=False):
 # with CUDA events recorded on the launching stream around each launch
 # --------------------------------------------------------------------------
 TIMERS = None
+TIMERS_ONLY = None      # set of launch names to time (None: all) -- bench.py
 
 
 def _launch(name, alg_bytes, fn, *args):
-    if TIMERS is None:
+    if TIMERS is None or (TIMERS_ONLY is not None and name not in TIMERS_ONLY):
         return fn(*args)
     t = torch()
     start, end = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
@@ -673,6 +674,22 @@ class SosPlan(_Plan):
                      _cur_stream())
         _abi.check(rc, "sos_exec")
         return out
+
+    def lookahead(self, zi, x, reverse=True):
+        """State left by filtering x (rows, n) -- reversed: last sample first -- from
+        ``zi * (first sample processed)``: the look-ahead pass of the forward-backward
+        filters as one call.  Returns the (rows, nsec, 2) state."""
+        rows, n = x.shape
+        zarr, zptr = _abi.as_double_array(zi)
+        assert zarr.shape == (self.nsec, 2)
+        state = empty((rows, self.nsec, 2))
+        f32 = x.dtype == torch().float32
+        xp, ldx = _rows_ptr(x)
+        fn = _abi.load().osz_sos_lookahead_f32 if f32 else _abi.load().osz_sos_lookahead_f64
+        rc = _launch("sos_state", (4 if f32 else 8) * rows * n, fn, self.handle, zptr, xp, ldx,
+                     rows, n, int(bool(reverse)), _vp(state.data_ptr()), _cur_stream())
+        _abi.check(rc, "sos_lookahead")
+        return state
 
     @property
     def has_weights(self):

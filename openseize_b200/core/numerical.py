@@ -192,9 +192,13 @@ class _TimeRing:
     span, as one contiguous halo'd view.  Replaces the concat-on-put /
     split-on-get of the reference's FIFOArray (core/queues.py:46-70)."""
 
-    def __init__(self, rows):
+    def __init__(self, rows, capacity=0):
         self.rows, self.buf, self.start, self.pos, self._pending = rows, None, 0, 0, None
         self.ready_event = None      # compute-stream point after which the buffer is ours
+        # samples the consumer lets pile up before it reads (a stage that batches small
+        # chunks): the buffer is sized for that once instead of being re-based -- with a
+        # copy of everything live -- every other block
+        self.capacity = int(capacity)
 
     def _reserve(self, n):
         live = self.pos - self.start
@@ -203,7 +207,7 @@ class _TimeRing:
             # as the blocks are): upstream kernels that move tiles with the TMA need
             # 16-byte aligned rows (csrc/sos_tile.cuh)
             lead = -live % 16
-            width = lead + live + 2 * n + 64
+            width = lead + max(live + 2 * n, self.capacity + 2 * n) + 64
             new = dv.empty_rows((self.rows, width + (-width % 16)))
             if live:
                 new[:, lead:lead + live].copy_(self.buf[:, self.start:self.pos])
@@ -484,6 +488,9 @@ class _Cascade:
             if (_LOOK_WEIGHTS and len(self.plans) == 1
                     and getattr(plan, "has_weights", False)):
                 return [plan.tail_state(fwd[:, :m], reverse=True)]
+        if len(self.plans) == 1:
+            # one call: start state zi * fwd[m - 1] and the reversed state-only pass
+            return [self.plans[0].lookahead(zi[:self.plans[0].nsec], fwd[:, :m])]
         look = self.state_from_sample(zi, fwd, m - 1)
         self.run(fwd[:, :m], look, reverse=True, want_output=False)
         return look
@@ -1140,7 +1147,7 @@ def _segment_batches(pro, axis, plan, pad_left=0, pad_right=0, batch_samples=1 <
     in _spectra_estimatives (reference numerical.py:817-849).  Small chunks are
     batched so each launch carries enough windows to fill the GPU."""
     rows = _layout_of(pro, axis).rows
-    ring = _TimeRing(rows)
+    ring = _TimeRing(rows, capacity=batch_samples // max(rows, 1))
     ring.push_zeros(pad_left)
 
     def flush():

@@ -680,7 +680,8 @@ bool tile_tma_ok<double>(const double *x, int64_t ldx, const double *y, int64_t 
 
 template <typename TIO>
 static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t rows, int64_t n,
-                      int reverse, double *state, TIO *y, int64_t ldy, void *stream) {
+                      int reverse, double *state, TIO *y, int64_t ldy, void *stream,
+                      const double *zi_host = nullptr /* start from zi * first sample */) {
     if (!p || !x || !state) return fail(OSZ_ERR_ARG, "osz_sos_exec: null argument");
     if (rows <= 0 || n <= 0) return OSZ_OK;
     cudaStream_t st = as_stream(stream);
@@ -740,7 +741,8 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
             if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
             sos_tile_tma_kernel<W><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                       \
                 prm1, mx, my, p->d_tiletab, xd, ldx, (int)rows, n, reverse, state, state, yd,  \
-                ldy, p->T16_lanepow, ticket, agg, incl, (int)ntile);                             \
+                ldy, p->T16_lanepow, ticket, agg, incl, (int)ntile, zi_host != nullptr,          \
+                zi_host ? zi_host[0] : 0.0, zi_host ? zi_host[1] : 0.0);                         \
             lerr = cudaGetLastError();                                                           \
         }                                                                                        \
     } while (0)
@@ -785,7 +787,8 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();           \
         sos_tile_kernel<W, TIO><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                         \
             prm1, p->d_tiletab, x, ldx, (int)rows, n, reverse, state, state, YY, LDY,         \
-            p->T16_lanepow, ticket, flag, agg, incl, (int)ntile);                               \
+            p->T16_lanepow, ticket, flag, agg, incl, (int)ntile, zi_host != nullptr,            \
+            zi_host ? zi_host[0] : 0.0, zi_host ? zi_host[1] : 0.0);                            \
     } while (0)
             if (y) OSZ_TILE_LAUNCH(true, y, ldy);
             else OSZ_TILE_LAUNCH(false, (TIO *)nullptr, 0);
@@ -798,6 +801,18 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return OSZ_OK;
         }
+    }
+    if (zi_host) {
+        // generic kernels: the start state zi * (first sample processed) as its own launch
+        SosZi z;
+        for (int sct = 0; sct < p->prm.nsec; ++sct) {
+            z.zi[sct][0] = zi_host[2 * sct];
+            z.zi[sct][1] = zi_host[2 * sct + 1];
+        }
+        const int64_t count = rows * p->prm.nsec * 2;
+        sos_state_from_sample_kernel<TIO><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+            z, p->prm.nsec, x, ldx, rows, reverse ? n - 1 : 0, state);
+        OSZ_LAUNCHED("sos_state_from_sample_kernel");
     }
     // Spans per row.  Splitting pays only while one CTA per row leaves SMs idle
     // (rows <= SM count).  Two ways to cut a row:
@@ -1003,6 +1018,20 @@ extern "C" {
 int osz_sos_exec_f64(const osz_sos_plan *p, const double *x, int64_t ldx, int64_t rows, int64_t n,
                      int reverse, double *state, double *y, int64_t ldy, void *stream) {
     return sos_exec_t<double>(p, x, ldx, rows, n, reverse, state, y, ldy, stream);
+}
+// Look-ahead pass of the forward-backward filters (numerical.py:397-399, :508-509) in one
+// call: the state left by filtering x from zi * (its first sample processed).
+int osz_sos_lookahead_f64(const osz_sos_plan *p, const double *zi_host, const double *x,
+                          int64_t ldx, int64_t rows, int64_t n, int reverse, double *state,
+                          void *stream) {
+    if (!zi_host) return fail(OSZ_ERR_ARG, "osz_sos_lookahead_f64: null zi");
+    return sos_exec_t<double>(p, x, ldx, rows, n, reverse, state, nullptr, 0, stream, zi_host);
+}
+int osz_sos_lookahead_f32(const osz_sos_plan *p, const double *zi_host, const float *x,
+                          int64_t ldx, int64_t rows, int64_t n, int reverse, double *state,
+                          void *stream) {
+    if (!zi_host) return fail(OSZ_ERR_ARG, "osz_sos_lookahead_f32: null zi");
+    return sos_exec_t<float>(p, x, ldx, rows, n, reverse, state, nullptr, 0, stream, zi_host);
 }
 // float32 I/O: float samples in and out; recurrence, scan and carried state in float64
 int osz_sos_exec_f32(const osz_sos_plan *p, const float *x, int64_t ldx, int64_t rows, int64_t n,

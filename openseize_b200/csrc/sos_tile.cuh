@@ -68,7 +68,8 @@ sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__res
                 TIO *__restrict__ y, int64_t ldy,
                 const double *__restrict__ lanepow /* [32][4]: A^(16 (lane + 1)) */,
                 unsigned *__restrict__ ticket, unsigned *__restrict__ flag /* [rows][ntile] */,
-                double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile) {
+                double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile,
+                int use_zi, double zi0, double zi1 /* start state = zi * first sample */) {
     constexpr int T = TILE_T, LD = T + 1, LOGT = 4;
     extern __shared__ __align__(16) unsigned char tile_smem[];
     TIO *stage0 = reinterpret_cast<TIO *>(tile_smem);  // SOS_NT * LD elements of TIO
@@ -113,7 +114,8 @@ sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__res
         if (t == 0) {
             // ---- the short first tile: generic path, from the carried state
             const int off = (int)(TILE - first_len);
-            if (tid < 2) carry[0][tid] = state_in[row * 2 + tid];
+            if (tid < 2)
+                carry[0][tid] = use_zi ? (tid ? zi1 : zi0) * (double)xr[0] : state_in[row * 2 + tid];
 #pragma unroll 8
             for (int e = tid; e < TILE; e += SOS_NT) {
                 TIO val = (TIO)0;
@@ -398,7 +400,8 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                     const double *__restrict__ x, int64_t ldx, int rows, int64_t n_total,
                     int reverse, const double *state_in, double *state, double *__restrict__ y,
                     int64_t ldy, const double *__restrict__ lanepow, unsigned *__restrict__ ticket,
-                    double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile) {
+                    double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile,
+                    int use_zi, double zi0, double zi1 /* start state = zi * first sample */) {
     constexpr int T = TILE_T;
     extern __shared__ unsigned char tile_smem_raw[];
     __shared__ __align__(8) uint64_t full[2];
@@ -464,7 +467,8 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
             //      stores; lines unswizzled, 16 samples per thread line)
             const double *xr = x + row * ldx + (reverse ? n_total - 1 : 0);
             const int off = (int)(TILE - first_len);
-            if (tid < 2) carry[0][tid] = state_in[row * 2 + tid];
+            if (tid < 2)
+                carry[0][tid] = use_zi ? (tid ? zi1 : zi0) * (double)xr[0] : state_in[row * 2 + tid];
 #pragma unroll 8
             for (int e = tid; e < TILE; e += SOS_NT) {
                 double val = 0.0;

@@ -58,6 +58,11 @@ class FakeSos:
         zi = np.asarray(zi, dtype=np.float64)
         return _t(zi[None, :, :] * x.numpy()[:, sample][:, None, None])
 
+    def lookahead(self, zi, x, reverse=True):
+        state = self.state_from_sample(zi, x, x.shape[1] - 1 if reverse else 0)
+        self.run(x, state, reverse=reverse, want_output=False)
+        return state
+
 
 class FakeTf:
     def __init__(self, b, a):

@@ -260,6 +260,13 @@ def test_sos_tile_lookback(dv, rows, n, tile, monkeypatch):
         state2 = _dev(dv, zi)
         assert plan.run(_dev(dv, x), state2, reverse=reverse, want_output=False) is None
         assert relerr(state2.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
+    # the look-ahead entry point: start state zi * (first sample processed), state only
+    zi0 = sps.sosfilt_zi(sos)
+    for reverse in (True, False):
+        got = plan.lookahead(zi0, _dev(dv, x), reverse=reverse).cpu().numpy()
+        xr = x[:, ::-1] if reverse else x
+        _, rz = sps.sosfilt(sos, xr, axis=-1, zi=zi0[:, None, :] * xr[None, :, :1])
+        assert relerr(got, np.transpose(rz, (1, 0, 2))) < 2e-8
     import torch
     x32 = torch.from_numpy(x.astype(np.float32)).cuda()
     state = _dev(dv, zi)
