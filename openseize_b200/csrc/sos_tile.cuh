@@ -409,6 +409,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
     __shared__ double carry[SOS_MAXSEC][2];
     __shared__ double s_in[2];
     __shared__ unsigned s_rank;
+    __shared__ double2 early[2][32];      // warp 0: descriptors polled before the scan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // (sos_scan_block only touches sec[0 .. nsec-1] of the block it is handed)
@@ -510,6 +511,18 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
             __syncthreads();
         } else {
             // ---- a full tile: its box was fetched while the previous tile ran
+            if (warp == 0 && (WRITE || t == ntile - 1)) {
+                // first poll of the look-back now, so that its round trip to L2 runs under
+                // the scan: predecessors dealt a round earlier have published long ago
+                const int idx = t - 1 - lane;
+                double2 I = make_double2(0.0, 0.0), A = make_double2(0.0, 0.0);
+                if (idx >= 0) {
+                    I = ld_desc(in + idx);
+                    A = ld_desc(ag + idx);
+                }
+                early[0][lane] = I;
+                early[1][lane] = A;
+            }
             mbar_wait(&full[stg], (phase >> stg) & 1u);
             phase ^= 1u << stg;
             {
@@ -582,6 +595,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                 double e0 = 0.0, e1 = 0.0;
                 double w0 = 1.0, w1 = 0.0, w2 = 0.0, w3 = 1.0;      // Phi^(32 windows)
                 int base = t - 1;
+                bool polled = true;              // the first window was polled before the scan
                 while (true) {
                     const int idx = base - lane;
                     double2 I = make_double2(0.0, 0.0), A = make_double2(0.0, 0.0);
@@ -589,11 +603,17 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                     while (true) {
                         bool has_i = true, has_a = true;
                         if (idx >= 0) {
-                            I = ld_desc(in + idx);
-                            A = ld_desc(ag + idx);
+                            if (polled) {
+                                I = early[0][lane];
+                                A = early[1][lane];
+                            } else {
+                                I = ld_desc(in + idx);
+                                A = ld_desc(ag + idx);
+                            }
                             has_i = __double_as_longlong(I.x) != TILE_EMPTY;
                             has_a = has_i || __double_as_longlong(A.x) != TILE_EMPTY;
                         }
+                        polled = false;
                         const unsigned incl_mask = __ballot_sync(0xffffffffu, has_i);
                         const unsigned ready = __ballot_sync(0xffffffffu, has_a);
                         first = incl_mask ? (unsigned)__ffs((int)incl_mask) - 1u : 32u;
