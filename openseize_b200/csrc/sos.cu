@@ -662,6 +662,22 @@ static bool tile_tensor_map(CUtensorMap *map, const double *base, int64_t ld, in
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Launch of a tile kernel: an ordinary launch with ticket dealing, a COOPERATIVE launch with
+// static dealing (the CTAs wait on each other's tiles, so a partly resident grid could wait
+// for CTAs that another kernel keeps off the SMs; the cooperative launch starts only when
+// the whole grid fits).
+template <typename... KArgs, typename... Args>
+static cudaError_t tile_launch(int dynamic, void (*kernel)(KArgs...), unsigned ctas, int smem,
+                               cudaStream_t st, Args... args) {
+    if (dynamic) {
+        kernel<<<ctas, SOS_NT, smem, st>>>(args...);
+        return cudaGetLastError();
+    }
+    void *ptrs[] = {(void *)&args...};
+    return cudaLaunchCooperativeKernel((const void *)kernel, dim3(ctas), dim3(SOS_NT), ptrs,
+                                       (size_t)smem, st);
+}
+
 template <typename TIO>
 static bool tile_tma_ok(const TIO *, int64_t, const TIO *, int64_t, int64_t, int64_t, int) {
     return false;
@@ -695,6 +711,11 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
     const int tile_mode = tile_env ? atoi(tile_env) : -1;
     if (p->d_tiletab && tile_mode != 0) {
         const int64_t ntile = (n + TILE - 1) / TILE;
+        // tickets where a row has few tiles in flight (predecessors mostly finished rounds
+        // ago: 256 rows 0.676 against 0.706 ms), static rounds below (32 rows 0.122 against
+        // 0.138 ms); OSZ_SOS_TILE_DEAL=0/1 forces static / tickets
+        const char *deal_env = getenv("OSZ_SOS_TILE_DEAL");
+        const int dynamic = deal_env ? (atoi(deal_env) != 0) : (rows > (int64_t)sm_count());
         SosParams1 prm1;
         prm1.nsec = 1;
         prm1.pad_ = 0;
@@ -739,11 +760,12 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         if (per_sm < 1) lerr = cudaErrorLaunchOutOfResources;                                    \
         if (lerr == cudaSuccess) {                                                               \
             if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
-            sos_tile_tma_kernel<W><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                       \
-                prm1, mx, my, p->d_tiletab, xd, ldx, (int)rows, n, reverse, state, state, yd,  \
-                ldy, p->T16_lanepow, ticket, agg, incl, (int)ntile, zi_host != nullptr,          \
-                zi_host ? zi_host[0] : 0.0, zi_host ? zi_host[1] : 0.0);                         \
-            lerr = cudaGetLastError();                                                           \
+            lerr = tile_launch(dynamic, sos_tile_tma_kernel<W>, (unsigned)ctas, tsmem, st, prm1, \
+                               mx, my, (const SosTileTab *)p->d_tiletab, xd, ldx, (int)rows, n,  \
+                               reverse, (const double *)state, state, yd, ldy,                   \
+                               (const double *)p->T16_lanepow, ticket, agg, incl, (int)ntile,    \
+                               (int)(zi_host != nullptr), zi_host ? zi_host[0] : 0.0,            \
+                               zi_host ? zi_host[1] : 0.0, dynamic);                             \
         }                                                                                        \
     } while (0)
                     if (y) OSZ_TMA_LAUNCH(true);
@@ -785,10 +807,12 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         }();                                                                                    \
         if (per_sm < 1) return fail(OSZ_ERR_CUDA, "sos_tile_kernel: no CTA fits an SM");        \
         if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();           \
-        sos_tile_kernel<W, TIO><<<(unsigned)ctas, SOS_NT, tsmem, st>>>(                         \
-            prm1, p->d_tiletab, x, ldx, (int)rows, n, reverse, state, state, YY, LDY,         \
-            p->T16_lanepow, ticket, flag, agg, incl, (int)ntile, zi_host != nullptr,            \
-            zi_host ? zi_host[0] : 0.0, zi_host ? zi_host[1] : 0.0);                            \
+        tile_launch(dynamic, sos_tile_kernel<W, TIO>, (unsigned)ctas, tsmem, st, prm1,          \
+                    (const SosTileTab *)p->d_tiletab, x, ldx, (int)rows, n, reverse,            \
+                    (const double *)state, state, YY, (int64_t)(LDY),                           \
+                    (const double *)p->T16_lanepow, ticket, flag, agg, incl, (int)ntile,        \
+                    (int)(zi_host != nullptr), zi_host ? zi_host[0] : 0.0,                      \
+                    zi_host ? zi_host[1] : 0.0, dynamic);                                       \
     } while (0)
             if (y) OSZ_TILE_LAUNCH(true, y, ldy);
             else OSZ_TILE_LAUNCH(false, (TIO *)nullptr, 0);

@@ -3,9 +3,9 @@
 // 8 GPUs; the short look-ahead pass of nm.sosfiltfilt / nm.filtfilt, reference
 // core/numerical.py:399-403,508-512) and as a load-balanced alternative when they can.
 //
-// A row is cut into tiles of 4096 samples.  CTAs are persistent and co-resident; tiles in
-// time-major order (tile t of every row before tile t + 1 of any) are dealt round-robin
-// over them, so the tiles a tile depends on are always being worked on.  A tile
+// A row is cut into tiles of 4096 samples.  CTAs are persistent and draw tiles from a
+// ticket counter in time-major order (tile t of every row before tile t + 1 of any), one
+// draw ahead, so the tiles a tile depends on always belong to CTAs that are running.  A tile
 //   1. loads its samples ONCE and scans them from rest (the same thread-level recurrence
 //      and Kogge-Stone combine as sos_scan_block, 16 samples per thread);
 //   2. publishes its aggregate (the state it would leave behind from rest);
@@ -69,14 +69,15 @@ sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__res
                 const double *__restrict__ lanepow /* [32][4]: A^(16 (lane + 1)) */,
                 unsigned *__restrict__ ticket, unsigned *__restrict__ flag /* [rows][ntile] */,
                 double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile,
-                int use_zi, double zi0, double zi1 /* start state = zi * first sample */) {
+                int use_zi, double zi0, double zi1 /* start state = zi * first sample */,
+                int dynamic /* tickets (any residency) / static round-robin (co-resident grid) */) {
     constexpr int T = TILE_T, LD = T + 1, LOGT = 4;
     extern __shared__ __align__(16) unsigned char tile_smem[];
     TIO *stage0 = reinterpret_cast<TIO *>(tile_smem);  // SOS_NT * LD elements of TIO
     __shared__ double wtot[2][SOS_NT / 32][2];
     __shared__ double carry[SOS_MAXSEC][2];
     __shared__ double s_in[2];
-    __shared__ unsigned s_rank;
+    __shared__ unsigned s_job[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // (sos_scan_block only touches sec[0 .. nsec-1] of the block it is handed)
@@ -91,16 +92,25 @@ sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__res
     const double *lp = lanepow + lane * 4;
     const double lp0 = ldg(lp + 0), lp1 = ldg(lp + 1), lp2 = ldg(lp + 2), lp3 = ldg(lp + 3);
 
-    // Jobs in time-major order, dealt round-robin over the CTAs by their START order (a
-    // CTA's rank is its draw from the ticket counter): every CTA walks rank, rank + G, ...
-    // so all CTAs work on the same round of consecutive tiles at the same time, a tile's
-    // predecessors are never parked behind unrelated work, and the next job is known in
-    // advance.  The grid is sized to be co-resident (sos.cu).
-    if (tid == 0) s_rank = atomicAdd(ticket, 1u);
+    // Jobs in time-major order, drawn from a ticket counter ONE job ahead (the draw for
+    // the next job is issued when this one starts, so its latency is hidden).  Every tile a
+    // job waits for has a smaller ticket, hence belongs to a CTA that is running: the oldest
+    // unfinished job is always being worked on and waits for nothing unfinished, so the
+    // scheme cannot deadlock whatever part of the grid is resident (another kernel may hold
+    // SMs).  Drawing further ahead is what must not be done: a CTA then parks tiles behind
+    // unrelated work and every tile depending on a parked one waits (measured: a constant
+    // 0.43 ms for any row count <= 32 when drawing two ahead).
+    // Static mode (dynamic == 0; the launch is COOPERATIVE, so the whole grid is resident):
+    // the first draw is the CTA's rank and it walks rank, rank + G, ... -- all CTAs then
+    // work on the same round of consecutive tiles at the same time, which is what keeps
+    // the look-back waits short when a row has many tiles in flight (few rows).
+    if (tid == 0) s_job[0] = atomicAdd(ticket, 1u);
     __syncthreads();
+    unsigned job = s_job[0];
     const unsigned G = gridDim.x;
-    unsigned job = s_rank;
+    int k = 0;
     while (job < total) {
+        if (tid == 0 && dynamic) s_job[(k + 1) & 1] = atomicAdd(ticket, 1u);
         TIO *buf = stage0;
         const int t = (int)(job / (unsigned)rows);
         const int64_t row = (int64_t)(job - (unsigned)t * (unsigned)rows);
@@ -337,8 +347,9 @@ sos_tile_kernel(const __grid_constant__ SosParams1 prm1, const SosTileTab *__res
                 }
             }
         }
-        __syncthreads();            // buf, wtot, s_in free
-        job += G;
+        __syncthreads();            // buf, wtot, s_in free; the next ticket visible
+        ++k;
+        job = dynamic ? s_job[k & 1] : job + G;
     }
 }
 
@@ -401,14 +412,15 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                     int reverse, const double *state_in, double *state, double *__restrict__ y,
                     int64_t ldy, const double *__restrict__ lanepow, unsigned *__restrict__ ticket,
                     double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile,
-                    int use_zi, double zi0, double zi1 /* start state = zi * first sample */) {
+                    int use_zi, double zi0, double zi1 /* start state = zi * first sample */,
+                    int dynamic /* tickets (any residency) / static round-robin (co-resident grid) */) {
     constexpr int T = TILE_T;
     extern __shared__ unsigned char tile_smem_raw[];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double wtot[2][SOS_NT / 32][2];
     __shared__ double carry[SOS_MAXSEC][2];
     __shared__ double s_in[2];
-    __shared__ unsigned s_rank;
+    __shared__ unsigned s_job[2];
     __shared__ double2 early[2][32];      // warp 0: descriptors polled before the scan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,15 +454,16 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
         tma_load_3d(stage0 + (size_t)stg * TILE_BYTES, &mx, 0, tile_coord(t), row, &full[stg]);
     };
 
-    if (tid == 0) s_rank = atomicAdd(ticket, 1u) + 1u;     // the counter starts at all-ones
+    // tickets one job ahead (see sos_tile_kernel); the counter starts at all-ones
+    if (tid == 0) s_job[0] = atomicAdd(ticket, 1u) + 1u;
     if (tid == PRODUCER) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         fence_barrier_init();
     }
     __syncthreads();
+    unsigned job = s_job[0];
     const unsigned G = gridDim.x;
-    unsigned job = s_rank;
     if (tid == PRODUCER) issue_load(job, 0);
     unsigned phase = 0;                               // bit s: parity to wait for on stage s
     int k = 0;
@@ -459,7 +472,8 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
         double *sb = reinterpret_cast<double *>(stage0 + (size_t)stg * TILE_BYTES);
         const int t = (int)(job / (unsigned)rows);
         const int64_t row = (int64_t)(job - (unsigned)t * (unsigned)rows);
-        const unsigned nextjob = job + G;
+        if (tid == 0)                                   // the next job; read behind a barrier
+            s_job[(k + 1) & 1] = dynamic ? atomicAdd(ticket, 1u) + 1u : job + G;
         double2 *ag = agg + row * ntile, *in = incl + row * ntile;
         double v[T];
 
@@ -482,7 +496,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
             __syncthreads();
             if (tid == PRODUCER) {
                 bulk_wait_read0();
-                issue_load(nextjob, stg ^ 1);
+                issue_load(s_job[(k + 1) & 1], stg ^ 1);
             }
 #pragma unroll
             for (int i = 0; i < T; ++i) v[i] = sb[tid * T + i];
@@ -576,7 +590,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
             if (tid == PRODUCER) {
                 // the other stage: its previous tile's store must have read it out
                 bulk_wait_read0();
-                issue_load(nextjob, stg ^ 1);
+                issue_load(s_job[(k + 1) & 1], stg ^ 1);
             }
             const double *qm = c.P[4];           // transition over one warp: A^512
             const bool last = t == ntile - 1;
@@ -721,8 +735,8 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                 }
             }
         }
-        job = nextjob;
         ++k;
+        job = s_job[k & 1];
     }
     if (tid == PRODUCER) bulk_wait0();
 }
