@@ -647,19 +647,36 @@ static osz_tmap_encode_fn tmap_encoder() {
     return fn;
 }
 
-// Rows of float64 samples as [rows][lines][16] with 256-line boxes and the 128-byte swizzle
-// (sos_tile_tma_kernel).  `base` must be 16-byte aligned and `ld` even.
-static bool tile_tensor_map(CUtensorMap *map, const double *base, int64_t ld, int64_t rows,
+// Rows of samples as [rows][lines][16] with 256-line boxes; 128-byte lines and swizzle for
+// float64, 64-byte lines and swizzle for float32 (sos_tile_tma_kernel).  `base` must be
+// 16-byte aligned and the row pitch a multiple of 16 bytes.
+template <typename TIO>
+static bool tile_tensor_map(CUtensorMap *map, const TIO *base, int64_t ld, int64_t rows,
                             int64_t lines) {
     osz_tmap_encode_fn enc = tmap_encoder();
     if (!enc) return false;
+    const bool f64 = sizeof(TIO) == 8;
     const cuuint64_t dims[3] = {(cuuint64_t)TILE_T, (cuuint64_t)lines, (cuuint64_t)rows};
-    const cuuint64_t strides[2] = {(cuuint64_t)TILE_T * 8, (cuuint64_t)ld * 8};
+    const cuuint64_t strides[2] = {(cuuint64_t)TILE_T * sizeof(TIO), (cuuint64_t)ld * sizeof(TIO)};
     const cuuint32_t box[3] = {(cuuint32_t)TILE_T, (cuuint32_t)SOS_NT, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides,
-               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    return enc(map, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+               const_cast<TIO *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               f64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename TIO>
+static bool tile_tma_ok(const TIO *x, int64_t ldx, const TIO *y, int64_t ldy, int64_t n,
+                        int64_t ntile, int reverse) {
+    if (ntile < 2) return false;
+    const int64_t first_len = n - (ntile - 1) * TILE;
+    const int64_t shift = reverse ? 0 : first_len;
+    const int64_t per16 = 16 / (int64_t)sizeof(TIO);          // elements per 16 bytes
+    auto ok = [&](const TIO *p, int64_t ld) {
+        return (reinterpret_cast<uintptr_t>(p + shift) & 15) == 0 && ld % per16 == 0 && ld >= n;
+    };
+    return ok(x, ldx) && (!y || ok(y, ldy));
 }
 
 // Launch of a tile kernel: an ordinary launch with ticket dealing, a COOPERATIVE launch with
@@ -676,22 +693,6 @@ static cudaError_t tile_launch(int dynamic, void (*kernel)(KArgs...), unsigned c
     void *ptrs[] = {(void *)&args...};
     return cudaLaunchCooperativeKernel((const void *)kernel, dim3(ctas), dim3(SOS_NT), ptrs,
                                        (size_t)smem, st);
-}
-
-template <typename TIO>
-static bool tile_tma_ok(const TIO *, int64_t, const TIO *, int64_t, int64_t, int64_t, int) {
-    return false;
-}
-template <>
-bool tile_tma_ok<double>(const double *x, int64_t ldx, const double *y, int64_t ldy, int64_t n,
-                         int64_t ntile, int reverse) {
-    if (ntile < 2) return false;
-    const int64_t first_len = n - (ntile - 1) * TILE;
-    const int64_t shift = reverse ? 0 : first_len;
-    auto ok = [&](const double *p, int64_t ld) {
-        return (reinterpret_cast<uintptr_t>(p + shift) & 15) == 0 && (ld & 1) == 0 && ld >= n;
-    };
-    return ok(x, ldx) && (!y || ok(y, ldy));
 }
 
 template <typename TIO>
@@ -729,10 +730,10 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
                 const int64_t shift = reverse ? 0 : first_len;
                 const int64_t lines = (ntile - 1) * SOS_NT;
                 alignas(64) CUtensorMap mx, my;
-                const double *xd = reinterpret_cast<const double *>(x);
-                double *yd = reinterpret_cast<double *>(y);
-                bool ok = tile_tensor_map(&mx, xd + shift, ldx, rows, lines);
-                if (ok && y) ok = tile_tensor_map(&my, yd + shift, ldy, rows, lines);
+                const TIO *xd = x;
+                TIO *yd = y;
+                bool ok = tile_tensor_map<TIO>(&mx, xd + shift, ldx, rows, lines);
+                if (ok && y) ok = tile_tensor_map<TIO>(&my, yd + shift, ldy, rows, lines);
                 if (ok) {
                     if (!y) my = mx;
                     char *scr = nullptr;
@@ -742,25 +743,27 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
                     unsigned *ticket = reinterpret_cast<unsigned *>(scr);
                     double2 *agg = reinterpret_cast<double2 *>(scr + 16);
                     double2 *incl = agg + total;
-                    const int tsmem = 2 * TILE_BYTES + 1024;
+                    const int tsmem = 2 * TILE * (int)sizeof(TIO) + 1024;
                     int64_t ctas = total;
                     cudaError_t lerr = cudaSuccess;
 #define OSZ_TMA_LAUNCH(W)                                                                        \
     do {                                                                                         \
         static const int per_sm = [] {   /* the CTAs wait on each other: co-resident grid */      \
             int v = 0;                                                                           \
-            if (cudaFuncSetAttribute(sos_tile_tma_kernel<W>,                                     \
+            if (cudaFuncSetAttribute(sos_tile_tma_kernel<W, TIO>,                                \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,                \
-                                     2 * TILE_BYTES + 1024) != cudaSuccess ||                    \
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, sos_tile_tma_kernel<W>, SOS_NT, \
-                                                              2 * TILE_BYTES + 1024) != cudaSuccess) \
+                                     2 * TILE * (int)sizeof(TIO) + 1024) != cudaSuccess ||       \
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
+                    &v, sos_tile_tma_kernel<W, TIO>, SOS_NT,                                     \
+                    2 * TILE * (int)sizeof(TIO) + 1024) != cudaSuccess)                          \
                 v = 0;                                                                           \
             return v;                                                                            \
         }();                                                                                     \
         if (per_sm < 1) lerr = cudaErrorLaunchOutOfResources;                                    \
         if (lerr == cudaSuccess) {                                                               \
             if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
-            lerr = tile_launch(dynamic, sos_tile_tma_kernel<W>, (unsigned)ctas, tsmem, st, prm1, \
+            lerr = tile_launch(dynamic, sos_tile_tma_kernel<W, TIO>, (unsigned)ctas, tsmem, st,  \
+                               prm1,                                                             \
                                mx, my, (const SosTileTab *)p->d_tiletab, xd, ldx, (int)rows, n,  \
                                reverse, (const double *)state, state, yd, ldy,                   \
                                (const double *)p->T16_lanepow, ticket, agg, incl, (int)ntile,    \

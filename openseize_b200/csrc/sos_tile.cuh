@@ -402,19 +402,82 @@ __device__ __forceinline__ void bulk_wait_read0() {
 }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-constexpr int TILE_BYTES = TILE * 8;               // 32 KB
+// A thread's line of a staged tile (16 samples, the 16-byte chunks swizzled as the TMA left
+// them) into / out of its registers, time-reversed for the backward pass.
+//   float64: 128-byte lines, SWIZZLE_128B -- chunk j of line r sits at chunk j ^ (r & 7)
+//   float32:  64-byte lines, SWIZZLE_64B  -- chunk j of line r sits at chunk j ^ ((r >> 1) & 3)
+// (the 16-byte chunk index is XORed with address bits 7.. of the line)
+template <typename TIO>
+struct TileLine;
+template <>
+struct TileLine<double> {
+    static __device__ __forceinline__ int key(int line) { return line & 7; }
+    static __device__ __forceinline__ void load(const double *ln_, int sw, bool reverse, double (&v)[TILE_T]) {
+        const double2 *ln = reinterpret_cast<const double2 *>(ln_);
+#pragma unroll
+        for (int j = 0; j < TILE_T / 2; ++j) {
+            const double2 d = ln[j ^ sw];
+            if (reverse) {
+                v[TILE_T - 1 - 2 * j] = d.x;
+                v[TILE_T - 2 - 2 * j] = d.y;
+            } else {
+                v[2 * j] = d.x;
+                v[2 * j + 1] = d.y;
+            }
+        }
+    }
+    static __device__ __forceinline__ void store(double *ln_, int sw, bool reverse, const double (&v)[TILE_T]) {
+        double2 *ln = reinterpret_cast<double2 *>(ln_);
+#pragma unroll
+        for (int j = 0; j < TILE_T / 2; ++j)
+            ln[j ^ sw] = reverse ? make_double2(v[TILE_T - 1 - 2 * j], v[TILE_T - 2 - 2 * j])
+                                 : make_double2(v[2 * j], v[2 * j + 1]);
+    }
+};
+template <>
+struct TileLine<float> {
+    static __device__ __forceinline__ int key(int line) { return (line >> 1) & 3; }
+    static __device__ __forceinline__ void load(const float *ln_, int sw, bool reverse, double (&v)[TILE_T]) {
+        const float4 *ln = reinterpret_cast<const float4 *>(ln_);
+#pragma unroll
+        for (int j = 0; j < TILE_T / 4; ++j) {
+            const float4 d = ln[j ^ sw];
+            if (reverse) {
+                v[TILE_T - 1 - 4 * j] = (double)d.x;
+                v[TILE_T - 2 - 4 * j] = (double)d.y;
+                v[TILE_T - 3 - 4 * j] = (double)d.z;
+                v[TILE_T - 4 - 4 * j] = (double)d.w;
+            } else {
+                v[4 * j] = (double)d.x;
+                v[4 * j + 1] = (double)d.y;
+                v[4 * j + 2] = (double)d.z;
+                v[4 * j + 3] = (double)d.w;
+            }
+        }
+    }
+    static __device__ __forceinline__ void store(float *ln_, int sw, bool reverse, const double (&v)[TILE_T]) {
+        float4 *ln = reinterpret_cast<float4 *>(ln_);
+#pragma unroll
+        for (int j = 0; j < TILE_T / 4; ++j)
+            ln[j ^ sw] = reverse ? make_float4((float)v[TILE_T - 1 - 4 * j], (float)v[TILE_T - 2 - 4 * j],
+                                               (float)v[TILE_T - 3 - 4 * j], (float)v[TILE_T - 4 - 4 * j])
+                                 : make_float4((float)v[4 * j], (float)v[4 * j + 1],
+                                               (float)v[4 * j + 2], (float)v[4 * j + 3]);
+    }
+};
 
-template <bool WRITE>
+template <bool WRITE, typename TIO>
 __global__ void __launch_bounds__(SOS_NT, 3)
 sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_constant__ CUtensorMap mx,
                     const __grid_constant__ CUtensorMap my, const SosTileTab *__restrict__ tab,
-                    const double *__restrict__ x, int64_t ldx, int rows, int64_t n_total,
-                    int reverse, const double *state_in, double *state, double *__restrict__ y,
+                    const TIO *__restrict__ x, int64_t ldx, int rows, int64_t n_total,
+                    int reverse, const double *state_in, double *state, TIO *__restrict__ y,
                     int64_t ldy, const double *__restrict__ lanepow, unsigned *__restrict__ ticket,
                     double2 *__restrict__ agg, double2 *__restrict__ incl, int ntile,
                     int use_zi, double zi0, double zi1 /* start state = zi * first sample */,
                     int dynamic /* tickets (any residency) / static round-robin (co-resident grid) */) {
     constexpr int T = TILE_T;
+    constexpr int TILE_BYTES = TILE * (int)sizeof(TIO);      // 32 KB / 16 KB per stage
     extern __shared__ unsigned char tile_smem_raw[];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double wtot[2][SOS_NT / 32][2];
@@ -440,7 +503,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
 
     // this thread's line of a tile and the swizzle of its chunks
     const int line = reverse ? SOS_NT - 1 - tid : tid;
-    const int sw = line & 7;
+    const int sw = TileLine<TIO>::key(line);
 
     constexpr int PRODUCER = 32;                      // warp 1, lane 0: issues every TMA copy
     auto tile_coord = [&](int t) { return (reverse ? ntile - 1 - t : t - 1) * SOS_NT; };
@@ -469,7 +532,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
     int k = 0;
     while (job < total) {
         const int stg = k & 1;
-        double *sb = reinterpret_cast<double *>(stage0 + (size_t)stg * TILE_BYTES);
+        TIO *sb = reinterpret_cast<TIO *>(stage0 + (size_t)stg * TILE_BYTES);
         const int t = (int)(job / (unsigned)rows);
         const int64_t row = (int64_t)(job - (unsigned)t * (unsigned)rows);
         if (tid == 0)                                   // the next job; read behind a barrier
@@ -480,13 +543,13 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
         if (t == 0) {
             // ---- the short first tile: generic path from the carried state (plain loads and
             //      stores; lines unswizzled, 16 samples per thread line)
-            const double *xr = x + row * ldx + (reverse ? n_total - 1 : 0);
+            const TIO *xr = x + row * ldx + (reverse ? n_total - 1 : 0);
             const int off = (int)(TILE - first_len);
             if (tid < 2)
                 carry[0][tid] = use_zi ? (tid ? zi1 : zi0) * (double)xr[0] : state_in[row * 2 + tid];
 #pragma unroll 8
             for (int e = tid; e < TILE; e += SOS_NT) {
-                double val = 0.0;
+                TIO val = (TIO)0;
                 if (e >= off) {
                     const int64_t s = e - off;
                     val = ld_stream(reverse ? xr - s : xr + s);
@@ -499,7 +562,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                 issue_load(s_job[(k + 1) & 1], stg ^ 1);
             }
 #pragma unroll
-            for (int i = 0; i < T; ++i) v[i] = sb[tid * T + i];
+            for (int i = 0; i < T; ++i) v[i] = (double)sb[tid * T + i];
             sos_scan_block<T, 0>(prm, v, false, off, carry, wtot, lanepow, tid, lane, warp);
             __syncthreads();                     // carry[] holds the leaving state
             if (tid == 0) {
@@ -512,9 +575,9 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                 }
             }
             if (WRITE) {
-                double *yr = y + row * ldy + (reverse ? n_total - 1 : 0);
+                TIO *yr = y + row * ldy + (reverse ? n_total - 1 : 0);
 #pragma unroll
-                for (int i = 0; i < T; ++i) sb[tid * T + i] = v[i];
+                for (int i = 0; i < T; ++i) sb[tid * T + i] = (TIO)v[i];
                 __syncthreads();
 #pragma unroll 4
                 for (int e = tid; e < TILE; e += SOS_NT) {
@@ -539,20 +602,7 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
             }
             mbar_wait(&full[stg], (phase >> stg) & 1u);
             phase ^= 1u << stg;
-            {
-                const double2 *ln = reinterpret_cast<const double2 *>(sb + line * T);
-#pragma unroll
-                for (int j = 0; j < T / 2; ++j) {
-                    const double2 d = ln[j ^ sw];
-                    if (reverse) {
-                        v[T - 1 - 2 * j] = d.x;
-                        v[T - 2 - 2 * j] = d.y;
-                    } else {
-                        v[2 * j] = d.x;
-                        v[2 * j + 1] = d.y;
-                    }
-                }
-            }
+            TileLine<TIO>::load(sb + line * T, sw, reverse != 0, v);
             const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
             // two independent 8-sample chains from rest
             double za0[2] = {0.0, 0.0}, za1[2] = {0.0, 0.0};
@@ -719,14 +769,8 @@ sos_tile_tma_kernel(const __grid_constant__ SosParams1 prm1, const __grid_consta
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[8 + i] = fma(c.g0[i], q0, fma(c.g1[i], q1, v[8 + i]));
-                {
-                    // back into this thread's own line (nobody else touches it)
-                    double2 *ln = reinterpret_cast<double2 *>(sb + line * T);
-#pragma unroll
-                    for (int j = 0; j < T / 2; ++j)
-                        ln[j ^ sw] = reverse ? make_double2(v[T - 1 - 2 * j], v[T - 2 - 2 * j])
-                                             : make_double2(v[2 * j], v[2 * j + 1]);
-                }
+                // back into this thread's own line (nobody else touches it)
+                TileLine<TIO>::store(sb + line * T, sw, reverse != 0, v);
                 fence_proxy_async();
                 __syncthreads();
                 if (tid == PRODUCER) {

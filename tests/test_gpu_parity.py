@@ -269,12 +269,16 @@ def test_sos_tile_lookback(dv, rows, n, tile, monkeypatch):
         assert relerr(got, np.transpose(rz, (1, 0, 2))) < 2e-8
     import torch
     x32 = torch.from_numpy(x.astype(np.float32)).cuda()
-    state = _dev(dv, zi)
-    y32 = plan.run(x32, state).cpu().numpy()
-    assert y32.dtype == np.float32
-    ry, _ = sps.sosfilt(sos, x.astype(np.float32).astype(np.float64), axis=-1,
-                        zi=np.transpose(zi, (1, 0, 2)))
-    assert np.max(np.abs(y32 - ry)) / np.max(np.abs(ry)) < 1e-6
+    for reverse in (False, True):
+        state = _dev(dv, zi)
+        y32 = plan.run(x32, state, reverse=reverse).cpu().numpy()
+        assert y32.dtype == np.float32
+        xr = x.astype(np.float32).astype(np.float64)
+        xr = xr[:, ::-1] if reverse else xr
+        ry, rz = sps.sosfilt(sos, xr, axis=-1, zi=np.transpose(zi, (1, 0, 2)))
+        ry = ry[:, ::-1] if reverse else ry
+        assert np.max(np.abs(y32 - ry)) / np.max(np.abs(ry)) < 1e-6
+        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
 @pytest.mark.parametrize("kind", ["notch", "butter2"])
