@@ -910,10 +910,28 @@ def run_ours(args):
             line["weak_scaling"] = weak
         if named:
             line["named_kernels"] = named
-            line["roofline_named"] = {k: {"bound": v.get("bound", "hbm"), "frac": v["frac"],
-                                          "achieved": v["achieved_GBps"], "peak": hbm_peak,
-                                          "unit": "GB/s"}
-                                      for k, v in named.items() if "f32" not in k}
+            # These float64 kernels are bound by the FP64 pipe, not by HBM (ncu: FP64 pipe
+            # 67 % / 67 % / 59 % busy with DRAM at 48 / 42 / 20 %, profiles/r02_ncu_summary.md
+            # A and r01 C): next to the HBM fraction north_star asks for, the fraction of the
+            # FP64 issue peak (SMs x 64 lanes x SM clock) the measured rate corresponds to,
+            # from the kernels' FP64 instructions per sample (ncu instruction counts).
+            fp64_per_sample = {"fir_oaconvolve_kaiser113": 48.6, "fir_oaconvolve_kaiser671": 56.4,
+                               "welch_psd_nfft4096": 54.4}
+            clk = (sampler.summary() or {}).get("sm_mhz") or 1965.0
+            fp64_peak = torch.cuda.get_device_properties(local).multi_processor_count * 64 * clk * 1e6
+            line["roofline_named"] = {}
+            for k, v in named.items():
+                if "f32" in k:
+                    continue
+                ent = {"bound": "fp64" if k in fp64_per_sample else "hbm", "frac": v["frac"],
+                       "achieved": v["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s"}
+                if k in fp64_per_sample:
+                    rate = v["channel_samples_per_s"] * fp64_per_sample[k]
+                    ent["fp64"] = {"instr_per_sample": fp64_per_sample[k],
+                                   "achieved_instr_per_s": rate, "peak_instr_per_s": fp64_peak,
+                                   "frac": rate / fp64_peak}
+                    ent["frac_note"] = "frac = algorithmic bytes / time / HBM peak (north_star's metric); the kernel's own bound is fp64.frac"
+                line["roofline_named"][k] = ent
         if e2e:
             line["e2e"] = e2e
         if cpu_line:

@@ -686,13 +686,19 @@ static bool tile_tma_ok(const TIO *x, int64_t ldx, const TIO *y, int64_t ldy, in
 template <typename... KArgs, typename... Args>
 static cudaError_t tile_launch(int dynamic, void (*kernel)(KArgs...), unsigned ctas, int smem,
                                cudaStream_t st, Args... args) {
-    if (dynamic) {
-        kernel<<<ctas, SOS_NT, smem, st>>>(args...);
-        return cudaGetLastError();
+    // (`dynamic` is the kernel's LAST parameter and is appended here)
+    if (!dynamic) {
+        int stat = 0;
+        void *ptrs[] = {(void *)&args..., (void *)&stat};
+        const cudaError_t err = cudaLaunchCooperativeKernel((const void *)kernel, dim3(ctas),
+                                                            dim3(SOS_NT), ptrs, (size_t)smem, st);
+        if (err == cudaSuccess) return err;
+        // the context cannot hold the whole grid at once (MPS share, green context, ...):
+        // ticket dealing does not need it to
+        (void)cudaGetLastError();
     }
-    void *ptrs[] = {(void *)&args...};
-    return cudaLaunchCooperativeKernel((const void *)kernel, dim3(ctas), dim3(SOS_NT), ptrs,
-                                       (size_t)smem, st);
+    kernel<<<ctas, SOS_NT, smem, st>>>(args..., 1);
+    return cudaGetLastError();
 }
 
 template <typename TIO>
@@ -768,7 +774,7 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
                                reverse, (const double *)state, state, yd, ldy,                   \
                                (const double *)p->T16_lanepow, ticket, agg, incl, (int)ntile,    \
                                (int)(zi_host != nullptr), zi_host ? zi_host[0] : 0.0,            \
-                               zi_host ? zi_host[1] : 0.0, dynamic);                             \
+                               zi_host ? zi_host[1] : 0.0);                                      \
         }                                                                                        \
     } while (0)
                     if (y) OSZ_TMA_LAUNCH(true);
@@ -815,7 +821,7 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
                     (const double *)state, state, YY, (int64_t)(LDY),                           \
                     (const double *)p->T16_lanepow, ticket, flag, agg, incl, (int)ntile,        \
                     (int)(zi_host != nullptr), zi_host ? zi_host[0] : 0.0,                      \
-                    zi_host ? zi_host[1] : 0.0, dynamic);                                       \
+                    zi_host ? zi_host[1] : 0.0);                                                \
     } while (0)
             if (y) OSZ_TILE_LAUNCH(true, y, ldy);
             else OSZ_TILE_LAUNCH(false, (TIO *)nullptr, 0);
