@@ -126,6 +126,36 @@ def test_short_source_still_flushes(fake_gpu):
     assert got.shape == ref.shape and np.max(np.abs(got - ref)) < 1e-12
 
 
+def test_time_ring_alignment_and_capacity(fake_gpu):
+    """The staging ring keeps its write position and row pitch on multiples of 16 samples
+    (the TMA-moved kernels upstream need 16-byte aligned rows) whatever is left live when it
+    re-bases, keeps the live samples intact, and a ring told how much its consumer lets
+    pile up is allocated once instead of being re-based every other block."""
+    ring = nm._TimeRing(3, capacity=0)
+    rng = np.random.default_rng(1)
+    kept = np.zeros((3, 0))
+    buffers = set()
+    for step in range(12):
+        n = 1600
+        block = nm.dv.from_host(rng.standard_normal((3, n)))
+        dst = ring.alloc(3, n)
+        assert ring.pos % 16 == 0 and ring.buf.shape[1] % 16 == 0
+        dst.copy_(block)
+        ring.push(dst)
+        kept = np.concatenate([kept, block.numpy()], -1)
+        drop = 1600 - 37 if step % 2 else 1600 - 5          # odd leftovers
+        ring.drop(drop)
+        kept = kept[:, drop:]
+        assert np.array_equal(ring.window().numpy(), kept)
+        buffers.add(ring.buf.data_ptr())
+    big = nm._TimeRing(3, capacity=20000)
+    for step in range(10):
+        dst = big.alloc(3, 1600)
+        dst.zero_()
+        big.push(dst)
+    assert big.buf.shape[1] >= 20000 + 2 * 1600 and big.start == 0    # never re-based
+
+
 def test_producer_mutation_contract(fake_gpu):
     """producer(Producer, cs, axis) mutates and returns the same object
     (reference core/producer.py:114-117); psd forces chunksize=int(fs)."""
