@@ -281,6 +281,50 @@ def test_sos_tile_lookback(dv, rows, n, tile, monkeypatch):
         assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
+@pytest.mark.parametrize("deal", ["0", "1"])
+def test_sos_tile_random_shapes(dv, deal, monkeypatch):
+    """Seeded sweep of the single-section scan over row counts, lengths, row pitches and
+    element offsets (views into wider buffers: aligned ones take the TMA kernel, odd
+    offsets / pitches the plain-load tile kernel or the row kernel), float64 and float32
+    samples, forward and reversed, output written into a view as well -- both ways of
+    dealing the tiles -- against the sequential recurrence."""
+    import torch
+
+    monkeypatch.setenv("OSZ_SOS_TILE_DEAL", deal)
+    rng = np.random.default_rng(2024)
+    b, a = sps.iirnotch(50, 8, fs=5000)
+    sos = np.concatenate([b, a])[None]
+    plan = dv.SosPlan(sos)
+    for case in range(28):
+        rows = int(rng.choice([1, 2, 5, 31, 64, 150, 300]))
+        n = int(rng.choice([1, 17, 4095, 4096, 4097, 8192, 12289, 40_000, 100_003, 262_144]))
+        if rows * n > 20_000_000:
+            n = 40_000
+        pad_l = int(rng.choice([0, 1, 2, 3, 16]))
+        pitch = n + pad_l + int(rng.choice([0, 1, 5, 16]))
+        f32 = bool(rng.integers(0, 2))
+        reverse = bool(rng.integers(0, 2))
+        npdt = np.float32 if f32 else np.float64
+        xfull = (rng.standard_normal((rows, pitch)) + 0.3).astype(npdt)
+        xdev = torch.from_numpy(xfull).cuda()
+        ydev = torch.zeros_like(xdev)
+        xv, yv = xdev[:, pad_l:pad_l + n], ydev[:, pad_l:pad_l + n]
+        zi = rng.standard_normal((rows, 1, 2)) * 0.1
+        state = _dev(dv, zi)
+        plan.run(xv, state, reverse=reverse, out=yv)
+        x64 = xfull[:, pad_l:pad_l + n].astype(np.float64)
+        xr = x64[:, ::-1] if reverse else x64
+        ry, rz = sps.sosfilt(sos, xr, axis=-1, zi=np.transpose(zi, (1, 0, 2)))
+        ry = ry[:, ::-1] if reverse else ry
+        got = ydev.cpu().numpy()
+        tol = 2e-6 if f32 else 1e-10
+        scale = max(np.max(np.abs(ry)), 1e-30)
+        assert np.max(np.abs(got[:, pad_l:pad_l + n] - ry)) / scale < tol, (case, rows, n, pad_l, pitch, f32, reverse)
+        # nothing outside the view was touched
+        assert not got[:, :pad_l].any() and not got[:, pad_l + n:].any(), (case, rows, n)
+        assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-7, (case, rows, n, f32)
+
+
 @pytest.mark.parametrize("kind", ["notch", "butter2"])
 def test_sos_tail_state(dv, kind):
     """State after a run of samples from rest as ONE weighted sum of the last `settle`
