@@ -57,7 +57,7 @@ __device__ __forceinline__ void ufd_mma_batch(Fetch fetch, const double *gp4, in
 // phase p in this lane's A row (segment g): window offset p + n * M.  The tensor pipe
 // issues one DMMA.8x8x4 per 16 clk and SM sub-partition (profiles/r02_ncu_summary.md),
 // so the loop has to stay well below 16 instructions per MMA: this form runs at ~4.
-constexpr int UFD_NSB = 8;
+constexpr int UFD_NSB = 14;    // k-steps per batch: 20 A + 14 B fragments up front, 56 MMAs behind them
 template <class Fetch>
 __device__ __forceinline__ void ufd_mma_ksteps(const UfdMmaGeom &gm, const double *gs, int k_lo,
                                                int k_hi, int wt, int g, int q, Fetch fetch,
@@ -87,13 +87,12 @@ __device__ __forceinline__ void ufd_mma_ksteps(const UfdMmaGeom &gm, const doubl
         for (; s0 + UFD_NSB <= s_end; s0 += UFD_NSB)
             ufd_mma_batch<UFD_NSB>(fp, gp + 4 * s0, nbase + 4 * s0, c);
         switch (s_end - s0) {        // the remainder, as one unguarded batch of its own size
-            case 7: ufd_mma_batch<7>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 6: ufd_mma_batch<6>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 5: ufd_mma_batch<5>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 4: ufd_mma_batch<4>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 3: ufd_mma_batch<3>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 2: ufd_mma_batch<2>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
-            case 1: ufd_mma_batch<1>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+#define OSZ_UFD_REM(NBR) \
+    case NBR: ufd_mma_batch<NBR>(fp, gp + 4 * s0, nbase + 4 * s0, c); break;
+            OSZ_UFD_REM(13) OSZ_UFD_REM(12) OSZ_UFD_REM(11) OSZ_UFD_REM(10) OSZ_UFD_REM(9)
+            OSZ_UFD_REM(8) OSZ_UFD_REM(7) OSZ_UFD_REM(6) OSZ_UFD_REM(5) OSZ_UFD_REM(4)
+            OSZ_UFD_REM(3) OSZ_UFD_REM(2) OSZ_UFD_REM(1)
+#undef OSZ_UFD_REM
             default: break;
         }
         kk += s_end - s;
