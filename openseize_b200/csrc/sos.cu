@@ -766,6 +766,10 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
             return v;                                                                            \
         }();                                                                                     \
         if (per_sm < 1) lerr = cudaErrorLaunchOutOfResources;                                    \
+        /* (the attribute is per device: a process that drives several sets it on each) */       \
+        if (lerr == cudaSuccess)                                                                 \
+            lerr = cudaFuncSetAttribute(sos_tile_tma_kernel<W, TIO>,                             \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem);     \
         if (lerr == cudaSuccess) {                                                               \
             if (ctas > (int64_t)per_sm * sm_count()) ctas = (int64_t)per_sm * sm_count();        \
             lerr = tile_launch(dynamic, sos_tile_tma_kernel<W, TIO>, (unsigned)ctas, tsmem, st,  \
