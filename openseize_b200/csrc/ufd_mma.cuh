@@ -119,10 +119,13 @@ inline std::vector<int> ufd_ksteps(int K, int M, int *smax_out, long *total_out)
 }
 
 // segment pad (doubles) that spreads the 16 lanes of a half warp (g * pitch + q * M)
-// over the most shared-memory banks
+// over the most shared-memory banks.  Only EVEN pitches are considered: the segments are
+// staged by 1-D TMA bulk copies, which need 16-byte aligned destinations.  For even M that
+// leaves a 2-way conflict on the A-fragment loads (8 of 16 banks; an odd pitch would reach 16
+// but has to be staged by 8-byte cp.async: 2.98 ms against 0.9 for 449 taps / M = 20).
 inline int ufd_best_pad(int SM, int M) {
     int best_pad = 0, best_score = -1;
-    for (int pad = 0; pad < 16; ++pad) {
+    for (int pad = (SM & 1); pad < 16; pad += 2) {
         bool seen[16] = {false};
         int score = 0;
         for (int g = 0; g < 4; ++g)

@@ -900,12 +900,14 @@ int osz_upfirdn_plan_set_kernel(osz_upfirdn_plan *p, int kernel) {
 int osz_upfirdn_plan_kernel(const osz_upfirdn_plan *p) {
     if (!p) return 0;
     if (!p->R) return OSZ_UFD_GENERAL;
-    // AUTO: the tensor-core kernel when at least 80 % of its MMA work is useful (long
-    // per-phase filters: 8 outputs share a window, so a phase of Q taps costs Q + 7) and
-    // its tiles can be staged by TMA (even segment pitch); measured on B200 (256 x 1e6):
-    // 1231 taps / M = 25: 1.30 ms against 1.55 ms for the CUDA-core kernel; 561 / 25
-    // (70 % useful): 0.99 against 0.96; 449 / 20 (cp.async staging): 1.5 against 0.97
-    const bool worth = p->mma && p->mma_useful >= 0.8 && (p->mg.P % 2 == 0);
+    // AUTO: the tensor-core kernel when enough of its MMA work is useful (long per-phase
+    // filters: 8 outputs share a window, so a phase of Q taps costs Q + 7).  Measured on B200
+    // (256 x 1e6): 1231 taps / M = 25 (86 % useful): 1.22 ms against 1.55 ms for the CUDA-core
+    // kernel; 561 / 25 (70 %): 0.82 against 0.95; 449 / 20 (70 %, even M: the even segment
+    // pitch the TMA staging needs leaves a 2-way bank conflict on the A fragments): 0.98
+    // against 0.96 -- so 68 % is enough for odd M, even M wants 80 %.
+    const double need = (p->down & 1) ? 0.68 : 0.8;
+    const bool worth = p->mma && p->mma_useful >= need && (p->mg.P % 2 == 0);
     if (p->kernel == OSZ_UFD_MMA || (p->kernel == OSZ_UFD_AUTO && worth && ufd_use_mma_default()))
         return OSZ_UFD_MMA;
     return OSZ_UFD_POLYPHASE;
