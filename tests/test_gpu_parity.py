@@ -281,6 +281,34 @@ def test_sos_tile_lookback(dv, rows, n, tile, monkeypatch):
         assert relerr(state.cpu().numpy(), np.transpose(rz, (1, 0, 2))) < 2e-8
 
 
+def test_sos_tile_nan_inputs(dv):
+    """NaNs in the samples -- including the all-ones NaN bit pattern, which is what the tile
+    descriptors use for "not published" -- must propagate like in the sequential recurrence
+    (everything after the first NaN of a row is NaN, rows without NaNs are untouched) and must
+    not stall the look-back."""
+    import torch
+
+    b, a = sps.iirnotch(60, 10, fs=30000)
+    sos = np.concatenate([b, a])[None]
+    plan = dv.SosPlan(sos)
+    rng = np.random.default_rng(11)
+    rows, n = 6, 4096 * 12 + 576
+    x = rng.standard_normal((rows, n))
+    x[1, 30000] = np.nan
+    x[3, 5] = np.inf
+    x[4, 20000] = np.frombuffer(np.array([-1], dtype=np.int64).tobytes(), dtype=np.float64)[0]
+    for reverse in (False, True):
+        state = dv.zeros((rows, 1, 2))
+        y = plan.run(torch.from_numpy(x).cuda(), state, reverse=reverse).cpu().numpy()
+        xr = x[:, ::-1] if reverse else x
+        with np.errstate(all="ignore"):
+            ry, _ = sps.sosfilt(sos, xr, axis=-1, zi=np.zeros((1, rows, 2)))
+        ry = ry[:, ::-1] if reverse else ry
+        assert np.array_equal(np.isfinite(y), np.isfinite(ry)), reverse
+        good = np.isfinite(ry)
+        assert np.max(np.abs(y[good] - ry[good])) / np.max(np.abs(ry[good])) < 1e-10
+
+
 @pytest.mark.parametrize("deal", ["0", "1"])
 def test_sos_tile_random_shapes(dv, deal, monkeypatch):
     """Seeded sweep of the single-section scan over row counts, lengths, row pitches and
