@@ -600,7 +600,7 @@ int osz_tf_exec_f64(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t 
     cudaStream_t st = as_stream(stream);
     // Which kernel (OSZ_TF_KERNEL=split|scan|seq forces one; read per call, the tests run
     // all three in one process):
-    //   split  spans of >= 4 settle lengths run concurrently after a warm-up: the sequential
+    //   split  spans of >= 2 settle lengths run concurrently after a warm-up: the sequential
     //          recurrence's rounding, every thread busy -- whenever the chunk holds two spans;
     //   scan   companion-matrix scan: only where its re-association is harmless (transient
     //          growth max ||A^i|| <= 16; measured: 4e3 eps per unit of growth);
@@ -608,7 +608,7 @@ int osz_tf_exec_f64(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t 
     const char *force = getenv("OSZ_TF_KERNEL");
     const int S = p->prm.S;
     const int64_t warm = p->settle > 0 ? (p->settle + TFP_B - 1) / TFP_B * TFP_B : 0;
-    bool split = warm > 0 && n >= 8 * warm && S >= 3 && S <= 12;
+    bool split = warm > 0 && n >= 4 * warm && S >= 3 && S <= 12;
     bool scan = !split && p->d_lanepow && p->growth <= 16.0;
     if (force) {
         const std::string f(force);
@@ -616,13 +616,12 @@ int osz_tf_exec_f64(const osz_tf_plan *p, const double *x, int64_t ldx, int64_t 
         scan = f == "scan" && p->d_lanepow != nullptr;
     }
     if (split) {
-        // enough spans to fill the GPU twice over, none shorter than 4 settle lengths
-        // enough spans to fill the GPU, none shorter than 4 settle lengths; a row's spans
+        // enough spans to fill the GPU, none shorter than 2 settle lengths; a row's spans
         // fill whole CTAs of 128 (k CTAs per row, rows * k close to two per SM)
         int64_t k = (2 * (int64_t)sm_count() + rows - 1) / rows;
         if (rows * k > 2 * (int64_t)sm_count() && k > 1) --k;
         int64_t len = ((n + k * TFP_NT - 1) / (k * TFP_NT) + TFP_B - 1) / TFP_B * TFP_B;
-        if (len < 4 * warm) len = 4 * warm;
+        if (len < 2 * warm) len = 2 * warm;     // (at most half of a thread's samples are warm-up)
         if (len < 256) len = 256;
         switch (S) {
 #define OSZ_TF_SPLIT(SS) \
