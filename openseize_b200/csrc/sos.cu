@@ -722,7 +722,9 @@ static int sos_exec_t(const osz_sos_plan *p, const TIO *x, int64_t ldx, int64_t 
         // ago: 256 rows 0.676 against 0.706 ms), static rounds below (32 rows 0.122 against
         // 0.138 ms); OSZ_SOS_TILE_DEAL=0/1 forces static / tickets
         const char *deal_env = getenv("OSZ_SOS_TILE_DEAL");
-        const int dynamic = deal_env ? (atoi(deal_env) != 0) : (rows > (int64_t)sm_count());
+        // (a state-only pass -- the look-ahead, one round of tiles -- always takes tickets: an
+        //  ordinary launch can start in the tail of the kernel before it, a cooperative one not)
+        const int dynamic = deal_env ? (atoi(deal_env) != 0) : (rows > (int64_t)sm_count() || !y);
         SosParams1 prm1;
         prm1.nsec = 1;
         prm1.pad_ = 0;
